@@ -1,0 +1,348 @@
+// LSD radix sort of 128-bit records on a byte range of the key, hand-written for sm_100a.
+//
+// Replaces the reference's two CPU sorts on the hot path:
+//   msd_sort   (MSDsort.c:404)  -- k-mer records of the GIX build, key = 40-mer (80 bits)
+//   rmsd_sort  (RSDsort.c:292)  -- adaptive-seed records, key = (jcont, band, anti, drem, lcp)
+// Both are in-place American-flag MSD sorts on byte-packed records (MSDsort.c:211-360); on the
+// device every record is widened to one 16-byte word so each pass is a perfectly coalesced
+// stream (read 16 B, write 16 B per record).  One pass = per-tile digit histogram, a row scan of
+// the (digit x tile) matrix, and a stable scatter that ranks records inside a 4096-record tile
+// with warp match-any multi-split, stages the tile in shared memory in digit order and writes
+// digit runs back coalesced.  HBM-bound integer work: no tensor cores.
+#include "common.cuh"
+
+#define SORT_THREADS 512
+#define SORT_ITEMS   8
+#define SORT_TILE    (SORT_THREADS*SORT_ITEMS)
+#define SORT_WARPS   (SORT_THREADS/32)
+
+static __device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane)
+{
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+    { unsigned t = __shfl_up_sync(0xffffffffu,v,o);
+      if (lane >= o) v += t;
+    }
+  return v;
+}
+
+//  Per-tile histogram of one key byte.  blockhist is digit-major: [256][ntiles].
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_hist_kernel(const rec128 *__restrict__ in, long long n, int byte,
+                 unsigned *__restrict__ blockhist, int ntiles)
+{ __shared__ unsigned h[256];
+  int tid = threadIdx.x;
+  if (tid < 256) h[tid] = 0;
+  __syncthreads();
+
+  long long tile0 = (long long) blockIdx.x * SORT_TILE;
+  const unsigned long long *half = reinterpret_cast<const unsigned long long *>(in) + (byte >= 8);
+  int sh = 8*(byte & 7);
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; it++)
+    { long long idx = tile0 + it*SORT_THREADS + tid;
+      bool valid = idx < n;
+      unsigned d = 0x100u | (tid & 31);
+      if (valid)
+        d = (unsigned) ((half[2*idx] >> sh) & 0xff);
+      unsigned peers = __match_any_sync(0xffffffffu,d);
+      if (valid && (tid & 31) == __ffs(peers)-1)
+        atomicAdd(&h[d],__popc(peers));
+    }
+  __syncthreads();
+  if (tid < 256)
+    blockhist[(long long) tid*ntiles + blockIdx.x] = h[tid];
+}
+
+//  Exclusive scan of each digit row (one block per digit); row totals out.
+
+__global__ void __launch_bounds__(1024)
+sort_rowscan_kernel(unsigned *__restrict__ blockhist, int ntiles, unsigned *__restrict__ rowtotal)
+{ __shared__ unsigned wsum[32];
+  __shared__ unsigned carry_s;
+  unsigned *row = blockhist + (long long) blockIdx.x * ntiles;
+  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < ntiles; base += 1024)
+    { int i = base + tid;
+      unsigned v = (i < ntiles) ? row[i] : 0;
+      unsigned inc = warp_incl_scan(v,lane);
+      if (lane == 31) wsum[w] = inc;
+      __syncthreads();
+      if (w == 0)
+        { unsigned s = wsum[lane];
+          unsigned si = warp_incl_scan(s,lane);
+          wsum[lane] = si - s;
+        }
+      __syncthreads();
+      unsigned carry = carry_s;
+      unsigned ex = carry + wsum[w] + inc - v;
+      if (i < ntiles) row[i] = ex;
+      __syncthreads();
+      if (tid == 1023) carry_s = ex + v;
+      __syncthreads();
+    }
+  if (tid == 0) rowtotal[blockIdx.x] = carry_s;
+}
+
+__global__ void sort_binbase_kernel(const unsigned *__restrict__ rowtotal, unsigned *__restrict__ binbase)
+{ __shared__ unsigned wsum[8];
+  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  unsigned v = rowtotal[tid];
+  unsigned inc = warp_incl_scan(v,lane);
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  unsigned pre = 0;
+  for (int i = 0; i < w; i++) pre += wsum[i];
+  binbase[tid] = pre + inc - v;
+}
+
+//  Stable scatter of one tile.
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_scatter_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, long long n, int byte,
+                    const unsigned *__restrict__ blockhist, const unsigned *__restrict__ binbase,
+                    int ntiles)
+{ extern __shared__ __align__(16) unsigned char smem_raw[];
+  rec128   *tile   = reinterpret_cast<rec128 *>(smem_raw);
+  unsigned *wcount = reinterpret_cast<unsigned *>(tile + SORT_TILE);   // [SORT_WARPS][256]
+  unsigned *bexcl  = wcount + SORT_WARPS*256;                           // [256]
+  unsigned *gbase  = bexcl + 256;                                       // [256]
+  unsigned *wtot   = gbase + 256;                                       // [8]
+
+  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  long long tile0 = (long long) blockIdx.x * SORT_TILE;
+  long long rem = n - tile0;
+  int cnt = rem < SORT_TILE ? (int) rem : SORT_TILE;
+
+  for (int i = tid; i < SORT_WARPS*256; i += SORT_THREADS)
+    wcount[i] = 0;
+  __syncthreads();
+
+  rec128   r[SORT_ITEMS];
+  unsigned rank[SORT_ITEMS];
+  int base = w*(32*SORT_ITEMS);
+  unsigned *myc = wcount + w*256;
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; it++)
+    { int idx = base + it*32 + lane;
+      bool valid = idx < cnt;
+      unsigned d = 0x100u | lane;
+      if (valid)
+        { r[it] = ld_rec(in + tile0 + idx);
+          d = rec_byte(r[it],byte);
+        }
+      unsigned peers = __match_any_sync(0xffffffffu,d);
+      int leader = __ffs(peers)-1;
+      unsigned b = 0;
+      if (valid && lane == leader)
+        { b = myc[d];
+          myc[d] = b + __popc(peers);
+        }
+      b = __shfl_sync(0xffffffffu,b,leader);
+      rank[it] = b + __popc(peers & lanemask_lt());
+      __syncwarp();
+    }
+  __syncthreads();
+
+  unsigned c = 0, inc = 0;
+  if (tid < 256)
+    { unsigned sum = 0;
+#pragma unroll
+      for (int ww = 0; ww < SORT_WARPS; ww++)
+        { unsigned t = wcount[ww*256+tid];
+          wcount[ww*256+tid] = sum;
+          sum += t;
+        }
+      c = sum;
+      inc = warp_incl_scan(c,lane);
+      if (lane == 31) wtot[w] = inc;
+    }
+  __syncthreads();
+  if (tid < 256)
+    { unsigned pre = 0;
+      for (int i = 0; i < w; i++) pre += wtot[i];
+      unsigned ex = pre + inc - c;
+      bexcl[tid] = ex;
+      gbase[tid] = binbase[tid] + blockhist[(long long) tid*ntiles + blockIdx.x] - ex;
+    }
+  __syncthreads();
+
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; it++)
+    { int idx = base + it*32 + lane;
+      if (idx < cnt)
+        { unsigned d = rec_byte(r[it],byte);
+          st_rec(tile + (bexcl[d] + myc[d] + rank[it]),r[it]);
+        }
+    }
+  __syncthreads();
+
+  for (int p = tid; p < cnt; p += SORT_THREADS)
+    { rec128 v = ld_rec(tile + p);
+      unsigned d = rec_byte(v,byte);
+      st_rec(out + (unsigned) (gbase[d] + p),v);
+    }
+}
+
+static const size_t SCATTER_SMEM = SORT_TILE*sizeof(rec128) + (SORT_WARPS*256 + 256 + 256 + 8)*sizeof(unsigned);
+
+extern "C" long long fgb_sort128_tmp_bytes(long long n)
+{ long long ntiles = (n + SORT_TILE - 1) / SORT_TILE;
+  if (ntiles < 1) ntiles = 1;
+  return (256*ntiles + 512) * (long long) sizeof(unsigned);
+}
+
+//  Sorts n records on key bytes [byte_lo,byte_hi) of the 128-bit little-endian value, stable.
+//  d_a holds the input; d_b is a same-size scratch.  Returns via *result_in_b where the sorted
+//  data landed (0 = d_a, 1 = d_b).  All pointers are device pointers.
+
+extern "C" int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo, int byte_hi,
+                                  void *d_tmp, long long tmp_bytes, int *result_in_b, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  if (n < 0 || byte_lo < 0 || byte_hi > 16 || byte_lo > byte_hi) return FGB_ERR_ARG;
+  if (n >= 0xffffffffll) return FGB_ERR_LIMIT;
+  *result_in_b = 0;
+  if (n <= 1 || byte_lo == byte_hi) return FGB_OK;
+  if (tmp_bytes < fgb_sort128_tmp_bytes(n)) return FGB_ERR_ARG;
+
+  int ntiles = (int) ((n + SORT_TILE - 1) / SORT_TILE);
+  unsigned *blockhist = (unsigned *) d_tmp;
+  unsigned *rowtotal  = blockhist + 256ll*ntiles;
+  unsigned *binbase   = rowtotal + 256;
+
+  static bool attr_set = false;
+  if (!attr_set)
+    { CUDA_TRY(cudaFuncSetAttribute(sort_scatter_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int) SCATTER_SMEM));
+      attr_set = true;
+    }
+
+  rec128 *src = (rec128 *) d_a, *dst = (rec128 *) d_b;
+  for (int b = byte_lo; b < byte_hi; b++)
+    { sort_hist_kernel<<<ntiles,SORT_THREADS,0,st>>>(src,n,b,blockhist,ntiles);
+      sort_rowscan_kernel<<<256,1024,0,st>>>(blockhist,ntiles,rowtotal);
+      sort_binbase_kernel<<<1,256,0,st>>>(rowtotal,binbase);
+      sort_scatter_kernel<<<ntiles,SORT_THREADS,SCATTER_SMEM,st>>>(src,dst,n,b,blockhist,binbase,ntiles);
+      rec128 *t = src; src = dst; dst = t;
+      *result_in_b ^= 1;
+    }
+  CUDA_TRY(cudaGetLastError());
+  return FGB_OK;
+}
+
+/***********************************************************************************************
+ *  Generic exclusive scan of a u32 array (reduce / scan-of-sums / downsweep), used for stream
+ *  compaction of syncmer posts, seeds and work lists.
+ **********************************************************************************************/
+
+#define SCAN_THREADS 1024
+#define SCAN_ITEMS   8
+#define SCAN_TILE    (SCAN_THREADS*SCAN_ITEMS)
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_reduce_kernel(const unsigned *__restrict__ data, long long n, unsigned long long *__restrict__ sums)
+{ __shared__ unsigned long long ws[32];
+  long long t0 = (long long) blockIdx.x * SCAN_TILE;
+  unsigned long long s = 0;
+  for (int i = 0; i < SCAN_ITEMS; i++)
+    { long long idx = t0 + i*SCAN_THREADS + threadIdx.x;
+      if (idx < n) s += data[idx];
+    }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu,s,o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32)
+    { s = ws[threadIdx.x];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu,s,o);
+      if (threadIdx.x == 0) sums[blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+scan_sums_kernel(unsigned long long *__restrict__ sums, int nb, unsigned long long *__restrict__ total)
+{ __shared__ unsigned long long ws[32];
+  __shared__ unsigned long long carry_s;
+  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024)
+    { int i = base + tid;
+      unsigned long long v = (i < nb) ? sums[i] : 0, inc = v;
+      for (int o = 1; o < 32; o <<= 1)
+        { unsigned long long t = __shfl_up_sync(0xffffffffu,inc,o);
+          if (lane >= o) inc += t;
+        }
+      if (lane == 31) ws[w] = inc;
+      __syncthreads();
+      if (w == 0)
+        { unsigned long long s = ws[lane], si = s;
+          for (int o = 1; o < 32; o <<= 1)
+            { unsigned long long t = __shfl_up_sync(0xffffffffu,si,o);
+              if (lane >= o) si += t;
+            }
+          ws[lane] = si - s;
+        }
+      __syncthreads();
+      unsigned long long ex = carry_s + ws[w] + inc - v;
+      if (i < nb) sums[i] = ex;
+      __syncthreads();
+      if (tid == 1023) carry_s = ex + v;
+      __syncthreads();
+    }
+  if (tid == 0 && total != NULL) *total = carry_s;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_down_kernel(unsigned *__restrict__ data, long long n, const unsigned long long *__restrict__ sums)
+{ __shared__ unsigned ws[32];
+  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  long long t0 = (long long) blockIdx.x * SCAN_TILE + (long long) tid * SCAN_ITEMS;
+  unsigned v[SCAN_ITEMS], s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++)
+    { v[i] = (t0 + i < n) ? data[t0+i] : 0;
+      s += v[i];
+    }
+  unsigned inc = warp_incl_scan(s,lane);
+  if (lane == 31) ws[w] = inc;
+  __syncthreads();
+  if (w == 0)
+    { unsigned x = ws[lane];
+      unsigned xi = warp_incl_scan(x,lane);
+      ws[lane] = xi - x;
+    }
+  __syncthreads();
+  unsigned ex = (unsigned) sums[blockIdx.x] + ws[w] + inc - s;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++)
+    { if (t0 + i < n) data[t0+i] = ex;
+      ex += v[i];
+    }
+}
+
+long long fgb_dev_scan_tmp_bytes(long long n)
+{ long long nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (nb < 1) nb = 1;
+  return nb * 8 + 64;
+}
+
+//  In-place exclusive scan (values mod 2^32); *d_total (device, may be NULL) gets the 64-bit sum.
+
+int fgb_dev_exclusive_scan_u32(unsigned *d_data, long long n, unsigned long long *d_total,
+                               void *d_tmp, long long tmp_bytes, cudaStream_t st)
+{ if (n <= 0)
+    { if (d_total) CUDA_TRY(cudaMemsetAsync(d_total,0,8,st));
+      return FGB_OK;
+    }
+  if (tmp_bytes < fgb_dev_scan_tmp_bytes(n)) return FGB_ERR_ARG;
+  int nb = (int) ((n + SCAN_TILE - 1) / SCAN_TILE);
+  unsigned long long *sums = (unsigned long long *) d_tmp;
+  scan_reduce_kernel<<<nb,SCAN_THREADS,0,st>>>(d_data,n,sums);
+  scan_sums_kernel<<<1,1024,0,st>>>(sums,nb,d_total);
+  scan_down_kernel<<<nb,SCAN_THREADS,0,st>>>(d_data,n,sums);
+  CUDA_TRY(cudaGetLastError());
+  return FGB_OK;
+}
