@@ -1,0 +1,397 @@
+// C-ABI of libfastga_b200.so: opaque handles (genome / GIX / seed set) over device memory and the
+// host-buffer entry points the reference-side host code binds (see include/fastga_b200.h and
+// INTEGRATION.md).  No torch types, no CPU fallback: every call runs the sm_100a kernels.
+#include "common.cuh"
+#include "handles.h"
+#include <vector>
+#include <algorithm>
+#include <string.h>
+
+typedef unsigned long long u64;
+
+extern "C" {
+int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo, int byte_hi,
+                       void *d_tmp, long long tmp_bytes, int *result_in_b, void *stream);
+long long fgb_sort128_tmp_bytes(long long n);
+int fgb_stage_genome_device(const void *d_bps, const long long *d_boff, const long long *d_clen,
+                            const long long *d_woff, int ncontig, long long total_words,
+                            void *d_seq, void *d_rseq, void *stream);
+int fgb_syncmer_count_device(const void *d_seq, const long long *d_clen, const long long *d_woff,
+                             const int *d_crank, const int *d_tile_contig, const int *d_tile_start,
+                             int ntiles, unsigned *d_tile_count, unsigned long long *d_buck1024,
+                             unsigned long long *d_total, void *d_tmp, long long tmp_bytes,
+                             void *stream);
+int fgb_syncmer_emit_device(const void *d_seq, const long long *d_clen, const long long *d_woff,
+                            const int *d_crank, const int *d_tile_contig, const int *d_tile_start,
+                            int ntiles, unsigned *d_tile_offset, void *d_records, void *stream);
+int fgb_kix_index_device(const void *d_tab, long long n, unsigned *d_pstart, void *stream);
+int fgb_ktab_export_device(const void *d_tab, long long n, int pbytes, int cbytes,
+                           const long long *d_part_first, int nparts, void *d_out, void *stream);
+int fgb_ktab_import_device(const void *d_ent, long long n, int pbytes, int cbytes,
+                           const long long *d_index, void *d_tab, void *stream);
+int fgb_sc_tile();
+int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2, const unsigned *d_pstart2,
+                     int freq, int anti_bits, int band_bits, int jc_bits, int ic_bits,
+                     long long amxpos, long long bmxpos, void *d_seeds, long long capacity,
+                     unsigned long long *d_counters, unsigned long long *h_nseeds,
+                     unsigned long long *h_sumlen, void *stream);
+}
+
+static fgb_timings g_timings;
+
+struct stage_timer
+{ cudaEvent_t a, b; cudaStream_t st; float *dst;
+  stage_timer(float *d, cudaStream_t s) : st(s), dst(d)
+    { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a,st); }
+  ~stage_timer()
+    { cudaEventRecord(b,st); cudaEventSynchronize(b);
+      float ms = 0; cudaEventElapsedTime(&ms,a,b); *dst += ms;
+      cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+};
+
+extern "C" void fgb_timings_reset() { memset(&g_timings,0,sizeof(g_timings)); }
+extern "C" void fgb_timings_get(fgb_timings *out) { *out = g_timings; }
+
+/***********************************************************************************************
+ *  Genome: the GDB as the path sees it (GDB.h:28-34 GDB_CONTIG {clen, boff} + the .bps image)
+ **********************************************************************************************/
+
+static const long long *g_sort_len;
+static int LSORT(const void *l, const void *r)          // GIXmake.c:1628-1633: decreasing length
+{ int x = *((const int *) l), y = *((const int *) r);
+  return (int) (g_sort_len[y] - g_sort_len[x]);
+}
+
+extern "C" int fgb_genome_create(const unsigned char *bps, long long bps_bytes, int ncontig,
+                                 const long long *clen, const long long *boff, int want_revcomp,
+                                 fgb_genome **out, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  if (ncontig <= 0 || ncontig > 0x7fff) return FGB_ERR_LIMIT;   // contig rank is a 15-bit field
+  fgb_genome *g = new fgb_genome();
+  g->ncontig = ncontig;
+  g->clen.assign(clen,clen+ncontig);
+  g->boff.assign(boff,boff+ncontig);
+  g->woff.resize(ncontig+1);
+  g->seqtot = 0; g->maxlen = 0;
+  long long w = 0;
+  for (int c = 0; c < ncontig; c++)
+    { if (clen[c] >= 0x7fffffffll) { delete g; return FGB_ERR_LIMIT; }
+      g->woff[c] = w;
+      w += ((clen[c] + 31) >> 5) + 2;          // zero pad so 64-bit window reads stay inside
+      w = (w + 1) & ~1ll;                      // 16-byte alignment of every contig
+      g->seqtot += clen[c];
+      if (clen[c] > g->maxlen) g->maxlen = clen[c];
+    }
+  g->woff[ncontig] = w;
+  g->total_words = w;
+
+  g->perm.resize(ncontig); g->crank.resize(ncontig);
+  for (int c = 0; c < ncontig; c++) g->perm[c] = c;
+  g_sort_len = clen;
+  qsort(g->perm.data(),ncontig,sizeof(int),LSORT);     // same libc call as GIXmake.c:1959
+  for (int c = 0; c < ncontig; c++) g->crank[g->perm[c]] = c;
+
+  unsigned char *d_bps = NULL;
+  long long *d_boff = NULL;
+  CUDA_TRY(cudaMalloc(&d_bps,bps_bytes + 16));
+  CUDA_TRY(cudaMalloc(&d_boff,sizeof(long long)*ncontig));
+  CUDA_TRY(cudaMalloc(&g->d_clen,sizeof(long long)*ncontig));
+  CUDA_TRY(cudaMalloc(&g->d_woff,sizeof(long long)*(ncontig+1)));
+  CUDA_TRY(cudaMalloc(&g->d_crank,sizeof(int)*ncontig));
+  CUDA_TRY(cudaMalloc(&g->d_perm,sizeof(int)*ncontig));
+  CUDA_TRY(cudaMalloc(&g->d_seq,sizeof(u64)*w));
+  if (want_revcomp) CUDA_TRY(cudaMalloc(&g->d_rseq,sizeof(u64)*w));
+  { stage_timer t(&g_timings.h2d_ms,st);
+    CUDA_TRY(cudaMemcpyAsync(d_bps,bps,bps_bytes,cudaMemcpyHostToDevice,st));
+    CUDA_TRY(cudaMemcpyAsync(d_boff,boff,sizeof(long long)*ncontig,cudaMemcpyHostToDevice,st));
+    CUDA_TRY(cudaMemcpyAsync(g->d_clen,clen,sizeof(long long)*ncontig,cudaMemcpyHostToDevice,st));
+    CUDA_TRY(cudaMemcpyAsync(g->d_woff,g->woff.data(),sizeof(long long)*(ncontig+1),cudaMemcpyHostToDevice,st));
+    CUDA_TRY(cudaMemcpyAsync(g->d_crank,g->crank.data(),sizeof(int)*ncontig,cudaMemcpyHostToDevice,st));
+    CUDA_TRY(cudaMemcpyAsync(g->d_perm,g->perm.data(),sizeof(int)*ncontig,cudaMemcpyHostToDevice,st));
+  }
+  g->h2d_bytes = bps_bytes + (long long) ncontig*(3*8+2*4) + 8;
+  int rc;
+  { stage_timer t(&g_timings.stage_ms,st);
+    rc = fgb_stage_genome_device(d_bps,d_boff,g->d_clen,g->d_woff,ncontig,w,g->d_seq,g->d_rseq,st);
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  cudaFree(d_bps); cudaFree(d_boff);
+  if (rc) { delete g; return rc; }
+  *out = g;
+  return FGB_OK;
+}
+
+extern "C" void fgb_genome_free(fgb_genome *g)
+{ if (!g) return;
+  cudaFree(g->d_clen); cudaFree(g->d_woff); cudaFree(g->d_crank); cudaFree(g->d_perm);
+  cudaFree(g->d_seq); cudaFree(g->d_rseq);
+  delete g;
+}
+
+extern "C" int fgb_genome_perm(const fgb_genome *g, int *perm_out)
+{ memcpy(perm_out,g->perm.data(),sizeof(int)*g->ncontig); return FGB_OK; }
+
+//  staged words back to the host (tests): seq (rev=0) or its reverse complement (rev=1)
+extern "C" int fgb_genome_download(const fgb_genome *g, int rev, unsigned long long *words,
+                                   long long *woff_out)
+{ const u64 *src = rev ? g->d_rseq : g->d_seq;
+  if (src == NULL) return FGB_ERR_ARG;
+  CUDA_TRY(cudaMemcpy(words,src,sizeof(u64)*g->total_words,cudaMemcpyDeviceToHost));
+  memcpy(woff_out,g->woff.data(),sizeof(long long)*(g->ncontig+1));
+  return FGB_OK;
+}
+extern "C" long long fgb_genome_words(const fgb_genome *g) { return g->total_words; }
+
+/***********************************************************************************************
+ *  GIX
+ **********************************************************************************************/
+
+extern "C" void fgb_gix_free(fgb_gix *x)
+{ if (!x) return;
+  cudaFree(x->d_tab); cudaFree(x->d_pstart);
+  delete x;
+}
+
+static void gix_bytes(const fgb_genome *g, fgb_gix *x)        // GIXmake.c:1888-1901
+{ long long cum;
+  x->post_bytes = 0;
+  for (cum = 1; cum < g->maxlen; cum *= 256) x->post_bytes += 1;
+  x->cont_bytes = 0;
+  for (cum = 1; cum < 2ll*g->ncontig; cum *= 256) x->cont_bytes += 1;
+}
+
+//  K1..K4: syncmer scan -> 128-bit records -> 10-pass byte radix sort on the 80-bit k-mer ->
+//  2^24 prefix index.
+
+extern "C" int fgb_gix_build(const fgb_genome *g, fgb_gix **out, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  int T = fgb_sc_tile();
+  std::vector<int> tc, ts;
+  for (int c = 0; c < g->ncontig; c++)
+    if (g->clen[c] >= 12 && g->boff[c] >= 0)
+      for (long long t0 = 0; t0 + 12 <= g->clen[c]; t0 += T)
+        { tc.push_back(c); ts.push_back((int) t0); }
+  int ntiles = (int) tc.size();
+
+  fgb_gix *x = new fgb_gix();
+  gix_bytes(g,x);
+  x->ncontig = g->ncontig;
+
+  int *d_tc = NULL, *d_ts = NULL; unsigned *d_cnt = NULL;
+  u64 *d_buck = NULL, *d_total = NULL; void *d_tmp = NULL;
+  long long tmpb = fgb_dev_scan_tmp_bytes(ntiles);
+  CUDA_TRY(cudaMalloc(&d_tc,sizeof(int)*(ntiles+1)));
+  CUDA_TRY(cudaMalloc(&d_ts,sizeof(int)*(ntiles+1)));
+  CUDA_TRY(cudaMalloc(&d_cnt,sizeof(unsigned)*(ntiles+1)));
+  CUDA_TRY(cudaMalloc(&d_buck,8*1024));
+  CUDA_TRY(cudaMalloc(&d_total,8));
+  CUDA_TRY(cudaMalloc(&d_tmp,tmpb));
+  CUDA_TRY(cudaMemcpyAsync(d_tc,tc.data(),sizeof(int)*ntiles,cudaMemcpyHostToDevice,st));
+  CUDA_TRY(cudaMemcpyAsync(d_ts,ts.data(),sizeof(int)*ntiles,cudaMemcpyHostToDevice,st));
+
+  int rc;
+  u64 total = 0;
+  { stage_timer t(&g_timings.scan_ms,st);
+    rc = fgb_syncmer_count_device(g->d_seq,g->d_clen,g->d_woff,g->d_crank,d_tc,d_ts,ntiles,d_cnt,
+                                  d_buck,d_total,d_tmp,tmpb,st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(&total,d_total,8,cudaMemcpyDeviceToHost,st));
+    CUDA_TRY(cudaMemcpyAsync(x->buck1024,d_buck,8*1024,cudaMemcpyDeviceToHost,st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  if (total >= 0xfffffff0ull) return FGB_ERR_LIMIT;
+  long long n = (long long) total;
+  x->n = n;
+
+  rec128 *d_a = NULL, *d_b = NULL; void *d_stmp = NULL;
+  long long stmpb = fgb_sort128_tmp_bytes(n);
+  CUDA_TRY(cudaMalloc(&d_a,sizeof(rec128)*(n+1)));
+  CUDA_TRY(cudaMalloc(&d_b,sizeof(rec128)*(n+1)));
+  CUDA_TRY(cudaMalloc(&d_stmp,stmpb));
+  { stage_timer t(&g_timings.scan_ms,st);
+    rc = fgb_syncmer_emit_device(g->d_seq,g->d_clen,g->d_woff,g->d_crank,d_tc,d_ts,ntiles,d_cnt,d_a,st);
+    if (rc) return rc;
+  }
+  int inb = 0;
+  { stage_timer t(&g_timings.ksort_ms,st);
+    rc = fgb_sort128_device(d_a,d_b,n,6,16,d_stmp,stmpb,&inb,st);
+    if (rc) return rc;
+  }
+  x->d_tab = inb ? d_b : d_a;
+  CUDA_TRY(cudaMalloc(&x->d_pstart,sizeof(unsigned)*((1<<24)+1)));
+  { stage_timer t(&g_timings.index_ms,st);
+    rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  cudaFree(inb ? d_a : d_b); cudaFree(d_stmp);
+  cudaFree(d_tc); cudaFree(d_ts); cudaFree(d_cnt); cudaFree(d_buck); cudaFree(d_total); cudaFree(d_tmp);
+  *out = x;
+  return FGB_OK;
+}
+
+extern "C" long long fgb_gix_size(const fgb_gix *x) { return x->n; }
+extern "C" int fgb_gix_post_bytes(const fgb_gix *x) { return x->post_bytes; }
+extern "C" int fgb_gix_cont_bytes(const fgb_gix *x) { return x->cont_bytes; }
+
+extern "C" int fgb_gix_download(const fgb_gix *x, void *tab /* n x 16 B */, unsigned *pstart /* 2^24+1 */,
+                                unsigned long long *buck1024)
+{ if (tab) CUDA_TRY(cudaMemcpy(tab,x->d_tab,sizeof(rec128)*x->n,cudaMemcpyDeviceToHost));
+  if (pstart) CUDA_TRY(cudaMemcpy(pstart,x->d_pstart,sizeof(unsigned)*((1<<24)+1),cudaMemcpyDeviceToHost));
+  if (buck1024) memcpy(buck1024,x->buck1024,8*1024);
+  return FGB_OK;
+}
+
+//  A GIX from host-side device-layout records (sorted) -- used to feed tables from elsewhere.
+extern "C" int fgb_gix_upload(const void *tab, long long n, int post_bytes, int cont_bytes,
+                              int ncontig, fgb_gix **out, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  if (n >= 0xfffffff0ll) return FGB_ERR_LIMIT;
+  fgb_gix *x = new fgb_gix();
+  x->n = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
+  CUDA_TRY(cudaMalloc(&x->d_tab,sizeof(rec128)*(n+1)));
+  CUDA_TRY(cudaMalloc(&x->d_pstart,sizeof(unsigned)*((1<<24)+1)));
+  CUDA_TRY(cudaMemcpyAsync(x->d_tab,tab,sizeof(rec128)*n,cudaMemcpyHostToDevice,st));
+  int rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (rc) return rc;
+  *out = x;
+  return FGB_OK;
+}
+
+//  A GIX from the reference's on-disk form: concatenated .ktab entries (all parts, in order) and
+//  the stub's cumulative 2^24 index (libfastk.c:815-840).
+extern "C" int fgb_gix_import_ktab(const unsigned char *entries, long long n, int post_bytes,
+                                   int cont_bytes, const long long *index, int ncontig,
+                                   fgb_gix **out, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  if (n >= 0xfffffff0ll || post_bytes > 4 || cont_bytes > 2) return FGB_ERR_LIMIT;
+  fgb_gix *x = new fgb_gix();
+  x->n = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
+  long long E = 9 + post_bytes + cont_bytes;
+  unsigned char *d_ent = NULL; long long *d_index = NULL;
+  CUDA_TRY(cudaMalloc(&d_ent,E*n + 16));
+  CUDA_TRY(cudaMalloc(&d_index,8ll<<24));
+  CUDA_TRY(cudaMalloc(&x->d_tab,sizeof(rec128)*(n+1)));
+  CUDA_TRY(cudaMalloc(&x->d_pstart,sizeof(unsigned)*((1<<24)+1)));
+  CUDA_TRY(cudaMemcpyAsync(d_ent,entries,E*n,cudaMemcpyHostToDevice,st));
+  CUDA_TRY(cudaMemcpyAsync(d_index,index,8ll<<24,cudaMemcpyHostToDevice,st));
+  int rc = fgb_ktab_import_device(d_ent,n,post_bytes,cont_bytes,d_index,x->d_tab,st);
+  if (!rc) rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  cudaFree(d_ent); cudaFree(d_index);
+  if (rc) return rc;
+  *out = x;
+  return FGB_OK;
+}
+
+//  On-disk entries for the whole table (host buffer of n*(9+pb+cb) bytes); part_first = entry
+//  index at which each .ktab part starts (its LCP byte is 0, MSDsort.c:485-488).
+extern "C" int fgb_gix_export_ktab(const fgb_gix *x, const long long *part_first, int nparts,
+                                   unsigned char *out, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  long long E = 9 + x->post_bytes + x->cont_bytes;
+  unsigned char *d_out = NULL; long long *d_pf = NULL;
+  CUDA_TRY(cudaMalloc(&d_out,E*x->n + 16));
+  CUDA_TRY(cudaMalloc(&d_pf,8*(nparts+1)));
+  CUDA_TRY(cudaMemcpyAsync(d_pf,part_first,8*nparts,cudaMemcpyHostToDevice,st));
+  int rc = fgb_ktab_export_device(x->d_tab,x->n,x->post_bytes,x->cont_bytes,d_pf,nparts,d_out,st);
+  if (!rc) CUDA_TRY(cudaMemcpyAsync(out,d_out,E*x->n,cudaMemcpyDeviceToHost,st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  cudaFree(d_out); cudaFree(d_pf);
+  return rc;
+}
+
+/***********************************************************************************************
+ *  Seeds: adaptamer merge + seed sort
+ **********************************************************************************************/
+
+static int bitlen(long long v) { int b = 0; while (v > 0) { b += 1; v >>= 1; } return b; }
+
+extern "C" void fgb_seeds_free(fgb_seeds *s)
+{ if (!s) return;
+  cudaFree(s->d_rec);
+  delete s;
+}
+
+extern "C" int fgb_seeds_find(const fgb_gix *x1, const fgb_gix *x2, long long amxpos,
+                              long long bmxpos, int freq, fgb_seeds **out, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  fgb_seeds *s = new fgb_seeds();
+  s->anti_bits = bitlen(amxpos + bmxpos);
+  s->band_bits = s->anti_bits > 6 ? s->anti_bits - 6 : 1;
+  s->jc_bits   = bitlen(x2->ncontig > 1 ? x2->ncontig-1 : 1);
+  s->ic_bits   = bitlen(x1->ncontig > 1 ? x1->ncontig-1 : 1);
+  s->amxpos = amxpos; s->bmxpos = bmxpos;
+  int keybits  = 12 + s->anti_bits + s->band_bits + s->jc_bits + s->ic_bits + 1;
+  if (keybits > 128) return FGB_ERR_LIMIT;
+
+  u64 *d_counters = NULL;
+  CUDA_TRY(cudaMalloc(&d_counters,16));
+  long long cap = x1->n + (x1->n >> 2) + 1024;
+  rec128 *d_a = NULL;
+  u64 nseeds = 0, sumlen = 0;
+  for (int attempt = 0; ; attempt++)
+    { CUDA_TRY(cudaMalloc(&d_a,sizeof(rec128)*(cap+1)));
+      int rc;
+      { stage_timer t(&g_timings.merge_ms,st);
+        rc = fgb_merge_device(x1->d_tab,x1->n,x2->d_tab,x2->d_pstart,freq,s->anti_bits,s->band_bits,
+                              s->jc_bits,s->ic_bits,amxpos,bmxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
+      }
+      if (rc == FGB_OK) break;
+      cudaFree(d_a); d_a = NULL;
+      if (rc != FGB_ERR_OVERFLOW || attempt > 0) { cudaFree(d_counters); return rc; }
+      cap = (long long) nseeds + 1024;
+      g_timings.merge_ms = 0;                  // only the successful launch is reported
+    }
+  cudaFree(d_counters);
+  if (nseeds >= 0xfffffff0ull) return FGB_ERR_LIMIT;
+  s->n = (long long) nseeds; s->sumlen = (long long) sumlen;
+
+  rec128 *d_b = NULL; void *d_tmp = NULL;
+  long long tmpb = fgb_sort128_tmp_bytes(s->n);
+  CUDA_TRY(cudaMalloc(&d_b,sizeof(rec128)*(s->n+1)));
+  CUDA_TRY(cudaMalloc(&d_tmp,tmpb));
+  int inb = 0, rc;
+  { stage_timer t(&g_timings.ssort_ms,st);
+    rc = fgb_sort128_device(d_a,d_b,s->n,0,(keybits+7)/8,d_tmp,tmpb,&inb,st);
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  s->d_rec = inb ? d_b : d_a;
+  cudaFree(inb ? d_a : d_b); cudaFree(d_tmp);
+  if (rc) return rc;
+  *out = s;
+  return FGB_OK;
+}
+
+extern "C" long long fgb_seeds_size(const fgb_seeds *s) { return s->n; }
+extern "C" long long fgb_seeds_sumlen(const fgb_seeds *s) { return s->sumlen; }
+extern "C" int fgb_seeds_layout(const fgb_seeds *s, int *bits /* anti, band, jc, ic */)
+{ bits[0] = s->anti_bits; bits[1] = s->band_bits; bits[2] = s->jc_bits; bits[3] = s->ic_bits; return FGB_OK; }
+extern "C" int fgb_seeds_download(const fgb_seeds *s, void *rec)
+{ CUDA_TRY(cudaMemcpy(rec,s->d_rec,sizeof(rec128)*s->n,cudaMemcpyDeviceToHost)); return FGB_OK; }
+
+//  Plain host-buffer sort of 16-byte records on key bytes [byte_lo,byte_hi): the building block
+//  behind both drop-in sort seams.
+extern "C" int fgb_sort128_host(void *recs, long long n, int byte_lo, int byte_hi, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  rec128 *d_a = NULL, *d_b = NULL; void *d_tmp = NULL;
+  long long tmpb = fgb_sort128_tmp_bytes(n);
+  CUDA_TRY(cudaMalloc(&d_a,sizeof(rec128)*(n+1)));
+  CUDA_TRY(cudaMalloc(&d_b,sizeof(rec128)*(n+1)));
+  CUDA_TRY(cudaMalloc(&d_tmp,tmpb));
+  CUDA_TRY(cudaMemcpyAsync(d_a,recs,sizeof(rec128)*n,cudaMemcpyHostToDevice,st));
+  int inb = 0;
+  int rc = fgb_sort128_device(d_a,d_b,n,byte_lo,byte_hi,d_tmp,tmpb,&inb,st);
+  if (!rc) CUDA_TRY(cudaMemcpyAsync(recs,inb ? d_b : d_a,sizeof(rec128)*n,cudaMemcpyDeviceToHost,st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  cudaFree(d_a); cudaFree(d_b); cudaFree(d_tmp);
+  return rc;
+}
+
+extern "C" int fgb_device_ready()
+{ int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return 0;
+  return 1;
+}

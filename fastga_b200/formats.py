@@ -1,0 +1,222 @@
+"""Host-side views of the reference's data formats on either side of the hot path.
+
+* ``Genome``            -- what the path needs of a GDB (GDB.h:28-34): contig lengths, byte
+                           offsets and the 2-bit ``.bps`` image (gene_core.c:349-400: base i of a
+                           contig in bits 2*(i&3) of byte i>>2, every contig on a byte boundary).
+* ``genome_from_fasta`` -- FASTA(.gz) -> Genome with Create_GDB's rules (GDB.c:350-366, :840-1030):
+                           a/c/g/t -> 0..3, n/N splits contigs (NCUT = 0), any other letter is 'a'.
+* ``read_gix`` / ``write_gix`` -- the ``<root>.gix`` stub + ``.<root>.ktab.<p>`` parts
+                           (GIXmake.c:1503-1580, libfastk.c:815-840).
+"""
+import gzip
+import os
+
+import numpy as np
+
+_LUT = np.zeros(256, dtype=np.uint8)
+_LUT[ord("c")] = _LUT[ord("C")] = 1
+_LUT[ord("g")] = _LUT[ord("G")] = 2
+_LUT[ord("t")] = _LUT[ord("T")] = 3
+_LUT[ord("n")] = _LUT[ord("N")] = 4
+
+
+class Genome:
+    def __init__(self, clen, bps, names=None, scaf=None, sbeg=None, slen=None):
+        self.clen = np.ascontiguousarray(clen, dtype=np.int64)
+        nb = (self.clen + 3) >> 2
+        self.boff = np.zeros(len(clen), dtype=np.int64)
+        if len(clen) > 1:
+            self.boff[1:] = np.cumsum(nb)[:-1]
+        self.bps = np.ascontiguousarray(bps, dtype=np.uint8)
+        assert self.bps.size == int(nb.sum()), (self.bps.size, int(nb.sum()))
+        self.names = names          # scaffold header strings
+        self.scaf = scaf            # contig -> scaffold index
+        self.sbeg = sbeg            # contig start inside its scaffold
+        self.slen = slen            # scaffold lengths (with gaps)
+        self._freq = None
+
+    @property
+    def ncontig(self):
+        return len(self.clen)
+
+    @property
+    def seqtot(self):
+        return int(self.clen.sum())
+
+    def contig(self, c):
+        """bases of contig c, one per byte (values 0..3)"""
+        n = int(self.clen[c])
+        b = self.bps[int(self.boff[c]): int(self.boff[c]) + ((n + 3) >> 2)]
+        out = np.empty(((n + 3) >> 2) * 4, dtype=np.uint8)
+        out[0::4] = b & 3
+        out[1::4] = (b >> 2) & 3
+        out[2::4] = (b >> 4) & 3
+        out[3::4] = (b >> 6) & 3
+        return out[:n]
+
+    @property
+    def freq(self):
+        """base frequencies exactly as Create_GDB stores them: float((1.*count)/seqtot)"""
+        if self._freq is None:
+            cnt = np.zeros(4, dtype=np.int64)
+            for c in range(self.ncontig):
+                cnt += np.bincount(self.contig(c), minlength=4)[:4]
+            tot = int(cnt.sum())
+            self._freq = np.array([np.float32((1.0 * int(x)) / tot) for x in cnt], dtype=np.float32)
+        return self._freq
+
+
+def pack_bases(a):
+    """uint8 bases 0..3 -> .bps bytes of one contig"""
+    n = len(a)
+    p = np.zeros(((n + 3) >> 2) * 4, dtype=np.uint8)
+    p[:n] = a
+    return (p[0::4] | (p[1::4] << 2) | (p[2::4] << 4) | (p[3::4] << 6)).astype(np.uint8)
+
+
+def genome_from_arrays(contigs, names=None, scaf=None, sbeg=None, slen=None):
+    clen = [len(c) for c in contigs]
+    bps = np.concatenate([pack_bases(c) for c in contigs]) if contigs else np.zeros(0, np.uint8)
+    return Genome(clen, bps, names, scaf, sbeg, slen)
+
+
+def genome_from_fasta(path):
+    op = gzip.open if path.endswith(".gz") else open
+    with op(path, "rb") as f:
+        data = f.read()
+    raw = np.frombuffer(data, dtype=np.uint8)
+    contigs, names, scaf, sbeg, slen = [], [], [], [], []
+    # record boundaries
+    starts = np.flatnonzero(raw == ord(">"))
+    starts = starts[(starts == 0) | (raw[np.maximum(starts - 1, 0)] == ord("\n"))]
+    for i, s in enumerate(starts):
+        e = starts[i + 1] if i + 1 < len(starts) else len(raw)
+        rec = raw[s:e]
+        nl = int(np.flatnonzero(rec == ord("\n"))[0]) if (rec == ord("\n")).any() else len(rec)
+        names.append(bytes(rec[1:nl]).decode())
+        body = rec[nl + 1:]
+        body = body[(body != ord("\n")) & (body != ord("\r"))]
+        codes = _LUT[body]
+        isn = codes == 4
+        # maximal runs of non-N
+        d = np.diff(np.concatenate([[1], isn.astype(np.int8), [1]]))
+        rb = np.flatnonzero(d == -1)
+        re = np.flatnonzero(d == 1)
+        for b0, e0 in zip(rb, re):
+            contigs.append(codes[b0:e0])
+            scaf.append(i)
+            sbeg.append(int(b0))
+        slen.append(len(body))
+    return genome_from_arrays(contigs, names, np.array(scaf, np.int32), np.array(sbeg, np.int64),
+                              np.array(slen, np.int64))
+
+
+def write_fasta(path, scaffolds, width=100):
+    """scaffolds: list of (name, uint8 code array with 4 = N)"""
+    alpha = np.frombuffer(b"acgtn", dtype=np.uint8)
+    op = gzip.open if path.endswith(".gz") else open
+    with op(path, "wb") as f:
+        for name, codes in scaffolds:
+            f.write(b">" + name.encode() + b"\n")
+            txt = alpha[codes]
+            n = len(txt)
+            full = (n // width) * width
+            if full:
+                lines = np.empty((n // width, width + 1), dtype=np.uint8)
+                lines[:, :width] = txt[:full].reshape(-1, width)
+                lines[:, width] = ord("\n")
+                f.write(lines.tobytes())
+            if n > full:
+                f.write(txt[full:].tobytes() + b"\n")
+
+
+# ------------------------------------------------------------------------------------------
+#  GIX files
+# ------------------------------------------------------------------------------------------
+
+class GixFile:
+    pass
+
+
+def _hidden(path, suffix):
+    d, b = os.path.split(path)
+    return os.path.join(d, "." + b + suffix)
+
+
+def read_gix(path):
+    """path: '<dir>/<root>.gix'.  Returns GixFile with the stub fields and all entries."""
+    g = GixFile()
+    root = path[:-4]
+    with open(path, "rb") as f:
+        hdr = np.frombuffer(f.read(16), dtype=np.int32)
+        g.kmer, g.nparts, g.minval, g.ibyte = (int(x) for x in hdr)
+        g.index = np.frombuffer(f.read(8 << 24), dtype=np.int64).copy()
+        t = np.frombuffer(f.read(12), dtype=np.int32)
+        g.post_bytes, g.cont_bytes, nparts2 = (int(x) for x in t)
+        g.maxpre = int(np.frombuffer(f.read(8), dtype=np.int64)[0])
+        t = np.frombuffer(f.read(8), dtype=np.int32)
+        g.freq, g.ncontig = int(t[0]), int(t[1])
+        g.perm = np.frombuffer(f.read(4 * g.ncontig), dtype=np.int32).copy()
+        g.marker = int(np.frombuffer(f.read(8), dtype=np.int64)[0])
+    g.esize = (g.kmer // 4 - 3) + 2 + g.post_bytes + g.cont_bytes
+    parts, g.part_n = [], []
+    for p in range(1, g.nparts + 1):
+        with open(_hidden(root, ".ktab.%d" % p), "rb") as f:
+            k = int(np.frombuffer(f.read(4), dtype=np.int32)[0])
+            n = int(np.frombuffer(f.read(8), dtype=np.int64)[0])
+            assert k == g.kmer
+            parts.append(np.frombuffer(f.read(n * g.esize), dtype=np.uint8))
+            g.part_n.append(n)
+    g.entries = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+    g.n = int(sum(g.part_n))
+    return g
+
+
+def write_gix(path, kmer, index, post_bytes, cont_bytes, maxpre, perm, entries, part_n):
+    """Writes '<root>.gix' + '.<root>.ktab.<p>' in the layout GIXmake.c:1503-1580 produces."""
+    root = path[:-4]
+    nparts = len(part_n)
+    esize = (kmer // 4 - 3) + 2 + post_bytes + cont_bytes
+    with open(path, "wb") as f:
+        f.write(np.array([kmer, nparts, 1, 3], dtype=np.int32).tobytes())
+        f.write(np.ascontiguousarray(index, dtype=np.int64).tobytes())
+        f.write(np.array([post_bytes, cont_bytes, nparts], dtype=np.int32).tobytes())
+        f.write(np.array([maxpre], dtype=np.int64).tobytes())
+        f.write(np.array([0, len(perm)], dtype=np.int32).tobytes())
+        f.write(np.ascontiguousarray(perm, dtype=np.int32).tobytes())
+        f.write(np.array([-1], dtype=np.int64).tobytes())
+    off = 0
+    for p, n in enumerate(part_n):
+        with open(_hidden(root, ".ktab.%d" % (p + 1)), "wb") as f:
+            f.write(np.array([kmer], dtype=np.int32).tobytes())
+            f.write(np.array([n], dtype=np.int64).tobytes())
+            f.write(entries[off * esize:(off + n) * esize].tobytes())
+        off += n
+
+
+def ksplit_from_buckets(buck1024, nparts):
+    """Part boundaries over the 1024 first-5-base buckets, as distribute() picks them
+    (GIXmake.c:655-691) from the sampler histogram."""
+    buck = np.cumsum(np.asarray(buck1024, dtype=np.int64))
+    ksplit = [0] * (nparts + 1)
+    n = 1
+    t = int(buck[-1]) // nparts
+    for i in range(1024):
+        if buck[i] >= t and n < nparts + 1:
+            prev = int(buck[i - 1]) if i > 0 else 0
+            if int(buck[i]) - t > t - prev:
+                ksplit[n] = i
+            else:
+                ksplit[n] = i + 1
+            n += 1
+            t = (n * int(buck[-1])) // nparts
+    ksplit[nparts] = 1024
+    return ksplit
+
+
+def gix_nparts(seqtot, ncontig, post_bytes, cont_bytes, nthreads=8, kmer=40):
+    """NPARTS of GIXmake.c:1907-1917"""
+    nels = 0x100000000 // (cont_bytes + post_bytes + kmer // 4 + 2)
+    nbit = int((.81 * (seqtot - (kmer - 1) * ncontig)) / nels)
+    nparts = ((nbit - 1) // nthreads + 1) * nthreads
+    return min(max(nparts, 8), 64)

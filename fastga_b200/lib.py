@@ -1,0 +1,247 @@
+"""ctypes binding of the C-ABI in include/fastga_b200.h (host buffers in, host buffers out)."""
+import ctypes as C
+
+import numpy as np
+
+from . import load_library
+
+c_void_p, c_int, c_ll = C.c_void_p, C.c_int, C.c_longlong
+
+ERRORS = {-1: "CUDA runtime error", -2: "bad argument", -3: "input exceeds a device-layout limit",
+          -4: "device arena overflow"}
+
+
+class FgbError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise FgbError("%s failed: %s (%d)" % (what, ERRORS.get(rc, "?"), rc))
+
+
+class Timings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in
+                ("h2d_ms", "stage_ms", "scan_ms", "ksort_ms", "index_ms", "merge_ms", "ssort_ms",
+                 "triples_ms", "extend_ms", "d2h_ms", "filter_ms")] + \
+               [("merge_launches", C.c_int), ("extend_launches", C.c_int)]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def _ptr(a):
+    return a.ctypes.data_as(c_void_p)
+
+
+def timings_reset():
+    load_library().fgb_timings_reset()
+
+
+def timings_get():
+    t = Timings()
+    load_library().fgb_timings_get(C.byref(t))
+    return t.asdict()
+
+
+def device_ready():
+    return bool(load_library().fgb_device_ready())
+
+
+class DeviceGenome:
+    """fgb_genome handle: the staged 2-bit contigs of one genome in HBM."""
+
+    def __init__(self, genome, want_revcomp=False, stream=None):
+        L = load_library()
+        self.genome = genome
+        self.h = c_void_p()
+        L.fgb_genome_create.argtypes = [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int,
+                                        C.POINTER(c_void_p), c_void_p]
+        _check(L.fgb_genome_create(_ptr(genome.bps), genome.bps.size, genome.ncontig,
+                                   _ptr(genome.clen), _ptr(genome.boff), int(want_revcomp),
+                                   C.byref(self.h), stream), "fgb_genome_create")
+        self.perm = np.zeros(genome.ncontig, dtype=np.int32)
+        L.fgb_genome_perm.argtypes = [c_void_p, c_void_p]
+        L.fgb_genome_perm(self.h, _ptr(self.perm))
+        self.crank = np.empty_like(self.perm)
+        self.crank[self.perm] = np.arange(genome.ncontig, dtype=np.int32)
+
+    def download(self, rev=False):
+        L = load_library()
+        L.fgb_genome_words.restype = c_ll
+        L.fgb_genome_words.argtypes = [c_void_p]
+        n = L.fgb_genome_words(self.h)
+        words = np.zeros(n, dtype=np.uint64)
+        woff = np.zeros(self.genome.ncontig + 1, dtype=np.int64)
+        L.fgb_genome_download.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
+        _check(L.fgb_genome_download(self.h, int(rev), _ptr(words), _ptr(woff)), "fgb_genome_download")
+        return words, woff
+
+    def close(self):
+        if self.h:
+            L = load_library()
+            L.fgb_genome_free.argtypes = [c_void_p]
+            L.fgb_genome_free(self.h)
+            self.h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceGix:
+    """fgb_gix handle: sorted 128-bit k-mer records + 2^24 prefix index in HBM."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def build(cls, dgenome, stream=None):
+        L = load_library()
+        h = c_void_p()
+        L.fgb_gix_build.argtypes = [c_void_p, C.POINTER(c_void_p), c_void_p]
+        _check(L.fgb_gix_build(dgenome.h, C.byref(h), stream), "fgb_gix_build")
+        return cls(h)
+
+    @classmethod
+    def upload(cls, tab, post_bytes, cont_bytes, ncontig, stream=None):
+        L = load_library()
+        h = c_void_p()
+        tab = np.ascontiguousarray(tab, dtype=np.uint64).reshape(-1, 2)
+        L.fgb_gix_upload.argtypes = [c_void_p, c_ll, c_int, c_int, c_int, C.POINTER(c_void_p), c_void_p]
+        _check(L.fgb_gix_upload(_ptr(tab), tab.shape[0], post_bytes, cont_bytes, ncontig,
+                                C.byref(h), stream), "fgb_gix_upload")
+        return cls(h)
+
+    @classmethod
+    def import_ktab(cls, gixfile, stream=None):
+        L = load_library()
+        h = c_void_p()
+        L.fgb_gix_import_ktab.argtypes = [c_void_p, c_ll, c_int, c_int, c_void_p, c_int,
+                                          C.POINTER(c_void_p), c_void_p]
+        ent = np.ascontiguousarray(gixfile.entries)
+        idx = np.ascontiguousarray(gixfile.index, dtype=np.int64)
+        _check(L.fgb_gix_import_ktab(_ptr(ent), gixfile.n, gixfile.post_bytes, gixfile.cont_bytes,
+                                     _ptr(idx), gixfile.ncontig, C.byref(h), stream),
+               "fgb_gix_import_ktab")
+        return cls(h)
+
+    @property
+    def n(self):
+        L = load_library()
+        L.fgb_gix_size.restype = c_ll
+        L.fgb_gix_size.argtypes = [c_void_p]
+        return L.fgb_gix_size(self.h)
+
+    @property
+    def post_bytes(self):
+        L = load_library()
+        L.fgb_gix_post_bytes.argtypes = [c_void_p]
+        return L.fgb_gix_post_bytes(self.h)
+
+    @property
+    def cont_bytes(self):
+        L = load_library()
+        L.fgb_gix_cont_bytes.argtypes = [c_void_p]
+        return L.fgb_gix_cont_bytes(self.h)
+
+    def download(self, want_index=True):
+        L = load_library()
+        n = self.n
+        tab = np.zeros((n, 2), dtype=np.uint64)
+        pstart = np.zeros((1 << 24) + 1, dtype=np.uint32) if want_index else None
+        buck = np.zeros(1024, dtype=np.uint64)
+        L.fgb_gix_download.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+        _check(L.fgb_gix_download(self.h, _ptr(tab), _ptr(pstart) if want_index else None, _ptr(buck)),
+               "fgb_gix_download")
+        return tab, pstart, buck
+
+    def export_ktab(self, part_first, stream=None):
+        L = load_library()
+        E = 9 + self.post_bytes + self.cont_bytes
+        out = np.zeros(self.n * E, dtype=np.uint8)
+        pf = np.ascontiguousarray(part_first, dtype=np.int64)
+        L.fgb_gix_export_ktab.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+        _check(L.fgb_gix_export_ktab(self.h, _ptr(pf), len(pf), _ptr(out), stream), "fgb_gix_export_ktab")
+        return out
+
+    def close(self):
+        if self.h:
+            L = load_library()
+            L.fgb_gix_free.argtypes = [c_void_p]
+            L.fgb_gix_free(self.h)
+            self.h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceSeeds:
+    """fgb_seeds handle: sorted adaptive-seed records in HBM."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def find(cls, gix1, gix2, amxpos, bmxpos, freq=10, stream=None):
+        L = load_library()
+        h = c_void_p()
+        L.fgb_seeds_find.argtypes = [c_void_p, c_void_p, c_ll, c_ll, c_int, C.POINTER(c_void_p), c_void_p]
+        _check(L.fgb_seeds_find(gix1.h, gix2.h, amxpos, bmxpos, freq, C.byref(h), stream), "fgb_seeds_find")
+        return cls(h)
+
+    @property
+    def n(self):
+        L = load_library()
+        L.fgb_seeds_size.restype = c_ll
+        L.fgb_seeds_size.argtypes = [c_void_p]
+        return L.fgb_seeds_size(self.h)
+
+    @property
+    def sumlen(self):
+        L = load_library()
+        L.fgb_seeds_sumlen.restype = c_ll
+        L.fgb_seeds_sumlen.argtypes = [c_void_p]
+        return L.fgb_seeds_sumlen(self.h)
+
+    @property
+    def layout(self):
+        L = load_library()
+        bits = (c_int * 4)()
+        L.fgb_seeds_layout.argtypes = [c_void_p, c_void_p]
+        L.fgb_seeds_layout(self.h, bits)
+        return tuple(bits)
+
+    def download(self):
+        L = load_library()
+        rec = np.zeros((self.n, 2), dtype=np.uint64)
+        L.fgb_seeds_download.argtypes = [c_void_p, c_void_p]
+        _check(L.fgb_seeds_download(self.h, _ptr(rec)), "fgb_seeds_download")
+        return rec
+
+    def close(self):
+        if self.h:
+            L = load_library()
+            L.fgb_seeds_free.argtypes = [c_void_p]
+            L.fgb_seeds_free(self.h)
+            self.h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sort128_host(recs, byte_lo, byte_hi, stream=None):
+    """In-place device sort of an (n,2) uint64 array of 128-bit records on key bytes [lo,hi)."""
+    L = load_library()
+    assert recs.dtype == np.uint64 and recs.flags.c_contiguous and recs.shape[1] == 2
+    L.fgb_sort128_host.argtypes = [c_void_p, c_ll, c_int, c_int, c_void_p]
+    _check(L.fgb_sort128_host(_ptr(recs), recs.shape[0], byte_lo, byte_hi, stream), "fgb_sort128_host")
+    return recs

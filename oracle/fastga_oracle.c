@@ -796,3 +796,216 @@ int orc_local_alignment(orc_work *w, const orc_spec *spec, const char *aseq, int
     }
   return 0;
 }
+
+/***********************************************************************************************
+ *  E.  Seed-chain detection + extension driver: align_contigs, search part
+ *      (FastGA.c:2973-3403) over the sorted seed records of section C.
+ *
+ *  Sorted order = (strand, A-contig rank, B-contig rank, band = diag>>6, anti, diag&63, lcp).
+ *  A "triple" is two adjacent 64-wide bands scanned together (b,m,e); the chain scan, the tube
+ *  stepping and the alast blocking follow the reference statement by statement.
+ **********************************************************************************************/
+
+typedef struct
+  { int chain_break, chain_min, align_min; double align_rate; } orc_params;
+
+typedef struct
+  { int comp, aread, bread;                 /* ORIGINAL contig numbers (Perm applied, :3007-3008) */
+    int abpos, bbpos, aepos, bepos, diffs, tlen;
+    int64_t toff;                           /* offset of the trace bytes in the trace pool */
+  } orc_ovl;
+
+typedef struct
+  { orc_ovl *ovl; int64_t novl, maxovl;
+    uint8_t *tpool; int64_t tlen, tmax;
+    int64_t nhit;
+  } orc_result;
+
+static void res_push(orc_result *R, const orc_ovl *o, const uint8_t *trace)
+{ if (R->novl >= R->maxovl)
+    { R->maxovl = R->maxovl*2 + 1024;
+      R->ovl = (orc_ovl *) realloc(R->ovl,sizeof(orc_ovl)*R->maxovl);
+    }
+  if (R->tlen + o->tlen > R->tmax)
+    { R->tmax = (R->tlen + o->tlen)*2 + 4096;
+      R->tpool = (uint8_t *) realloc(R->tpool,R->tmax);
+    }
+  R->ovl[R->novl] = *o;
+  R->ovl[R->novl].toff = R->tlen;
+  memcpy(R->tpool+R->tlen,trace,o->tlen);
+  R->tlen += o->tlen;
+  R->novl += 1;
+}
+
+orc_result *orc_new_result(void) { return (orc_result *) calloc(1,sizeof(orc_result)); }
+void orc_free_result(orc_result *R) { free(R->ovl); free(R->tpool); free(R); }
+int64_t  orc_result_count(orc_result *R) { return R->novl; }
+int64_t  orc_result_hits(orc_result *R) { return R->nhit; }
+orc_ovl *orc_result_ovls(orc_result *R) { return R->ovl; }
+uint8_t *orc_result_traces(orc_result *R) { return R->tpool; }
+
+#define BUCK_SHIFT 6
+#define BUCK_WIDTH 64
+#define BUCK_ANTI  128
+
+/* aseq[c], bseq[c]: contig c (ORIGINAL numbering), one base per byte with a sentinel 4 at [-1]
+   and [len]; acseq[c]: reverse complement of A contig c, same framing (Complement_Seq). */
+
+int64_t orc_search(const rec128 *seeds, int64_t n, const orc_layout *L, const orc_params *P,
+                   const orc_spec *spec, const int *perm1, const int *perm2,
+                   const char **aseq, const char **acseq, const int64_t *alens,
+                   const char **bseq, const int64_t *blens, orc_result *R)
+{ int p_anti = 12, p_band = p_anti + L->anti_bits, p_jc = p_band + L->band_bits;
+  int p_ic = p_jc + L->jc_bits, p_cp = p_ic + L->ic_bits;
+  int64_t amxpos = L->amxpos, bmxpos = L->bmxpos, maxdag = amxpos + bmxpos;
+  int alnMin = P->align_min - 50;
+  double alnRate = P->align_rate + .05;
+  orc_work *work = orc_new_work();
+  orc_path path; memset(&path,0,sizeof(path));
+  int64_t g0 = 0;
+
+#define ANTI(i) ((int64_t) get_bits(seeds+(i),p_anti,L->anti_bits))
+#define BAND(i) ((int64_t) get_bits(seeds+(i),p_band,L->band_bits))
+#define GRP(i)  (get_bits(seeds+(i),p_jc,L->jc_bits + L->ic_bits + 1))
+
+  while (g0 < n)
+    { int64_t g1 = g0;
+      uint64_t gk = GRP(g0);
+      while (g1 < n && GRP(g1) == gk) g1 += 1;
+      { int comp = (int) get_bits(seeds+g0,p_cp,1);
+        int ctg1 = perm1[get_bits(seeds+g0,p_ic,L->ic_bits)];
+        int ctg2 = perm2[get_bits(seeds+g0,p_jc,L->jc_bits)];
+        int64_t alen = alens[ctg1], blen = blens[ctg2], mlen = alen+blen;
+        int64_t doffset = alen - maxdag, aoffset = alen - amxpos;
+        const char *as = comp ? acseq[ctg1] : aseq[ctg1];
+        const char *bs = bseq[ctg2];
+        int64_t b, m, e, cdiag;
+        int     isnew, aux;
+
+        b = e = g0;
+        cdiag = BAND(e);
+        while (e < g1 && BAND(e) == cdiag) e += 1;
+        isnew = 1;
+        while (1)
+          { m = e; aux = 0;
+            while (e < g1 && BAND(e) == cdiag+1) { e += 1; aux = 1; }
+
+            if (isnew || aux)
+              { int     go, lcp, wch, mix, cov, dgmin, dgmax, dg;
+                int64_t ahgh, alow, amid, alast, anti, eant, ipost, apost, s, t;
+
+                alast = -1;
+                s = b; t = m;
+                ipost = ANTI(s);
+                apost = aux ? ANTI(t) : INT64_MAX;
+                dgmin = 2*BUCK_WIDTH; dgmax = 0;
+                ahgh  = -P->chain_break;
+                alow  = (apost < ipost) ? apost : ipost;
+                cov = 0; go = 1; mix = 0;
+                while (go)
+                  { if (apost < ipost)
+                      { lcp  = (int) get_bits(seeds+t,0,6);
+                        dg   = (int) get_bits(seeds+t,6,6) + BUCK_WIDTH;
+                        anti = apost;
+                        t += 1;
+                        apost = (t >= e) ? INT64_MAX : ANTI(t);
+                        wch = 0x2;
+                      }
+                    else
+                      { if (s < m)
+                          { lcp = (int) get_bits(seeds+s,0,6);
+                            dg  = (int) get_bits(seeds+s,6,6);
+                          }
+                        else
+                          { lcp = 0; dg = 0; }       /* reference reads past the band: values unused */
+                        anti = ipost;
+                        s += 1;
+                        if (s >= m)
+                          { if (s > m) go = 0; else ipost = INT64_MAX; }
+                        else
+                          ipost = ANTI(s);
+                        wch = 0x1;
+                      }
+                    lcp <<= 1;
+
+                    if (anti < ahgh + P->chain_break)
+                      { int64_t cps = anti + lcp;
+                        if (cps > ahgh)
+                          { if (anti >= ahgh) cov += lcp; else cov += (int) (cps-ahgh);
+                            ahgh = cps;
+                          }
+                        mix |= wch;
+                        if (dg < dgmin) dgmin = dg; else if (dg > dgmax) dgmax = dg;
+                      }
+                    else
+                      { if (cov >= P->chain_min && (mix != 1 || isnew))
+                          { R->nhit += 1;
+                            dgmin += (int) (cdiag<<BUCK_SHIFT);
+                            dgmax += (int) (cdiag<<BUCK_SHIFT);
+                            if (comp)
+                              { dgmin += (int) doffset; dgmax += (int) doffset;
+                                alow += aoffset; ahgh += aoffset;
+                              }
+                            else
+                              { dgmin -= (int) bmxpos; dgmax -= (int) bmxpos; }
+
+                            if (ahgh > alast)
+                              { if (alow < alast) alow = alast;
+                                ahgh -= BUCK_ANTI;
+                                do
+                                  { int rlen;
+                                    amid = alow + BUCK_ANTI;
+                                    if (amid > ahgh)
+                                      { amid = ahgh;
+                                        if (amid + dgmin < 0)
+                                          { dgmin = (int) -amid;
+                                            if (dgmin > dgmax) break;
+                                          }
+                                      }
+                                    orc_local_alignment(work,spec,as,(int) alen,bs,(int) blen,comp,
+                                                        dgmin,dgmax,(int) amid,-1,-1,&path);
+                                    rlen = path.aepos - path.abpos;
+                                    if (rlen >= alnMin && alnRate*rlen >= path.diffs)
+                                      { orc_ovl o;
+                                        o.comp = comp; o.aread = ctg1; o.bread = ctg2;
+                                        o.abpos = path.abpos; o.bbpos = path.bbpos;
+                                        o.aepos = path.aepos; o.bepos = path.bepos;
+                                        o.diffs = path.diffs; o.tlen = path.tlen; o.toff = 0;
+                                        res_push(R,&o,path.trace);
+                                      }
+                                    if (comp) eant = mlen - (path.abpos + path.bbpos);
+                                    else      eant = path.aepos + path.bepos;
+                                    if (eant <= alow) alow = amid; else alow = eant;
+                                  }
+                                while (alow < ahgh);
+                                alast = alow;
+                              }
+                          }
+                        if (go)
+                          { cov = lcp; ahgh = anti + lcp; mix = wch; alow = anti;
+                            dgmin = dgmax = dg;
+                          }
+                      }
+                  }
+              }
+
+            if (e >= g1) break;
+            if (aux)
+              { b = m; cdiag += 1; isnew = 0; }
+            else
+              { b = e;
+                cdiag = BAND(e);
+                while (e < g1 && BAND(e) == cdiag) e += 1;
+                isnew = 1;
+              }
+          }
+      }
+      g0 = g1;
+    }
+#undef ANTI
+#undef BAND
+#undef GRP
+  free(path.trace);
+  orc_free_work(work);
+  return R->novl;
+}

@@ -1,0 +1,184 @@
+"""TEST INFRASTRUCTURE: ctypes access to oracle/liboracle.so (the CPU restatement) and to the
+unmodified reference built into oracle/_ref (binaries + libfastga_ref.so)."""
+import ctypes as C
+import hashlib
+import os
+import re
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+REF_SO = os.path.join(REF_DIR, "libfastga_ref.so")
+
+_orc = None
+
+
+def have_ref():
+    return os.path.exists(os.path.join(REF_DIR, "FastGA")) and os.path.exists(REF_SO)
+
+
+def orc():
+    global _orc
+    if _orc is None:
+        if not os.path.exists(ORACLE_SO):
+            subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", ORACLE_SO,
+                                   os.path.join(ROOT, "oracle", "fastga_oracle.c")])
+        _orc = C.CDLL(ORACLE_SO)
+        _orc.orc_gix_build.restype = C.c_int64
+        _orc.orc_merge.restype = C.c_int64
+        _orc.orc_syncmers.restype = C.c_int64
+        _orc.orc_new_work.restype = C.c_void_p
+        if hasattr(_orc, "orc_search"):
+            _orc.orc_search.restype = C.c_int64
+    return _orc
+
+
+class OrcSeed(C.Structure):
+    _fields_ = [("plen", C.c_uint8), ("comp", C.c_uint8), ("icont", C.c_uint16), ("jcont", C.c_uint16),
+                ("ipost", C.c_uint32), ("jpost", C.c_uint32)]
+
+
+SEED_DT = np.dtype([("plen", "u1"), ("comp", "u1"), ("icont", "u2"), ("jcont", "u2"),
+                    ("ipost", "u4"), ("jpost", "u4")], align=True)
+
+
+class OrcLayout(C.Structure):
+    _fields_ = [("anti_bits", C.c_int), ("band_bits", C.c_int), ("jc_bits", C.c_int), ("ic_bits", C.c_int),
+                ("amxpos", C.c_int64), ("bmxpos", C.c_int64)]
+
+
+def contig_rank(clen):
+    """rank of each contig in the decreasing-length order; lengths must be pairwise distinct so
+    the libc qsort tie order (GIXmake.c:1959) cannot matter"""
+    clen = np.asarray(clen)
+    perm = np.argsort(-clen, kind="stable").astype(np.int32)
+    rank = np.empty_like(perm)
+    rank[perm] = np.arange(len(clen), dtype=np.int32)
+    return perm, rank
+
+
+def gix_build(genome, crank):
+    """oracle table of a formats.Genome: (n,2) uint64 records [lo,hi] + pstart"""
+    o = orc()
+    nc = genome.ncontig
+    seqs = [np.ascontiguousarray(genome.contig(c)) for c in range(nc)]
+    arr = (C.c_void_p * nc)(*[s.ctypes.data for s in seqs])
+    tab = C.c_void_p()
+    pstart = np.zeros((1 << 24) + 1, dtype=np.uint32)
+    crank = np.ascontiguousarray(crank, dtype=np.int32)
+    n = o.orc_gix_build(nc, arr, genome.clen.ctypes.data_as(C.c_void_p), crank.ctypes.data_as(C.c_void_p),
+                        C.byref(tab), pstart.ctypes.data_as(C.c_void_p))
+    out = np.ctypeslib.as_array(C.cast(tab, C.POINTER(C.c_uint64)), shape=(max(n, 1), 2))[:n].copy()
+    o.orc_free(tab)
+    return out, pstart
+
+
+def merge(T1, T2, pstart2, freq=10):
+    o = orc()
+    T1 = np.ascontiguousarray(T1, dtype=np.uint64)
+    T2 = np.ascontiguousarray(T2, dtype=np.uint64)
+    sl = C.c_int64()
+    args = [T1.ctypes.data_as(C.c_void_p), C.c_int64(len(T1)), T2.ctypes.data_as(C.c_void_p),
+            C.c_int64(len(T2)), pstart2.ctypes.data_as(C.c_void_p), C.c_int(freq)]
+    n = o.orc_merge(*args, None, C.byref(sl))
+    seeds = np.zeros(n, dtype=SEED_DT)
+    o.orc_merge(*args, seeds.ctypes.data_as(C.c_void_p), C.byref(sl))
+    return seeds, sl.value
+
+
+def seed_records(seeds, layout, sort=True):
+    o = orc()
+    out = np.zeros((len(seeds), 2), dtype=np.uint64)
+    L = OrcLayout(*layout)
+    o.orc_seed_records(seeds.ctypes.data_as(C.c_void_p), C.c_int64(len(seeds)), C.byref(L),
+                       out.ctypes.data_as(C.c_void_p), C.c_int(1 if sort else 0))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+#  the unmodified reference
+# ------------------------------------------------------------------------------------------
+
+def ref_env():
+    env = dict(os.environ)
+    env["PATH"] = REF_DIR + os.pathsep + env.get("PATH", "")
+    return env
+
+
+def run_ref(args, cwd, timeout=3600):
+    r = subprocess.run(args, cwd=cwd, env=ref_env(), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError("reference command failed: %s\n%s" % (" ".join(args), r.stdout[-2000:]))
+    return r.stdout
+
+
+def ref_fastga(workdir, a, b, out="ref", threads=8, extra=()):
+    """FastGA -v -k -T<n> -1:<out> a b in workdir; returns the -v log"""
+    return run_ref(["FastGA", "-v", "-k", "-T%d" % threads, "-P" + workdir, "-1:" + out] + list(extra) + [a, b],
+                   cwd=workdir)
+
+
+def parse_fastga_log(log):
+    log = log.replace("\r", "\n")
+    d = {}
+    m = re.search(r"Total seeds = ([\d,]+), ave\. len = ([\d.]+)", log)
+    if m:
+        d["seeds"] = int(m.group(1).replace(",", ""))
+        d["avelen"] = float(m.group(2))
+    m = re.search(r"Total hits over \d+bp = (\d+), (\d+) aln's, (\d+) non-redundant", log)
+    if m:
+        d["hits"], d["alns"], d["kept"] = int(m.group(1)), int(m.group(2)), int(m.group(3))
+    return d
+
+
+def oneview_records(path):
+    """Canonical form of a .1aln: one text line per alignment ('A ..| R | D ..| T ..| X ..'),
+    sorted."""
+    out = subprocess.run([os.path.join(REF_DIR, "ONEview"), path], stdout=subprocess.PIPE, text=True,
+                         check=True).stdout
+    recs, cur = [], None
+    for line in out.split("\n"):
+        if line.startswith("A "):
+            if cur is not None:
+                recs.append(cur)
+            cur = line
+        elif cur is not None and line[:2] in ("R", "R ", "D ", "T ", "X "):
+            cur += " | " + line
+        elif cur is not None and line.startswith("R"):
+            cur += " | " + line
+    if cur is not None:
+        recs.append(cur)
+    recs.sort()
+    return recs
+
+
+def md5_lines(lines):
+    h = hashlib.md5()
+    for l in lines:
+        h.update(l.encode() + b"\n")
+    return h.hexdigest()
+
+
+def read_gdb_ascii(path):
+    """contig lengths, scaffold names etc. of a .1gdb through ONEview"""
+    out = subprocess.run([os.path.join(REF_DIR, "ONEview"), path], stdout=subprocess.PIPE, text=True,
+                         check=True).stdout
+    clen, names, scaf, sbeg = [], [], [], []
+    pos = 0
+    for line in out.split("\n"):
+        if line.startswith("S "):
+            names.append(line.split(" ", 2)[2])
+            pos = 0
+        elif line.startswith("G "):
+            pos += int(line.split()[1])
+        elif line.startswith("C "):
+            n = int(line.split()[1])
+            clen.append(n)
+            scaf.append(len(names) - 1)
+            sbeg.append(pos)
+            pos += n
+    return np.array(clen, np.int64), names, np.array(scaf, np.int32), np.array(sbeg, np.int64)
