@@ -50,6 +50,12 @@ struct stage_timer
     }
 };
 
+void fgb_timing_add(int which, float ms)
+{ if (which == 0) g_timings.triples_ms += ms;
+  else if (which == 1) { g_timings.extend_ms += ms; g_timings.extend_launches += 1; }
+  else g_timings.d2h_ms += ms;
+}
+
 extern "C" void fgb_timings_reset() { memset(&g_timings,0,sizeof(g_timings)); }
 extern "C" void fgb_timings_get(fgb_timings *out) { *out = g_timings; }
 

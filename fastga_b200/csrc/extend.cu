@@ -1,0 +1,1111 @@
+// Seed-chain detection and wave-based local alignment extension on the device.
+//
+// Replaces (reference file:line):
+//   search_seeds / align_contigs, search part   FastGA.c:3716-3798, 2973-3403
+//   Local_Alignment, forward_wave, reverse_wave align.c:1423-1576, 352-874, 878-1418
+//   Compress_TraceTo8                           align.c:3892
+//
+// Unit of parallel work = one TRIPLE (two adjacent 64-wide diagonal bands of one
+// (strand, A-contig, B-contig) group): inside a triple the reference carries `alast` from chain
+// to chain and the next Local_Alignment starts where the previous ended, so a triple is a
+// sequential program; triples are independent (FastGA.c:3087).  One warp owns one triple:
+//   * the chain scan runs warp-uniformly (every lane executes the same scalar code);
+//   * a wave is data-parallel over its diagonals: lane l owns diagonal top-l of each 32-wide
+//     chunk; per-diagonal state (V, T, HA, HM, NA) lives in shared memory, indexed circularly;
+//   * the running maxima besta/lasta/trim* (strict '>' in descending-k order) are reproduced
+//     with a warp prefix-max and ballots;
+//   * pebbles (trace-point crossings) go to a per-warp arena in HBM, allocated by ballot;
+//   * the two wave routines are one direction-normalised routine (see oracle/fastga_oracle.c D).
+// Sequences are the 2-bit staged contigs (gix.cu); a snake step compares 32 bases per 64-bit XOR.
+// Integer / branch work: no tensor cores.
+#include "common.cuh"
+#include "handles.h"
+#include <limits.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+
+typedef unsigned long long u64;
+
+#define EX_WARPS     8
+#define EX_W         256                 // diagonals of wave state per warp (shared memory)
+#define FULL         0xffffffffu
+
+#define TRIM_LEN     15
+#define DUB_TRIM     45
+#define PATH_INT     0x0fffffffffffffffull
+#define PATH_WIN     0x1fffffffffffffffull
+#define TRIM_MASK    0x7fff
+#define TRIM_MLAG    250
+#define WAVE_LAG     70
+#define BUCK_SHIFT   6
+#define BUCK_WIDTH   64
+#define BUCK_ANTI    128
+
+#define ST_OK        0
+#define ST_BAND      1                   // band wider than the state capacity
+#define ST_CELLS     2                   // pebble arena full
+#define ST_STAGE     3                   // trace staging full
+
+struct __align__(16) Peb { int ptr, diag, diff, mark; };
+
+struct ext_params
+{ const rec128 *seeds; long long nseeds;
+  int p_anti, anti_bits, p_band, band_bits, p_jc, jc_bits, p_ic, ic_bits, p_cp;
+  long long amxpos, bmxpos;
+  const unsigned *seg_start; int nseg;
+  const unsigned *work; int nwork; unsigned *queue;
+  const u64 *aseq, *arseq; const long long *awoff, *aclen; const int *aperm;
+  const u64 *bseq;         const long long *bwoff, *bclen; const int *bperm;
+  int chain_break, chain_min, aln_min; double aln_rate;
+  int tspace, path_ave; const short *score, *table;
+  Peb *cells; long long cells_per_warp;
+  unsigned char *stage; int stage_bytes;               // per warp: 2 x stage_bytes
+  unsigned char *out; u64 out_cap; u64 *out_used;
+  u64 *counters;                                       // 0 hits 1 LA calls 2 waves 3 cells 4 records
+  unsigned *failed; unsigned *nfailed;                 // triples that overflowed an arena
+};
+
+struct Ctx
+{ const u64 *A, *B; int alen, blen; long long anw, bnw;
+  int *V, *HA, *HM, *NA; u64 *T; int *carry;
+  Peb *cells; int cmax, avail;
+  unsigned char *fstage, *rstage; int smax;
+  int tspace, path_ave; const short *score, *table;
+  u64 nwaves, ncells;
+};
+
+#define IX(k) ((k) & (EX_W-1))
+
+static __device__ __forceinline__ u64 get_bits(const rec128 &r, int pos, int n)
+{ u64 v;
+  if (pos >= 64) v = r.hi >> (pos-64);
+  else if (pos == 0) v = r.lo;
+  else v = (r.lo >> pos) | (r.hi << (64-pos));
+  return n >= 64 ? v : (v & ((1ull << n) - 1));
+}
+
+static __device__ __forceinline__ u64 win(const u64 *__restrict__ w, long long nw, long long boff)
+{ long long q = boff >> 5;
+  int s = (int) (boff & 31) << 1;
+  u64 a = (q >= 0 && q < nw) ? w[q] : 0ull;
+  if (s == 0) return a;
+  u64 b = (q+1 >= 0 && q+1 < nw) ? w[q+1] : 0ull;
+  return (a >> s) | (b << (64-s));
+}
+
+static __device__ __forceinline__ int base_at(const u64 *__restrict__ w, int len, int i)
+{ if (i < 0 || i >= len) return 4;
+  return (int) (w[i >> 5] >> ((i & 31) << 1)) & 3;
+}
+
+static __device__ __forceinline__ int a_at(const Ctx &c, int s, int xn)
+{ return base_at(c.A,c.alen,(s > 0) ? xn : -xn-1); }
+static __device__ __forceinline__ int b_at(const Ctx &c, int s, int yn)
+{ return base_at(c.B,c.blen,(s > 0) ? yn : -yn-1); }
+
+//  slide along diagonal kk from normalised xn; returns #matches, flag 0 mismatch / 1 B end / 2 A end
+//    (B is tested first, align.c:683-697)
+
+static __device__ __forceinline__ int snake(const Ctx &c, int s, int xn, int kk, int &flag)
+{ int yn = xn - kk, t = 0, tmax;
+  if (s > 0)
+    { int x = xn, y = yn;
+      if (y < 0 || y >= c.blen) { flag = 1; return 0; }
+      if (x < 0 || x >= c.alen) { flag = 2; return 0; }
+      tmax = min(c.alen - x,c.blen - y);
+      while (t < tmax)
+        { u64 d = win(c.A,c.anw,(long long) x+t) ^ win(c.B,c.bnw,(long long) y+t);
+          if (d) { t += (__ffsll((long long) d)-1) >> 1; break; }
+          t += 32;
+        }
+      if (t >= tmax) { t = tmax; flag = (y + t == c.blen) ? 1 : 2; }
+      else flag = 0;
+    }
+  else
+    { int x = -xn, y = -yn;
+      if (y-1 < 0 || y-1 >= c.blen) { flag = 1; return 0; }
+      if (x-1 < 0 || x-1 >= c.alen) { flag = 2; return 0; }
+      tmax = min(x,y);
+      while (t < tmax)
+        { u64 d = win(c.A,c.anw,(long long) x-t-32) ^ win(c.B,c.bnw,(long long) y-t-32);
+          if (d) { t += __clzll((long long) d) >> 1; break; }
+          t += 32;
+        }
+      if (t >= tmax) { t = tmax; flag = (y - t == 0) ? 1 : 2; }
+      else flag = 0;
+    }
+  return t;
+}
+
+static __device__ __forceinline__ int warp_prefix_max_excl(int v, int lane)
+{ int r = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+    { int t = __shfl_up_sync(FULL,r,o);
+      if (lane >= o) r = max(r,t);
+    }
+  int e = __shfl_up_sync(FULL,r,1);
+  return lane == 0 ? INT_MIN : e;
+}
+
+//  One wave pass (direction s) from anti-diagonal mida over diagonals [low,hgh].
+//  Outputs the trim point (original coordinates), its diffs and the pebble chain head.
+
+static __device__ int wave(Ctx &c, const int s, int low, int hgh, const int mida, int minp, int maxp,
+                           const int aoff, int &endx, int &endy, int &diffs, int &trimha_out)
+{ const int lane = threadIdx.x & 31;
+  const unsigned lt = lanemask_lt();
+  const int FRESH = (s > 0) ? -1 : -INT_MAX;
+  const int tspace = c.tspace;
+  int lowk, hghk, minpn, maxpn;
+
+  if (s > 0) { lowk = low;  hghk = hgh;  minpn = minp;  maxpn = maxp; }
+  else       { lowk = -hgh; hghk = -low; minpn = -maxp; maxpn = -minp; }
+  if (hghk - lowk + 5 > EX_W) return ST_BAND;
+
+  c.avail = 0;
+  int dif = 0, more = 1;
+  int besta = s*mida, trima = besta, lasta = besta;
+  int bestx = s*((mida+hgh)>>1), trimx = bestx;
+  int trimd = 0, trimha = 0;
+  int aclip = INT_MAX, bclip = -INT_MAX;
+  bool anyhit = false;
+
+  //  wave 0 (align.c:426-507 / :956-1036)
+  for (int top = hghk; top >= lowk; top -= 32)
+    { int kk = top - lane;
+      bool act = kk >= lowk;
+      int k = s*kk, x = (mida+k)>>1;
+      int na, mark0, nan;
+      if (s > 0)
+        { na = ((x+(tspace-aoff))/tspace-1)*tspace+aoff; mark0 = na; nan = na + tspace; }
+      else
+        { na = ((x+(tspace-aoff)-1)/tspace-1)*tspace+aoff; mark0 = x; nan = -na; }
+      if (c.avail + 32 > c.cmax) return ST_CELLS;
+      unsigned am = __ballot_sync(FULL,act);
+      int ha = c.avail + __popc(am & lt);
+      c.avail += __popc(am);
+      int hm = mark0;
+      if (act)
+        { Peb p; p.ptr = -1; p.diag = k; p.diff = 0; p.mark = mark0;
+          c.cells[ha] = p;
+        }
+      int xn = s*x, flag = 0;
+      if (act) xn += snake(c,s,xn,kk,flag);
+      int cc = 2*xn - kk;
+      bool need = act && xn >= nan;
+      while (__any_sync(FULL,need))
+        { if (c.avail + 32 > c.cmax) return ST_CELLS;
+          unsigned m = __ballot_sync(FULL,need);
+          int idx = c.avail + __popc(m & lt);
+          c.avail += __popc(m);
+          if (need)
+            { Peb p; p.ptr = ha; p.diag = k; p.diff = 0; p.mark = s*nan;
+              c.cells[idx] = p;
+              ha = idx; hm = s*nan; nan += tspace;
+            }
+          need = act && xn >= nan;
+        }
+      //  running maximum, descending kk = ascending lane
+      int ex = max(warp_prefix_max_excl(act ? cc : INT_MIN,lane),besta);
+      unsigned rm = __ballot_sync(FULL,act && cc > ex);
+      if (rm)
+        { int L = 31 - __clz(rm);
+          besta = trima = lasta = __shfl_sync(FULL,cc,L);
+          bestx = trimx = __shfl_sync(FULL,xn,L);
+          trimha = __shfl_sync(FULL,ha,L);
+        }
+      unsigned hb = __ballot_sync(FULL,act && flag == 1);
+      unsigned hq = __ballot_sync(FULL,act && flag == 2);
+      if (hb) { anyhit = true; int v = top - (__ffs(hb)-1); if (bclip < v) bclip = v; }
+      if (hq) { anyhit = true; aclip = top - (31 - __clz(hq)); }
+      if (act)
+        { c.V[IX(kk)] = cc; c.T[IX(kk)] = PATH_INT; c.HA[IX(kk)] = ha; c.HM[IX(kk)] = hm;
+          c.NA[IX(kk)] = nan;
+        }
+    }
+  __syncwarp();
+  if (anyhit)
+    { more = (b_at(c,s,besta-bestx) != 4 && a_at(c,s,bestx) != 4);
+      if (hghk >= aclip) hghk = aclip-1;
+      if (lowk <= bclip) lowk = bclip+1;
+      aclip = INT_MAX; bclip = -INT_MAX; anyhit = false;
+    }
+
+  //  successive waves (align.c:546-800 / :1077-1330)
+  while (more && lasta >= besta - TRIM_MLAG)
+    { lowk -= 1; hghk += 1;
+      if (hghk - lowk + 5 > EX_W) return ST_BAND;
+      if (lane == 0)
+        { if (lowk >= minpn) { c.NA[IX(lowk)] = c.NA[IX(lowk+1)]; c.V[IX(lowk)] = FRESH; }
+          if (hghk <= maxpn) { c.NA[IX(hghk)] = c.NA[IX(hghk-1)]; c.V[IX(hghk)] = FRESH; }
+        }
+      if (lowk < minpn) lowk += 1;
+      if (hghk > maxpn) hghk -= 1;
+      dif += 1;
+      if (lane == 0)
+        { c.V[IX(hghk+1)] = FRESH; c.V[IX(lowk-1)] = FRESH;
+          c.carry[0] = FRESH; c.carry[1] = (int) (unsigned) PATH_INT;
+          c.carry[2] = (int) (PATH_INT >> 32); c.carry[3] = -1; c.carry[4] = 0;
+        }
+      __syncwarp();
+      c.nwaves += 1; c.ncells += (u64) (hghk - lowk + 1);
+
+      for (int top = hghk; top >= lowk; top -= 32)
+        { int kk = top - lane;
+          bool act = kk >= lowk;
+          int ap = (lane == 0) ? c.carry[0] : c.V[IX(kk+1)];
+          int ac = c.V[IX(kk)];
+          int am = c.V[IX(kk-1)];
+          int pred, cc;
+          if (ac < am) { if (am < ap) { pred = 1; cc = ap+1; } else { pred = -1; cc = am+1; } }
+          else         { if (ac < ap) { pred = 1; cc = ap+1; } else { pred = 0;  cc = ac+2; } }
+          u64 b; int ha, hm;
+          if (pred == 1 && lane == 0)
+            { b  = (u64) (unsigned) c.carry[1] | ((u64) (unsigned) c.carry[2] << 32);
+              ha = c.carry[3]; hm = c.carry[4];
+            }
+          else
+            { int si = IX(kk+pred);
+              b = c.T[si]; ha = c.HA[si]; hm = c.HM[si];
+            }
+          int nan = c.NA[IX(kk)];
+          //  lane 31's own old state is the next chunk's "kk+1"
+          int  o_v = 0, o_ha = 0, o_hm = 0; u64 o_t = 0;
+          if (lane == 31) { o_v = ac; o_t = c.T[IX(kk)]; o_ha = c.HA[IX(kk)]; o_hm = c.HM[IX(kk)]; }
+          __syncwarp();                              // all reads of old state done
+          if (lane == 31)
+            { c.carry[0] = o_v; c.carry[1] = (int) (unsigned) o_t; c.carry[2] = (int) (o_t >> 32);
+              c.carry[3] = o_ha; c.carry[4] = o_hm;
+            }
+
+          b <<= 1;
+          int xn = (cc + kk) >> 1, flag = 0, k = s*kk;
+          if (act)
+            { int t = snake(c,s,xn,kk,flag);
+              xn += t;
+              b = (t >= 64) ? ~0ull : ((b << t) | ((1ull << t) - 1));
+            }
+          cc = 2*xn - kk;
+
+          bool need = act && xn >= nan;
+          while (__any_sync(FULL,need))
+            { bool create = need && (s*hm < nan);
+              if (c.avail + 32 > c.cmax) return ST_CELLS;
+              unsigned m = __ballot_sync(FULL,create);
+              int idx = c.avail + __popc(m & lt);
+              c.avail += __popc(m);
+              if (create)
+                { Peb p; p.ptr = ha; p.diag = k; p.diff = dif; p.mark = s*nan;
+                  c.cells[idx] = p;
+                  ha = idx; hm = s*nan;
+                }
+              if (need) nan += tspace;
+              need = act && xn >= nan;
+            }
+
+          int ex = max(warp_prefix_max_excl(act ? cc : INT_MIN,lane),besta);
+          bool rec = act && cc > ex;
+          unsigned rm = __ballot_sync(FULL,rec);
+          if (rm)
+            { int L = 31 - __clz(rm);
+              besta = __shfl_sync(FULL,cc,L);
+              bestx = __shfl_sync(FULL,xn,L);
+              bool qual = rec && __popcll(b & PATH_WIN) >= c.path_ave;
+              unsigned qm = __ballot_sync(FULL,qual);
+              if (qm)
+                { lasta = __shfl_sync(FULL,cc,31 - __clz(qm));
+                  bool tq = false;
+                  if (qual)
+                    { int lo15 = (int) (b & TRIM_MASK), hi15 = (int) ((b >> TRIM_LEN) & TRIM_MASK);
+                      if (__ldg(c.table + lo15) >= 0)
+                        tq = ((int) __ldg(c.table + hi15) + (int) __ldg(c.score + lo15) >= 0);
+                    }
+                  unsigned tm = __ballot_sync(FULL,tq);
+                  if (tm)
+                    { int L3 = 31 - __clz(tm);
+                      trima  = __shfl_sync(FULL,cc,L3);
+                      trimx  = __shfl_sync(FULL,xn,L3);
+                      trimha = __shfl_sync(FULL,ha,L3);
+                      trimd  = dif;
+                    }
+                }
+            }
+          unsigned hb = __ballot_sync(FULL,act && flag == 1);
+          unsigned hq = __ballot_sync(FULL,act && flag == 2);
+          if (hb) { anyhit = true; int v = top - (__ffs(hb)-1); if (bclip < v) bclip = v; }
+          if (hq) { anyhit = true; aclip = top - (31 - __clz(hq)); }
+          if (act)
+            { c.V[IX(kk)] = cc; c.T[IX(kk)] = b; c.HA[IX(kk)] = ha; c.HM[IX(kk)] = hm;
+              c.NA[IX(kk)] = nan;
+            }
+          __syncwarp();
+        }
+
+      if (anyhit)
+        { more = (b_at(c,s,besta-bestx) != 4 && a_at(c,s,bestx) != 4);
+          if (hghk >= aclip) hghk = aclip-1;
+          if (lowk <= bclip) lowk = bclip+1;
+          aclip = INT_MAX; bclip = -INT_MAX; anyhit = false;
+        }
+
+      //  trim the band to points within WAVE_LAG of the best (align.c:782-790)
+      { int n = besta - WAVE_LAG, nh = lowk-1;
+        for (int top = hghk; top >= lowk; top -= 32)
+          { int kk = top - lane;
+            unsigned m = __ballot_sync(FULL,kk >= lowk && c.V[IX(kk)] >= n);
+            if (m) { nh = top - (__ffs(m)-1); break; }
+          }
+        hghk = nh;
+        for (int bot = lowk; bot <= hghk; bot += 32)
+          { int kk = bot + lane;
+            unsigned m = __ballot_sync(FULL,kk <= hghk && c.V[IX(kk)] >= n);
+            if (m) { lowk = bot + (__ffs(m)-1); break; }
+          }
+      }
+    }
+
+  endx = s*trimx;
+  endy = s*(trima - trimx);
+  diffs = trimd;
+  trimha_out = trimha;
+  return ST_OK;
+}
+
+//  Forward read-out (align.c:805-870) into c.fstage as bytes.  Warp-uniform; lane 0 stores.
+
+static __device__ int fwd_extract(Ctx &c, int trimha, int mida, int trimx, int trimy, int trimd,
+                                  int &tlen, int &root_diag)
+{ const int lane = threadIdx.x & 31;
+  int n = 0, h;
+  for (h = trimha; h >= 0; h = c.cells[h].ptr) n += 1;
+  Peb tip = c.cells[trimha];
+  int kt = tip.diag, bt, et;
+  if (tip.ptr < 0) { bt = (mida - kt) >> 1; et = 0; }
+  else             { bt = tip.mark - kt;    et = tip.diff; }
+  int extra = (bt + kt != trimx);
+  int len = 2*(n-1) + (extra ? 2 : 0);
+  if (len > c.smax) return ST_STAGE;
+  int addd = 0, addb = 0;                                 // adjustment of the last pair
+  if (extra)
+    { if (lane == 0)
+        { c.fstage[len-2] = (unsigned char) (trimd - et);
+          c.fstage[len-1] = (unsigned char) (trimy - bt);
+        }
+    }
+  else if (bt != trimy)
+    { addd = trimd - et; addb = trimy - bt; }
+  int idx = n-1;
+  Peb cur = tip;
+  root_diag = kt;
+  while (cur.ptr >= 0)
+    { Peb prv = c.cells[cur.ptr];
+      int a = cur.mark - cur.diag, d = cur.diff, bp, ep;
+      if (prv.ptr < 0) { bp = (mida - prv.diag) >> 1; ep = 0; }
+      else             { bp = prv.mark - prv.diag;    ep = prv.diff; }
+      int pd = d - ep, pb = a - bp;
+      if (idx == n-1) { pd += addd; pb += addb; }
+      if (lane == 0)
+        { c.fstage[2*(idx-1)]   = (unsigned char) pd;
+          c.fstage[2*(idx-1)+1] = (unsigned char) pb;
+        }
+      idx -= 1;
+      cur = prv;
+      root_diag = cur.diag;
+    }
+  tlen = len;
+  return ST_OK;
+}
+
+//  Reverse read-out (align.c:1334-1414): pairs in FINAL order (tip first) into c.rstage; the
+//  start-not-on-a-trace-point case folds its pair into the first forward pair (c.fstage[0..1]).
+
+static __device__ int rev_extract(Ctx &c, int trimha, int aoff, int trimx, int trimy, int trimd,
+                                  int ftlen, int &rtlen)
+{ const int lane = threadIdx.x & 31;
+  int n = 0, h, root = trimha;
+  for (h = trimha; h >= 0; h = c.cells[h].ptr) { n += 1; root = h; }
+  Peb r0 = c.cells[root];
+  int b0 = r0.mark - r0.diag;
+  bool offpt = ((b0 + r0.diag) % c.tspace != aoff);
+  int wr = 0;                                        // bytes written to rstage so far
+
+  if (n == 1)
+    { if (offpt)                                     // single pair (trimd, b0 - trimy), h < 0 after
+        { int pd = trimd, pb = b0 - trimy;
+          if (ftlen == 0)
+            { if (2 > c.smax) return ST_STAGE;
+              if (lane == 0) { c.rstage[0] = (unsigned char) pd; c.rstage[1] = (unsigned char) pb; }
+              wr = 2;
+            }
+          else if (lane == 0)
+            { c.fstage[0] = (unsigned char) (c.fstage[0] + pd);
+              c.fstage[1] = (unsigned char) (c.fstage[1] + pb);
+            }
+        }
+      else
+        { int k = r0.diag, b = b0, e = 0;
+          if (b + k != trimx)
+            { if (2 > c.smax) return ST_STAGE;
+              if (lane == 0)
+                { c.rstage[0] = (unsigned char) (trimd - e); c.rstage[1] = (unsigned char) (b - trimy); }
+              wr = 2;
+            }
+          else if (b != trimy && lane == 0)          // adjusts the first forward pair (atrace[atlen])
+            { c.fstage[0] = (unsigned char) (c.fstage[0] + (trimd - e));
+              c.fstage[1] = (unsigned char) (c.fstage[1] + (b - trimy));
+            }
+        }
+      __syncwarp();
+      rtlen = wr;
+      return ST_OK;
+    }
+
+  //  n >= 2: pairs i = n-1 .. 1 between chain cells c_i and c_(i-1); pair 1 is merged into the
+  //  forward trace when the root is off a trace point and a forward trace exists.
+  Peb tip = c.cells[trimha];
+  int kt = tip.diag, bt = tip.mark - kt, et = tip.diff;
+  bool extra = (bt + kt != trimx);
+  int addd = 0, addb = 0;
+  bool merged = offpt && ftlen != 0;
+  int npairs = (n-1) - (merged ? 1 : 0) + (extra ? 1 : 0);
+  if (2*npairs > c.smax) return ST_STAGE;
+  if (extra)
+    { if (lane == 0)
+        { c.rstage[0] = (unsigned char) (trimd - et); c.rstage[1] = (unsigned char) (bt - trimy); }
+      wr = 2;
+    }
+  else if (bt != trimy)
+    { addd = trimd - et; addb = bt - trimy; }        // onto the most recently generated pair
+  Peb cur = tip;
+  int idx = n-1;
+  while (cur.ptr >= 0)
+    { Peb prv = c.cells[cur.ptr];
+      int a = cur.mark - cur.diag, d = cur.diff;
+      int bp = prv.mark - prv.diag, ep = (prv.ptr < 0) ? 0 : prv.diff;
+      int pd = d - ep, pb = bp - a;
+      if (idx == n-1) { pd += addd; pb += addb; }
+      if (idx == 1 && merged)
+        { if (lane == 0)
+            { c.fstage[0] = (unsigned char) (c.fstage[0] + pd);
+              c.fstage[1] = (unsigned char) (c.fstage[1] + pb);
+            }
+        }
+      else
+        { if (lane == 0) { c.rstage[wr] = (unsigned char) pd; c.rstage[wr+1] = (unsigned char) pb; }
+          wr += 2;
+        }
+      idx -= 1;
+      cur = prv;
+    }
+  __syncwarp();
+  rtlen = wr;
+  return ST_OK;
+}
+
+struct LAres { int abpos, bbpos, aepos, bepos, diffs, ftlen, rtlen; };
+
+//  Local_Alignment (align.c:1423-1576), lbord = hbord = -1 and A != B (non-self).
+
+static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int anti, LAres &R)
+{ int minp = -INT_MAX, maxp = INT_MAX;
+  int aoff = acomp ? (c.alen % c.tspace) : 0;
+  int ex, ey, df, tha, st, rootd = 0;
+
+  while (((anti-hgh)>>1) < 0) hgh -= 1;
+
+  R.ftlen = R.rtlen = 0; R.diffs = 0;
+  st = wave(c,+1,low,hgh,anti,minp,maxp,aoff,ex,ey,df,tha);
+  if (st) return st;
+  st = fwd_extract(c,tha,anti,ex,ey,df,R.ftlen,rootd);
+  if (st) return st;
+  __syncwarp();
+  R.aepos = ex; R.bepos = ey; R.diffs = df;
+  low = rootd;
+  bool fshort = ((R.aepos + R.bepos) - anti < DUB_TRIM);
+
+  st = wave(c,-1,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
+  if (st) return st;
+  st = rev_extract(c,tha,aoff,ex,ey,df,R.ftlen,R.rtlen);
+  if (st) return st;
+  R.abpos = ex; R.bbpos = ey; R.diffs += df;
+  bool rshort = (anti - (R.abpos + R.bbpos) < DUB_TRIM);
+
+  if (fshort)
+    { if (rshort)
+        { R.aepos = R.abpos = (R.abpos + R.aepos) >> 1;
+          R.bepos = R.bbpos = (R.bbpos + R.bepos) >> 1;
+          R.ftlen = R.rtlen = 0;
+        }
+      else
+        { low  = R.abpos - R.bbpos;
+          anti = R.abpos + R.bbpos;
+          R.ftlen = R.rtlen = 0;
+          st = wave(c,+1,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
+          if (st) return st;
+          st = fwd_extract(c,tha,anti,ex,ey,df,R.ftlen,rootd);
+          if (st) return st;
+          R.aepos = ex; R.bepos = ey; R.diffs = df;
+        }
+    }
+  else if (rshort)
+    { low  = R.aepos - R.bepos;
+      anti = R.aepos + R.bepos;
+      R.ftlen = R.rtlen = 0; R.diffs = 0;
+      st = wave(c,-1,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
+      if (st) return st;
+      st = rev_extract(c,tha,aoff,ex,ey,df,0,R.rtlen);
+      if (st) return st;
+      R.abpos = ex; R.bbpos = ey; R.diffs += df;
+    }
+  __syncwarp();
+  return ST_OK;
+}
+
+#define OUT_HDR 40        // bytes: triple, seq, pairkey, abpos, bbpos, aepos, bepos, diffs, tlen, 0
+
+//  Appends one alignment record; ACOMP flip of coordinates and trace order (align.c:1534-1557).
+
+static __device__ void emit_record(const ext_params &P, Ctx &c, const LAres &R, int acomp,
+                                   unsigned triple, int seq, unsigned pairkey)
+{ const int lane = threadIdx.x & 31;
+  int tlen = R.rtlen + R.ftlen;
+  u64 need = OUT_HDR + ((tlen + 7) & ~7);
+  u64 off = 0;
+  if (lane == 0) off = atomicAdd(P.out_used,need);
+  off = __shfl_sync(FULL,off,0);
+  if (off + need > P.out_cap) return;                 // host sees out_used > cap and retries
+  unsigned char *o = P.out + off;
+  if (lane == 0)
+    { int *h = (int *) o;
+      int ab = R.abpos, bb = R.bbpos, ae = R.aepos, be = R.bepos;
+      if (acomp)
+        { ab = c.alen - R.aepos; ae = c.alen - R.abpos;
+          bb = c.blen - R.bepos; be = c.blen - R.bbpos;
+        }
+      h[0] = (int) triple; h[1] = seq; h[2] = (int) pairkey;
+      h[3] = ab; h[4] = bb; h[5] = ae; h[6] = be; h[7] = R.diffs; h[8] = tlen; h[9] = 0;
+    }
+  unsigned char *t = o + OUT_HDR;
+  for (int i = lane*2; i < tlen; i += 64)             // pair i/2 of the un-flipped trace
+    { const unsigned char *src = (i < R.rtlen) ? (c.rstage + i) : (c.fstage + (i - R.rtlen));
+      int dst = acomp ? (tlen - 2 - i) : i;
+      t[dst] = src[0]; t[dst+1] = src[1];
+    }
+}
+
+//  Walks one triple: chain scan (FastGA.c:3087-3162), tube stepping (:3205-3340).
+//  ALIGN = false: count qualifying chains only (prefilter).
+
+template<bool ALIGN>
+static __device__ int scan_triple(const ext_params &P, Ctx &c, unsigned j, unsigned &nhit_out,
+                                  u64 &nla)
+{ const rec128 *S = P.seeds;
+  unsigned b = P.seg_start[j], m = P.seg_start[j+1];
+  rec128 r0 = S[b];
+  u64 grp = get_bits(r0,P.p_jc,P.jc_bits + P.ic_bits + 1);
+  long long cdiag = (long long) get_bits(r0,P.p_band,P.band_bits);
+  bool isnew = true, aux = false;
+  if (j > 0)
+    { rec128 rp = S[P.seg_start[j-1]];
+      if (get_bits(rp,P.p_jc,P.jc_bits + P.ic_bits + 1) == grp &&
+          (long long) get_bits(rp,P.p_band,P.band_bits) == cdiag-1)
+        isnew = false;
+    }
+  unsigned e = m;
+  if (j+1 < (unsigned) P.nseg)
+    { rec128 rn = S[m];
+      if (get_bits(rn,P.p_jc,P.jc_bits + P.ic_bits + 1) == grp &&
+          (long long) get_bits(rn,P.p_band,P.band_bits) == cdiag+1)
+        { aux = true; e = P.seg_start[j+2]; }
+    }
+  nhit_out = 0;
+  if (!isnew && !aux) return ST_OK;
+
+  int comp = (int) get_bits(r0,P.p_cp,1);
+  unsigned pairkey = (unsigned) get_bits(r0,P.p_jc,P.jc_bits + P.ic_bits + 1);
+  long long alen = 0, blen = 0, mlen = 0, doffset = 0, aoffset = 0;
+  if (ALIGN)
+    { int ctg1 = P.aperm[get_bits(r0,P.p_ic,P.ic_bits)];
+      int ctg2 = P.bperm[get_bits(r0,P.p_jc,P.jc_bits)];
+      alen = P.aclen[ctg1]; blen = P.bclen[ctg2]; mlen = alen + blen;
+      doffset = alen - (P.amxpos + P.bmxpos); aoffset = alen - P.amxpos;
+      c.A = (comp ? P.arseq : P.aseq) + P.awoff[ctg1];
+      c.B = P.bseq + P.bwoff[ctg2];
+      c.alen = (int) alen; c.blen = (int) blen;
+      c.anw = (alen + 31) >> 5; c.bnw = (blen + 31) >> 5;
+    }
+
+  const long long LMAX = 0x7fffffffffffffffll;
+  long long alast = -1, ahgh, alow, amid, anti, eant, ipost, apost;
+  unsigned s = b, t = m;
+  int go = 1, lcp, wch, mix = 0, cov = 0, dgmin, dgmax, dg, seq = 0;
+
+  ipost = (long long) get_bits(S[s],P.p_anti,P.anti_bits);
+  apost = aux ? (long long) get_bits(S[t],P.p_anti,P.anti_bits) : LMAX;
+  dgmin = 2*BUCK_WIDTH; dgmax = 0;
+  ahgh  = -P.chain_break;
+  alow  = (apost < ipost) ? apost : ipost;
+  while (go)
+    { if (apost < ipost)
+        { rec128 r = S[t];
+          lcp = (int) (r.lo & 63); dg = (int) ((r.lo >> 6) & 63) + BUCK_WIDTH;
+          anti = apost;
+          t += 1;
+          apost = (t >= e) ? LMAX : (long long) get_bits(S[t],P.p_anti,P.anti_bits);
+          wch = 2;
+        }
+      else
+        { if (s < m) { rec128 r = S[s]; lcp = (int) (r.lo & 63); dg = (int) ((r.lo >> 6) & 63); }
+          else       { lcp = 0; dg = 0; }
+          anti = ipost;
+          s += 1;
+          if (s >= m) { if (s > m) go = 0; else ipost = LMAX; }
+          else ipost = (long long) get_bits(S[s],P.p_anti,P.anti_bits);
+          wch = 1;
+        }
+      lcp <<= 1;
+
+      if (anti < ahgh + P.chain_break)
+        { long long cps = anti + lcp;
+          if (cps > ahgh)
+            { if (anti >= ahgh) cov += lcp; else cov += (int) (cps - ahgh);
+              ahgh = cps;
+            }
+          mix |= wch;
+          if (dg < dgmin) dgmin = dg; else if (dg > dgmax) dgmax = dg;
+        }
+      else
+        { if (cov >= P.chain_min && (mix != 1 || isnew))
+            { nhit_out += 1;
+              if (ALIGN)
+                { dgmin += (int) (cdiag << BUCK_SHIFT);
+                  dgmax += (int) (cdiag << BUCK_SHIFT);
+                  if (comp)
+                    { dgmin += (int) doffset; dgmax += (int) doffset; alow += aoffset; ahgh += aoffset; }
+                  else
+                    { dgmin -= (int) P.bmxpos; dgmax -= (int) P.bmxpos; }
+                  if (ahgh > alast)
+                    { if (alow < alast) alow = alast;
+                      ahgh -= BUCK_ANTI;
+                      do
+                        { amid = alow + BUCK_ANTI;
+                          if (amid > ahgh)
+                            { amid = ahgh;
+                              if (amid + dgmin < 0)
+                                { dgmin = (int) -amid;
+                                  if (dgmin > dgmax) break;
+                                }
+                            }
+                          LAres R;
+                          int st = local_alignment(c,comp,dgmin,dgmax,(int) amid,R);
+                          if (st) return st;
+                          nla += 1;
+                          int ab = R.abpos, bb = R.bbpos, ae = R.aepos, be = R.bepos;
+                          int rlen = ae - ab;              // same after the ACOMP flip
+                          if (rlen >= P.aln_min && P.aln_rate*rlen >= (double) R.diffs)
+                            { emit_record(P,c,R,comp,j,seq,pairkey);
+                              seq += 1;
+                            }
+                          //  eant in the flipped frame (FastGA.c:3309-3312) == un-flipped end
+                          if (comp) eant = mlen - ((alen - ae) + (blen - be));
+                          else      eant = (long long) ae + be;
+                          (void) ab; (void) bb;
+                          if (eant <= alow) alow = amid; else alow = eant;
+                        }
+                      while (alow < ahgh);
+                      alast = alow;
+                    }
+                }
+            }
+          if (go)
+            { cov = lcp; ahgh = anti + lcp; mix = wch; alow = anti; dgmin = dgmax = dg; }
+        }
+    }
+  return ST_OK;
+}
+
+static __device__ __forceinline__ bool upper_differs(const rec128 &a, const rec128 &b, int pos)
+{ if (pos < 64) return a.hi != b.hi || (a.lo >> pos) != (b.lo >> pos);
+  return (a.hi >> (pos-64)) != (b.hi >> (pos-64));
+}
+
+//  K7: marks the start of every band segment: seeds i-1 and i differ above the anti field.
+
+__global__ void seg_flag_kernel(const rec128 *__restrict__ seeds, long long n, int p_band,
+                                unsigned *__restrict__ flag)
+{ long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned f = 1;
+  if (i > 0)
+    { rec128 a = seeds[i-1], b = seeds[i];
+      f = upper_differs(a,b,p_band);
+    }
+  flag[i] = f;
+}
+
+//  (heads are recomputed from the seeds, so the scan can run in place on the flag array)
+__global__ void seg_fill2_kernel(const rec128 *__restrict__ seeds, long long n, int p_band,
+                                 const unsigned *__restrict__ pos, unsigned *__restrict__ seg_start,
+                                 unsigned nseg)
+{ long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { seg_start[nseg] = (unsigned) n; return; }
+  bool head = true;
+  if (i > 0)
+    { rec128 a = seeds[i-1], b = seeds[i];
+      head = upper_differs(a,b,p_band);
+    }
+  if (head) seg_start[pos[i]] = (unsigned) i;
+}
+
+//  K7 prefilter: one thread per segment; triples with at least one qualifying chain go to the
+//  work list, and the total number of qualifying chains ("hits") is counted.
+
+__global__ void prefilter_kernel(ext_params P, unsigned *__restrict__ work, unsigned *__restrict__ nwork)
+{ unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned nh = 0;
+  if (j < (unsigned) P.nseg)
+    { Ctx c; u64 nla = 0;
+      scan_triple<false>(P,c,j,nh,nla);
+      if (nh > 0)
+        { unsigned o = atomicAdd(nwork,1u);
+          work[o] = j;
+        }
+    }
+  u64 v = nh;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL,v,o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.counters[0],v);
+}
+
+#define STATE_BYTES (EX_W*(4*4+8) + 32)
+
+__global__ void __launch_bounds__(EX_WARPS*32)
+extend_kernel(ext_params P)
+{ extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const long long gw = (long long) blockIdx.x * EX_WARPS + wp;
+  unsigned char *sb = smem + (size_t) wp * STATE_BYTES;
+  Ctx c;
+  c.T  = (u64 *) sb;
+  c.V  = (int *) (sb + EX_W*8);
+  c.HA = c.V + EX_W; c.HM = c.HA + EX_W; c.NA = c.HM + EX_W;
+  c.carry = c.NA + EX_W;
+  c.cells = P.cells + gw * P.cells_per_warp;
+  c.cmax  = (int) P.cells_per_warp;
+  c.avail = 0;
+  c.fstage = P.stage + gw * 2ll * P.stage_bytes;
+  c.rstage = c.fstage + P.stage_bytes;
+  c.smax = P.stage_bytes;
+  c.tspace = P.tspace; c.path_ave = P.path_ave; c.score = P.score; c.table = P.table;
+  c.nwaves = 0; c.ncells = 0;
+  u64 nla = 0;
+
+  while (true)
+    { unsigned w = 0;
+      if (lane == 0) w = atomicAdd(P.queue,1u);
+      w = __shfl_sync(FULL,w,0);
+      if (w >= (unsigned) P.nwork) break;
+      unsigned j = P.work[w], nh = 0;
+      int st = scan_triple<true>(P,c,j,nh,nla);
+      if (st != ST_OK && lane == 0)
+        { unsigned o = atomicAdd(P.nfailed,1u);
+          P.failed[o] = j;
+        }
+      __syncwarp();
+    }
+  if (lane == 0)
+    { atomicAdd(&P.counters[1],nla);
+      atomicAdd(&P.counters[2],c.nwaves);
+      atomicAdd(&P.counters[3],c.ncells);
+    }
+}
+
+/***********************************************************************************************
+ *  Host side of the stage
+ **********************************************************************************************/
+
+struct fgb_overlaps
+{ long long nrec = 0, nbytes = 0;
+  unsigned char *h_buf = nullptr;          // packed records (OUT_HDR + trace padded to 8)
+  unsigned long long counters[8] = {0};
+  long long nseg = 0, nwork = 0;
+  bool pinned = false;
+};
+
+extern "C" void fgb_overlaps_free(fgb_overlaps *o)
+{ if (!o) return;
+  if (o->h_buf) { if (o->pinned) cudaFreeHost(o->h_buf); else free(o->h_buf); }
+  delete o;
+}
+//  Wraps packed records produced elsewhere (tests feed the host filter without a GPU).
+extern "C" int fgb_overlaps_from_buffer(const unsigned char *buf, long long nbytes, fgb_overlaps **out)
+{ fgb_overlaps *o = new fgb_overlaps();
+  o->h_buf = (unsigned char *) malloc(nbytes + 64);
+  memcpy(o->h_buf,buf,nbytes);
+  o->nbytes = nbytes;
+  *out = o;
+  return FGB_OK;
+}
+extern "C" long long fgb_overlaps_bytes(const fgb_overlaps *o) { return o->nbytes; }
+extern "C" const unsigned char *fgb_overlaps_data(const fgb_overlaps *o) { return o->h_buf; }
+extern "C" void fgb_overlaps_counters(const fgb_overlaps *o, unsigned long long *out)
+{ for (int i = 0; i < 8; i++) out[i] = o->counters[i];
+  out[5] = (unsigned long long) o->nseg; out[6] = (unsigned long long) o->nwork;
+}
+
+void fgb_timing_add(int which, float ms);
+
+struct ev_timer
+{ cudaEvent_t a, b; cudaStream_t st; int which;
+  ev_timer(int w, cudaStream_t s) : st(s), which(w)
+    { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a,st); }
+  ~ev_timer()
+    { cudaEventRecord(b,st); cudaEventSynchronize(b);
+      float ms = 0; cudaEventElapsedTime(&ms,a,b); fgb_timing_add(which,ms);
+      cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+};
+
+//  tables: 2 x 32768 int16 (score, then table) and ave_path from New_Align_Spec's arithmetic,
+//  computed by the host caller (align.c:222-268 is float/double set-up, kept on the host).
+
+extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_genome *B,
+                          int chain_break, int chain_min, int align_min, double align_rate,
+                          const short *tables, int ave_path, int tspace,
+                          fgb_overlaps **out, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  if (A->d_rseq == NULL) return FGB_ERR_ARG;
+  if (S->n >= 0xfffffff0ll) return FGB_ERR_LIMIT;
+  fgb_overlaps *O = new fgb_overlaps();
+  long long n = S->n;
+
+  ext_params P;
+  memset(&P,0,sizeof(P));
+  P.seeds = S->d_rec; P.nseeds = n;
+  P.p_anti = 12; P.anti_bits = S->anti_bits;
+  P.p_band = P.p_anti + S->anti_bits; P.band_bits = S->band_bits;
+  P.p_jc = P.p_band + S->band_bits; P.jc_bits = S->jc_bits;
+  P.p_ic = P.p_jc + S->jc_bits; P.ic_bits = S->ic_bits;
+  P.p_cp = P.p_ic + S->ic_bits;
+  P.amxpos = S->amxpos; P.bmxpos = S->bmxpos;
+  P.aseq = A->d_seq; P.arseq = A->d_rseq; P.awoff = A->d_woff; P.aclen = A->d_clen; P.aperm = A->d_perm;
+  P.bseq = B->d_seq; P.bwoff = B->d_woff; P.bclen = B->d_clen; P.bperm = B->d_perm;
+  P.chain_break = chain_break; P.chain_min = chain_min;
+  P.aln_min = align_min - 50; P.aln_rate = align_rate + .05;      // FastGA.c:3013-3014
+  P.tspace = tspace; P.path_ave = ave_path;
+
+  short *d_tables = NULL;
+  u64 *d_counters = NULL, *d_total = NULL;
+  unsigned *d_flag = NULL, *d_seg = NULL, *d_work = NULL, *d_misc = NULL, *d_failed = NULL;
+  void *d_tmp = NULL;
+  CUDA_TRY(cudaMalloc(&d_tables,65536*sizeof(short)));
+  CUDA_TRY(cudaMemcpyAsync(d_tables,tables,65536*sizeof(short),cudaMemcpyHostToDevice,st));
+  P.score = d_tables; P.table = d_tables + 32768;
+  CUDA_TRY(cudaMalloc(&d_counters,8*8));
+  CUDA_TRY(cudaMemsetAsync(d_counters,0,8*8,st));
+  CUDA_TRY(cudaMalloc(&d_total,8));
+  CUDA_TRY(cudaMalloc(&d_misc,64));
+  CUDA_TRY(cudaMemsetAsync(d_misc,0,64,st));
+  P.counters = d_counters;
+
+  unsigned nseg = 0, nwork = 0;
+  if (n > 0)
+    { ev_timer t(0,st);
+      long long tmpb = fgb_dev_scan_tmp_bytes(n);
+      CUDA_TRY(cudaMalloc(&d_flag,sizeof(unsigned)*(n+1)));
+      CUDA_TRY(cudaMalloc(&d_tmp,tmpb));
+      int nb = (int) ((n + 255) / 256);
+      seg_flag_kernel<<<nb,256,0,st>>>(S->d_rec,n,P.p_band,d_flag);
+      int rc = fgb_dev_exclusive_scan_u32(d_flag,n,d_total,d_tmp,tmpb,st);
+      if (rc) return rc;
+      u64 tot = 0;
+      CUDA_TRY(cudaMemcpyAsync(&tot,d_total,8,cudaMemcpyDeviceToHost,st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      nseg = (unsigned) tot;
+      CUDA_TRY(cudaMalloc(&d_seg,sizeof(unsigned)*(nseg+2)));
+      CUDA_TRY(cudaMalloc(&d_work,sizeof(unsigned)*(nseg+1)));
+      nb = (int) ((n + 1 + 255) / 256);
+      seg_fill2_kernel<<<nb,256,0,st>>>(S->d_rec,n,P.p_band,d_flag,d_seg,nseg);
+      P.seg_start = d_seg; P.nseg = (int) nseg;
+      prefilter_kernel<<<(nseg + 127)/128,128,0,st>>>(P,d_work,d_misc);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaMemcpyAsync(&nwork,d_misc,4,cudaMemcpyDeviceToHost,st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+    }
+  O->nseg = nseg; O->nwork = nwork;
+
+  unsigned char *d_out = NULL;
+  u64 out_cap = 0, out_used = 0;
+  if (nwork > 0)
+    { int dev = 0, nsm = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&nsm,cudaDevAttrMultiProcessorCount,dev);
+      size_t smem = (size_t) EX_WARPS * STATE_BYTES;
+      CUDA_TRY(cudaFuncSetAttribute(extend_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem));
+      int bps = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps,extend_kernel,EX_WARPS*32,smem));
+      if (bps < 1) bps = 1;
+      long long nblocks = (long long) nsm * bps;
+      long long want = ((long long) nwork + EX_WARPS - 1) / EX_WARPS;
+      if (nblocks > want) nblocks = want;
+      long long nwarps = nblocks * EX_WARPS;
+
+      CUDA_TRY(cudaMalloc(&d_failed,sizeof(unsigned)*(nwork+1)));
+      P.work = d_work; P.nwork = (int) nwork;
+      P.queue = d_misc + 1; P.nfailed = d_misc + 2; P.failed = d_failed;
+      P.out_used = (u64 *) (d_misc + 4);
+
+      long long cells_per_warp = 1ll << 17;          // 128 K pebbles = 2 MB per warp
+      int stage_bytes = 1 << 15;
+      out_cap = (u64) nwork * 512 + (64ull << 20);
+      std::vector<unsigned> todo;                    // triples that were re-run at least once
+      unsigned *d_list = d_work; unsigned nlist = nwork;
+      unsigned *d_work2 = NULL;
+      u64 used_before = 0;
+      for (int attempt = 0; ; attempt++)
+        { Peb *d_cells = NULL; unsigned char *d_stage = NULL;
+          CUDA_TRY(cudaMalloc(&d_cells,sizeof(Peb)*cells_per_warp*nwarps));
+          CUDA_TRY(cudaMalloc(&d_stage,2ll*stage_bytes*nwarps));
+          if (d_out == NULL) CUDA_TRY(cudaMalloc(&d_out,out_cap));
+          P.cells = d_cells; P.cells_per_warp = cells_per_warp;
+          P.stage = d_stage; P.stage_bytes = stage_bytes;
+          P.out = d_out; P.out_cap = out_cap;
+          P.work = d_list; P.nwork = (int) nlist;
+          CUDA_TRY(cudaMemsetAsync(d_misc+1,0,8,st));          // queue, nfailed
+          { ev_timer t(1,st);
+            extend_kernel<<<(unsigned) nblocks,EX_WARPS*32,smem,st>>>(P);
+          }
+          CUDA_TRY(cudaGetLastError());
+          unsigned misc[8];
+          CUDA_TRY(cudaMemcpyAsync(misc,d_misc,32,cudaMemcpyDeviceToHost,st));
+          CUDA_TRY(cudaStreamSynchronize(st));
+          cudaFree(d_cells); cudaFree(d_stage);
+          out_used = ((u64) misc[5] << 32) | misc[4];
+          unsigned nfailed = misc[2];
+          if (out_used > out_cap)
+            { //  record buffer too small: grow it (keeping earlier attempts' records) and
+              //  repeat this attempt
+              if (attempt > 12) return FGB_ERR_OVERFLOW;
+              unsigned char *d_new = NULL;
+              u64 ncap = out_used * 2 + (64ull << 20);
+              CUDA_TRY(cudaMalloc(&d_new,ncap));
+              if (used_before) CUDA_TRY(cudaMemcpy(d_new,d_out,used_before,cudaMemcpyDeviceToDevice));
+              cudaFree(d_out); d_out = d_new; out_cap = ncap;
+              CUDA_TRY(cudaMemcpy(d_misc+4,&used_before,8,cudaMemcpyHostToDevice));
+              out_used = used_before;
+              continue;
+            }
+          used_before = out_used;
+          if (nfailed == 0) break;
+          if (attempt > 12 || cells_per_warp > (1ll << 27)) return FGB_ERR_OVERFLOW;
+          //  rerun only the failed triples with larger arenas on fewer warps; the records they
+          //  emitted before failing are dropped by the host below.
+          std::vector<unsigned> f(nfailed);
+          CUDA_TRY(cudaMemcpy(f.data(),d_failed,sizeof(unsigned)*nfailed,cudaMemcpyDeviceToHost));
+          todo.insert(todo.end(),f.begin(),f.end());
+          if (d_work2 == NULL) CUDA_TRY(cudaMalloc(&d_work2,sizeof(unsigned)*(nwork+1)));
+          CUDA_TRY(cudaMemcpy(d_work2,f.data(),sizeof(unsigned)*nfailed,cudaMemcpyHostToDevice));
+          d_list = d_work2; nlist = nfailed;
+          cells_per_warp *= 8; stage_bytes *= 4;
+          long long nb2 = ((long long) nfailed + EX_WARPS - 1) / EX_WARPS;
+          long long maxb = (24ll << 30) / ((long long) sizeof(Peb) * cells_per_warp * EX_WARPS);
+          if (maxb < 1) maxb = 1;
+          nblocks = nb2 < maxb ? nb2 : maxb;
+          nwarps = nblocks * EX_WARPS;
+        }
+      cudaFree(d_work2);
+
+      //  bring the records back and drop partial output of triples that were re-run
+      O->nbytes = (long long) out_used;
+      CUDA_TRY(cudaMallocHost(&O->h_buf,out_used + 64));
+      O->pinned = true;
+      { ev_timer t(2,st);
+        CUDA_TRY(cudaMemcpyAsync(O->h_buf,d_out,out_used,cudaMemcpyDeviceToHost,st));
+      }
+      CUDA_TRY(cudaStreamSynchronize(st));
+      if (!todo.empty())
+        { //  a re-run triple may have emitted records before it failed: keep only the LAST
+          //  complete run = records after its final failure.  Runs are appended in time order,
+          //  so scan backwards keeping records until an earlier run of the same triple is met.
+          std::sort(todo.begin(),todo.end());
+          todo.erase(std::unique(todo.begin(),todo.end()),todo.end());
+          std::vector<long long> offs;
+          for (long long off = 0; off < O->nbytes; )
+            { int *h = (int *) (O->h_buf + off);
+              offs.push_back(off);
+              off += OUT_HDR + ((h[8] + 7) & ~7);
+            }
+          //  a record of triple t with seq s is stale if a later record of t has seq <= s
+          std::vector<char> keep(offs.size(),1);
+          std::vector<int> minseq(todo.size(),INT_MAX);
+          for (long long i = (long long) offs.size()-1; i >= 0; i--)
+            { int *h = (int *) (O->h_buf + offs[i]);
+              unsigned t = (unsigned) h[0];
+              auto it = std::lower_bound(todo.begin(),todo.end(),t);
+              if (it == todo.end() || *it != t) continue;
+              size_t k = it - todo.begin();
+              if (h[1] >= minseq[k]) keep[i] = 0;
+              else minseq[k] = h[1];
+            }
+          long long w = 0;
+          for (size_t i = 0; i < offs.size(); i++)
+            { int *h = (int *) (O->h_buf + offs[i]);
+              long long sz = OUT_HDR + ((h[8] + 7) & ~7);
+              if (keep[i])
+                { if (w != offs[i]) memmove(O->h_buf + w,O->h_buf + offs[i],sz);
+                  w += sz;
+                }
+            }
+          O->nbytes = w;
+        }
+    }
+  CUDA_TRY(cudaMemcpy(O->counters,d_counters,8*8,cudaMemcpyDeviceToHost));
+  { long long cnt = 0;
+    for (long long off = 0; off < O->nbytes; )
+      { int *h = (int *) (O->h_buf + off);
+        off += OUT_HDR + ((h[8] + 7) & ~7);
+        cnt += 1;
+      }
+    O->nrec = cnt;
+  }
+  cudaFree(d_tables); cudaFree(d_counters); cudaFree(d_total); cudaFree(d_misc); cudaFree(d_flag);
+  cudaFree(d_seg); cudaFree(d_work); cudaFree(d_failed); cudaFree(d_tmp); cudaFree(d_out);
+  *out = O;
+  return FGB_OK;
+}
+
+extern "C" long long fgb_overlaps_count(const fgb_overlaps *o) { return o->nrec; }
+
+/***********************************************************************************************
+ *  Alignment specification: New_Align_Spec's float/double arithmetic (align.c:222-268) stays
+ *  on the host; the two 32768-entry int16 tables (score, then table) and ave_path go to HBM.
+ **********************************************************************************************/
+
+static void spec_table(int bit, int prefix, int score, int mx, int mscore, int dscore,
+                       short *table, short *sc)
+{ if (bit >= TRIM_LEN)
+    { table[prefix] = (short) (score - mx);
+      sc[prefix]    = (short) score;
+    }
+  else
+    { if (score > mx) mx = score;
+      spec_table(bit+1,(prefix << 1),    score - dscore,mx,mscore,dscore,table,sc);
+      spec_table(bit+1,(prefix << 1) | 1,score + mscore,mx,mscore,dscore,table,sc);
+    }
+}
+
+extern "C" int fgb_align_spec(double ave_corr, const float *freq, short *tables, int *ave_path)
+{ static const double bias_factor[10] = { .690, .690, .690, .690, .780, .850, .900, .933, .966, 1.000 };
+  double match = freq[0] + freq[3];
+  if ((match <= 0.) == (match > 0.)) match = .5;
+  if (match > .5) match = 1. - match;
+  int bias = (int) ((match + .025)*20. - 1.);
+  if (match < .2) bias = 3;
+  *ave_path  = (int) (60 * (1. - bias_factor[bias] * (1. - ave_corr)));
+  int mscore = (int) (1000 * bias_factor[bias] * (1. - ave_corr));
+  int dscore = 1000 - mscore;
+  spec_table(0,0,0,0,mscore,dscore,tables + 32768,tables);
+  return FGB_OK;
+}

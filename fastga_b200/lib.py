@@ -245,3 +245,145 @@ def sort128_host(recs, byte_lo, byte_hi, stream=None):
     L.fgb_sort128_host.argtypes = [c_void_p, c_ll, c_int, c_int, c_void_p]
     _check(L.fgb_sort128_host(_ptr(recs), recs.shape[0], byte_lo, byte_hi, stream), "fgb_sort128_host")
     return recs
+
+
+OVL_DT = np.dtype([("triple", "i4"), ("seq", "i4"), ("pairkey", "i4"), ("abpos", "i4"), ("bbpos", "i4"),
+                   ("aepos", "i4"), ("bepos", "i4"), ("diffs", "i4"), ("tlen", "i4"), ("toff", "i8")])
+
+
+def align_spec(ave_corr, freq):
+    """(tables[65536] int16, ave_path) of New_Align_Spec (align.c:222-268)"""
+    L = load_library()
+    tables = np.zeros(65536, dtype=np.int16)
+    ave = c_int()
+    f = np.ascontiguousarray(freq, dtype=np.float32)
+    L.fgb_align_spec.argtypes = [C.c_double, c_void_p, c_void_p, C.POINTER(c_int)]
+    _check(L.fgb_align_spec(float(ave_corr), _ptr(f), _ptr(tables), C.byref(ave)), "fgb_align_spec")
+    return tables, ave.value
+
+
+class DeviceOverlaps:
+    """fgb_overlaps handle: raw local alignments (before the redundancy filter), host resident."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def extend(cls, seeds, dgenomeA, dgenomeB, freq, chain_break=2000, chain_min=170, align_min=100,
+               align_rate=0.3, tspace=100, stream=None):
+        L = load_library()
+        tables, ave = align_spec(1.0 - align_rate, freq)
+        h = c_void_p()
+        L.fgb_extend.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, C.c_double, c_void_p,
+                                 c_int, c_int, C.POINTER(c_void_p), c_void_p]
+        _check(L.fgb_extend(seeds.h, dgenomeA.h, dgenomeB.h, chain_break, chain_min, align_min,
+                            float(align_rate), _ptr(tables), ave, tspace, C.byref(h), stream), "fgb_extend")
+        return cls(h)
+
+    def counters(self):
+        L = load_library()
+        out = (C.c_ulonglong * 8)()
+        L.fgb_overlaps_counters.argtypes = [c_void_p, c_void_p]
+        L.fgb_overlaps_counters(self.h, out)
+        v = list(out)
+        return {"hits": v[0], "la_calls": v[1], "waves": v[2], "cells": v[3], "nseg": v[5], "nwork": v[6]}
+
+    def records(self):
+        """(structured array sorted in reference discovery order, trace byte pool)"""
+        L = load_library()
+        L.fgb_overlaps_bytes.restype = c_ll
+        L.fgb_overlaps_bytes.argtypes = [c_void_p]
+        L.fgb_overlaps_data.restype = c_void_p
+        L.fgb_overlaps_data.argtypes = [c_void_p]
+        nb = L.fgb_overlaps_bytes(self.h)
+        if nb == 0:
+            return np.zeros(0, dtype=OVL_DT), np.zeros(0, dtype=np.uint8)
+        buf = np.ctypeslib.as_array(C.cast(L.fgb_overlaps_data(self.h), C.POINTER(C.c_uint8)), shape=(nb,)).copy()
+        recs = []
+        off = 0
+        while off < nb:
+            h = np.frombuffer(buf[off:off + 40].tobytes(), dtype=np.int32)
+            recs.append((h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], off + 40))
+            off += 40 + ((int(h[8]) + 7) & ~7)
+        arr = np.array(recs, dtype=OVL_DT)
+        order = np.lexsort((arr["seq"], arr["triple"]))
+        return arr[order], buf
+
+    def close(self):
+        if self.h:
+            L = load_library()
+            L.fgb_overlaps_free.argtypes = [c_void_p]
+            L.fgb_overlaps_free(self.h)
+            self.h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+ALN_FIELDS = ("comp", "aread", "bread", "abpos", "bbpos", "aepos", "bepos", "diffs", "tlen")
+
+
+class Alignments:
+    """Final local alignments (after the redundancy filter, in .1aln order)."""
+
+    def __init__(self, fields, toff, pool, nraw):
+        self.fields = fields        # (n, 9) int32, columns ALN_FIELDS
+        self.toff = toff
+        self.pool = pool
+        self.nraw = nraw
+
+    def __len__(self):
+        return self.fields.shape[0]
+
+    def trace(self, i):
+        return self.pool[int(self.toff[i]):int(self.toff[i]) + int(self.fields[i, 8])]
+
+    def canonical_lines(self):
+        """One text line per alignment in ONEview's form 'A .. | R | D .. | T .. | X ..', sorted."""
+        out = []
+        for i in range(len(self)):
+            comp, ar, br, ab, bb, ae, be, df, tl = (int(x) for x in self.fields[i])
+            t = self.trace(i)
+            line = "A %d %d %d %d %d %d" % (ar, ab, ae, br, bb, be)
+            if comp:
+                line += " | R"
+            line += " | D %d" % df
+            line += " | T %d" % (tl // 2) + "".join(" %d" % v for v in t[1::2])
+            line += " | X %d" % (tl // 2) + "".join(" %d" % v for v in t[0::2])
+            out.append(line)
+        out.sort()
+        return out
+
+
+def filter_overlaps(ovl_handle, perm1, perm2, jc_bits, ic_bits, do_filter=True):
+    L = load_library()
+    h = c_void_p()
+    p1 = np.ascontiguousarray(perm1, dtype=np.int32)
+    p2 = np.ascontiguousarray(perm2, dtype=np.int32)
+    L.fgb_filter.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(c_void_p)]
+    _check(L.fgb_filter(ovl_handle, _ptr(p1), _ptr(p2), jc_bits, ic_bits, int(do_filter), C.byref(h)),
+           "fgb_filter")
+    for f in ("fgb_alns_count", "fgb_alns_raw_count", "fgb_alns_pool_bytes"):
+        getattr(L, f).restype = c_ll
+        getattr(L, f).argtypes = [c_void_p]
+    n, nraw, pb = L.fgb_alns_count(h), L.fgb_alns_raw_count(h), L.fgb_alns_pool_bytes(h)
+    fields = np.zeros((n, 9), dtype=np.int32)
+    toff = np.zeros(n, dtype=np.int64)
+    pool = np.zeros(max(pb, 1), dtype=np.uint8)
+    L.fgb_alns_get.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    _check(L.fgb_alns_get(h, _ptr(fields), _ptr(toff), _ptr(pool)), "fgb_alns_get")
+    L.fgb_alns_free.argtypes = [c_void_p]
+    L.fgb_alns_free(h)
+    return Alignments(fields, toff, pool, nraw)
+
+
+def overlaps_from_buffer(buf):
+    L = load_library()
+    h = c_void_p()
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    L.fgb_overlaps_from_buffer.argtypes = [c_void_p, c_ll, C.POINTER(c_void_p)]
+    _check(L.fgb_overlaps_from_buffer(_ptr(buf), buf.size, C.byref(h)), "fgb_overlaps_from_buffer")
+    return DeviceOverlaps(h)

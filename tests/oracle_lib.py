@@ -182,3 +182,81 @@ def read_gdb_ascii(path):
             sbeg.append(pos)
             pos += n
     return np.array(clen, np.int64), names, np.array(scaf, np.int32), np.array(sbeg, np.int64)
+
+
+# ------------------------------------------------------------------------------------------
+#  chain scan + extension through the oracle
+# ------------------------------------------------------------------------------------------
+
+class OrcSpec(C.Structure):
+    _fields_ = [("tspace", C.c_int), ("path_ave", C.c_int), ("score", C.POINTER(C.c_int16)),
+                ("table", C.POINTER(C.c_int16))]
+
+
+class OrcParams(C.Structure):
+    _fields_ = [("chain_break", C.c_int), ("chain_min", C.c_int), ("align_min", C.c_int),
+                ("align_rate", C.c_double)]
+
+
+OVL_DT = np.dtype([("comp", "i4"), ("aread", "i4"), ("bread", "i4"), ("abpos", "i4"), ("bbpos", "i4"),
+                   ("aepos", "i4"), ("bepos", "i4"), ("diffs", "i4"), ("tlen", "i4"), ("toff", "i8")],
+                  align=True)
+
+
+def make_spec(freq, ave_corr=0.7, tspace=100):
+    o = orc()
+    tabs = np.zeros(65536, dtype=np.int16)
+    ave = C.c_int()
+    f = np.ascontiguousarray(freq, dtype=np.float32)
+    o.orc_align_spec(C.c_double(ave_corr), f.ctypes.data_as(C.c_void_p), tabs.ctypes.data_as(C.c_void_p),
+                     C.byref(ave))
+    spec = OrcSpec(tspace, ave.value, C.cast(tabs.ctypes.data, C.POINTER(C.c_int16)),
+                   C.cast(tabs.ctypes.data + 65536, C.POINTER(C.c_int16)))
+    return spec, tabs, ave.value
+
+
+def _framed(a):
+    b = np.empty(len(a) + 2, dtype=np.int8)
+    b[0] = 4
+    b[-1] = 4
+    b[1:-1] = a
+    return b
+
+
+def search(recs, layout, gA, gB, perm1, perm2, freq, chain_break=2000, chain_min=170, align_min=100,
+           align_rate=0.3):
+    """oracle alignments in reference discovery order: (records, trace pool, nhit)"""
+    o = orc()
+    spec, tabs, _ = make_spec(freq, 1.0 - align_rate)
+    A = [_framed(gA.contig(c)) for c in range(gA.ncontig)]
+    AC = [_framed(3 - gA.contig(c)[::-1]) for c in range(gA.ncontig)]
+    B = [_framed(gB.contig(c)) for c in range(gB.ncontig)]
+    pa = (C.c_void_p * gA.ncontig)(*[x.ctypes.data + 1 for x in A])
+    pac = (C.c_void_p * gA.ncontig)(*[x.ctypes.data + 1 for x in AC])
+    pb = (C.c_void_p * gB.ncontig)(*[x.ctypes.data + 1 for x in B])
+    L = OrcLayout(*layout)
+    P = OrcParams(chain_break, chain_min, align_min, align_rate)
+    o.orc_new_result.restype = C.c_void_p
+    R = C.c_void_p(o.orc_new_result())
+    recs = np.ascontiguousarray(recs, dtype=np.uint64)
+    p1 = np.ascontiguousarray(perm1, dtype=np.int32)
+    p2 = np.ascontiguousarray(perm2, dtype=np.int32)
+    n = o.orc_search(recs.ctypes.data_as(C.c_void_p), C.c_int64(len(recs)), C.byref(L), C.byref(P),
+                     C.byref(spec), p1.ctypes.data_as(C.c_void_p), p2.ctypes.data_as(C.c_void_p),
+                     pa, pac, gA.clen.ctypes.data_as(C.c_void_p), pb, gB.clen.ctypes.data_as(C.c_void_p), R)
+    o.orc_result_ovls.restype = C.c_void_p
+    o.orc_result_traces.restype = C.c_void_p
+    o.orc_result_hits.restype = C.c_int64
+    o.orc_result_ovls.argtypes = o.orc_result_traces.argtypes = o.orc_result_hits.argtypes = [C.c_void_p]
+    nhit = o.orc_result_hits(R)
+    if n > 0:
+        ov = np.ctypeslib.as_array(C.cast(o.orc_result_ovls(R), C.POINTER(C.c_uint8)),
+                                   shape=(n * OVL_DT.itemsize,)).view(OVL_DT).copy()
+        tl = int((ov["toff"] + ov["tlen"]).max())
+        tp = np.ctypeslib.as_array(C.cast(o.orc_result_traces(R), C.POINTER(C.c_uint8)), shape=(max(tl, 1),)).copy()
+    else:
+        ov = np.zeros(0, dtype=OVL_DT)
+        tp = np.zeros(0, dtype=np.uint8)
+    o.orc_free_result.argtypes = [C.c_void_p]
+    o.orc_free_result(R)
+    return ov, tp, nhit

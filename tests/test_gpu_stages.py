@@ -75,3 +75,39 @@ def test_merge_and_seed_sort_match_oracle(small_pair):
     want = ol.seed_records(seeds, ds.layout + (amx, bmx), sort=True)
     got = ds.download()
     assert np.array_equal(got, want)
+
+
+def _canon(recs, pool, aread=None, bread=None, comp=None):
+    out = []
+    for i, r in enumerate(recs):
+        tr = bytes(pool[int(r["toff"]):int(r["toff"]) + int(r["tlen"])])
+        out.append((int(comp[i]) if comp is not None else int(r["comp"]),
+                    int(aread[i]) if aread is not None else int(r["aread"]),
+                    int(bread[i]) if bread is not None else int(r["bread"]),
+                    int(r["abpos"]), int(r["bbpos"]), int(r["aepos"]), int(r["bepos"]), int(r["diffs"]), tr))
+    return out
+
+
+def test_extend_matches_oracle(small_pair):
+    gA, gB = small_pair
+    dA, dB = lib.DeviceGenome(gA, want_revcomp=True), lib.DeviceGenome(gB)
+    xA, xB = lib.DeviceGix.build(dA), lib.DeviceGix.build(dB)
+    amx, bmx = int(gA.clen.max()), int(gB.clen.max())
+    ds = lib.DeviceSeeds.find(xA, xB, amx, bmx, 10)
+    seeds = ds.download()
+    layout = ds.layout + (amx, bmx)
+    want, wpool, whits = ol.search(seeds, layout, gA, gB, dA.perm, dB.perm, gA.freq)
+    ov = lib.DeviceOverlaps.extend(ds, dA, dB, gA.freq)
+    got, gpool = ov.records()
+    cnt = ov.counters()
+    assert cnt["hits"] == whits
+    # pairkey = (comp, icont rank, jcont rank) packed as in the seed record
+    jb, ib = layout[2], layout[3]
+    pk = got["pairkey"].astype(np.int64)
+    jc = pk & ((1 << jb) - 1)
+    ic = (pk >> jb) & ((1 << ib) - 1)
+    comp = pk >> (jb + ib)
+    g = _canon(got, gpool, dA.perm[ic], dB.perm[jc], comp)
+    w = _canon(want, wpool)
+    assert len(g) == len(w)
+    assert g == w          # same records in the same (reference discovery) order
