@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- Gbp aligned/s of the FastGA seed-and-extend hot path on B200 (BASELINE.json metric).
+
+One "step" = one pass of the whole path over one synthetic genome pair:
+  GIX build of both genomes (syncmer scan, record build, radix sort, prefix index) -> adaptamer
+  merge -> seed sort -> chain scan + wave extension -> D2H of the raw alignments -> host
+  redundancy filter.
+`value`  : inputs (the staged 2-bit genomes) already resident in HBM when the timed region starts.
+`e2e`    : the reference-facing C-ABI call fgb_fastga on HOST buffers (.bps images), H2D and D2H
+           inside the timed region.
+N > 1    : genome-1 contigs are sharded over the ranks (no data-path collective; every rank holds
+           all of genome 2), per-rank results are gathered to rank 0 with torch.distributed.
+--impl reference : the UNMODIFIED reference (oracle/_ref/FastGA -T<cores>) on a bounded sample of
+           the same workload, on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20260924
+PER_GPU_BP = 100_000_000          # BASELINE.json configs[1]: 100 Mbp genome vs 5 %-diverged copy
+DIV = 0.05
+NCONTIG = 8
+SV_EVERY = 200_000
+
+
+def workload(n_gpus, per_gpu_bp=PER_GPU_BP):
+    from fastga_b200 import synth
+    return synth.make_pair(SEED, per_gpu_bp * n_gpus, NCONTIG * n_gpus, DIV, sv_every=SV_EVERY)
+
+
+def shard_contigs(contigs, rank, world):
+    """greedy length balance of genome-1 contigs over ranks (same rule on every rank)"""
+    order = np.argsort([-len(c) for c in contigs], kind="stable")
+    load = [0] * world
+    owner = {}
+    for i in order:
+        r = int(np.argmin(load))
+        owner[int(i)] = r
+        load[r] += len(contigs[i])
+    return [i for i in range(len(contigs)) if owner[i] == rank]
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = False
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE,
+                                     text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference_sample(sample_bp, ncontig, steps, warmup, threads):
+    """times oracle/_ref/FastGA on a bounded sample of the workload; returns (Gbp/s, ms/step, info)"""
+    from fastga_b200 import formats, synth
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref, "FastGA")):
+        raise RuntimeError("oracle/_ref/FastGA missing: run __graft_entry__.build() where /root/reference exists")
+    A, B = synth.make_pair(SEED, sample_bp, ncontig, DIV, sv_every=SV_EVERY)
+    gbp = (sum(len(a) for a in A) + sum(len(b) for b in B)) / 1e9
+    env = dict(os.environ)
+    env["PATH"] = ref + os.pathsep + env.get("PATH", "")
+    times = []
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as wd:
+        formats.write_fasta(os.path.join(wd, "A.fasta"), synth.scaffolds_of(A, "sa", 1))
+        formats.write_fasta(os.path.join(wd, "B.fasta"), synth.scaffolds_of(B, "sb", 1))
+        for s in range(warmup + steps):
+            for f in os.listdir(wd):
+                if not f.endswith(".fasta"):
+                    os.remove(os.path.join(wd, f))
+            t0 = time.time()
+            r = subprocess.run(["FastGA", "-T%d" % threads, "-P" + wd, "-1:ref", "A.fasta", "B.fasta"], cwd=wd,
+                               env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            dt = time.time() - t0
+            if r.returncode != 0:
+                raise RuntimeError("reference FastGA failed:\n" + r.stdout[-2000:])
+            if s >= warmup:
+                times.append(dt)
+    ms = 1000.0 * float(np.mean(times))
+    return gbp / (ms / 1000.0), ms, {"sample_gbp": gbp, "threads": threads}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--per-gpu-bp", type=int, default=PER_GPU_BP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = min(cores, 32)          # GIXmake refuses -T > 32 (GIXmake.c:1723)
+        sample_bp = 20_000_000
+        val, ms, info = run_reference_sample(sample_bp, 4, max(1, args.steps), min(args.warmup, 1), threads)
+        line = {"impl": "reference", "metric": "Gbp aligned/sec (genome x genome)", "value": val,
+                "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic",
+                "config": {"workload": "synthetic %d Mbp genome vs 5%%-diverged copy (bounded sample of the "
+                                       "100 Mbp/GPU workload), reference FastGA -T%d end to end from FASTA"
+                                       % (sample_bp // 1_000_000, threads)},
+                "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": threads, "kind": "reference",
+                                 "sample": "%.3f Gbp pair, FastGA incl. FAtoGDB+GIXmake, tmp on /dev/shm" % info["sample_gbp"]},
+                "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from fastga_b200 import formats, lib
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    A, B = workload(world, args.per_gpu_bp)
+    mine = shard_contigs(A, rank, world)
+    gA = formats.genome_from_arrays([A[i] for i in mine])
+    gB = formats.genome_from_arrays(B)
+    freqA = formats.genome_from_arrays(A).freq if world > 1 else gA.freq
+    total_gbp = (sum(len(a) for a in A) + sum(len(b) for b in B)) / 1e9
+
+    dA = lib.DeviceGenome(gA, want_revcomp=True)
+    dB = lib.DeviceGenome(gB)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        outs = [fn() for _ in range(steps)]
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item()) / steps, outs
+
+    step = lambda: lib.align_resident(dA, dB, freqA)
+    for _ in range(args.warmup):
+        step()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.timings_reset()
+    ms_step, outs = timed(step, args.steps)
+    tm = lib.timings_get()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    alns, stats = outs[-1]
+
+    # end to end through the reference-facing call on host buffers
+    e2e_step = lambda: lib.fastga(gA, gB)
+    e2e_step()
+    ms_e2e, outs2 = timed(e2e_step, max(1, min(args.steps, 3)))
+    st2 = outs2[-1][1]
+
+    # gather the per-rank record streams on rank 0 (variable length)
+    nrec = len(alns)
+    if world > 1:
+        payload = torch.from_numpy(np.concatenate([alns.fields.reshape(-1).view(np.uint8), alns.pool])).cuda()
+        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([payload.numel()], dtype=torch.int64, device="cuda"))
+        mx = int(max(int(s.item()) for s in sizes))
+        pad = torch.zeros(mx, dtype=torch.uint8, device="cuda")
+        pad[:payload.numel()] = payload
+        bufs = [torch.zeros(mx, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, bufs, dst=0)
+        cnt = torch.tensor([nrec], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cnt)
+        nrec = int(cnt.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    steps = args.steps
+    # roofline of the seed-merge kernel (the kernel north_star grades): algorithmic bytes on the
+    # on-disk widths, B = (N1+N2)*E + H*R  
+    pb = max(1, (int(max(gA.clen.max(), gB.clen.max())).bit_length() + 7) // 8)
+    E1 = 9 + pb + 1
+    R = 1 + 2 * (pb + 1)
+    algo = (stats["nkmers1"] + stats["nkmers2"]) * E1 + stats["nseeds"] * R
+    merge_ms = tm["merge_ms"] / max(1, tm["merge_launches"])
+    peak, peak_src = measured_peak_hbm()
+    ach = algo / (merge_ms * 1e-3) / 1e9 if merge_ms > 0 else 0.0
+    dev_ms = {k: v / steps for k, v in tm.items() if k.endswith("_ms")}
+
+    line = {"metric": "Gbp aligned/sec (genome x genome)", "value": total_gbp / (ms_step / 1000.0),
+            "unit": "Gbp/s", "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic",
+            "config": {"workload": "synthetic %d Mbp genome (%d contigs) vs 5%%-diverged copy per GPU, SV breaks "
+                                   "every ~%d kbp, seed %d; FastGA defaults -f10 -c85 -s1000 -l100 -i.7; "
+                                   "k-mer tables and seed sets are larger than L2 (no flush needed)"
+                                   % (args.per_gpu_bp // 1_000_000, NCONTIG, SV_EVERY // 1000, SEED),
+                       "sharding": "genome-1 contigs by rank, genome 2 replicated", "alignments": nrec,
+                       "seeds": stats["nseeds"], "kmers": [stats["nkmers1"], stats["nkmers2"]],
+                       "hits": stats["nhits"], "la_calls": stats["nla"], "waves": stats["nwaves"],
+                       "wave_cells": stats["ncells"], "stage_ms": dev_ms},
+            "roofline": {"bound": "hbm", "kernel": "adaptamer_merge_kernel", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": algo, "kernel_ms": merge_ms},
+            "extend_kernel": {"ms": tm["extend_ms"] / steps, "cell_updates_per_s":
+                              stats["ncells"] / max(1e-9, tm["extend_ms"] / steps / 1000.0)},
+            "clocks": sampler.summary(),
+            "e2e": {"value": total_gbp / (ms_e2e / 1000.0), "unit": "Gbp/s",
+                    "h2d_bytes_per_step": st2["h2d_bytes"], "d2h_bytes_per_step": st2["d2h_bytes"],
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": tm["launches"]}
+
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            threads = min(cores, 32)
+            val, ms, info = run_reference_sample(10_000_000, 4, 1, 0, threads)
+            line["cpu_baseline"] = {"value": val, "unit": "Gbp/s", "cores": threads, "kind": "reference",
+                                    "sample": "%.3f Gbp pair of the same generator (10 Mbp/genome), reference "
+                                              "FastGA -T%d end to end from FASTA, %.1f s" % (info["sample_gbp"], threads, ms / 1000)}
+        except Exception as ex:      # the reference arm must never sink the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "Gbp/s", "cores": cores, "kind": "reference",
+                                    "sample": "failed: %s" % str(ex)[:200]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

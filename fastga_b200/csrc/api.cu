@@ -53,8 +53,11 @@ struct stage_timer
 void fgb_timing_add(int which, float ms)
 { if (which == 0) g_timings.triples_ms += ms;
   else if (which == 1) { g_timings.extend_ms += ms; g_timings.extend_launches += 1; }
+  else if (which == 3) { g_timings.merge_ms += ms; g_timings.merge_launches += 1; }
   else g_timings.d2h_ms += ms;
 }
+
+void fgb_count_launch(int n) { g_timings.launches += n; }
 
 extern "C" void fgb_timings_reset() { memset(&g_timings,0,sizeof(g_timings)); }
 extern "C" void fgb_timings_get(fgb_timings *out) { *out = g_timings; }
@@ -341,15 +344,13 @@ extern "C" int fgb_seeds_find(const fgb_gix *x1, const fgb_gix *x2, long long am
   for (int attempt = 0; ; attempt++)
     { CUDA_TRY(cudaMalloc(&d_a,sizeof(rec128)*(cap+1)));
       int rc;
-      { stage_timer t(&g_timings.merge_ms,st);
-        rc = fgb_merge_device(x1->d_tab,x1->n,x2->d_tab,x2->d_pstart,freq,s->anti_bits,s->band_bits,
-                              s->jc_bits,s->ic_bits,amxpos,bmxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
-      }
+      rc = fgb_merge_device(x1->d_tab,x1->n,x2->d_tab,x2->d_pstart,freq,s->anti_bits,s->band_bits,
+                            s->jc_bits,s->ic_bits,amxpos,bmxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
       if (rc == FGB_OK) break;
       cudaFree(d_a); d_a = NULL;
       if (rc != FGB_ERR_OVERFLOW || attempt > 0) { cudaFree(d_counters); return rc; }
       cap = (long long) nseeds + 1024;
-      g_timings.merge_ms = 0;                  // only the successful launch is reported
+      g_timings.merge_ms = 0; g_timings.merge_launches = 0;   // only the successful launch is reported
     }
   cudaFree(d_counters);
   if (nseeds >= 0xfffffff0ull) return FGB_ERR_LIMIT;
@@ -400,4 +401,81 @@ extern "C" int fgb_device_ready()
 { int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return 0;
   return 1;
+}
+
+/***********************************************************************************************
+ *  Whole path, host buffers in / host records out: what `FastGA -1:<out> A B` computes between
+ *  Read_GDB and la_merge (FastGA.c:4927-5205), GIX construction included.
+ **********************************************************************************************/
+
+struct fgb_overlaps;
+struct fgb_alns;
+extern "C" {
+int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_genome *B, int chain_break,
+               int chain_min, int align_min, double align_rate, const short *tables, int ave_path,
+               int tspace, fgb_overlaps **out, void *stream);
+int fgb_align_spec(double ave_corr, const float *freq, short *tables, int *ave_path);
+void fgb_overlaps_free(fgb_overlaps *o);
+long long fgb_overlaps_bytes(const fgb_overlaps *o);
+void fgb_overlaps_counters(const fgb_overlaps *o, unsigned long long *out);
+int fgb_filter(const fgb_overlaps *O, const int *perm1, const int *perm2, int jc_bits, int ic_bits,
+               int do_filter, fgb_alns **out);
+}
+
+struct fgb_run_stats
+{ long long nkmers1, nkmers2, nseeds, sumlen, nhits, nla, nwaves, ncells, nraw, h2d_bytes, d2h_bytes; };
+
+//  Device-resident genomes in, final alignments out (the timed "step" of bench.py).
+extern "C" int fgb_align_resident(const fgb_genome *A, const fgb_genome *B, const float *freqA,
+                                  int freq, int chain_break, int chain_min, int align_min,
+                                  double align_rate, fgb_alns **out, fgb_run_stats *stats, void *stream)
+{ fgb_gix *x1 = NULL, *x2 = NULL; fgb_seeds *sd = NULL; fgb_overlaps *ov = NULL;
+  int rc;
+  if ((rc = fgb_gix_build(A,&x1,stream))) return rc;
+  if ((rc = fgb_gix_build(B,&x2,stream))) { fgb_gix_free(x1); return rc; }
+  rc = fgb_seeds_find(x1,x2,A->maxlen,B->maxlen,freq,&sd,stream);
+  long long n1 = x1->n, n2 = x2->n;
+  fgb_gix_free(x1); fgb_gix_free(x2);
+  if (rc) return rc;
+  short *tables = (short *) malloc(65536*sizeof(short));
+  int ave = 0;
+  fgb_align_spec(1.-align_rate,freqA,tables,&ave);           // FastGA.c:3760
+  rc = fgb_extend(sd,A,B,chain_break,chain_min,align_min,align_rate,tables,ave,100,&ov,stream);
+  free(tables);
+  long long nseeds = sd->n, sumlen = sd->sumlen;
+  int jb = sd->jc_bits, ib = sd->ic_bits;
+  fgb_seeds_free(sd);
+  if (rc) return rc;
+  { cudaEvent_t a, b;                                         // host filter: wall time, not device
+    (void) a; (void) b;
+  }
+  rc = fgb_filter(ov,A->perm.data(),B->perm.data(),jb,ib,1,out);
+  if (stats)
+    { unsigned long long c[8];
+      fgb_overlaps_counters(ov,c);
+      stats->nkmers1 = n1; stats->nkmers2 = n2; stats->nseeds = nseeds; stats->sumlen = sumlen;
+      stats->nhits = (long long) c[0]; stats->nla = (long long) c[1]; stats->nwaves = (long long) c[2];
+      stats->ncells = (long long) c[3]; stats->nraw = 0;
+      stats->h2d_bytes = A->h2d_bytes + B->h2d_bytes + 65536*2;
+      stats->d2h_bytes = fgb_overlaps_bytes(ov) + 16 + 8*1024*2 + 64;
+    }
+  fgb_overlaps_free(ov);
+  return rc;
+}
+
+//  The reference-facing call: host .bps images + contig tables in, alignments out; every
+//  host<->device copy happens inside.
+extern "C" int fgb_fastga(const unsigned char *bpsA, long long nbA, int ncA, const long long *clenA,
+                          const long long *boffA, const float *freqA,
+                          const unsigned char *bpsB, long long nbB, int ncB, const long long *clenB,
+                          const long long *boffB,
+                          int freq, int chain_break, int chain_min, int align_min, double align_rate,
+                          fgb_alns **out, fgb_run_stats *stats, void *stream)
+{ fgb_genome *A = NULL, *B = NULL;
+  int rc;
+  if ((rc = fgb_genome_create(bpsA,nbA,ncA,clenA,boffA,1,&A,stream))) return rc;
+  if ((rc = fgb_genome_create(bpsB,nbB,ncB,clenB,boffB,0,&B,stream))) { fgb_genome_free(A); return rc; }
+  rc = fgb_align_resident(A,B,freqA,freq,chain_break,chain_min,align_min,align_rate,out,stats,stream);
+  fgb_genome_free(A); fgb_genome_free(B);
+  return rc;
 }

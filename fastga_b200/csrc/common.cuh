@@ -53,3 +53,6 @@ static __device__ __forceinline__ unsigned lanemask_lt()
 int fgb_dev_exclusive_scan_u32(unsigned *d_data, long long n, unsigned long long *d_total,
                                void *d_tmp, long long tmp_bytes, cudaStream_t st);
 long long fgb_dev_scan_tmp_bytes(long long n);
+
+void fgb_timing_add(int which, float ms);     // 0 triples 1 extend 2 d2h 3 merge kernel
+void fgb_count_launch(int n);                 // kernels launched (bench.py gpu_launches)

@@ -855,7 +855,6 @@ extern "C" void fgb_overlaps_counters(const fgb_overlaps *o, unsigned long long 
   out[5] = (unsigned long long) o->nseg; out[6] = (unsigned long long) o->nwork;
 }
 
-void fgb_timing_add(int which, float ms);
 
 struct ev_timer
 { cudaEvent_t a, b; cudaStream_t st; int which;
@@ -930,6 +929,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       seg_fill2_kernel<<<nb,256,0,st>>>(S->d_rec,n,P.p_band,d_flag,d_seg,nseg);
       P.seg_start = d_seg; P.nseg = (int) nseg;
       prefilter_kernel<<<(nseg + 127)/128,128,0,st>>>(P,d_work,d_misc);
+      fgb_count_launch(3);
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaMemcpyAsync(&nwork,d_misc,4,cudaMemcpyDeviceToHost,st));
       CUDA_TRY(cudaStreamSynchronize(st));
@@ -977,6 +977,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           { ev_timer t(1,st);
             extend_kernel<<<(unsigned) nblocks,EX_WARPS*32,smem,st>>>(P);
           }
+          fgb_count_launch(1);
           CUDA_TRY(cudaGetLastError());
           unsigned misc[8];
           CUDA_TRY(cudaMemcpyAsync(misc,d_misc,32,cudaMemcpyDeviceToHost,st));

@@ -398,6 +398,7 @@ extern "C" int fgb_stage_genome_device(const void *d_bps, const long long *d_bof
   if (d_rseq != NULL)
     revcomp_contigs_kernel<<<nb,256,0,st>>>((const u64 *) d_seq,d_clen,d_woff,ncontig,
                                             (u64 *) d_rseq,total_words);
+  fgb_count_launch(d_rseq != NULL ? 2 : 1);
   CUDA_TRY(cudaGetLastError());
   return FGB_OK;
 }
@@ -419,6 +420,7 @@ extern "C" int fgb_syncmer_count_device(const void *d_seq, const long long *d_cl
     syncmer_kernel<0><<<ntiles,SC_THREADS,0,st>>>((const u64 *) d_seq,d_clen,d_woff,d_crank,
                                                    d_tile_contig,d_tile_start,d_tile_count,
                                                    d_buck1024,NULL);
+  fgb_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return fgb_dev_exclusive_scan_u32(d_tile_count,ntiles,d_total,d_tmp,tmp_bytes,st);
 }
@@ -432,6 +434,7 @@ extern "C" int fgb_syncmer_emit_device(const void *d_seq, const long long *d_cle
     syncmer_kernel<1><<<ntiles,SC_THREADS,0,st>>>((const u64 *) d_seq,d_clen,d_woff,d_crank,
                                                    d_tile_contig,d_tile_start,d_tile_offset,
                                                    NULL,(rec128 *) d_records);
+  fgb_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return FGB_OK;
 }
@@ -440,6 +443,7 @@ extern "C" int fgb_kix_index_device(const void *d_tab, long long n, unsigned *d_
 { cudaStream_t st = (cudaStream_t) stream;
   int nb = (int) ((n + 1 + 255) / 256);
   kix_index_kernel<<<nb,256,0,st>>>((const rec128 *) d_tab,n,d_pstart);
+  fgb_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return FGB_OK;
 }

@@ -5,7 +5,7 @@
 struct fgb_timings            // device milliseconds per stage (CUDA events on the call's stream)
 { float h2d_ms, stage_ms, scan_ms, ksort_ms, index_ms, merge_ms, ssort_ms, triples_ms, extend_ms,
         d2h_ms, filter_ms;
-  int   merge_launches, extend_launches;
+  int   merge_launches, extend_launches, launches;
 };
 
 struct fgb_genome

@@ -188,10 +188,19 @@ extern "C" int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2
   CUDA_TRY(cudaMemsetAsync(d_counters,0,16,st));
   if (n1 > 0)
     { unsigned nb = (unsigned) ((n1 + MG_THREADS - 1) / MG_THREADS);
+      cudaEvent_t ea, eb;
+      cudaEventCreate(&ea); cudaEventCreate(&eb);
+      cudaEventRecord(ea,st);
       adaptamer_merge_kernel<<<nb,MG_THREADS,0,st>>>((const rec128 *) d_T1,(unsigned) n1,
                                                      (const rec128 *) d_T2,d_pstart2,freq,L,
                                                      (rec128 *) d_seeds,(unsigned long long) capacity,
                                                      d_counters);
+      cudaEventRecord(eb,st);
+      cudaEventSynchronize(eb);
+      float ms = 0; cudaEventElapsedTime(&ms,ea,eb);
+      fgb_timing_add(3,ms);
+      fgb_count_launch(1);
+      cudaEventDestroy(ea); cudaEventDestroy(eb);
     }
   CUDA_TRY(cudaGetLastError());
   unsigned long long h[2];

@@ -226,6 +226,7 @@ extern "C" int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo
       sort_rowscan_kernel<<<256,1024,0,st>>>(blockhist,ntiles,rowtotal);
       sort_binbase_kernel<<<1,256,0,st>>>(rowtotal,binbase);
       sort_scatter_kernel<<<ntiles,SORT_THREADS,SCATTER_SMEM,st>>>(src,dst,n,b,blockhist,binbase,ntiles);
+      fgb_count_launch(4);
       rec128 *t = src; src = dst; dst = t;
       *result_in_b ^= 1;
     }
@@ -343,6 +344,7 @@ int fgb_dev_exclusive_scan_u32(unsigned *d_data, long long n, unsigned long long
   scan_reduce_kernel<<<nb,SCAN_THREADS,0,st>>>(d_data,n,sums);
   scan_sums_kernel<<<1,1024,0,st>>>(sums,nb,d_total);
   scan_down_kernel<<<nb,SCAN_THREADS,0,st>>>(d_data,n,sums);
+  fgb_count_launch(3);
   CUDA_TRY(cudaGetLastError());
   return FGB_OK;
 }

@@ -220,3 +220,86 @@ def gix_nparts(seqtot, ncontig, post_bytes, cont_bytes, nthreads=8, kmer=40):
     nbit = int((.81 * (seqtot - (kmer - 1) * ncontig)) / nels)
     nparts = ((nbit - 1) // nthreads + 1) * nthreads
     return min(max(nparts, 8), 64)
+
+
+def _clz64(v):
+    r = np.zeros(len(v), dtype=np.int64)
+    vv = v.copy()
+    for s in (32, 16, 8, 4, 2, 1):
+        m = (vv >> np.uint64(64 - s)) == 0
+        r[m] += s
+        vv[m] = vv[m] << np.uint64(s)
+    return r
+
+
+def table_lcp(tab, part_first):
+    """LCP byte of every entry of a sorted device-layout table (n,2 uint64 [lo,hi]): true LCP in
+    bases with the predecessor, 40 for a duplicate, 0 for the first entry of a part."""
+    n = len(tab)
+    lcp = np.zeros(n, dtype=np.int64)
+    if n > 1:
+        hi, lo = tab[:, 1], tab[:, 0]
+        x = hi[1:] ^ hi[:-1]
+        y = (lo[1:] ^ lo[:-1]) >> np.uint64(48)
+        lcp[1:] = np.where(x != 0, _clz64(x) >> 1, np.where(y != 0, 32 + ((_clz64(y) - 48) >> 1), 40))
+    lcp[np.asarray(part_first, dtype=np.int64)] = 0
+    return lcp
+
+
+def ktab_entries_from_table(tab, post_bytes, cont_bytes, part_first):
+    """numpy restatement of the .ktab entry layout (GIXmake.c:1235-1261) from device-layout records"""
+    n = len(tab)
+    E = 9 + post_bytes + cont_bytes
+    out = np.zeros((n, E), dtype=np.uint8)
+    hi, lo = tab[:, 1], tab[:, 0]
+    suf = ((hi & np.uint64(0xffffffffff)) << np.uint64(16)) | (lo >> np.uint64(48))
+    for k in range(7):
+        out[:, k] = ((suf >> np.uint64(8 * (6 - k))) & np.uint64(0xff)).astype(np.uint8)
+    out[:, 8] = table_lcp(tab, part_first).astype(np.uint8)
+    post = lo & np.uint64(0xffffffff)
+    for k in range(post_bytes):
+        out[:, 9 + k] = ((post >> np.uint64(8 * k)) & np.uint64(0xff)).astype(np.uint8)
+    cs = (lo >> np.uint64(32)) & np.uint64(0xffff)
+    cv = (cs & np.uint64(0x7fff)) | ((cs >> np.uint64(15)) << np.uint64(8 * cont_bytes - 1))
+    for k in range(cont_bytes):
+        out[:, 9 + post_bytes + k] = ((cv >> np.uint64(8 * k)) & np.uint64(0xff)).astype(np.uint8)
+    return out.reshape(-1)
+
+
+def gix_bytes(genome, nthreads=8):
+    """PostBytes / ContBytes of GIXmake.c:1888-1901 (ncontig padded to NTHREADS by short_GDB_fix,
+    GIXmake.c:1605-1624)"""
+    pb, cum = 0, 1
+    while cum < int(genome.clen.max()):
+        cum *= 256
+        pb += 1
+    nc = max(genome.ncontig, nthreads)
+    cb, cum = 0, 1
+    while cum < 2 * nc:
+        cum *= 256
+        cb += 1
+    return pb, cb
+
+
+def canonical_ktab(entries, esize, index):
+    """.ktab entries in a run-to-run reproducible form.  Two things in the reference's output are
+    not reproducible: the order of equal k-mers (its in-place MSD sort is not stable,
+    MSDsort.c:285-323) -- payloads of every run of equal k-mers are put in sorted order here --
+    and the LCP byte of the three entries at which the FIRST base changes: compress_thread
+    temporarily stores 12 into the next panel's LCP slot (GIXmake.c:1229-1231) while another
+    thread may be reading it, so those bytes come out 0 or 12 depending on timing; zeroed here.
+    index = the stub's cumulative 2^24 table."""
+    ent = np.ascontiguousarray(entries, dtype=np.uint8).reshape(-1, esize).copy()
+    if len(ent) == 0:
+        return ent.reshape(-1)
+    for x in (0x3fffff, 0x7fffff, 0xbfffff):
+        i = int(index[x])
+        if i < len(ent):
+            ent[i, 8] = 0
+    run = np.cumsum(ent[:, 8] != 40)
+    pay = np.zeros(len(ent), dtype=np.uint64)
+    for k in range(9, esize):
+        pay |= ent[:, k].astype(np.uint64) << np.uint64(8 * (k - 9))
+    order = np.lexsort((pay, run))
+    ent[:, 9:] = ent[order, 9:]
+    return ent.reshape(-1)

@@ -24,7 +24,7 @@ class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in
                 ("h2d_ms", "stage_ms", "scan_ms", "ksort_ms", "index_ms", "merge_ms", "ssort_ms",
                  "triples_ms", "extend_ms", "d2h_ms", "filter_ms")] + \
-               [("merge_launches", C.c_int), ("extend_launches", C.c_int)]
+               [("merge_launches", C.c_int), ("extend_launches", C.c_int), ("launches", C.c_int)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -366,6 +366,31 @@ def filter_overlaps(ovl_handle, perm1, perm2, jc_bits, ic_bits, do_filter=True):
     L.fgb_filter.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(c_void_p)]
     _check(L.fgb_filter(ovl_handle, _ptr(p1), _ptr(p2), jc_bits, ic_bits, int(do_filter), C.byref(h)),
            "fgb_filter")
+    return _alns_out(h)
+
+
+def overlaps_from_buffer(buf):
+    L = load_library()
+    h = c_void_p()
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    L.fgb_overlaps_from_buffer.argtypes = [c_void_p, c_ll, C.POINTER(c_void_p)]
+    _check(L.fgb_overlaps_from_buffer(_ptr(buf), buf.size, C.byref(h)), "fgb_overlaps_from_buffer")
+    return DeviceOverlaps(h)
+
+
+class RunStats(C.Structure):
+    _fields_ = [(n, c_ll) for n in ("nkmers1", "nkmers2", "nseeds", "sumlen", "nhits", "nla", "nwaves",
+                                    "ncells", "nraw", "h2d_bytes", "d2h_bytes")]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+DEFAULTS = dict(freq=10, chain_break=2000, chain_min=170, align_min=100, align_rate=0.3)
+
+
+def _alns_out(h):
+    L = load_library()
     for f in ("fgb_alns_count", "fgb_alns_raw_count", "fgb_alns_pool_bytes"):
         getattr(L, f).restype = c_ll
         getattr(L, f).argtypes = [c_void_p]
@@ -380,10 +405,36 @@ def filter_overlaps(ovl_handle, perm1, perm2, jc_bits, ic_bits, do_filter=True):
     return Alignments(fields, toff, pool, nraw)
 
 
-def overlaps_from_buffer(buf):
+def align_resident(dA, dB, freqA, stream=None, **kw):
+    """Whole path from device-resident genomes: returns (Alignments, stats dict)"""
+    p = dict(DEFAULTS)
+    p.update(kw)
     L = load_library()
     h = c_void_p()
-    buf = np.ascontiguousarray(buf, dtype=np.uint8)
-    L.fgb_overlaps_from_buffer.argtypes = [c_void_p, c_ll, C.POINTER(c_void_p)]
-    _check(L.fgb_overlaps_from_buffer(_ptr(buf), buf.size, C.byref(h)), "fgb_overlaps_from_buffer")
-    return DeviceOverlaps(h)
+    st = RunStats()
+    f = np.ascontiguousarray(freqA, dtype=np.float32)
+    L.fgb_align_resident.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, C.c_double,
+                                     C.POINTER(c_void_p), C.POINTER(RunStats), c_void_p]
+    _check(L.fgb_align_resident(dA.h, dB.h, _ptr(f), p["freq"], p["chain_break"], p["chain_min"],
+                                p["align_min"], float(p["align_rate"]), C.byref(h), C.byref(st), stream),
+           "fgb_align_resident")
+    return _alns_out(h), st.asdict()
+
+
+def fastga(gA, gB, stream=None, **kw):
+    """The reference-facing call on host buffers (formats.Genome x2) -> (Alignments, stats)"""
+    p = dict(DEFAULTS)
+    p.update(kw)
+    L = load_library()
+    h = c_void_p()
+    st = RunStats()
+    f = np.ascontiguousarray(gA.freq, dtype=np.float32)
+    L.fgb_fastga.argtypes = [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_ll, c_int, c_void_p, c_void_p,
+                             c_int, c_int, c_int, c_int, C.c_double,
+                             C.POINTER(c_void_p), C.POINTER(RunStats), c_void_p]
+    _check(L.fgb_fastga(_ptr(gA.bps), gA.bps.size, gA.ncontig, _ptr(gA.clen), _ptr(gA.boff), _ptr(f),
+                        _ptr(gB.bps), gB.bps.size, gB.ncontig, _ptr(gB.clen), _ptr(gB.boff),
+                        p["freq"], p["chain_break"], p["chain_min"], p["align_min"], float(p["align_rate"]),
+                        C.byref(h), C.byref(st), stream), "fgb_fastga")
+    return _alns_out(h), st.asdict()

@@ -1,0 +1,137 @@
+/* fastga_b200.h -- C-ABI of libfastga_b200.so, the B200 (sm_100a) implementation of FastGA's
+ * seed-and-extend hot path.  Plain pointers and sizes only; every function returns 0 (FGB_OK) or a
+ * negative FGB_ERR_* code, and prints CUDA errors to stderr.  There is no CPU fallback: without a
+ * CUDA device every compute entry point fails.
+ *
+ * FASTGA (the reference) has no plugin/FFI layer: its seams are ordinary C calls between
+ * FastGA.c / GIXmake.c and MSDsort.c / RSDsort.c / align.c, plus the files.  Each entry point
+ * below names the reference interface it replaces (file:line in thegenemyers/FASTGA).  The
+ * reference-side stubs a maintainer would add are in INTEGRATION.md.
+ *
+ * `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); all work of a
+ * call is issued on it and the call returns after the stream has drained.
+ */
+#ifndef FASTGA_B200_H
+#define FASTGA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGB_OK            0
+#define FGB_ERR_CUDA     -1   /* a CUDA runtime call failed                                     */
+#define FGB_ERR_ARG      -2   /* bad argument                                                   */
+#define FGB_ERR_LIMIT    -3   /* input exceeds a device-layout limit (see DESIGN.md "Limits")   */
+#define FGB_ERR_OVERFLOW -4   /* a device arena overflowed even after the retry ladder          */
+
+typedef struct fgb_genome   fgb_genome;    /* staged 2-bit contigs of one genome in HBM        */
+typedef struct fgb_gix      fgb_gix;       /* sorted k-mer table + 2^24 prefix index in HBM    */
+typedef struct fgb_seeds    fgb_seeds;     /* sorted adaptive-seed records in HBM              */
+typedef struct fgb_overlaps fgb_overlaps;  /* raw local alignments, host resident              */
+typedef struct fgb_alns     fgb_alns;      /* final alignments in .1aln order, host resident   */
+
+typedef struct
+{ long long nkmers1, nkmers2, nseeds, sumlen, nhits, nla, nwaves, ncells, nraw, h2d_bytes, d2h_bytes;
+} fgb_run_stats;
+
+typedef struct
+{ float h2d_ms, stage_ms, scan_ms, ksort_ms, index_ms, merge_ms, ssort_ms, triples_ms, extend_ms,
+        d2h_ms, filter_ms;
+  int   merge_launches, extend_launches, launches;
+} fgb_timings;
+
+/* ---- the whole path -----------------------------------------------------------------------
+ * Replaces, inside `FastGA -1:<out> A B`, everything between Read_GDB and la_merge
+ * (FastGA.c:4927-5205): GIXmake's k_sort/distribute for both genomes (GIXmake.c:616-716,
+ * :1300-1596), adaptamer_merge (FastGA.c:2281), pair_sort_search (FastGA.c:4135) incl.
+ * rmsd_sort, search_seeds/align_contigs and Local_Alignment, and la_sort's order.
+ * Inputs are the GDB as Read_GDB leaves it: the .bps image, per contig clen and boff
+ * (GDB.h:28-34) and the base frequencies gdb1->freq (GDB.h:72).  Defaults of the reference CLI:
+ * freq 10, chain_break 2000, chain_min 170, align_min 100, align_rate .3 (FastGA.c:4451-4459). */
+int fgb_fastga(const unsigned char *bpsA, long long bps_bytesA, int ncontigA, const long long *clenA,
+               const long long *boffA, const float *freqA,
+               const unsigned char *bpsB, long long bps_bytesB, int ncontigB, const long long *clenB,
+               const long long *boffB,
+               int freq, int chain_break, int chain_min, int align_min, double align_rate,
+               fgb_alns **out, fgb_run_stats *stats, void *stream);
+
+/* Same from device-resident genomes (bench.py's timed step). */
+int fgb_align_resident(const fgb_genome *A, const fgb_genome *B, const float *freqA,
+                       int freq, int chain_break, int chain_min, int align_min, double align_rate,
+                       fgb_alns **out, fgb_run_stats *stats, void *stream);
+
+/* ---- genome (GDB.h:28-72; Get_Contig / Get_Contig_Piece GDB.c:1739,1841; Complement_Seq) ---- */
+int  fgb_genome_create(const unsigned char *bps, long long bps_bytes, int ncontig,
+                       const long long *clen, const long long *boff, int want_revcomp,
+                       fgb_genome **out, void *stream);
+void fgb_genome_free(fgb_genome *g);
+int  fgb_genome_perm(const fgb_genome *g, int *perm_out);   /* Perm of GIXmake.c:1950-1963 */
+int  fgb_genome_download(const fgb_genome *g, int rev, unsigned long long *words, long long *woff_out);
+long long fgb_genome_words(const fgb_genome *g);
+
+/* ---- GIX (GIXmake.c distribute + k_sort; MSDsort.c msd_sort; libfastk.c Kmer_Stream) ---- */
+int  fgb_gix_build(const fgb_genome *g, fgb_gix **out, void *stream);
+int  fgb_gix_upload(const void *tab, long long n, int post_bytes, int cont_bytes, int ncontig,
+                    fgb_gix **out, void *stream);
+/* entries = concatenated .ktab parts, index = the stub's cumulative 2^24 table (libfastk.c:815-840) */
+int  fgb_gix_import_ktab(const unsigned char *entries, long long n, int post_bytes, int cont_bytes,
+                         const long long *index, int ncontig, fgb_gix **out, void *stream);
+/* on-disk entries (GIXmake.c:1235-1261); part_first[p] = first entry index of .ktab part p+1 */
+int  fgb_gix_export_ktab(const fgb_gix *x, const long long *part_first, int nparts,
+                         unsigned char *out, void *stream);
+int  fgb_gix_download(const fgb_gix *x, void *tab, unsigned *pstart, unsigned long long *buck1024);
+long long fgb_gix_size(const fgb_gix *x);
+int  fgb_gix_post_bytes(const fgb_gix *x);
+int  fgb_gix_cont_bytes(const fgb_gix *x);
+void fgb_gix_free(fgb_gix *x);
+
+/* ---- seeds (adaptamer_merge FastGA.c:2281 + new_merge_thread :610; reimport_thread :2641;
+ *             rmsd_sort RSDsort.c:292) ---- */
+int  fgb_seeds_find(const fgb_gix *x1, const fgb_gix *x2, long long amxpos, long long bmxpos,
+                    int freq, fgb_seeds **out, void *stream);
+long long fgb_seeds_size(const fgb_seeds *s);
+long long fgb_seeds_sumlen(const fgb_seeds *s);
+int  fgb_seeds_layout(const fgb_seeds *s, int *bits /* anti, band, jcont, icont */);
+int  fgb_seeds_download(const fgb_seeds *s, void *rec);
+void fgb_seeds_free(fgb_seeds *s);
+
+/* ---- extension (search_seeds / align_contigs FastGA.c:3716,2973; Local_Alignment align.c:1423;
+ *                 New_Align_Spec align.c:222; Compress_TraceTo8 align.c:3892) ---- */
+int  fgb_align_spec(double ave_corr, const float *freq, short *tables /* 65536 */, int *ave_path);
+int  fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_genome *B,
+                int chain_break, int chain_min, int align_min, double align_rate,
+                const short *tables, int ave_path, int tspace, fgb_overlaps **out, void *stream);
+int  fgb_overlaps_from_buffer(const unsigned char *buf, long long nbytes, fgb_overlaps **out);
+long long fgb_overlaps_bytes(const fgb_overlaps *o);
+long long fgb_overlaps_count(const fgb_overlaps *o);
+const unsigned char *fgb_overlaps_data(const fgb_overlaps *o);
+void fgb_overlaps_counters(const fgb_overlaps *o, unsigned long long *out /* 8 */);
+void fgb_overlaps_free(fgb_overlaps *o);
+
+/* ---- redundancy filter + final order (FastGA.c:3407-3685, :2818 entwine, :3800 SORT_MAP) ---- */
+int  fgb_filter(const fgb_overlaps *O, const int *perm1, const int *perm2, int jc_bits, int ic_bits,
+                int do_filter, fgb_alns **out);
+long long fgb_alns_count(const fgb_alns *a);
+long long fgb_alns_raw_count(const fgb_alns *a);
+long long fgb_alns_pool_bytes(const fgb_alns *a);
+/* fields: n x 9 ints (comp aread bread abpos bbpos aepos bepos diffs tlen); toff: n; pool: traces */
+int  fgb_alns_get(const fgb_alns *a, int *fields, long long *toff, unsigned char *pool);
+void fgb_alns_free(fgb_alns *a);
+
+/* ---- sort seam (building block of msd_sort / rmsd_sort, MSDsort.c:404 / RSDsort.c:292) ---- */
+int  fgb_sort128_host(void *recs, long long n, int byte_lo, int byte_hi, void *stream);
+int  fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo, int byte_hi,
+                        void *d_tmp, long long tmp_bytes, int *result_in_b, void *stream);
+long long fgb_sort128_tmp_bytes(long long n);
+
+/* ---- housekeeping ---- */
+int  fgb_device_ready(void);
+void fgb_timings_reset(void);
+void fgb_timings_get(fgb_timings *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

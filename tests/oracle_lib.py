@@ -260,3 +260,45 @@ def search(recs, layout, gA, gB, perm1, perm2, freq, chain_break=2000, chain_min
     o.orc_free_result.argtypes = [C.c_void_p]
     o.orc_free_result(R)
     return ov, tp, nhit
+
+
+def pack_overlaps(ov, tp, rank1, rank2, jb, ib):
+    """oracle alignments (discovery order) -> the packed record buffer the device stage emits, so the
+    product's host filter can be run on them"""
+    from fastga_b200 import lib
+    parts = []
+    for i, r in enumerate(ov):
+        pk = (int(r["comp"]) << (jb + ib)) | (int(rank1[r["aread"]]) << jb) | int(rank2[r["bread"]])
+        h = np.array([i, 0, pk, r["abpos"], r["bbpos"], r["aepos"], r["bepos"], r["diffs"], r["tlen"], 0],
+                     dtype=np.int32)
+        tr = bytes(tp[int(r["toff"]):int(r["toff"]) + int(r["tlen"])])
+        tr += b"\0" * ((-len(tr)) % 8)
+        parts.append(h.tobytes())
+        parts.append(tr)
+    buf = np.frombuffer(b"".join(parts), dtype=np.uint8) if parts else np.zeros(0, np.uint8)
+    return lib.overlaps_from_buffer(buf)
+
+
+def seed_layout(gA, gB):
+    amx, bmx = int(gA.clen.max()), int(gB.clen.max())
+    ab = int(amx + bmx).bit_length()
+    return (ab, max(ab - 6, 1), int(max(gB.ncontig - 1, 1)).bit_length(),
+            int(max(gA.ncontig - 1, 1)).bit_length(), amx, bmx)
+
+
+def oracle_pipeline(gA, gB, **kw):
+    """The whole path through the CPU oracle + the product's host filter.  Returns a dict."""
+    from fastga_b200 import lib
+    pa, ra = contig_rank(gA.clen)
+    pb, rb = contig_rank(gB.clen)
+    tA, sA = gix_build(gA, ra)
+    tB, sB = gix_build(gB, rb)
+    seeds, sumlen = merge(tA, tB, sB, kw.get("freq", 10))
+    layout = seed_layout(gA, gB)
+    recs = seed_records(seeds, layout)
+    skw = {k: v for k, v in kw.items() if k in ("chain_break", "chain_min", "align_min", "align_rate")}
+    ov, tp, nhit = search(recs, layout, gA, gB, pa, pb, gA.freq, **skw)
+    O = pack_overlaps(ov, tp, ra, rb, layout[2], layout[3])
+    al = lib.filter_overlaps(O.h, pa, pb, layout[2], layout[3])
+    return dict(tabA=tA, tabB=tB, pstartA=sA, pstartB=sB, nseeds=len(seeds), sumlen=sumlen, seedrecs=recs,
+                nhit=nhit, nraw=len(ov), alns=al, lines=al.canonical_lines(), perm1=pa, perm2=pb)

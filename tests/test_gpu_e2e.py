@@ -1,0 +1,59 @@
+"""-m gpu: the reference-facing call (fgb_fastga, host buffers) against the UNMODIFIED reference run
+on the same box (oracle/_ref/FastGA), records compared bit-exactly after the canonical sort."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from fastga_b200 import formats, lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _vs_reference(seed, total, ncontig, div, sv, threads=8, per_scaffold=1):
+    A, B = synth.make_pair(seed, total, ncontig, div, sv_every=sv)
+    with tempfile.TemporaryDirectory() as wd:
+        formats.write_fasta(os.path.join(wd, "A.fasta"), synth.scaffolds_of(A, "sa", per_scaffold))
+        formats.write_fasta(os.path.join(wd, "B.fasta"), synth.scaffolds_of(B, "sb", per_scaffold))
+        log = ol.ref_fastga(wd, "A", "B", threads=threads)
+        st = ol.parse_fastga_log(log)
+        ref = ol.oneview_records(os.path.join(wd, "ref.1aln"))
+        gA = formats.genome_from_fasta(os.path.join(wd, "A.fasta"))
+        gB = formats.genome_from_fasta(os.path.join(wd, "B.fasta"))
+        assert np.array_equal(np.fromfile(os.path.join(wd, ".A.bps"), dtype=np.uint8), gA.bps)
+    alns, stats = lib.fastga(gA, gB)
+    assert stats["nseeds"] == st["seeds"]
+    assert stats["nhits"] == st["hits"]
+    assert alns.nraw == st["alns"]
+    assert len(alns) == st["kept"]
+    mine = alns.canonical_lines()
+    assert ol.md5_lines(mine) == ol.md5_lines(ref)
+    return stats
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
+def test_small_pair_bit_exact_vs_reference():
+    _vs_reference(11, 1_200_000, 3, 0.05, 60_000)
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
+def test_scaffolded_15pct_bit_exact_vs_reference():
+    _vs_reference(12, 2_000_000, 6, 0.15, 40_000, per_scaffold=3)
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
+def test_long_alignments_exercise_arena_retry():
+    # no SV breaks: contig-long alignments -> pebble arenas overflow and the retry path runs
+    _vs_reference(13, 6_000_000, 3, 0.03, 0)
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
+def test_10mbp_bit_exact_vs_reference():
+    _vs_reference(14, 10_000_000, 5, 0.05, 200_000)
+
+
+def test_smoke_entry():
+    import __graft_entry__
+    __graft_entry__.smoke()
