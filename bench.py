@@ -52,6 +52,10 @@ def shard_contigs(contigs, rank, world):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons DURING the timed region, through NVML in-process (spawning
+    nvidia-smi five times a second stalls the CUDA driver calls of the measured process)."""
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
@@ -61,27 +65,29 @@ class ClockSampler(threading.Thread):
         self.max_mhz = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            getr = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        except Exception:
+            return
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE,
-                                     text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = int(getr(h))
+                for bit, name in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
 def measured_peak_hbm():
@@ -254,7 +260,10 @@ def main():
                        "sharding": "genome-1 contigs by rank, genome 2 replicated", "alignments": nrec,
                        "seeds": stats["nseeds"], "kmers": [stats["nkmers1"], stats["nkmers2"]],
                        "hits": stats["nhits"], "la_calls": stats["nla"], "waves": stats["nwaves"],
-                       "wave_cells": stats["ncells"], "stage_ms": dev_ms},
+                       "wave_cells": stats["ncells"], "stage_ms": dev_ms,
+                       "triples": [stats["nseg"], stats["nwork"]],
+                       "host_wall_us": {k: stats[k] for k in ("us_gix", "us_seeds", "us_extend", "us_filter")},
+                       "extend_cycles": {k: stats[k] for k in ("warp_cycles", "wave_cycles", "extract_cycles")}},
             "roofline": {"bound": "hbm", "kernel": "adaptamer_merge_kernel", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes": algo, "kernel_ms": merge_ms},

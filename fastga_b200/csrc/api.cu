@@ -6,8 +6,12 @@
 #include <vector>
 #include <algorithm>
 #include <string.h>
+#include <chrono>
 
 typedef unsigned long long u64;
+
+static inline long long now_us()
+{ return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 extern "C" {
 int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo, int byte_hi,
@@ -59,6 +63,24 @@ void fgb_timing_add(int which, float ms)
 
 void fgb_count_launch(int n) { g_timings.launches += n; }
 
+static bool pool_ready = false;
+
+cudaError_t fgb_dmalloc(void **p, size_t bytes, cudaStream_t st)
+{ if (!pool_ready)
+    { int dev = 0;
+      cudaMemPool_t pool;
+      unsigned long long keep = ~0ull;                 // never give pages back between steps
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool,dev) == cudaSuccess)
+        cudaMemPoolSetAttribute(pool,cudaMemPoolAttrReleaseThreshold,&keep);
+      pool_ready = true;
+    }
+  if (bytes == 0) bytes = 16;
+  return cudaMallocAsync(p,bytes,st);
+}
+
+void fgb_dfree(void *p, cudaStream_t st)
+{ if (p != NULL) cudaFreeAsync(p,st); }
+
 extern "C" void fgb_timings_reset() { memset(&g_timings,0,sizeof(g_timings)); }
 extern "C" void fgb_timings_get(fgb_timings *out) { *out = g_timings; }
 
@@ -103,14 +125,14 @@ extern "C" int fgb_genome_create(const unsigned char *bps, long long bps_bytes, 
 
   unsigned char *d_bps = NULL;
   long long *d_boff = NULL;
-  CUDA_TRY(cudaMalloc(&d_bps,bps_bytes + 16));
-  CUDA_TRY(cudaMalloc(&d_boff,sizeof(long long)*ncontig));
-  CUDA_TRY(cudaMalloc(&g->d_clen,sizeof(long long)*ncontig));
-  CUDA_TRY(cudaMalloc(&g->d_woff,sizeof(long long)*(ncontig+1)));
-  CUDA_TRY(cudaMalloc(&g->d_crank,sizeof(int)*ncontig));
-  CUDA_TRY(cudaMalloc(&g->d_perm,sizeof(int)*ncontig));
-  CUDA_TRY(cudaMalloc(&g->d_seq,sizeof(u64)*w));
-  if (want_revcomp) CUDA_TRY(cudaMalloc(&g->d_rseq,sizeof(u64)*w));
+  CUDA_TRY(fgb_dmalloc((void **) &d_bps,bps_bytes + 16,st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_boff,sizeof(long long)*ncontig,st));
+  CUDA_TRY(fgb_dmalloc((void **) &g->d_clen,sizeof(long long)*ncontig,st));
+  CUDA_TRY(fgb_dmalloc((void **) &g->d_woff,sizeof(long long)*(ncontig+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &g->d_crank,sizeof(int)*ncontig,st));
+  CUDA_TRY(fgb_dmalloc((void **) &g->d_perm,sizeof(int)*ncontig,st));
+  CUDA_TRY(fgb_dmalloc((void **) &g->d_seq,sizeof(u64)*w,st));
+  if (want_revcomp) CUDA_TRY(fgb_dmalloc((void **) &g->d_rseq,sizeof(u64)*w,st));
   { stage_timer t(&g_timings.h2d_ms,st);
     CUDA_TRY(cudaMemcpyAsync(d_bps,bps,bps_bytes,cudaMemcpyHostToDevice,st));
     CUDA_TRY(cudaMemcpyAsync(d_boff,boff,sizeof(long long)*ncontig,cudaMemcpyHostToDevice,st));
@@ -125,16 +147,17 @@ extern "C" int fgb_genome_create(const unsigned char *bps, long long bps_bytes, 
     rc = fgb_stage_genome_device(d_bps,d_boff,g->d_clen,g->d_woff,ncontig,w,g->d_seq,g->d_rseq,st);
   }
   CUDA_TRY(cudaStreamSynchronize(st));
-  cudaFree(d_bps); cudaFree(d_boff);
+  fgb_dfree(d_bps,st); fgb_dfree(d_boff,st);
   if (rc) { delete g; return rc; }
   *out = g;
   return FGB_OK;
 }
 
 extern "C" void fgb_genome_free(fgb_genome *g)
-{ if (!g) return;
-  cudaFree(g->d_clen); cudaFree(g->d_woff); cudaFree(g->d_crank); cudaFree(g->d_perm);
-  cudaFree(g->d_seq); cudaFree(g->d_rseq);
+{ cudaStream_t st = 0;
+  if (!g) return;
+  fgb_dfree(g->d_clen,st); fgb_dfree(g->d_woff,st); fgb_dfree(g->d_crank,st); fgb_dfree(g->d_perm,st);
+  fgb_dfree(g->d_seq,st); fgb_dfree(g->d_rseq,st);
   delete g;
 }
 
@@ -157,8 +180,9 @@ extern "C" long long fgb_genome_words(const fgb_genome *g) { return g->total_wor
  **********************************************************************************************/
 
 extern "C" void fgb_gix_free(fgb_gix *x)
-{ if (!x) return;
-  cudaFree(x->d_tab); cudaFree(x->d_pstart);
+{ cudaStream_t st = 0;
+  if (!x) return;
+  fgb_dfree(x->d_tab,st); fgb_dfree(x->d_pstart,st);
   delete x;
 }
 
@@ -190,12 +214,12 @@ extern "C" int fgb_gix_build(const fgb_genome *g, fgb_gix **out, void *stream)
   int *d_tc = NULL, *d_ts = NULL; unsigned *d_cnt = NULL;
   u64 *d_buck = NULL, *d_total = NULL; void *d_tmp = NULL;
   long long tmpb = fgb_dev_scan_tmp_bytes(ntiles);
-  CUDA_TRY(cudaMalloc(&d_tc,sizeof(int)*(ntiles+1)));
-  CUDA_TRY(cudaMalloc(&d_ts,sizeof(int)*(ntiles+1)));
-  CUDA_TRY(cudaMalloc(&d_cnt,sizeof(unsigned)*(ntiles+1)));
-  CUDA_TRY(cudaMalloc(&d_buck,8*1024));
-  CUDA_TRY(cudaMalloc(&d_total,8));
-  CUDA_TRY(cudaMalloc(&d_tmp,tmpb));
+  CUDA_TRY(fgb_dmalloc((void **) &d_tc,sizeof(int)*(ntiles+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_ts,sizeof(int)*(ntiles+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_cnt,sizeof(unsigned)*(ntiles+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_buck,8*1024,st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_total,8,st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_tmp,tmpb,st));
   CUDA_TRY(cudaMemcpyAsync(d_tc,tc.data(),sizeof(int)*ntiles,cudaMemcpyHostToDevice,st));
   CUDA_TRY(cudaMemcpyAsync(d_ts,ts.data(),sizeof(int)*ntiles,cudaMemcpyHostToDevice,st));
 
@@ -215,9 +239,9 @@ extern "C" int fgb_gix_build(const fgb_genome *g, fgb_gix **out, void *stream)
 
   rec128 *d_a = NULL, *d_b = NULL; void *d_stmp = NULL;
   long long stmpb = fgb_sort128_tmp_bytes(n);
-  CUDA_TRY(cudaMalloc(&d_a,sizeof(rec128)*(n+1)));
-  CUDA_TRY(cudaMalloc(&d_b,sizeof(rec128)*(n+1)));
-  CUDA_TRY(cudaMalloc(&d_stmp,stmpb));
+  CUDA_TRY(fgb_dmalloc((void **) &d_a,sizeof(rec128)*(n+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_b,sizeof(rec128)*(n+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_stmp,stmpb,st));
   { stage_timer t(&g_timings.scan_ms,st);
     rc = fgb_syncmer_emit_device(g->d_seq,g->d_clen,g->d_woff,g->d_crank,d_tc,d_ts,ntiles,d_cnt,d_a,st);
     if (rc) return rc;
@@ -228,14 +252,14 @@ extern "C" int fgb_gix_build(const fgb_genome *g, fgb_gix **out, void *stream)
     if (rc) return rc;
   }
   x->d_tab = inb ? d_b : d_a;
-  CUDA_TRY(cudaMalloc(&x->d_pstart,sizeof(unsigned)*((1<<24)+1)));
+  CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
   { stage_timer t(&g_timings.index_ms,st);
     rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
     if (rc) return rc;
   }
   CUDA_TRY(cudaStreamSynchronize(st));
-  cudaFree(inb ? d_a : d_b); cudaFree(d_stmp);
-  cudaFree(d_tc); cudaFree(d_ts); cudaFree(d_cnt); cudaFree(d_buck); cudaFree(d_total); cudaFree(d_tmp);
+  fgb_dfree(inb ? d_a : d_b,st); fgb_dfree(d_stmp,st);
+  fgb_dfree(d_tc,st); fgb_dfree(d_ts,st); fgb_dfree(d_cnt,st); fgb_dfree(d_buck,st); fgb_dfree(d_total,st); fgb_dfree(d_tmp,st);
   *out = x;
   return FGB_OK;
 }
@@ -259,8 +283,8 @@ extern "C" int fgb_gix_upload(const void *tab, long long n, int post_bytes, int 
   if (n >= 0xfffffff0ll) return FGB_ERR_LIMIT;
   fgb_gix *x = new fgb_gix();
   x->n = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
-  CUDA_TRY(cudaMalloc(&x->d_tab,sizeof(rec128)*(n+1)));
-  CUDA_TRY(cudaMalloc(&x->d_pstart,sizeof(unsigned)*((1<<24)+1)));
+  CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
   CUDA_TRY(cudaMemcpyAsync(x->d_tab,tab,sizeof(rec128)*n,cudaMemcpyHostToDevice,st));
   int rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
   CUDA_TRY(cudaStreamSynchronize(st));
@@ -280,16 +304,16 @@ extern "C" int fgb_gix_import_ktab(const unsigned char *entries, long long n, in
   x->n = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
   long long E = 9 + post_bytes + cont_bytes;
   unsigned char *d_ent = NULL; long long *d_index = NULL;
-  CUDA_TRY(cudaMalloc(&d_ent,E*n + 16));
-  CUDA_TRY(cudaMalloc(&d_index,8ll<<24));
-  CUDA_TRY(cudaMalloc(&x->d_tab,sizeof(rec128)*(n+1)));
-  CUDA_TRY(cudaMalloc(&x->d_pstart,sizeof(unsigned)*((1<<24)+1)));
+  CUDA_TRY(fgb_dmalloc((void **) &d_ent,E*n + 16,st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_index,8ll<<24,st));
+  CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
   CUDA_TRY(cudaMemcpyAsync(d_ent,entries,E*n,cudaMemcpyHostToDevice,st));
   CUDA_TRY(cudaMemcpyAsync(d_index,index,8ll<<24,cudaMemcpyHostToDevice,st));
   int rc = fgb_ktab_import_device(d_ent,n,post_bytes,cont_bytes,d_index,x->d_tab,st);
   if (!rc) rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
   CUDA_TRY(cudaStreamSynchronize(st));
-  cudaFree(d_ent); cudaFree(d_index);
+  fgb_dfree(d_ent,st); fgb_dfree(d_index,st);
   if (rc) return rc;
   *out = x;
   return FGB_OK;
@@ -302,13 +326,13 @@ extern "C" int fgb_gix_export_ktab(const fgb_gix *x, const long long *part_first
 { cudaStream_t st = (cudaStream_t) stream;
   long long E = 9 + x->post_bytes + x->cont_bytes;
   unsigned char *d_out = NULL; long long *d_pf = NULL;
-  CUDA_TRY(cudaMalloc(&d_out,E*x->n + 16));
-  CUDA_TRY(cudaMalloc(&d_pf,8*(nparts+1)));
+  CUDA_TRY(fgb_dmalloc((void **) &d_out,E*x->n + 16,st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_pf,8*(nparts+1),st));
   CUDA_TRY(cudaMemcpyAsync(d_pf,part_first,8*nparts,cudaMemcpyHostToDevice,st));
   int rc = fgb_ktab_export_device(x->d_tab,x->n,x->post_bytes,x->cont_bytes,d_pf,nparts,d_out,st);
   if (!rc) CUDA_TRY(cudaMemcpyAsync(out,d_out,E*x->n,cudaMemcpyDeviceToHost,st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  cudaFree(d_out); cudaFree(d_pf);
+  fgb_dfree(d_out,st); fgb_dfree(d_pf,st);
   return rc;
 }
 
@@ -319,8 +343,9 @@ extern "C" int fgb_gix_export_ktab(const fgb_gix *x, const long long *part_first
 static int bitlen(long long v) { int b = 0; while (v > 0) { b += 1; v >>= 1; } return b; }
 
 extern "C" void fgb_seeds_free(fgb_seeds *s)
-{ if (!s) return;
-  cudaFree(s->d_rec);
+{ cudaStream_t st = 0;
+  if (!s) return;
+  fgb_dfree(s->d_rec,st);
   delete s;
 }
 
@@ -337,36 +362,36 @@ extern "C" int fgb_seeds_find(const fgb_gix *x1, const fgb_gix *x2, long long am
   if (keybits > 128) return FGB_ERR_LIMIT;
 
   u64 *d_counters = NULL;
-  CUDA_TRY(cudaMalloc(&d_counters,16));
+  CUDA_TRY(fgb_dmalloc((void **) &d_counters,16,st));
   long long cap = x1->n + (x1->n >> 2) + 1024;
   rec128 *d_a = NULL;
   u64 nseeds = 0, sumlen = 0;
   for (int attempt = 0; ; attempt++)
-    { CUDA_TRY(cudaMalloc(&d_a,sizeof(rec128)*(cap+1)));
+    { CUDA_TRY(fgb_dmalloc((void **) &d_a,sizeof(rec128)*(cap+1),st));
       int rc;
       rc = fgb_merge_device(x1->d_tab,x1->n,x2->d_tab,x2->d_pstart,freq,s->anti_bits,s->band_bits,
                             s->jc_bits,s->ic_bits,amxpos,bmxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
       if (rc == FGB_OK) break;
-      cudaFree(d_a); d_a = NULL;
-      if (rc != FGB_ERR_OVERFLOW || attempt > 0) { cudaFree(d_counters); return rc; }
+      fgb_dfree(d_a,st); d_a = NULL;
+      if (rc != FGB_ERR_OVERFLOW || attempt > 0) { fgb_dfree(d_counters,st); return rc; }
       cap = (long long) nseeds + 1024;
       g_timings.merge_ms = 0; g_timings.merge_launches = 0;   // only the successful launch is reported
     }
-  cudaFree(d_counters);
+  fgb_dfree(d_counters,st);
   if (nseeds >= 0xfffffff0ull) return FGB_ERR_LIMIT;
   s->n = (long long) nseeds; s->sumlen = (long long) sumlen;
 
   rec128 *d_b = NULL; void *d_tmp = NULL;
   long long tmpb = fgb_sort128_tmp_bytes(s->n);
-  CUDA_TRY(cudaMalloc(&d_b,sizeof(rec128)*(s->n+1)));
-  CUDA_TRY(cudaMalloc(&d_tmp,tmpb));
+  CUDA_TRY(fgb_dmalloc((void **) &d_b,sizeof(rec128)*(s->n+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_tmp,tmpb,st));
   int inb = 0, rc;
   { stage_timer t(&g_timings.ssort_ms,st);
     rc = fgb_sort128_device(d_a,d_b,s->n,0,(keybits+7)/8,d_tmp,tmpb,&inb,st);
   }
   CUDA_TRY(cudaStreamSynchronize(st));
   s->d_rec = inb ? d_b : d_a;
-  cudaFree(inb ? d_a : d_b); cudaFree(d_tmp);
+  fgb_dfree(inb ? d_a : d_b,st); fgb_dfree(d_tmp,st);
   if (rc) return rc;
   *out = s;
   return FGB_OK;
@@ -385,15 +410,15 @@ extern "C" int fgb_sort128_host(void *recs, long long n, int byte_lo, int byte_h
 { cudaStream_t st = (cudaStream_t) stream;
   rec128 *d_a = NULL, *d_b = NULL; void *d_tmp = NULL;
   long long tmpb = fgb_sort128_tmp_bytes(n);
-  CUDA_TRY(cudaMalloc(&d_a,sizeof(rec128)*(n+1)));
-  CUDA_TRY(cudaMalloc(&d_b,sizeof(rec128)*(n+1)));
-  CUDA_TRY(cudaMalloc(&d_tmp,tmpb));
+  CUDA_TRY(fgb_dmalloc((void **) &d_a,sizeof(rec128)*(n+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_b,sizeof(rec128)*(n+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_tmp,tmpb,st));
   CUDA_TRY(cudaMemcpyAsync(d_a,recs,sizeof(rec128)*n,cudaMemcpyHostToDevice,st));
   int inb = 0;
   int rc = fgb_sort128_device(d_a,d_b,n,byte_lo,byte_hi,d_tmp,tmpb,&inb,st);
   if (!rc) CUDA_TRY(cudaMemcpyAsync(recs,inb ? d_b : d_a,sizeof(rec128)*n,cudaMemcpyDeviceToHost,st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  cudaFree(d_a); cudaFree(d_b); cudaFree(d_tmp);
+  fgb_dfree(d_a,st); fgb_dfree(d_b,st); fgb_dfree(d_tmp,st);
   return rc;
 }
 
@@ -423,7 +448,9 @@ int fgb_filter(const fgb_overlaps *O, const int *perm1, const int *perm2, int jc
 }
 
 struct fgb_run_stats
-{ long long nkmers1, nkmers2, nseeds, sumlen, nhits, nla, nwaves, ncells, nraw, h2d_bytes, d2h_bytes; };
+{ long long nkmers1, nkmers2, nseeds, sumlen, nhits, nla, nwaves, ncells, nraw, h2d_bytes, d2h_bytes,
+            nseg, nwork, warp_cycles, wave_cycles, extract_cycles,
+            us_gix, us_seeds, us_extend, us_filter; };
 
 //  Device-resident genomes in, final alignments out (the timed "step" of bench.py).
 extern "C" int fgb_align_resident(const fgb_genome *A, const fgb_genome *B, const float *freqA,
@@ -431,17 +458,21 @@ extern "C" int fgb_align_resident(const fgb_genome *A, const fgb_genome *B, cons
                                   double align_rate, fgb_alns **out, fgb_run_stats *stats, void *stream)
 { fgb_gix *x1 = NULL, *x2 = NULL; fgb_seeds *sd = NULL; fgb_overlaps *ov = NULL;
   int rc;
+  long long t0 = now_us(), t1, t2, t3, t4;
   if ((rc = fgb_gix_build(A,&x1,stream))) return rc;
   if ((rc = fgb_gix_build(B,&x2,stream))) { fgb_gix_free(x1); return rc; }
+  t1 = now_us();
   rc = fgb_seeds_find(x1,x2,A->maxlen,B->maxlen,freq,&sd,stream);
   long long n1 = x1->n, n2 = x2->n;
   fgb_gix_free(x1); fgb_gix_free(x2);
   if (rc) return rc;
+  t2 = now_us();
   short *tables = (short *) malloc(65536*sizeof(short));
   int ave = 0;
   fgb_align_spec(1.-align_rate,freqA,tables,&ave);           // FastGA.c:3760
   rc = fgb_extend(sd,A,B,chain_break,chain_min,align_min,align_rate,tables,ave,100,&ov,stream);
   free(tables);
+  t3 = now_us();
   long long nseeds = sd->n, sumlen = sd->sumlen;
   int jb = sd->jc_bits, ib = sd->ic_bits;
   fgb_seeds_free(sd);
@@ -450,12 +481,16 @@ extern "C" int fgb_align_resident(const fgb_genome *A, const fgb_genome *B, cons
     (void) a; (void) b;
   }
   rc = fgb_filter(ov,A->perm.data(),B->perm.data(),jb,ib,1,out);
+  t4 = now_us();
   if (stats)
-    { unsigned long long c[8];
+    { stats->us_gix = t1-t0; stats->us_seeds = t2-t1; stats->us_extend = t3-t2; stats->us_filter = t4-t3; unsigned long long c[16];
       fgb_overlaps_counters(ov,c);
       stats->nkmers1 = n1; stats->nkmers2 = n2; stats->nseeds = nseeds; stats->sumlen = sumlen;
       stats->nhits = (long long) c[0]; stats->nla = (long long) c[1]; stats->nwaves = (long long) c[2];
       stats->ncells = (long long) c[3]; stats->nraw = 0;
+      stats->nseg = (long long) c[5]; stats->nwork = (long long) c[6];
+      stats->warp_cycles = (long long) c[8]; stats->wave_cycles = (long long) c[9];
+      stats->extract_cycles = (long long) c[10];
       stats->h2d_bytes = A->h2d_bytes + B->h2d_bytes + 65536*2;
       stats->d2h_bytes = fgb_overlaps_bytes(ov) + 16 + 8*1024*2 + 64;
     }

@@ -58,7 +58,7 @@ struct ext_params
   const u64 *aseq, *arseq; const long long *awoff, *aclen; const int *aperm;
   const u64 *bseq;         const long long *bwoff, *bclen; const int *bperm;
   int chain_break, chain_min, aln_min; double aln_rate;
-  int tspace, path_ave; const short *score, *table;
+  int tspace, path_ave, dscore; const short *score, *table;
   Peb *cells; long long cells_per_warp;
   unsigned char *stage; int stage_bytes;               // per warp: 2 x stage_bytes
   unsigned char *out; u64 out_cap; u64 *out_used;
@@ -71,8 +71,8 @@ struct Ctx
   int *V, *HA, *HM, *NA; u64 *T; int *carry;
   Peb *cells; int cmax, avail;
   unsigned char *fstage, *rstage; int smax;
-  int tspace, path_ave; const short *score, *table;
-  u64 nwaves, ncells;
+  int tspace, path_ave; const short *score, *table; const short2 *tt1, *tt2;
+  u64 nwaves, ncells, cyc_wave, cyc_extract;
 };
 
 #define IX(k) ((k) & (EX_W-1))
@@ -136,6 +136,22 @@ static __device__ __forceinline__ int snake(const Ctx &c, int s, int xn, int kk,
       else flag = 0;
     }
   return t;
+}
+
+//  TABLE[x] / SCORE[x] of align.c:207-220 for a 15-bit column pattern x, from two small shared
+//  tables instead of the 2 x 64 KB arrays: the pattern is scored MSB first with +mscore / -dscore;
+//  SCORE = final score, TABLE = final score - max over the proper prefixes (incl. the empty one).
+//  tt1[u] (first 8 columns): x = score after them, y = max prefix score before each of them;
+//  tt2[v] (last 7 columns):  x = their score, y = max partial score before each of them (>= 0).
+
+static __device__ __forceinline__ bool trim_ok(const Ctx &c, u64 b)
+{ int lo15 = (int) (b & TRIM_MASK), hi15 = (int) ((b >> TRIM_LEN) & TRIM_MASK);
+  short2 l1 = c.tt1[lo15 >> 7], l2 = c.tt2[lo15 & 127];
+  int ltot = l1.x + l2.x, lmax = max((int) l1.y,l1.x + l2.y);
+  if (ltot - lmax < 0) return false;                       // TABLE[b & MASK] >= 0
+  short2 h1 = c.tt1[hi15 >> 7], h2 = c.tt2[hi15 & 127];
+  int htot = h1.x + h2.x, hmax = max((int) h1.y,h1.x + h2.y);
+  return (htot - hmax) + ltot >= 0;                        // TABLE[hi] + SCORE[lo] >= 0
 }
 
 static __device__ __forceinline__ int warp_prefix_max_excl(int v, int lane)
@@ -251,6 +267,8 @@ static __device__ int wave(Ctx &c, const int s, int low, int hgh, const int mida
         }
       __syncwarp();
       c.nwaves += 1; c.ncells += (u64) (hghk - lowk + 1);
+      const bool single = (hghk - lowk < 32);
+      int lastcc = 0, lasttop = hghk;
 
       for (int top = hghk; top >= lowk; top -= 32)
         { int kk = top - lane;
@@ -273,9 +291,10 @@ static __device__ int wave(Ctx &c, const int s, int low, int hgh, const int mida
           int nan = c.NA[IX(kk)];
           //  lane 31's own old state is the next chunk's "kk+1"
           int  o_v = 0, o_ha = 0, o_hm = 0; u64 o_t = 0;
-          if (lane == 31) { o_v = ac; o_t = c.T[IX(kk)]; o_ha = c.HA[IX(kk)]; o_hm = c.HM[IX(kk)]; }
+          const bool morechunks = (top - 32 >= lowk);
+          if (lane == 31 && morechunks) { o_v = ac; o_t = c.T[IX(kk)]; o_ha = c.HA[IX(kk)]; o_hm = c.HM[IX(kk)]; }
           __syncwarp();                              // all reads of old state done
-          if (lane == 31)
+          if (lane == 31 && morechunks)
             { c.carry[0] = o_v; c.carry[1] = (int) (unsigned) o_t; c.carry[2] = (int) (o_t >> 32);
               c.carry[3] = o_ha; c.carry[4] = o_hm;
             }
@@ -305,24 +324,27 @@ static __device__ int wave(Ctx &c, const int s, int low, int hgh, const int mida
               need = act && xn >= nan;
             }
 
-          int ex = max(warp_prefix_max_excl(act ? cc : INT_MIN,lane),besta);
-          bool rec = act && cc > ex;
-          unsigned rm = __ballot_sync(FULL,rec);
-          if (rm)
-            { int L = 31 - __clz(rm);
-              besta = __shfl_sync(FULL,cc,L);
-              bestx = __shfl_sync(FULL,xn,L);
-              bool qual = rec && __popcll(b & PATH_WIN) >= c.path_ave;
-              unsigned qm = __ballot_sync(FULL,qual);
-              if (qm)
-                { lasta = __shfl_sync(FULL,cc,31 - __clz(qm));
-                  bool tq = false;
-                  if (qual)
-                    { int lo15 = (int) (b & TRIM_MASK), hi15 = (int) ((b >> TRIM_LEN) & TRIM_MASK);
-                      if (__ldg(c.table + lo15) >= 0)
-                        tq = ((int) __ldg(c.table + hi15) + (int) __ldg(c.score + lo15) >= 0);
-                    }
-                  unsigned tm = __ballot_sync(FULL,tq);
+          int cm = act ? cc : INT_MIN;
+          int mx = __reduce_max_sync(FULL,cm);
+          if (mx > besta)
+            { //  Lb = first lane (highest diagonal) reaching the wave maximum = the last record
+              //  setter of the sequential scan.  If it passes both quality tests it alone decides
+              //  lasta and the trim point; otherwise fall back to the full prefix-max.
+              unsigned eq = __ballot_sync(FULL,cm == mx);
+              int Lb = __ffs(eq) - 1;
+              bool qual = act && cc > besta && __popcll(b & PATH_WIN) >= c.path_ave;
+              bool tq = qual && trim_ok(c,b);
+              unsigned ql = __ballot_sync(FULL,qual), tl = __ballot_sync(FULL,tq);
+              if ((tl >> Lb) & 1)
+                { lasta = mx; trima = mx; trimd = dif;
+                  trimx  = __shfl_sync(FULL,xn,Lb);
+                  trimha = __shfl_sync(FULL,ha,Lb);
+                }
+              else
+                { int ex = max(warp_prefix_max_excl(cm,lane),besta);
+                  unsigned rm = __ballot_sync(FULL,act && cc > ex);
+                  unsigned qm = rm & ql, tm = rm & tl;
+                  if (qm) lasta = __shfl_sync(FULL,cc,31 - __clz(qm));
                   if (tm)
                     { int L3 = 31 - __clz(tm);
                       trima  = __shfl_sync(FULL,cc,L3);
@@ -331,11 +353,17 @@ static __device__ int wave(Ctx &c, const int s, int low, int hgh, const int mida
                       trimd  = dif;
                     }
                 }
+              besta = mx;
+              bestx = __shfl_sync(FULL,xn,Lb);
             }
-          unsigned hb = __ballot_sync(FULL,act && flag == 1);
-          unsigned hq = __ballot_sync(FULL,act && flag == 2);
-          if (hb) { anyhit = true; int v = top - (__ffs(hb)-1); if (bclip < v) bclip = v; }
-          if (hq) { anyhit = true; aclip = top - (31 - __clz(hq)); }
+          if (__any_sync(FULL,act && flag != 0))
+            { unsigned hb = __ballot_sync(FULL,act && flag == 1);
+              unsigned hq = __ballot_sync(FULL,act && flag == 2);
+              anyhit = true;
+              if (hb) { int v = top - (__ffs(hb)-1); if (bclip < v) bclip = v; }
+              if (hq) aclip = top - (31 - __clz(hq));
+            }
+          lastcc = cc; lasttop = top;
           if (act)
             { c.V[IX(kk)] = cc; c.T[IX(kk)] = b; c.HA[IX(kk)] = ha; c.HM[IX(kk)] = hm;
               c.NA[IX(kk)] = nan;
@@ -351,6 +379,13 @@ static __device__ int wave(Ctx &c, const int s, int low, int hgh, const int mida
         }
 
       //  trim the band to points within WAVE_LAG of the best (align.c:782-790)
+      if (single)
+        { int n = besta - WAVE_LAG, kk = lasttop - lane;
+          unsigned m = __ballot_sync(FULL,kk >= lowk && kk <= hghk && lastcc >= n);
+          if (m == 0) hghk = lowk-1;
+          else { hghk = lasttop - (__ffs(m)-1); lowk = lasttop - (31 - __clz(m)); }
+        }
+      else
       { int n = besta - WAVE_LAG, nh = lowk-1;
         for (int top = hghk; top >= lowk; top -= 32)
           { int kk = top - lane;
@@ -516,19 +551,25 @@ static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int a
   while (((anti-hgh)>>1) < 0) hgh -= 1;
 
   R.ftlen = R.rtlen = 0; R.diffs = 0;
+  long long tk = clock64();
   st = wave(c,+1,low,hgh,anti,minp,maxp,aoff,ex,ey,df,tha);
   if (st) return st;
+  c.cyc_wave += (u64) (clock64() - tk); tk = clock64();
   st = fwd_extract(c,tha,anti,ex,ey,df,R.ftlen,rootd);
   if (st) return st;
+  c.cyc_extract += (u64) (clock64() - tk);
   __syncwarp();
   R.aepos = ex; R.bepos = ey; R.diffs = df;
   low = rootd;
   bool fshort = ((R.aepos + R.bepos) - anti < DUB_TRIM);
 
+  tk = clock64();
   st = wave(c,-1,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
   if (st) return st;
+  c.cyc_wave += (u64) (clock64() - tk); tk = clock64();
   st = rev_extract(c,tha,aoff,ex,ey,df,R.ftlen,R.rtlen);
   if (st) return st;
+  c.cyc_extract += (u64) (clock64() - tk);
   R.abpos = ex; R.bbpos = ey; R.diffs += df;
   bool rshort = (anti - (R.abpos + R.bbpos) < DUB_TRIM);
 
@@ -598,11 +639,35 @@ static __device__ void emit_record(const ext_params &P, Ctx &c, const LAres &R, 
 //  Walks one triple: chain scan (FastGA.c:3087-3162), tube stepping (:3205-3340).
 //  ALIGN = false: count qualifying chains only (prefilter).
 
+//  Sequential reader over the sorted seeds.  STAGED (warp-uniform callers): a 32-record window
+//  is staged in shared memory with one coalesced 512-byte load, so the serial chain scan sees
+//  shared-memory latency instead of a dependent HBM/L2 round trip per seed.
+
+template<bool STAGED> struct SeedRd
+{ const rec128 *S; rec128 *buf; unsigned base, n;
+  __device__ __forceinline__ void init(const rec128 *s, rec128 *b, unsigned nn)
+    { S = s; buf = b; n = nn; base = 0xffffffffu; }
+  __device__ __forceinline__ rec128 get(unsigned i)
+    { if (!STAGED) return S[i];
+      if (i - base >= 32u)
+        { __syncwarp();
+          base = i;
+          unsigned k = i + (threadIdx.x & 31);
+          if (k < n) st_rec(buf + (threadIdx.x & 31),ld_rec(S + k));
+          __syncwarp();
+        }
+      return buf[i - base];
+    }
+};
+
 template<bool ALIGN>
 static __device__ int scan_triple(const ext_params &P, Ctx &c, unsigned j, unsigned &nhit_out,
-                                  u64 &nla)
+                                  u64 &nla, rec128 *stagebuf)
 { const rec128 *S = P.seeds;
   unsigned b = P.seg_start[j], m = P.seg_start[j+1];
+  SeedRd<ALIGN> RL, RU;
+  RL.init(S,stagebuf,(unsigned) P.nseeds);
+  RU.init(S,stagebuf + 32,(unsigned) P.nseeds);
   rec128 r0 = S[b];
   u64 grp = get_bits(r0,P.p_jc,P.jc_bits + P.ic_bits + 1);
   long long cdiag = (long long) get_bits(r0,P.p_band,P.band_bits);
@@ -642,27 +707,27 @@ static __device__ int scan_triple(const ext_params &P, Ctx &c, unsigned j, unsig
   unsigned s = b, t = m;
   int go = 1, lcp, wch, mix = 0, cov = 0, dgmin, dgmax, dg, seq = 0;
 
-  ipost = (long long) get_bits(S[s],P.p_anti,P.anti_bits);
-  apost = aux ? (long long) get_bits(S[t],P.p_anti,P.anti_bits) : LMAX;
+  ipost = (long long) get_bits(RL.get(s),P.p_anti,P.anti_bits);
+  apost = aux ? (long long) get_bits(RU.get(t),P.p_anti,P.anti_bits) : LMAX;
   dgmin = 2*BUCK_WIDTH; dgmax = 0;
   ahgh  = -P.chain_break;
   alow  = (apost < ipost) ? apost : ipost;
   while (go)
     { if (apost < ipost)
-        { rec128 r = S[t];
+        { rec128 r = RU.get(t);
           lcp = (int) (r.lo & 63); dg = (int) ((r.lo >> 6) & 63) + BUCK_WIDTH;
           anti = apost;
           t += 1;
-          apost = (t >= e) ? LMAX : (long long) get_bits(S[t],P.p_anti,P.anti_bits);
+          apost = (t >= e) ? LMAX : (long long) get_bits(RU.get(t),P.p_anti,P.anti_bits);
           wch = 2;
         }
       else
-        { if (s < m) { rec128 r = S[s]; lcp = (int) (r.lo & 63); dg = (int) ((r.lo >> 6) & 63); }
+        { if (s < m) { rec128 r = RL.get(s); lcp = (int) (r.lo & 63); dg = (int) ((r.lo >> 6) & 63); }
           else       { lcp = 0; dg = 0; }
           anti = ipost;
           s += 1;
           if (s >= m) { if (s > m) go = 0; else ipost = LMAX; }
-          else ipost = (long long) get_bits(S[s],P.p_anti,P.anti_bits);
+          else ipost = (long long) get_bits(RL.get(s),P.p_anti,P.anti_bits);
           wch = 1;
         }
       lcp <<= 1;
@@ -760,26 +825,50 @@ __global__ void seg_fill2_kernel(const rec128 *__restrict__ seeds, long long n, 
   if (head) seg_start[pos[i]] = (unsigned) i;
 }
 
-//  K7 prefilter: one thread per segment; triples with at least one qualifying chain go to the
-//  work list, and the total number of qualifying chains ("hits") is counted.
+//  K7 prefilter: one thread per band segment.  A chain needs cov >= chain_min and one seed covers
+//  at most 80 anti-diagonals, so triples with too few seeds are dropped outright; short triples
+//  are scanned exactly by their thread; long ones (their serial scan would be a straggler) go
+//  to the warp stage unconditionally -- it scans them with staged, coalesced seed loads.
 
-__global__ void prefilter_kernel(ext_params P, unsigned *__restrict__ work, unsigned *__restrict__ nwork)
+#define PREF_LONG 64
+
+__global__ void prefilter_kernel(ext_params P, unsigned *__restrict__ work_long, unsigned *__restrict__ work_short,
+                                 unsigned *__restrict__ nwork /* [0] long [1] short */)
 { unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned nh = 0;
-  if (j < (unsigned) P.nseg)
-    { Ctx c; u64 nla = 0;
-      scan_triple<false>(P,c,j,nh,nla);
-      if (nh > 0)
-        { unsigned o = atomicAdd(nwork,1u);
-          work[o] = j;
-        }
+  if (j >= (unsigned) P.nseg) return;
+  const rec128 *S = P.seeds;
+  unsigned b = P.seg_start[j], m = P.seg_start[j+1], e = m;
+  unsigned minseeds = (unsigned) ((P.chain_min + 79) / 80);
+  rec128 r0 = S[b];
+  u64 grp = get_bits(r0,P.p_jc,P.jc_bits + P.ic_bits + 1);
+  long long cdiag = (long long) get_bits(r0,P.p_band,P.band_bits);
+  if (j+1 < (unsigned) P.nseg)
+    { rec128 rn = S[m];
+      if (get_bits(rn,P.p_jc,P.jc_bits + P.ic_bits + 1) == grp &&
+          (long long) get_bits(rn,P.p_band,P.band_bits) == cdiag+1)
+        e = P.seg_start[j+2];
     }
-  u64 v = nh;
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL,v,o);
-  if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.counters[0],v);
+  if (e - b < minseeds) return;
+  if (e - b > PREF_LONG)
+    { bool isnew = true;
+      if (j > 0)
+        { rec128 rp = S[P.seg_start[j-1]];
+          if (get_bits(rp,P.p_jc,P.jc_bits + P.ic_bits + 1) == grp &&
+              (long long) get_bits(rp,P.p_band,P.band_bits) == cdiag-1)
+            isnew = false;
+        }
+      if (isnew || e != m)
+        work_long[atomicAdd(nwork,1u)] = j;
+      return;
+    }
+  Ctx c; u64 nla = 0; unsigned nh = 0;
+  scan_triple<false>(P,c,j,nh,nla,NULL);
+  if (nh > 0)
+    work_short[atomicAdd(nwork+1,1u)] = j;
 }
 
-#define STATE_BYTES (EX_W*(4*4+8) + 32)
+#define STATE_BYTES (EX_W*(4*4+8) + 32 + 64*16)
+#define TT_BYTES    ((256+128)*4)
 
 __global__ void __launch_bounds__(EX_WARPS*32)
 extend_kernel(ext_params P)
@@ -792,6 +881,21 @@ extend_kernel(ext_params P)
   c.V  = (int *) (sb + EX_W*8);
   c.HA = c.V + EX_W; c.HM = c.HA + EX_W; c.NA = c.HM + EX_W;
   c.carry = c.NA + EX_W;
+  rec128 *stagebuf = (rec128 *) (sb + EX_W*(4*4+8) + 32);
+  { short2 *tt = (short2 *) (smem + (size_t) EX_WARPS * STATE_BYTES);
+    int msc = 1000 - P.dscore, dsc = P.dscore;
+    for (int u = threadIdx.x; u < 384; u += blockDim.x)
+      { int nb = (u < 256) ? 8 : 7, x = (u < 256) ? u : u - 256, sc = 0, mxp = 0;
+        for (int i = nb-1; i >= 0; i--)
+          { if (sc > mxp) mxp = sc;
+            sc += ((x >> i) & 1) ? msc : -dsc;
+          }
+        tt[u] = make_short2((short) sc,(short) mxp);
+      }
+    c.tt1 = tt; c.tt2 = tt + 256;
+    __syncthreads();
+  }
+  long long t_start = clock64();
   c.cells = P.cells + gw * P.cells_per_warp;
   c.cmax  = (int) P.cells_per_warp;
   c.avail = 0;
@@ -799,8 +903,8 @@ extend_kernel(ext_params P)
   c.rstage = c.fstage + P.stage_bytes;
   c.smax = P.stage_bytes;
   c.tspace = P.tspace; c.path_ave = P.path_ave; c.score = P.score; c.table = P.table;
-  c.nwaves = 0; c.ncells = 0;
-  u64 nla = 0;
+  c.nwaves = 0; c.ncells = 0; c.cyc_wave = 0; c.cyc_extract = 0;
+  u64 nla = 0, nhits = 0;
 
   while (true)
     { unsigned w = 0;
@@ -808,17 +912,25 @@ extend_kernel(ext_params P)
       w = __shfl_sync(FULL,w,0);
       if (w >= (unsigned) P.nwork) break;
       unsigned j = P.work[w], nh = 0;
-      int st = scan_triple<true>(P,c,j,nh,nla);
-      if (st != ST_OK && lane == 0)
-        { unsigned o = atomicAdd(P.nfailed,1u);
-          P.failed[o] = j;
+      int st = scan_triple<true>(P,c,j,nh,nla,stagebuf);
+      if (st != ST_OK)
+        { if (lane == 0)
+            { unsigned o = atomicAdd(P.nfailed,1u);
+              P.failed[o] = j;
+            }
         }
+      else
+        nhits += nh;
       __syncwarp();
     }
   if (lane == 0)
-    { atomicAdd(&P.counters[1],nla);
+    { atomicAdd(&P.counters[0],nhits);
+      atomicAdd(&P.counters[1],nla);
       atomicAdd(&P.counters[2],c.nwaves);
       atomicAdd(&P.counters[3],c.ncells);
+      atomicAdd(&P.counters[8],(u64) (clock64() - t_start));
+      atomicAdd(&P.counters[9],c.cyc_wave);
+      atomicAdd(&P.counters[10],c.cyc_extract);
     }
 }
 
@@ -829,7 +941,7 @@ extend_kernel(ext_params P)
 struct fgb_overlaps
 { long long nrec = 0, nbytes = 0;
   unsigned char *h_buf = nullptr;          // packed records (OUT_HDR + trace padded to 8)
-  unsigned long long counters[8] = {0};
+  unsigned long long counters[16] = {0};
   long long nseg = 0, nwork = 0;
   bool pinned = false;
 };
@@ -851,7 +963,7 @@ extern "C" int fgb_overlaps_from_buffer(const unsigned char *buf, long long nbyt
 extern "C" long long fgb_overlaps_bytes(const fgb_overlaps *o) { return o->nbytes; }
 extern "C" const unsigned char *fgb_overlaps_data(const fgb_overlaps *o) { return o->h_buf; }
 extern "C" void fgb_overlaps_counters(const fgb_overlaps *o, unsigned long long *out)
-{ for (int i = 0; i < 8; i++) out[i] = o->counters[i];
+{ for (int i = 0; i < 16; i++) out[i] = o->counters[i];          /* out: 16 entries */
   out[5] = (unsigned long long) o->nseg; out[6] = (unsigned long long) o->nwork;
 }
 
@@ -894,18 +1006,19 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
   P.chain_break = chain_break; P.chain_min = chain_min;
   P.aln_min = align_min - 50; P.aln_rate = align_rate + .05;      // FastGA.c:3013-3014
   P.tspace = tspace; P.path_ave = ave_path;
+  P.dscore = -tables[0] / TRIM_LEN;                     // SCORE[0] = -15 * dscore
 
   short *d_tables = NULL;
   u64 *d_counters = NULL, *d_total = NULL;
   unsigned *d_flag = NULL, *d_seg = NULL, *d_work = NULL, *d_misc = NULL, *d_failed = NULL;
   void *d_tmp = NULL;
-  CUDA_TRY(cudaMalloc(&d_tables,65536*sizeof(short)));
+  CUDA_TRY(fgb_dmalloc((void **) &d_tables,65536*sizeof(short),st));
   CUDA_TRY(cudaMemcpyAsync(d_tables,tables,65536*sizeof(short),cudaMemcpyHostToDevice,st));
   P.score = d_tables; P.table = d_tables + 32768;
-  CUDA_TRY(cudaMalloc(&d_counters,8*8));
-  CUDA_TRY(cudaMemsetAsync(d_counters,0,8*8,st));
-  CUDA_TRY(cudaMalloc(&d_total,8));
-  CUDA_TRY(cudaMalloc(&d_misc,64));
+  CUDA_TRY(fgb_dmalloc((void **) &d_counters,16*8,st));
+  CUDA_TRY(cudaMemsetAsync(d_counters,0,16*8,st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_total,8,st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_misc,64,st));
   CUDA_TRY(cudaMemsetAsync(d_misc,0,64,st));
   P.counters = d_counters;
 
@@ -913,8 +1026,8 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
   if (n > 0)
     { ev_timer t(0,st);
       long long tmpb = fgb_dev_scan_tmp_bytes(n);
-      CUDA_TRY(cudaMalloc(&d_flag,sizeof(unsigned)*(n+1)));
-      CUDA_TRY(cudaMalloc(&d_tmp,tmpb));
+      CUDA_TRY(fgb_dmalloc((void **) &d_flag,sizeof(unsigned)*(n+1),st));
+      CUDA_TRY(fgb_dmalloc((void **) &d_tmp,tmpb,st));
       int nb = (int) ((n + 255) / 256);
       seg_flag_kernel<<<nb,256,0,st>>>(S->d_rec,n,P.p_band,d_flag);
       int rc = fgb_dev_exclusive_scan_u32(d_flag,n,d_total,d_tmp,tmpb,st);
@@ -923,16 +1036,21 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       CUDA_TRY(cudaMemcpyAsync(&tot,d_total,8,cudaMemcpyDeviceToHost,st));
       CUDA_TRY(cudaStreamSynchronize(st));
       nseg = (unsigned) tot;
-      CUDA_TRY(cudaMalloc(&d_seg,sizeof(unsigned)*(nseg+2)));
-      CUDA_TRY(cudaMalloc(&d_work,sizeof(unsigned)*(nseg+1)));
+      CUDA_TRY(fgb_dmalloc((void **) &d_seg,sizeof(unsigned)*(nseg+2),st));
+      CUDA_TRY(fgb_dmalloc((void **) &d_work,sizeof(unsigned)*(2ll*nseg+2),st));
       nb = (int) ((n + 1 + 255) / 256);
       seg_fill2_kernel<<<nb,256,0,st>>>(S->d_rec,n,P.p_band,d_flag,d_seg,nseg);
       P.seg_start = d_seg; P.nseg = (int) nseg;
-      prefilter_kernel<<<(nseg + 127)/128,128,0,st>>>(P,d_work,d_misc);
+      prefilter_kernel<<<(nseg + 127)/128,128,0,st>>>(P,d_work,d_work + nseg + 1,d_misc + 6);
       fgb_count_launch(3);
       CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaMemcpyAsync(&nwork,d_misc,4,cudaMemcpyDeviceToHost,st));
+      unsigned nw2[2];
+      CUDA_TRY(cudaMemcpyAsync(nw2,d_misc + 6,8,cudaMemcpyDeviceToHost,st));
       CUDA_TRY(cudaStreamSynchronize(st));
+      //  long triples first (they are the stragglers), then the exact short hits
+      CUDA_TRY(cudaMemcpyAsync(d_work + nw2[0],d_work + nseg + 1,sizeof(unsigned)*nw2[1],
+                               cudaMemcpyDeviceToDevice,st));
+      nwork = nw2[0] + nw2[1];
     }
   O->nseg = nseg; O->nwork = nwork;
 
@@ -942,7 +1060,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
     { int dev = 0, nsm = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&nsm,cudaDevAttrMultiProcessorCount,dev);
-      size_t smem = (size_t) EX_WARPS * STATE_BYTES;
+      size_t smem = (size_t) EX_WARPS * STATE_BYTES + TT_BYTES;
       CUDA_TRY(cudaFuncSetAttribute(extend_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem));
       int bps = 0;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps,extend_kernel,EX_WARPS*32,smem));
@@ -952,7 +1070,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       if (nblocks > want) nblocks = want;
       long long nwarps = nblocks * EX_WARPS;
 
-      CUDA_TRY(cudaMalloc(&d_failed,sizeof(unsigned)*(nwork+1)));
+      CUDA_TRY(fgb_dmalloc((void **) &d_failed,sizeof(unsigned)*(nwork+1),st));
       P.work = d_work; P.nwork = (int) nwork;
       P.queue = d_misc + 1; P.nfailed = d_misc + 2; P.failed = d_failed;
       P.out_used = (u64 *) (d_misc + 4);
@@ -966,9 +1084,9 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       u64 used_before = 0;
       for (int attempt = 0; ; attempt++)
         { Peb *d_cells = NULL; unsigned char *d_stage = NULL;
-          CUDA_TRY(cudaMalloc(&d_cells,sizeof(Peb)*cells_per_warp*nwarps));
-          CUDA_TRY(cudaMalloc(&d_stage,2ll*stage_bytes*nwarps));
-          if (d_out == NULL) CUDA_TRY(cudaMalloc(&d_out,out_cap));
+          CUDA_TRY(fgb_dmalloc((void **) &d_cells,sizeof(Peb)*cells_per_warp*nwarps,st));
+          CUDA_TRY(fgb_dmalloc((void **) &d_stage,2ll*stage_bytes*nwarps,st));
+          if (d_out == NULL) CUDA_TRY(fgb_dmalloc((void **) &d_out,out_cap,st));
           P.cells = d_cells; P.cells_per_warp = cells_per_warp;
           P.stage = d_stage; P.stage_bytes = stage_bytes;
           P.out = d_out; P.out_cap = out_cap;
@@ -982,7 +1100,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           unsigned misc[8];
           CUDA_TRY(cudaMemcpyAsync(misc,d_misc,32,cudaMemcpyDeviceToHost,st));
           CUDA_TRY(cudaStreamSynchronize(st));
-          cudaFree(d_cells); cudaFree(d_stage);
+          fgb_dfree(d_cells,st); fgb_dfree(d_stage,st);
           out_used = ((u64) misc[5] << 32) | misc[4];
           unsigned nfailed = misc[2];
           if (out_used > out_cap)
@@ -991,9 +1109,9 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
               if (attempt > 12) return FGB_ERR_OVERFLOW;
               unsigned char *d_new = NULL;
               u64 ncap = out_used * 2 + (64ull << 20);
-              CUDA_TRY(cudaMalloc(&d_new,ncap));
+              CUDA_TRY(fgb_dmalloc((void **) &d_new,ncap,st));
               if (used_before) CUDA_TRY(cudaMemcpy(d_new,d_out,used_before,cudaMemcpyDeviceToDevice));
-              cudaFree(d_out); d_out = d_new; out_cap = ncap;
+              fgb_dfree(d_out,st); d_out = d_new; out_cap = ncap;
               CUDA_TRY(cudaMemcpy(d_misc+4,&used_before,8,cudaMemcpyHostToDevice));
               out_used = used_before;
               continue;
@@ -1016,7 +1134,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           nblocks = nb2 < maxb ? nb2 : maxb;
           nwarps = nblocks * EX_WARPS;
         }
-      cudaFree(d_work2);
+      fgb_dfree(d_work2,st);
 
       //  bring the records back and drop partial output of triples that were re-run
       O->nbytes = (long long) out_used;
@@ -1062,7 +1180,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           O->nbytes = w;
         }
     }
-  CUDA_TRY(cudaMemcpy(O->counters,d_counters,8*8,cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(O->counters,d_counters,16*8,cudaMemcpyDeviceToHost));
   { long long cnt = 0;
     for (long long off = 0; off < O->nbytes; )
       { int *h = (int *) (O->h_buf + off);
@@ -1071,8 +1189,8 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       }
     O->nrec = cnt;
   }
-  cudaFree(d_tables); cudaFree(d_counters); cudaFree(d_total); cudaFree(d_misc); cudaFree(d_flag);
-  cudaFree(d_seg); cudaFree(d_work); cudaFree(d_failed); cudaFree(d_tmp); cudaFree(d_out);
+  fgb_dfree(d_tables,st); fgb_dfree(d_counters,st); fgb_dfree(d_total,st); fgb_dfree(d_misc,st); fgb_dfree(d_flag,st);
+  fgb_dfree(d_seg,st); fgb_dfree(d_work,st); fgb_dfree(d_failed,st); fgb_dfree(d_tmp,st); fgb_dfree(d_out,st);
   *out = O;
   return FGB_OK;
 }

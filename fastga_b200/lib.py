@@ -282,11 +282,12 @@ class DeviceOverlaps:
 
     def counters(self):
         L = load_library()
-        out = (C.c_ulonglong * 8)()
+        out = (C.c_ulonglong * 16)()
         L.fgb_overlaps_counters.argtypes = [c_void_p, c_void_p]
         L.fgb_overlaps_counters(self.h, out)
         v = list(out)
-        return {"hits": v[0], "la_calls": v[1], "waves": v[2], "cells": v[3], "nseg": v[5], "nwork": v[6]}
+        return {"hits": v[0], "la_calls": v[1], "waves": v[2], "cells": v[3], "nseg": v[5], "nwork": v[6],
+                "warp_cycles": v[8], "wave_cycles": v[9], "extract_cycles": v[10]}
 
     def records(self):
         """(structured array sorted in reference discovery order, trace byte pool)"""
@@ -380,7 +381,8 @@ def overlaps_from_buffer(buf):
 
 class RunStats(C.Structure):
     _fields_ = [(n, c_ll) for n in ("nkmers1", "nkmers2", "nseeds", "sumlen", "nhits", "nla", "nwaves",
-                                    "ncells", "nraw", "h2d_bytes", "d2h_bytes")]
+                                    "ncells", "nraw", "h2d_bytes", "d2h_bytes", "nseg", "nwork", "warp_cycles",
+                                    "wave_cycles", "extract_cycles", "us_gix", "us_seeds", "us_extend", "us_filter")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -33,7 +33,9 @@ typedef struct fgb_overlaps fgb_overlaps;  /* raw local alignments, host residen
 typedef struct fgb_alns     fgb_alns;      /* final alignments in .1aln order, host resident   */
 
 typedef struct
-{ long long nkmers1, nkmers2, nseeds, sumlen, nhits, nla, nwaves, ncells, nraw, h2d_bytes, d2h_bytes;
+{ long long nkmers1, nkmers2, nseeds, sumlen, nhits, nla, nwaves, ncells, nraw, h2d_bytes, d2h_bytes,
+            nseg, nwork, warp_cycles, wave_cycles, extract_cycles,
+            us_gix, us_seeds, us_extend, us_filter;      /* host wall microseconds per phase */
 } fgb_run_stats;
 
 typedef struct
@@ -107,7 +109,7 @@ int  fgb_overlaps_from_buffer(const unsigned char *buf, long long nbytes, fgb_ov
 long long fgb_overlaps_bytes(const fgb_overlaps *o);
 long long fgb_overlaps_count(const fgb_overlaps *o);
 const unsigned char *fgb_overlaps_data(const fgb_overlaps *o);
-void fgb_overlaps_counters(const fgb_overlaps *o, unsigned long long *out /* 8 */);
+void fgb_overlaps_counters(const fgb_overlaps *o, unsigned long long *out /* 16 */);
 void fgb_overlaps_free(fgb_overlaps *o);
 
 /* ---- redundancy filter + final order (FastGA.c:3407-3685, :2818 entwine, :3800 SORT_MAP) ---- */

@@ -651,7 +651,7 @@ static void fwd_trace(orc_work *w, const wave_out *r, int mida, orc_path *p)
     { p->trace[p->tlen++] = (uint8_t) (trimd-e);
       p->trace[p->tlen++] = (uint8_t) (trimy-b);
     }
-  else if (b != trimy)
+  else if (b != trimy && p->tlen >= 2)     /* with no pair the reference's write lands in scratch */
     { p->trace[p->tlen-1] = (uint8_t) (p->trace[p->tlen-1] + (trimy-b));
       p->trace[p->tlen-2] = (uint8_t) (p->trace[p->tlen-2] + (trimd-e));
     }
@@ -708,7 +708,7 @@ static void rev_trace(orc_work *w, const wave_out *r, int tspace, int aoff, orc_
             { pre[np-1] = (uint8_t) (pre[np-1] + (b-trimy));
               pre[np-2] = (uint8_t) (pre[np-2] + (trimd-e));
             }
-          else
+          else if (p->tlen >= 2)
             { p->trace[1] = (uint8_t) (p->trace[1] + (b-trimy));
               p->trace[0] = (uint8_t) (p->trace[0] + (trimd-e));
             }

@@ -57,3 +57,24 @@ def test_10mbp_bit_exact_vs_reference():
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+EX_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "EXAMPLE")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(EX_DIR, "HAP1.fasta.gz")),
+                    reason="EXAMPLE FASTA not staged under tests/data (data, git-ignored)")
+def test_example_hap1_hap2_bit_exact():
+    """BASELINE.json configs[0]: EXAMPLE/HAP1 x HAP2 -- 323 569 records, canonical md5 of the
+    reference's .1aln (tests/golden/example_golden.json)."""
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "example_golden.json")))
+    gA = formats.genome_from_fasta(os.path.join(EX_DIR, "HAP1.fasta.gz"))
+    gB = formats.genome_from_fasta(os.path.join(EX_DIR, "HAP2.fasta.gz"))
+    alns, stats = lib.fastga(gA, gB)
+    assert [stats["nkmers1"], stats["nkmers2"]] == gold["kmers"]
+    assert stats["nseeds"] == gold["seeds"]
+    assert stats["nhits"] == gold["hits"]
+    assert alns.nraw == gold["alns"]
+    assert len(alns) == gold["kept"]
+    assert ol.md5_lines(alns.canonical_lines()) == gold["aln_md5"]
