@@ -39,18 +39,6 @@ def workload(n_gpus, per_gpu_bp=PER_GPU_BP):
     return synth.make_pair(SEED, per_gpu_bp * n_gpus, NCONTIG * n_gpus, DIV, sv_every=SV_EVERY)
 
 
-def shard_contigs(contigs, rank, world):
-    """greedy length balance of genome-1 contigs over ranks (same rule on every rank)"""
-    order = np.argsort([-len(c) for c in contigs], kind="stable")
-    load = [0] * world
-    owner = {}
-    for i in order:
-        r = int(np.argmin(load))
-        owner[int(i)] = r
-        load[r] += len(contigs[i])
-    return [i for i in range(len(contigs)) if owner[i] == rank]
-
-
 class ClockSampler(threading.Thread):
     """SM clock + throttle reasons DURING the timed region, through NVML in-process (spawning
     nvidia-smi five times a second stalls the CUDA driver calls of the measured process)."""
@@ -170,7 +158,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     A, B = workload(world, args.per_gpu_bp)
-    mine = shard_contigs(A, rank, world)
+    from fastga_b200 import shard
+    mine = shard.shard_contigs([len(a) for a in A], rank, world)
     gA = formats.genome_from_arrays([A[i] for i in mine])
     gB = formats.genome_from_arrays(B)
     freqA = formats.genome_from_arrays(A).freq if world > 1 else gA.freq
@@ -217,20 +206,12 @@ def main():
     ms_e2e, outs2 = timed(e2e_step, max(1, min(args.steps, 3)))
     st2 = outs2[-1][1]
 
-    # gather the per-rank record streams on rank 0 (variable length)
+    # gather the per-rank record streams on rank 0 (variable length; the path's only collective)
     nrec = len(alns)
     if world > 1:
-        payload = torch.from_numpy(np.concatenate([alns.fields.reshape(-1).view(np.uint8), alns.pool])).cuda()
-        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([payload.numel()], dtype=torch.int64, device="cuda"))
-        mx = int(max(int(s.item()) for s in sizes))
-        pad = torch.zeros(mx, dtype=torch.uint8, device="cuda")
-        pad[:payload.numel()] = payload
-        bufs = [torch.zeros(mx, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, bufs, dst=0)
-        cnt = torch.tensor([nrec], dtype=torch.int64, device="cuda")
-        dist.all_reduce(cnt)
-        nrec = int(cnt.item())
+        merged = shard.gather_alignments(alns, np.array(mine, dtype=np.int32), dist, torch.device("cuda", local_rank))
+        if rank == 0:
+            nrec = len(merged)
 
     if rank != 0:
         if world > 1:

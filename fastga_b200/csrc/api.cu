@@ -63,23 +63,67 @@ void fgb_timing_add(int which, float ms)
 
 void fgb_count_launch(int n) { g_timings.launches += n; }
 
-static bool pool_ready = false;
+//  Device memory for the stages comes from a process-wide caching allocator: blocks are rounded
+//  to size classes, kept on a free list when released and handed out again on the next step, so
+//  the steady state of a repeated workload makes no cudaMalloc/cudaFree calls at all (both stall
+//  the device; the stream-ordered pool turned out to take 1-800 ms for the multi-GB arenas).
+//  All work of a call is issued on one stream, so reuse after release is stream-ordered.
+
+#include <map>
+#include <unordered_map>
+#include <mutex>
+
+static std::multimap<size_t,void *> g_free;
+static std::unordered_map<void *,size_t> g_live;
+static std::mutex g_mem_lock;
+
+static size_t size_class(size_t b)
+{ if (b < 4096) return 4096;
+  size_t p = 4096;
+  while (p < b) p <<= 1;                 // p/2 < b <= p
+  size_t step = p >> 4;                  // 8 classes per octave
+  return ((b + step - 1) / step) * step;
+}
 
 cudaError_t fgb_dmalloc(void **p, size_t bytes, cudaStream_t st)
-{ if (!pool_ready)
-    { int dev = 0;
-      cudaMemPool_t pool;
-      unsigned long long keep = ~0ull;                 // never give pages back between steps
-      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool,dev) == cudaSuccess)
-        cudaMemPoolSetAttribute(pool,cudaMemPoolAttrReleaseThreshold,&keep);
-      pool_ready = true;
+{ (void) st;
+  size_t c = size_class(bytes);
+  std::lock_guard<std::mutex> g(g_mem_lock);
+  auto it = g_free.lower_bound(c);
+  if (it != g_free.end() && it->first <= c + (c >> 2))
+    { *p = it->second;
+      g_live[*p] = it->first;
+      g_free.erase(it);
+      return cudaSuccess;
     }
-  if (bytes == 0) bytes = 16;
-  return cudaMallocAsync(p,bytes,st);
+  cudaError_t e = cudaMalloc(p,c);
+  if (e != cudaSuccess)                  // out of memory: drop the cache and retry once
+    { cudaGetLastError();
+      for (auto &kv : g_free) cudaFree(kv.second);
+      g_free.clear();
+      e = cudaMalloc(p,c);
+      if (e != cudaSuccess) return e;
+    }
+  g_live[*p] = c;
+  return cudaSuccess;
 }
 
 void fgb_dfree(void *p, cudaStream_t st)
-{ if (p != NULL) cudaFreeAsync(p,st); }
+{ (void) st;
+  if (p == NULL) return;
+  std::lock_guard<std::mutex> g(g_mem_lock);
+  auto it = g_live.find(p);
+  if (it == g_live.end()) { cudaFree(p); return; }
+  g_free.insert(std::make_pair(it->second,p));
+  g_live.erase(it);
+}
+
+//  Gives every cached block back to the driver.
+extern "C" void fgb_release_cache()
+{ std::lock_guard<std::mutex> g(g_mem_lock);
+  for (auto &kv : g_free) cudaFree(kv.second);
+  g_free.clear();
+}
 
 extern "C" void fgb_timings_reset() { memset(&g_timings,0,sizeof(g_timings)); }
 extern "C" void fgb_timings_get(fgb_timings *out) { *out = g_timings; }
@@ -105,7 +149,7 @@ extern "C" int fgb_genome_create(const unsigned char *bps, long long bps_bytes, 
   g->boff.assign(boff,boff+ncontig);
   g->woff.resize(ncontig+1);
   g->seqtot = 0; g->maxlen = 0;
-  long long w = 0;
+  long long w = 2;                             // 16 zero bytes ahead of the first contig too
   for (int c = 0; c < ncontig; c++)
     { if (clen[c] >= 0x7fffffffll) { delete g; return FGB_ERR_LIMIT; }
       g->woff[c] = w;

@@ -67,7 +67,7 @@ struct ext_params
 };
 
 struct Ctx
-{ const u64 *A, *B; int alen, blen; long long anw, bnw;
+{ const unsigned *A, *B; int alen, blen; long long anw, bnw;
   int *V, *HA, *HM, *NA; u64 *T; int *carry;
   Peb *cells; int cmax, avail;
   unsigned char *fstage, *rstage; int smax;
@@ -85,37 +85,39 @@ static __device__ __forceinline__ u64 get_bits(const rec128 &r, int pos, int n)
   return n >= 64 ? v : (v & ((1ull << n) - 1));
 }
 
-static __device__ __forceinline__ u64 win(const u64 *__restrict__ w, long long nw, long long boff)
-{ long long q = boff >> 5;
-  int s = (int) (boff & 31) << 1;
-  u64 a = (q >= 0 && q < nw) ? w[q] : 0ull;
-  if (s == 0) return a;
-  u64 b = (q+1 >= 0 && q+1 < nw) ? w[q+1] : 0ull;
-  return (a >> s) | (b << (64-s));
+//  32 bases starting at base offset boff of a staged contig (32-bit word view).  Contigs are
+//  zero-padded by 16 bytes on both sides (fgb_genome_create), so boff in [-32, len+32) needs no
+//  bounds test: three aligned loads and two funnel shifts.
+
+static __device__ __forceinline__ u64 win(const unsigned *__restrict__ w, int boff)
+{ int q = boff >> 4, s = (boff & 15) << 1;
+  unsigned w0 = w[q], w1 = w[q+1], w2 = w[q+2];
+  return (u64) __funnelshift_r(w0,w1,s) | ((u64) __funnelshift_r(w1,w2,s) << 32);
 }
 
-static __device__ __forceinline__ int base_at(const u64 *__restrict__ w, int len, int i)
+static __device__ __forceinline__ int base_at(const unsigned *__restrict__ w, int len, int i)
 { if (i < 0 || i >= len) return 4;
-  return (int) (w[i >> 5] >> ((i & 31) << 1)) & 3;
+  return (int) (w[i >> 4] >> ((i & 15) << 1)) & 3;
 }
 
-static __device__ __forceinline__ int a_at(const Ctx &c, int s, int xn)
-{ return base_at(c.A,c.alen,(s > 0) ? xn : -xn-1); }
-static __device__ __forceinline__ int b_at(const Ctx &c, int s, int yn)
-{ return base_at(c.B,c.blen,(s > 0) ? yn : -yn-1); }
+template<int S> static __device__ __forceinline__ int a_at(const Ctx &c, int xn)
+{ return base_at(c.A,c.alen,(S > 0) ? xn : -xn-1); }
+template<int S> static __device__ __forceinline__ int b_at(const Ctx &c, int yn)
+{ return base_at(c.B,c.blen,(S > 0) ? yn : -yn-1); }
 
 //  slide along diagonal kk from normalised xn; returns #matches, flag 0 mismatch / 1 B end / 2 A end
 //    (B is tested first, align.c:683-697)
 
-static __device__ __forceinline__ int snake(const Ctx &c, int s, int xn, int kk, int &flag)
+template<int S>
+static __device__ __forceinline__ int snake(const Ctx &c, int xn, int kk, int &flag)
 { int yn = xn - kk, t = 0, tmax;
-  if (s > 0)
+  if (S > 0)
     { int x = xn, y = yn;
       if (y < 0 || y >= c.blen) { flag = 1; return 0; }
       if (x < 0 || x >= c.alen) { flag = 2; return 0; }
       tmax = min(c.alen - x,c.blen - y);
       while (t < tmax)
-        { u64 d = win(c.A,c.anw,(long long) x+t) ^ win(c.B,c.bnw,(long long) y+t);
+        { u64 d = win(c.A,x+t) ^ win(c.B,y+t);
           if (d) { t += (__ffsll((long long) d)-1) >> 1; break; }
           t += 32;
         }
@@ -128,7 +130,7 @@ static __device__ __forceinline__ int snake(const Ctx &c, int s, int xn, int kk,
       if (x-1 < 0 || x-1 >= c.alen) { flag = 2; return 0; }
       tmax = min(x,y);
       while (t < tmax)
-        { u64 d = win(c.A,c.anw,(long long) x-t-32) ^ win(c.B,c.bnw,(long long) y-t-32);
+        { u64 d = win(c.A,x-t-32) ^ win(c.B,y-t-32);
           if (d) { t += __clzll((long long) d) >> 1; break; }
           t += 32;
         }
@@ -168,7 +170,8 @@ static __device__ __forceinline__ int warp_prefix_max_excl(int v, int lane)
 //  One wave pass (direction s) from anti-diagonal mida over diagonals [low,hgh].
 //  Outputs the trim point (original coordinates), its diffs and the pebble chain head.
 
-static __device__ int wave(Ctx &c, const int s, int low, int hgh, const int mida, int minp, int maxp,
+template<int s>
+static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, int maxp,
                            const int aoff, int &endx, int &endy, int &diffs, int &trimha_out)
 { const int lane = threadIdx.x & 31;
   const unsigned lt = lanemask_lt();
@@ -208,7 +211,7 @@ static __device__ int wave(Ctx &c, const int s, int low, int hgh, const int mida
           c.cells[ha] = p;
         }
       int xn = s*x, flag = 0;
-      if (act) xn += snake(c,s,xn,kk,flag);
+      if (act) xn += snake<s>(c,xn,kk,flag);
       int cc = 2*xn - kk;
       bool need = act && xn >= nan;
       while (__any_sync(FULL,need))
@@ -243,7 +246,7 @@ static __device__ int wave(Ctx &c, const int s, int low, int hgh, const int mida
     }
   __syncwarp();
   if (anyhit)
-    { more = (b_at(c,s,besta-bestx) != 4 && a_at(c,s,bestx) != 4);
+    { more = (b_at<s>(c,besta-bestx) != 4 && a_at<s>(c,bestx) != 4);
       if (hghk >= aclip) hghk = aclip-1;
       if (lowk <= bclip) lowk = bclip+1;
       aclip = INT_MAX; bclip = -INT_MAX; anyhit = false;
@@ -302,7 +305,7 @@ static __device__ int wave(Ctx &c, const int s, int low, int hgh, const int mida
           b <<= 1;
           int xn = (cc + kk) >> 1, flag = 0, k = s*kk;
           if (act)
-            { int t = snake(c,s,xn,kk,flag);
+            { int t = snake<s>(c,xn,kk,flag);
               xn += t;
               b = (t >= 64) ? ~0ull : ((b << t) | ((1ull << t) - 1));
             }
@@ -372,7 +375,7 @@ static __device__ int wave(Ctx &c, const int s, int low, int hgh, const int mida
         }
 
       if (anyhit)
-        { more = (b_at(c,s,besta-bestx) != 4 && a_at(c,s,bestx) != 4);
+        { more = (b_at<s>(c,besta-bestx) != 4 && a_at<s>(c,bestx) != 4);
           if (hghk >= aclip) hghk = aclip-1;
           if (lowk <= bclip) lowk = bclip+1;
           aclip = INT_MAX; bclip = -INT_MAX; anyhit = false;
@@ -552,7 +555,7 @@ static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int a
 
   R.ftlen = R.rtlen = 0; R.diffs = 0;
   long long tk = clock64();
-  st = wave(c,+1,low,hgh,anti,minp,maxp,aoff,ex,ey,df,tha);
+  st = wave<1>(c,low,hgh,anti,minp,maxp,aoff,ex,ey,df,tha);
   if (st) return st;
   c.cyc_wave += (u64) (clock64() - tk); tk = clock64();
   st = fwd_extract(c,tha,anti,ex,ey,df,R.ftlen,rootd);
@@ -564,7 +567,7 @@ static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int a
   bool fshort = ((R.aepos + R.bepos) - anti < DUB_TRIM);
 
   tk = clock64();
-  st = wave(c,-1,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
+  st = wave<-1>(c,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
   if (st) return st;
   c.cyc_wave += (u64) (clock64() - tk); tk = clock64();
   st = rev_extract(c,tha,aoff,ex,ey,df,R.ftlen,R.rtlen);
@@ -583,7 +586,7 @@ static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int a
         { low  = R.abpos - R.bbpos;
           anti = R.abpos + R.bbpos;
           R.ftlen = R.rtlen = 0;
-          st = wave(c,+1,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
+          st = wave<1>(c,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
           if (st) return st;
           st = fwd_extract(c,tha,anti,ex,ey,df,R.ftlen,rootd);
           if (st) return st;
@@ -594,7 +597,7 @@ static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int a
     { low  = R.aepos - R.bepos;
       anti = R.aepos + R.bepos;
       R.ftlen = R.rtlen = 0; R.diffs = 0;
-      st = wave(c,-1,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
+      st = wave<-1>(c,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
       if (st) return st;
       st = rev_extract(c,tha,aoff,ex,ey,df,0,R.rtlen);
       if (st) return st;
@@ -696,8 +699,8 @@ static __device__ int scan_triple(const ext_params &P, Ctx &c, unsigned j, unsig
       int ctg2 = P.bperm[get_bits(r0,P.p_jc,P.jc_bits)];
       alen = P.aclen[ctg1]; blen = P.bclen[ctg2]; mlen = alen + blen;
       doffset = alen - (P.amxpos + P.bmxpos); aoffset = alen - P.amxpos;
-      c.A = (comp ? P.arseq : P.aseq) + P.awoff[ctg1];
-      c.B = P.bseq + P.bwoff[ctg2];
+      c.A = (const unsigned *) ((comp ? P.arseq : P.aseq) + P.awoff[ctg1]);
+      c.B = (const unsigned *) (P.bseq + P.bwoff[ctg2]);
       c.alen = (int) alen; c.blen = (int) blen;
       c.anw = (alen + 31) >> 5; c.bnw = (blen + 31) >> 5;
     }
@@ -791,6 +794,224 @@ static __device__ int scan_triple(const ext_params &P, Ctx &c, unsigned j, unsig
   return ST_OK;
 }
 
+/***********************************************************************************************
+ *  Warp-parallel chain scan of one triple (the extension stage's version of the loop above).
+ *
+ *  The serial scan keeps ahgh = running maximum of anti+2*lcp over the current chain and breaks
+ *  the chain when anti >= ahgh + CHAIN_BREAK.  Because seeds arrive in anti order and one seed
+ *  spans at most 80 anti-diagonals, every seed of an earlier chain ends more than CHAIN_BREAK-80
+ *  below the current one, so the chain-local running maximum equals the running maximum over
+ *  ALL earlier seeds of the triple.  Breaks, the coverage increments, and the per-chain
+ *  reductions (cov, mix, dgmin, dgmax, alow, ahgh) therefore come from warp prefix-max /
+ *  prefix-sum / ballots over 32 merged seeds at a time; only completed chains that qualify
+ *  (cov >= CHAIN_MIN) enter the sequential tube stepping, in order, exactly as FastGA.c:3157-3340.
+ **********************************************************************************************/
+
+struct TripleCtx
+{ unsigned j, pairkey; int comp, seq; bool isnew;
+  long long cdiag, alen, blen, mlen, doffset, aoffset, alast;
+};
+
+static __device__ int handle_hit(const ext_params &P, Ctx &c, TripleCtx &T, long long alow,
+                                 long long ahgh, int dgmin, int dgmax, u64 &nla)
+{ long long amid, eant;
+  dgmin += (int) (T.cdiag << BUCK_SHIFT);
+  dgmax += (int) (T.cdiag << BUCK_SHIFT);
+  if (T.comp)
+    { dgmin += (int) T.doffset; dgmax += (int) T.doffset; alow += T.aoffset; ahgh += T.aoffset; }
+  else
+    { dgmin -= (int) P.bmxpos; dgmax -= (int) P.bmxpos; }
+  if (ahgh > T.alast)
+    { if (alow < T.alast) alow = T.alast;
+      ahgh -= BUCK_ANTI;
+      do
+        { amid = alow + BUCK_ANTI;
+          if (amid > ahgh)
+            { amid = ahgh;
+              if (amid + dgmin < 0)
+                { dgmin = (int) -amid;
+                  if (dgmin > dgmax) break;
+                }
+            }
+          LAres R;
+          int st = local_alignment(c,T.comp,dgmin,dgmax,(int) amid,R);
+          if (st) return st;
+          nla += 1;
+          int rlen = R.aepos - R.abpos;                    // same after the ACOMP flip
+          if (rlen >= P.aln_min && P.aln_rate*rlen >= (double) R.diffs)
+            { emit_record(P,c,R,T.comp,T.j,T.seq,T.pairkey);
+              T.seq += 1;
+            }
+          eant = (long long) R.aepos + R.bepos;            // un-flipped end (FastGA.c:3309-3312)
+          if (eant <= alow) alow = amid; else alow = eant;
+        }
+      while (alow < ahgh);
+      T.alast = alow;
+    }
+  return ST_OK;
+}
+
+#define SCAN_SMEM 1536          // per warp: La Ua (32 x i64) Lm Um (32 x int) Ma (64 x i64) Mm (64 x int)
+
+static __device__ int scan_triple_warp(const ext_params &P, Ctx &c, unsigned j, unsigned &nhit_out,
+                                       u64 &nla, unsigned char *wsm)
+{ const int lane = threadIdx.x & 31;
+  const rec128 *S = P.seeds;
+  long long *La = (long long *) wsm, *Ua = La + 32, *Ma = Ua + 32;
+  int *Lm = (int *) (Ma + 64), *Um = Lm + 32, *Mm = Um + 32;
+
+  unsigned b = P.seg_start[j], m = P.seg_start[j+1], e = m;
+  rec128 r0 = S[b];
+  u64 grp = get_bits(r0,P.p_jc,P.jc_bits + P.ic_bits + 1);
+  TripleCtx T;
+  T.cdiag = (long long) get_bits(r0,P.p_band,P.band_bits);
+  T.isnew = true;
+  bool aux = false;
+  if (j > 0)
+    { rec128 rp = S[P.seg_start[j-1]];
+      if (get_bits(rp,P.p_jc,P.jc_bits + P.ic_bits + 1) == grp &&
+          (long long) get_bits(rp,P.p_band,P.band_bits) == T.cdiag-1)
+        T.isnew = false;
+    }
+  if (j+1 < (unsigned) P.nseg)
+    { rec128 rn = S[m];
+      if (get_bits(rn,P.p_jc,P.jc_bits + P.ic_bits + 1) == grp &&
+          (long long) get_bits(rn,P.p_band,P.band_bits) == T.cdiag+1)
+        { aux = true; e = P.seg_start[j+2]; }
+    }
+  nhit_out = 0;
+  if (!T.isnew && !aux) return ST_OK;
+
+  T.j = j; T.seq = 0; T.alast = -1;
+  T.comp = (int) get_bits(r0,P.p_cp,1);
+  T.pairkey = (unsigned) grp;
+  { int ctg1 = P.aperm[get_bits(r0,P.p_ic,P.ic_bits)];
+    int ctg2 = P.bperm[get_bits(r0,P.p_jc,P.jc_bits)];
+    T.alen = P.aclen[ctg1]; T.blen = P.bclen[ctg2]; T.mlen = T.alen + T.blen;
+    T.doffset = T.alen - (P.amxpos + P.bmxpos); T.aoffset = T.alen - P.amxpos;
+    c.A = (const unsigned *) ((T.comp ? P.arseq : P.aseq) + P.awoff[ctg1]);
+    c.B = (const unsigned *) (P.bseq + P.bwoff[ctg2]);
+    c.alen = (int) T.alen; c.blen = (int) T.blen;
+    c.anw = (T.alen + 31) >> 5; c.bnw = (T.blen + 31) >> 5;
+  }
+
+  const long long NEG = -0x7fffffffffffffffll;
+  const long long CB = P.chain_break;
+  long long carryP = -CB, c_alow = 0;
+  int c_cov = 0, c_mix = 0, c_dgmin = 2*BUCK_WIDTH, c_dgmax = 0;
+  unsigned s = b, t = m;
+
+  while (s < m || t < e)
+    { int nl = (int) min(32u,m - s), nu = (int) min(32u,e - t);
+      __syncwarp();
+      if (lane < nl)
+        { rec128 r = ld_rec(S + s + lane);
+          La[lane] = (long long) get_bits(r,P.p_anti,P.anti_bits);
+          Lm[lane] = (int) ((r.lo & 63) << 1) | (int) (((r.lo >> 6) & 63) << 8) | (1 << 16);
+        }
+      if (lane < nu)
+        { rec128 r = ld_rec(S + t + lane);
+          Ua[lane] = (long long) get_bits(r,P.p_anti,P.anti_bits);
+          Um[lane] = (int) ((r.lo & 63) << 1) | (int) ((((r.lo >> 6) & 63) + BUCK_WIDTH) << 8) | (2 << 16);
+        }
+      __syncwarp();
+      //  merged rank of every window element (ties: lower band first, FastGA.c:3111)
+      int rankL = 0x7fffffff, rankU = 0x7fffffff;
+      if (lane < nl)
+        { long long a = La[lane]; int lo = 0, hi = nu;             // # U with anti < a
+          while (lo < hi) { int md = (lo+hi) >> 1; if (Ua[md] < a) lo = md+1; else hi = md; }
+          rankL = lane + lo;
+        }
+      if (lane < nu)
+        { long long a = Ua[lane]; int lo = 0, hi = nl;             // # L with anti <= a
+          while (lo < hi) { int md = (lo+hi) >> 1; if (La[md] <= a) lo = md+1; else hi = md; }
+          rankU = lane + lo;
+        }
+      //  only ranks up to the end of the first exhausted window are final
+      int valid = nl + nu;
+      if (nl > 0 && s + nl < m) valid = min(valid,__shfl_sync(FULL,rankL,nl-1) + 1);
+      if (nu > 0 && t + nu < e) valid = min(valid,__shfl_sync(FULL,rankU,nu-1) + 1);
+      if (rankL < valid) { Ma[rankL] = La[lane]; Mm[rankL] = Lm[lane]; }
+      if (rankU < valid) { Ma[rankU] = Ua[lane]; Mm[rankU] = Um[lane]; }
+      s += __popc(__ballot_sync(FULL,rankL < valid));
+      t += __popc(__ballot_sync(FULL,rankU < valid));
+      __syncwarp();
+
+      for (int base = 0; base < valid; base += 32)
+        { int n = min(32,valid - base);
+          bool act = lane < n;
+          long long anti = act ? Ma[base+lane] : 0;
+          int meta = act ? Mm[base+lane] : 0;
+          int lcp2 = meta & 0xff, dg = (meta >> 8) & 0xff, wch = meta >> 16;
+          long long cps = act ? anti + lcp2 : NEG;
+          long long pm = cps;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1)
+            { long long v = __shfl_up_sync(FULL,pm,o);
+              if (lane >= o && v > pm) pm = v;
+            }
+          long long pe = __shfl_up_sync(FULL,pm,1);
+          if (lane == 0) pe = NEG;
+          long long Pl = pe > carryP ? pe : carryP;             // ahgh seen by this seed
+          bool brk = act && anti >= Pl + CB;
+          int inc = 0;
+          if (act)
+            { if (brk) inc = lcp2;
+              else if (cps > Pl) inc = (anti >= Pl) ? lcp2 : (int) (cps - Pl);
+            }
+          int Ssum = inc;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1)
+            { int v = __shfl_up_sync(FULL,Ssum,o);
+              if (lane >= o) Ssum += v;
+            }
+          unsigned bm = __ballot_sync(FULL,brk);
+          unsigned w1 = __ballot_sync(FULL,act && wch == 1), w2 = __ballot_sync(FULL,act && wch == 2);
+          int seglo = 0;
+          bool cont = true;
+          unsigned rem = bm;
+          while (true)
+            { int q = rem ? (__ffs(rem) - 1) : n;                 // segment [seglo,q)
+              bool last = (rem == 0);
+              rem &= rem - 1;
+              unsigned R = ((q >= 32) ? 0xffffffffu : ((1u << q) - 1)) & ~((1u << seglo) - 1);
+              int cov = (q > 0 ? __shfl_sync(FULL,Ssum,q-1) : 0) - (seglo > 0 ? __shfl_sync(FULL,Ssum,seglo-1) : 0);
+              int mix = ((w1 & R) ? 1 : 0) | ((w2 & R) ? 2 : 0);
+              bool inR = (R >> lane) & 1;
+              int dmin = __reduce_min_sync(FULL,inR ? dg : 255);
+              int dmax = __reduce_max_sync(FULL,inR ? dg : -1);
+              long long alow = c_alow;
+              if (cont)
+                { cov += c_cov; mix |= c_mix;
+                  dmin = min(dmin,c_dgmin); dmax = max(dmax,c_dgmax);
+                }
+              else
+                alow = __shfl_sync(FULL,anti,seglo);
+              if (last)                                           // open chain -> carry
+                { c_cov = cov; c_mix = mix; c_dgmin = dmin; c_dgmax = dmax; c_alow = alow;
+                  break;
+                }
+              long long ahgh = __shfl_sync(FULL,Pl,q);
+              if (cov >= P.chain_min && (mix != 1 || T.isnew))
+                { nhit_out += 1;
+                  int st = handle_hit(P,c,T,alow,ahgh,dmin,dmax,nla);
+                  if (st) return st;
+                }
+              seglo = q; cont = false;
+            }
+          long long pmx = __shfl_sync(FULL,pm,n-1);
+          if (pmx > carryP) carryP = pmx;
+        }
+    }
+  //  the scan's final iteration (anti = MAX) closes the last chain
+  if (c_cov >= P.chain_min && (c_mix != 1 || T.isnew))
+    { nhit_out += 1;
+      int st = handle_hit(P,c,T,c_alow,carryP,c_dgmin,c_dgmax,nla);
+      if (st) return st;
+    }
+  return ST_OK;
+}
+
 static __device__ __forceinline__ bool upper_differs(const rec128 &a, const rec128 &b, int pos)
 { if (pos < 64) return a.hi != b.hi || (a.lo >> pos) != (b.lo >> pos);
   return (a.hi >> (pos-64)) != (b.hi >> (pos-64));
@@ -867,7 +1088,7 @@ __global__ void prefilter_kernel(ext_params P, unsigned *__restrict__ work_long,
     work_short[atomicAdd(nwork+1,1u)] = j;
 }
 
-#define STATE_BYTES (EX_W*(4*4+8) + 32 + 64*16)
+#define STATE_BYTES (EX_W*(4*4+8) + 32 + SCAN_SMEM)
 #define TT_BYTES    ((256+128)*4)
 
 __global__ void __launch_bounds__(EX_WARPS*32)
@@ -912,7 +1133,7 @@ extend_kernel(ext_params P)
       w = __shfl_sync(FULL,w,0);
       if (w >= (unsigned) P.nwork) break;
       unsigned j = P.work[w], nh = 0;
-      int st = scan_triple<true>(P,c,j,nh,nla,stagebuf);
+      int st = scan_triple_warp(P,c,j,nh,nla,(unsigned char *) stagebuf);
       if (st != ST_OK)
         { if (lane == 0)
             { unsigned o = atomicAdd(P.nfailed,1u);
@@ -968,6 +1189,18 @@ extern "C" void fgb_overlaps_counters(const fgb_overlaps *o, unsigned long long 
 }
 
 
+#include <chrono>
+static long long tr_t0 = 0;
+static void tr_mark(const char *what)
+{ static int on = -1;
+  if (on < 0) on = (getenv("FGB_TRACE") != NULL);
+  if (!on) return;
+  long long t = std::chrono::duration_cast<std::chrono::microseconds>(
+                  std::chrono::steady_clock::now().time_since_epoch()).count();
+  fprintf(stderr,"[fgb_trace] %-28s +%8.3f ms\n",what,tr_t0 ? (t - tr_t0)/1000.0 : 0.0);
+  tr_t0 = t;
+}
+
 struct ev_timer
 { cudaEvent_t a, b; cudaStream_t st; int which;
   ev_timer(int w, cudaStream_t s) : st(s), which(w)
@@ -991,6 +1224,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
   if (S->n >= 0xfffffff0ll) return FGB_ERR_LIMIT;
   fgb_overlaps *O = new fgb_overlaps();
   long long n = S->n;
+  tr_mark("extend: enter");
 
   ext_params P;
   memset(&P,0,sizeof(P));
@@ -1053,6 +1287,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       nwork = nw2[0] + nw2[1];
     }
   O->nseg = nseg; O->nwork = nwork;
+  tr_mark("extend: triples+prefilter");
 
   unsigned char *d_out = NULL;
   u64 out_cap = 0, out_used = 0;
@@ -1091,6 +1326,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           P.stage = d_stage; P.stage_bytes = stage_bytes;
           P.out = d_out; P.out_cap = out_cap;
           P.work = d_list; P.nwork = (int) nlist;
+          tr_mark("extend: arenas allocated");
           CUDA_TRY(cudaMemsetAsync(d_misc+1,0,8,st));          // queue, nfailed
           { ev_timer t(1,st);
             extend_kernel<<<(unsigned) nblocks,EX_WARPS*32,smem,st>>>(P);
@@ -1100,6 +1336,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           unsigned misc[8];
           CUDA_TRY(cudaMemcpyAsync(misc,d_misc,32,cudaMemcpyDeviceToHost,st));
           CUDA_TRY(cudaStreamSynchronize(st));
+          tr_mark("extend: kernel done");
           fgb_dfree(d_cells,st); fgb_dfree(d_stage,st);
           out_used = ((u64) misc[5] << 32) | misc[4];
           unsigned nfailed = misc[2];
@@ -1138,12 +1375,22 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
 
       //  bring the records back and drop partial output of triples that were re-run
       O->nbytes = (long long) out_used;
-      CUDA_TRY(cudaMallocHost(&O->h_buf,out_used + 64));
-      O->pinned = true;
+      tr_mark("extend: attempts done");
+      //  D2H through a grow-only pinned staging buffer (cudaMallocHost per step costs ms)
+      static unsigned char *pin = NULL; static u64 pin_cap = 0;
+      if (out_used + 64 > pin_cap)
+        { if (pin) cudaFreeHost(pin);
+          pin_cap = out_used * 2 + (8ull << 20);
+          CUDA_TRY(cudaMallocHost(&pin,pin_cap));
+        }
+      O->h_buf = (unsigned char *) malloc(out_used + 64);
+      O->pinned = false;
       { ev_timer t(2,st);
-        CUDA_TRY(cudaMemcpyAsync(O->h_buf,d_out,out_used,cudaMemcpyDeviceToHost,st));
+        CUDA_TRY(cudaMemcpyAsync(pin,d_out,out_used,cudaMemcpyDeviceToHost,st));
       }
       CUDA_TRY(cudaStreamSynchronize(st));
+      memcpy(O->h_buf,pin,out_used);
+      tr_mark("extend: d2h");
       if (!todo.empty())
         { //  a re-run triple may have emitted records before it failed: keep only the LAST
           //  complete run = records after its final failure.  Runs are appended in time order,
@@ -1191,6 +1438,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
   }
   fgb_dfree(d_tables,st); fgb_dfree(d_counters,st); fgb_dfree(d_total,st); fgb_dfree(d_misc,st); fgb_dfree(d_flag,st);
   fgb_dfree(d_seg,st); fgb_dfree(d_work,st); fgb_dfree(d_failed,st); fgb_dfree(d_tmp,st); fgb_dfree(d_out,st);
+  tr_mark("extend: leave");
   *out = O;
   return FGB_OK;
 }

@@ -96,7 +96,7 @@ __global__ void stage_contigs_kernel(const unsigned char *__restrict__ bps,
   long long nbytes = (clen[lo]+3) >> 2;
   long long b0 = q*8;
   u64 v = 0;
-  if (boff[lo] >= 0)
+  if (boff[lo] >= 0 && q >= 0)
     { const unsigned char *p = bps + boff[lo];
       for (int i = 0; i < 8; i++)
         if (b0+i < nbytes)
@@ -120,6 +120,7 @@ __global__ void revcomp_contigs_kernel(const u64 *__restrict__ seq, const long l
   long long q = g - woff[lo];
   long long L = clen[lo];
   long long nw = (lo+1 < ncontig ? woff[lo+1] : total_words) - woff[lo];
+  if (q < 0) { rseq[g] = 0; return; }
   //  output bases i = 32q .. 32q+31 : out[i] = 3 - in[L-1-i]  ->  in bases L-32-32q .. L-1-32q
   u64 e = bases64(seq + woff[lo],nw,L - 32 - 32*q);
   u64 v = ~rev2(e);

@@ -28,40 +28,9 @@ struct seed_layout                 // bit positions inside the 128-bit seed reco
 static __host__ __device__ __forceinline__ int seed_key_bits(const seed_layout &L)
 { return 12 + L.anti_bits + L.band_bits + L.jc_bits + L.ic_bits + 1; }
 
-static __device__ __forceinline__ void put_bits(rec128 &r, int pos, u64 v)
-{ if (pos < 64)
-    { r.lo |= v << pos;
-      if (pos > 0) r.hi |= v >> (64-pos);     // spill (v is narrower than 64 bits)
-    }
-  else
-    r.hi |= v << (pos-64);
-}
-
-static __device__ __forceinline__ rec128 make_seed(const seed_layout &L, int comp, unsigned icont,
-                                                   unsigned jcont, long long ipost, long long jpost,
-                                                   int plen)
-{ long long diag, anti;
-  if (comp)                                        // FastGA.c:2705-2712
-    { diag = (L.amxpos + L.bmxpos) - (ipost + jpost);
-      anti = L.amxpos - (ipost - jpost);
-    }
-  else
-    { diag = L.bmxpos + (ipost - jpost);
-      anti = ipost + jpost;
-    }
-  rec128 r; r.lo = 0; r.hi = 0;
-  int pos = 0;
-  put_bits(r,pos,(u64) plen);            pos += 6;
-  put_bits(r,pos,(u64) (diag & 63));     pos += 6;
-  put_bits(r,pos,(u64) anti);            pos += L.anti_bits;
-  put_bits(r,pos,(u64) (diag >> 6));     pos += L.band_bits;
-  put_bits(r,pos,(u64) jcont);           pos += L.jc_bits;
-  put_bits(r,pos,(u64) icont);           pos += L.ic_bits;
-  put_bits(r,pos,(u64) comp);
-  return r;
-}
-
 #define MG_THREADS 256
+#define MG_WARPS   (MG_THREADS/32)
+#define MG_TILE    64                     // T1 entries per warp
 
 //  lcp (in bases, 0..28) of two 56-bit suffixes
 static __device__ __forceinline__ int lcp56(u64 a, u64 b)
@@ -76,94 +45,137 @@ static __device__ __forceinline__ u64 suffix_of(const rec128 *__restrict__ T, un
   return ((hi & 0xffffffffffull) << 16) | (lo >> 48);
 }
 
+struct seed_pack                          // kernel-uniform packing constants
+{ int p_band, s_jc, s_ic, s_cp;           // band position; shifts inside the upper word
+  long long amxpos, bmxpos, maxdag;
+};
+
+//  One warp owns MG_TILE consecutive T1 entries:
+//   1. two coalesced 512-byte loads; forward-strand entries (the only ones that seed,
+//      FastGA.c:921-928) are compacted into shared memory by ballot so the search lanes are dense;
+//   2. each lane searches its entry in the T2 panel (binary search + bounded walk);
+//   3. the seeds of the 32 lanes are expanded load-balanced: output slot o is built by lane
+//      o mod 32 (prefix sums in shared memory), so every lane builds one seed per step and the
+//      128-bit stores of a step are contiguous.
+
 __global__ void __launch_bounds__(MG_THREADS)
 adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
                        const rec128 *__restrict__ T2, const unsigned *__restrict__ pstart2,
-                       int freq, seed_layout L,
+                       int freq, seed_pack K,
                        rec128 *__restrict__ seeds, unsigned long long capacity,
                        unsigned long long *__restrict__ counters /* [0]=nseeds [1]=sum plen */)
-{ __shared__ unsigned wsum[MG_THREADS/32];
-  __shared__ unsigned long long blockbase;
+{ __shared__ __align__(16) rec128 sbuf[MG_WARPS][MG_TILE];
+  __shared__ unsigned s_excl[MG_WARPS][33];
+  __shared__ unsigned s_lowi[MG_WARPS][32];
+  __shared__ unsigned s_plen[MG_WARPS][32];
+  __shared__ unsigned long long s_pay[MG_WARPS][32];
+  __shared__ unsigned long long s_sum[MG_WARPS];
 
-  unsigned i = blockIdx.x * MG_THREADS + threadIdx.x;
-  unsigned cnt = 0, lowi = 0;
-  int plen = 0;
-  rec128 r1; r1.lo = r1.hi = 0;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const unsigned lt = lanemask_lt();
+  unsigned long long base = ((unsigned long long) blockIdx.x * MG_WARPS + wp) * MG_TILE;
+  unsigned long long sumlen = 0;
 
-  if (i < n1)
-    { r1 = ld_rec(T1 + i);
-      if (((r1.lo >> 47) & 1) == 0)                       // forward-strand entries only (:921-928)
-        { unsigned p  = KREC_PREFIX24(r1.hi);
-          unsigned lo = pstart2[p], hi = pstart2[p+1];
-          if (lo < hi)
-            { u64 s1 = KREC_SUFFIX56(r1);
-              unsigned a = lo, b = hi;                    // lower bound of s1 in T2[lo,hi)
-              while (a < b)
-                { unsigned m = (a + b) >> 1;
-                  if (suffix_of(T2,m) < s1) a = m+1; else b = m;
-                }
-              int ll = (a > lo) ? lcp56(s1,suffix_of(T2,a-1)) : -1;
-              int lr = (a < hi) ? lcp56(s1,suffix_of(T2,a))   : -1;
-              int m  = ll > lr ? ll : lr;
-              plen = 12 + m;
-              //  block of T2 entries sharing the first m suffix bases with s1: walk out from a
-              unsigned lft = a, rgt = a;
-              int sh = 56 - 2*m;                           // m <= 28 -> sh >= 0
-              u64 key = (sh >= 56) ? 0 : (s1 >> sh);
-              while (lft > lo && rgt - lft < (unsigned) freq)
-                { u64 s = suffix_of(T2,lft-1);
-                  if (((sh >= 56) ? 0 : (s >> sh)) != key) break;
-                  lft -= 1;
-                }
-              while (rgt < hi && rgt - lft < (unsigned) freq)
-                { u64 s = suffix_of(T2,rgt);
-                  if (((sh >= 56) ? 0 : (s >> sh)) != key) break;
-                  rgt += 1;
-                }
-              if (rgt - lft < (unsigned) freq)             // |R| < FREQ (:799-823)
-                { cnt  = rgt - lft;
-                  lowi = lft;
+  if (base < n1)
+    { unsigned i0 = (unsigned) base + lane, i1 = i0 + 32;
+      rec128 e0, e1;
+      bool f0 = false, f1 = false;
+      if (i0 < n1) { e0 = ld_rec(T1 + i0); f0 = ((e0.lo >> 47) & 1) == 0; }
+      if (i1 < n1) { e1 = ld_rec(T1 + i1); f1 = ((e1.lo >> 47) & 1) == 0; }
+      unsigned m0 = __ballot_sync(0xffffffffu,f0), m1 = __ballot_sync(0xffffffffu,f1);
+      int n0 = __popc(m0), nd = n0 + __popc(m1);
+      if (f0) st_rec(&sbuf[wp][__popc(m0 & lt)],e0);
+      if (f1) st_rec(&sbuf[wp][n0 + __popc(m1 & lt)],e1);
+      __syncwarp();
+
+      for (int r0 = 0; r0 < nd; r0 += 32)
+        { int idx = r0 + lane;
+          unsigned cnt = 0, lowi = 0;
+          int plen = 0;
+          rec128 r1; r1.lo = r1.hi = 0;
+          if (idx < nd)
+            { r1 = ld_rec(&sbuf[wp][idx]);
+              unsigned p  = KREC_PREFIX24(r1.hi);
+              unsigned lo = pstart2[p], hi = pstart2[p+1];
+              if (lo < hi)
+                { u64 s1 = KREC_SUFFIX56(r1);
+                  unsigned a = lo, b = hi;                    // lower bound of s1 in T2[lo,hi)
+                  while (a < b)
+                    { unsigned m = (a + b) >> 1;
+                      if (suffix_of(T2,m) < s1) a = m+1; else b = m;
+                    }
+                  int ll = (a > lo) ? lcp56(s1,suffix_of(T2,a-1)) : -1;
+                  int lr = (a < hi) ? lcp56(s1,suffix_of(T2,a))   : -1;
+                  int m  = ll > lr ? ll : lr;
+                  plen = 12 + m;
+                  unsigned lft = a, rgt = a;
+                  int sh = 56 - 2*m;
+                  u64 key = s1 >> sh;
+                  while (lft > lo && rgt - lft < (unsigned) freq)
+                    { if ((suffix_of(T2,lft-1) >> sh) != key) break;
+                      lft -= 1;
+                    }
+                  while (rgt < hi && rgt - lft < (unsigned) freq)
+                    { if ((suffix_of(T2,rgt) >> sh) != key) break;
+                      rgt += 1;
+                    }
+                  if (rgt - lft < (unsigned) freq)             // |R| < FREQ (:799-823)
+                    { cnt = rgt - lft; lowi = lft; }
                 }
             }
+
+          unsigned inc = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1)
+            { unsigned t = __shfl_up_sync(0xffffffffu,inc,o);
+              if (lane >= o) inc += t;
+            }
+          unsigned total = __shfl_sync(0xffffffffu,inc,31);
+          if (total == 0) continue;
+          sumlen += (unsigned long long) __reduce_add_sync(0xffffffffu,cnt * (unsigned) plen);
+          unsigned long long gbase = 0;
+          if (lane == 0) gbase = atomicAdd(&counters[0],(unsigned long long) total);
+          gbase = __shfl_sync(0xffffffffu,gbase,0);
+          s_excl[wp][lane] = inc - cnt;
+          if (lane == 31) s_excl[wp][32] = total;
+          s_lowi[wp][lane] = lowi;
+          s_plen[wp][lane] = (unsigned) plen;
+          s_pay[wp][lane]  = r1.lo & 0xffffffffffffull;
+          __syncwarp();
+
+          for (unsigned o = lane; o < total; o += 32)
+            { int j = 0;                                       // last lane with s_excl <= o
+#pragma unroll
+              for (int st = 16; st > 0; st >>= 1)
+                if (s_excl[wp][j + st] <= o) j += st;
+              unsigned k = o - s_excl[wp][j];
+              rec128 r2 = ld_rec(T2 + s_lowi[wp][j] + k);
+              unsigned long long pay = s_pay[wp][j];
+              long long ipost = (long long) (unsigned) pay, jpost = (long long) (unsigned) r2.lo;
+              unsigned icont = (unsigned) (pay >> 32) & 0x7fff;
+              unsigned cs = (unsigned) (r2.lo >> 32) & 0xffff;
+              unsigned comp = cs >> 15, jcont = cs & 0x7fff;
+              long long diag, anti;
+              if (comp) { diag = K.maxdag - (ipost + jpost); anti = K.amxpos - (ipost - jpost); }
+              else      { diag = K.bmxpos + (ipost - jpost); anti = ipost + jpost; }
+              u64 X = (u64) s_plen[wp][j] | ((u64) (diag & 63) << 6) | ((u64) anti << 12);
+              u64 Y = (u64) (diag >> 6) | ((u64) jcont << K.s_jc) | ((u64) icont << K.s_ic)
+                                        | ((u64) comp << K.s_cp);
+              rec128 sd;
+              sd.lo = X | (Y << K.p_band);
+              sd.hi = Y >> (64 - K.p_band);
+              if (gbase + o < capacity) st_rec(seeds + gbase + o,sd);
+            }
+          __syncwarp();
         }
     }
 
-  //  block-level compaction
-  int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  unsigned inc = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1)
-    { unsigned t = __shfl_up_sync(0xffffffffu,inc,o);
-      if (lane >= o) inc += t;
-    }
-  if (lane == 31) wsum[wp] = inc;
+  if (lane == 0) s_sum[wp] = sumlen;
   __syncthreads();
-  unsigned pre = 0, tot = 0;
-#pragma unroll
-  for (int k = 0; k < MG_THREADS/32; k++)
-    { if (k < wp) pre += wsum[k];
-      tot += wsum[k];
-    }
   if (threadIdx.x == 0)
-    blockbase = tot ? atomicAdd(&counters[0],(unsigned long long) tot) : 0ull;
-  //  sum of plen (for the "ave len" statistic, FastGA.c:2485-2492)
-  unsigned long long pl = (unsigned long long) cnt * plen;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    pl += __shfl_down_sync(0xffffffffu,pl,o);
-  if (lane == 0 && pl) atomicAdd(&counters[1],pl);
-  __syncthreads();
-  if (cnt == 0) return;
-
-  unsigned long long o = blockbase + pre + inc - cnt;
-  if (o + cnt > capacity) return;                         // host sees counters[0] > capacity, retries
-  unsigned icont = (unsigned) (r1.lo >> 32) & 0x7fff;
-  long long ipost = (long long) (unsigned) r1.lo;
-  for (unsigned k = 0; k < cnt; k++)
-    { rec128 r2 = ld_rec(T2 + lowi + k);
-      unsigned cs = (unsigned) (r2.lo >> 32) & 0xffff;
-      st_rec(seeds + o + k,
-             make_seed(L,cs >> 15,icont,cs & 0x7fff,ipost,(long long) (unsigned) r2.lo,plen));
+    { unsigned long long t = 0;
+      for (int k = 0; k < MG_WARPS; k++) t += s_sum[k];
+      if (t) atomicAdd(&counters[1],t);
     }
 }
 
@@ -186,13 +198,18 @@ extern "C" int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2
   if (seed_key_bits(L) > 128 || freq < 1 || freq > 255) return FGB_ERR_LIMIT;
   if (n1 >= 0xffffffffll) return FGB_ERR_LIMIT;
   CUDA_TRY(cudaMemsetAsync(d_counters,0,16,st));
+  seed_pack K;
+  K.p_band = 12 + anti_bits;
+  K.s_jc = band_bits; K.s_ic = band_bits + jc_bits; K.s_cp = band_bits + jc_bits + ic_bits;
+  K.amxpos = amxpos; K.bmxpos = bmxpos; K.maxdag = amxpos + bmxpos;
+  if (K.s_cp + 1 > 64 || K.p_band >= 64 || K.p_band < 13) return FGB_ERR_LIMIT;
   if (n1 > 0)
-    { unsigned nb = (unsigned) ((n1 + MG_THREADS - 1) / MG_THREADS);
+    { unsigned nb = (unsigned) ((n1 + MG_WARPS*MG_TILE - 1) / (MG_WARPS*MG_TILE));
       cudaEvent_t ea, eb;
       cudaEventCreate(&ea); cudaEventCreate(&eb);
       cudaEventRecord(ea,st);
       adaptamer_merge_kernel<<<nb,MG_THREADS,0,st>>>((const rec128 *) d_T1,(unsigned) n1,
-                                                     (const rec128 *) d_T2,d_pstart2,freq,L,
+                                                     (const rec128 *) d_T2,d_pstart2,freq,K,
                                                      (rec128 *) d_seeds,(unsigned long long) capacity,
                                                      d_counters);
       cudaEventRecord(eb,st);

@@ -344,6 +344,9 @@ class Alignments:
 
     def canonical_lines(self):
         """One text line per alignment in ONEview's form 'A .. | R | D .. | T .. | X ..', sorted."""
+        return sorted(self.canonical_lines_unsorted())
+
+    def canonical_lines_unsorted(self):
         out = []
         for i in range(len(self)):
             comp, ar, br, ab, bb, ae, be, df, tl = (int(x) for x in self.fields[i])
@@ -355,7 +358,6 @@ class Alignments:
             line += " | T %d" % (tl // 2) + "".join(" %d" % v for v in t[1::2])
             line += " | X %d" % (tl // 2) + "".join(" %d" % v for v in t[0::2])
             out.append(line)
-        out.sort()
         return out
 
 

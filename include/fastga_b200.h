@@ -130,6 +130,7 @@ long long fgb_sort128_tmp_bytes(long long n);
 
 /* ---- housekeeping ---- */
 int  fgb_device_ready(void);
+void fgb_release_cache(void);      /* return cached device blocks to the driver */
 void fgb_timings_reset(void);
 void fgb_timings_get(fgb_timings *out);
 
