@@ -64,6 +64,7 @@ struct ext_params
   unsigned char *out; u64 out_cap; u64 *out_used;
   u64 *counters;                                       // 0 hits 1 LA calls 2 waves 3 cells 4 records
   unsigned *failed; unsigned *nfailed;                 // triples that overflowed an arena
+  unsigned char *bigstate;                             // wide-band kernel: per-warp wave state in HBM
 };
 
 struct Ctx
@@ -75,7 +76,8 @@ struct Ctx
   u64 nwaves, ncells, cyc_wave, cyc_extract;
 };
 
-#define IX(k) ((k) & (EX_W-1))
+#define EX_WBIG      8192                // diagonals of wave state per warp in the wide-band retry kernel (HBM)
+#define IX(k) ((k) & (W-1))
 
 static __device__ __forceinline__ u64 get_bits(const rec128 &r, int pos, int n)
 { u64 v;
@@ -170,7 +172,7 @@ static __device__ __forceinline__ int warp_prefix_max_excl(int v, int lane)
 //  One wave pass (direction s) from anti-diagonal mida over diagonals [low,hgh].
 //  Outputs the trim point (original coordinates), its diffs and the pebble chain head.
 
-template<int s>
+template<int s, int W>
 static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, int maxp,
                            const int aoff, int &endx, int &endy, int &diffs, int &trimha_out)
 { const int lane = threadIdx.x & 31;
@@ -181,7 +183,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
 
   if (s > 0) { lowk = low;  hghk = hgh;  minpn = minp;  maxpn = maxp; }
   else       { lowk = -hgh; hghk = -low; minpn = -maxp; maxpn = -minp; }
-  if (hghk - lowk + 5 > EX_W) return ST_BAND;
+  if (hghk - lowk + 5 > W) return ST_BAND;
 
   c.avail = 0;
   int dif = 0, more = 1;
@@ -255,7 +257,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
   //  successive waves (align.c:546-800 / :1077-1330)
   while (more && lasta >= besta - TRIM_MLAG)
     { lowk -= 1; hghk += 1;
-      if (hghk - lowk + 5 > EX_W) return ST_BAND;
+      if (hghk - lowk + 5 > W) return ST_BAND;
       if (lane == 0)
         { if (lowk >= minpn) { c.NA[IX(lowk)] = c.NA[IX(lowk+1)]; c.V[IX(lowk)] = FRESH; }
           if (hghk <= maxpn) { c.NA[IX(hghk)] = c.NA[IX(hghk-1)]; c.V[IX(hghk)] = FRESH; }
@@ -546,6 +548,7 @@ struct LAres { int abpos, bbpos, aepos, bepos, diffs, ftlen, rtlen; };
 
 //  Local_Alignment (align.c:1423-1576), lbord = hbord = -1 and A != B (non-self).
 
+template<int W>
 static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int anti, LAres &R)
 { int minp = -INT_MAX, maxp = INT_MAX;
   int aoff = acomp ? (c.alen % c.tspace) : 0;
@@ -555,7 +558,7 @@ static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int a
 
   R.ftlen = R.rtlen = 0; R.diffs = 0;
   long long tk = clock64();
-  st = wave<1>(c,low,hgh,anti,minp,maxp,aoff,ex,ey,df,tha);
+  st = wave<1,W>(c,low,hgh,anti,minp,maxp,aoff,ex,ey,df,tha);
   if (st) return st;
   c.cyc_wave += (u64) (clock64() - tk); tk = clock64();
   st = fwd_extract(c,tha,anti,ex,ey,df,R.ftlen,rootd);
@@ -567,7 +570,7 @@ static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int a
   bool fshort = ((R.aepos + R.bepos) - anti < DUB_TRIM);
 
   tk = clock64();
-  st = wave<-1>(c,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
+  st = wave<-1,W>(c,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
   if (st) return st;
   c.cyc_wave += (u64) (clock64() - tk); tk = clock64();
   st = rev_extract(c,tha,aoff,ex,ey,df,R.ftlen,R.rtlen);
@@ -586,7 +589,7 @@ static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int a
         { low  = R.abpos - R.bbpos;
           anti = R.abpos + R.bbpos;
           R.ftlen = R.rtlen = 0;
-          st = wave<1>(c,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
+          st = wave<1,W>(c,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
           if (st) return st;
           st = fwd_extract(c,tha,anti,ex,ey,df,R.ftlen,rootd);
           if (st) return st;
@@ -597,7 +600,7 @@ static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int a
     { low  = R.aepos - R.bepos;
       anti = R.aepos + R.bepos;
       R.ftlen = R.rtlen = 0; R.diffs = 0;
-      st = wave<-1>(c,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
+      st = wave<-1,W>(c,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
       if (st) return st;
       st = rev_extract(c,tha,aoff,ex,ey,df,0,R.rtlen);
       if (st) return st;
@@ -767,7 +770,7 @@ static __device__ int scan_triple(const ext_params &P, Ctx &c, unsigned j, unsig
                                 }
                             }
                           LAres R;
-                          int st = local_alignment(c,comp,dgmin,dgmax,(int) amid,R);
+                          int st = local_alignment<EX_W>(c,comp,dgmin,dgmax,(int) amid,R);
                           if (st) return st;
                           nla += 1;
                           int ab = R.abpos, bb = R.bbpos, ae = R.aepos, be = R.bepos;
@@ -812,6 +815,7 @@ struct TripleCtx
   long long cdiag, alen, blen, mlen, doffset, aoffset, alast;
 };
 
+template<int W>
 static __device__ int handle_hit(const ext_params &P, Ctx &c, TripleCtx &T, long long alow,
                                  long long ahgh, int dgmin, int dgmax, u64 &nla)
 { long long amid, eant;
@@ -834,7 +838,7 @@ static __device__ int handle_hit(const ext_params &P, Ctx &c, TripleCtx &T, long
                 }
             }
           LAres R;
-          int st = local_alignment(c,T.comp,dgmin,dgmax,(int) amid,R);
+          int st = local_alignment<W>(c,T.comp,dgmin,dgmax,(int) amid,R);
           if (st) return st;
           nla += 1;
           int rlen = R.aepos - R.abpos;                    // same after the ACOMP flip
@@ -853,6 +857,7 @@ static __device__ int handle_hit(const ext_params &P, Ctx &c, TripleCtx &T, long
 
 #define SCAN_SMEM 1536          // per warp: La Ua (32 x i64) Lm Um (32 x int) Ma (64 x i64) Mm (64 x int)
 
+template<int W>
 static __device__ int scan_triple_warp(const ext_params &P, Ctx &c, unsigned j, unsigned &nhit_out,
                                        u64 &nla, unsigned char *wsm)
 { const int lane = threadIdx.x & 31;
@@ -994,7 +999,7 @@ static __device__ int scan_triple_warp(const ext_params &P, Ctx &c, unsigned j, 
               long long ahgh = __shfl_sync(FULL,Pl,q);
               if (cov >= P.chain_min && (mix != 1 || T.isnew))
                 { nhit_out += 1;
-                  int st = handle_hit(P,c,T,alow,ahgh,dmin,dmax,nla);
+                  int st = handle_hit<W>(P,c,T,alow,ahgh,dmin,dmax,nla);
                   if (st) return st;
                 }
               seglo = q; cont = false;
@@ -1006,7 +1011,7 @@ static __device__ int scan_triple_warp(const ext_params &P, Ctx &c, unsigned j, 
   //  the scan's final iteration (anti = MAX) closes the last chain
   if (c_cov >= P.chain_min && (c_mix != 1 || T.isnew))
     { nhit_out += 1;
-      int st = handle_hit(P,c,T,c_alow,carryP,c_dgmin,c_dgmax,nla);
+      int st = handle_hit<W>(P,c,T,c_alow,carryP,c_dgmin,c_dgmax,nla);
       if (st) return st;
     }
   return ST_OK;
@@ -1088,22 +1093,28 @@ __global__ void prefilter_kernel(ext_params P, unsigned *__restrict__ work_long,
     work_short[atomicAdd(nwork+1,1u)] = j;
 }
 
-#define STATE_BYTES (EX_W*(4*4+8) + 32 + SCAN_SMEM)
+#define WSTATE_BYTES(W) ((W)*(4*4+8) + 32)
+#define STATE_BYTES (WSTATE_BYTES(EX_W) + SCAN_SMEM)
+#define BIG_SMEM_PER_WARP (SCAN_SMEM)
 #define TT_BYTES    ((256+128)*4)
 
+template<int W>
 __global__ void __launch_bounds__(EX_WARPS*32)
 extend_kernel(ext_params P)
 { extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const long long gw = (long long) blockIdx.x * EX_WARPS + wp;
-  unsigned char *sb = smem + (size_t) wp * STATE_BYTES;
+  const size_t per_warp = (W == EX_W) ? STATE_BYTES : BIG_SMEM_PER_WARP;
+  unsigned char *sb = (W == EX_W) ? (smem + (size_t) wp * STATE_BYTES)
+                                  : (P.bigstate + (size_t) gw * WSTATE_BYTES(EX_WBIG));
   Ctx c;
   c.T  = (u64 *) sb;
-  c.V  = (int *) (sb + EX_W*8);
-  c.HA = c.V + EX_W; c.HM = c.HA + EX_W; c.NA = c.HM + EX_W;
-  c.carry = c.NA + EX_W;
-  rec128 *stagebuf = (rec128 *) (sb + EX_W*(4*4+8) + 32);
-  { short2 *tt = (short2 *) (smem + (size_t) EX_WARPS * STATE_BYTES);
+  c.V  = (int *) (sb + W*8);
+  c.HA = c.V + W; c.HM = c.HA + W; c.NA = c.HM + W;
+  c.carry = c.NA + W;
+  rec128 *stagebuf = (W == EX_W) ? (rec128 *) (sb + WSTATE_BYTES(EX_W))
+                                 : (rec128 *) (smem + (size_t) wp * BIG_SMEM_PER_WARP);
+  { short2 *tt = (short2 *) (smem + (size_t) EX_WARPS * per_warp);
     int msc = 1000 - P.dscore, dsc = P.dscore;
     for (int u = threadIdx.x; u < 384; u += blockDim.x)
       { int nb = (u < 256) ? 8 : 7, x = (u < 256) ? u : u - 256, sc = 0, mxp = 0;
@@ -1133,7 +1144,7 @@ extend_kernel(ext_params P)
       w = __shfl_sync(FULL,w,0);
       if (w >= (unsigned) P.nwork) break;
       unsigned j = P.work[w], nh = 0;
-      int st = scan_triple_warp(P,c,j,nh,nla,(unsigned char *) stagebuf);
+      int st = scan_triple_warp<W>(P,c,j,nh,nla,(unsigned char *) stagebuf);
       if (st != ST_OK)
         { if (lane == 0)
             { unsigned o = atomicAdd(P.nfailed,1u);
@@ -1296,9 +1307,10 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&nsm,cudaDevAttrMultiProcessorCount,dev);
       size_t smem = (size_t) EX_WARPS * STATE_BYTES + TT_BYTES;
-      CUDA_TRY(cudaFuncSetAttribute(extend_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem));
+      size_t smem_big = (size_t) EX_WARPS * BIG_SMEM_PER_WARP + TT_BYTES;
+      CUDA_TRY(cudaFuncSetAttribute(extend_kernel<EX_W>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem));
       int bps = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps,extend_kernel,EX_WARPS*32,smem));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps,extend_kernel<EX_W>,EX_WARPS*32,smem));
       if (bps < 1) bps = 1;
       long long nblocks = (long long) nsm * bps;
       long long want = ((long long) nwork + EX_WARPS - 1) / EX_WARPS;
@@ -1326,10 +1338,18 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           P.stage = d_stage; P.stage_bytes = stage_bytes;
           P.out = d_out; P.out_cap = out_cap;
           P.work = d_list; P.nwork = (int) nlist;
+          unsigned char *d_big = NULL;
+          if (attempt > 0)                                     // retries: wide-band kernel, state in HBM
+            { CUDA_TRY(fgb_dmalloc((void **) &d_big,(size_t) nwarps * WSTATE_BYTES(EX_WBIG),st));
+              P.bigstate = d_big;
+            }
           tr_mark("extend: arenas allocated");
           CUDA_TRY(cudaMemsetAsync(d_misc+1,0,8,st));          // queue, nfailed
           { ev_timer t(1,st);
-            extend_kernel<<<(unsigned) nblocks,EX_WARPS*32,smem,st>>>(P);
+            if (attempt == 0)
+              extend_kernel<EX_W><<<(unsigned) nblocks,EX_WARPS*32,smem,st>>>(P);
+            else
+              extend_kernel<EX_WBIG><<<(unsigned) nblocks,EX_WARPS*32,smem_big,st>>>(P);
           }
           fgb_count_launch(1);
           CUDA_TRY(cudaGetLastError());
@@ -1337,7 +1357,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           CUDA_TRY(cudaMemcpyAsync(misc,d_misc,32,cudaMemcpyDeviceToHost,st));
           CUDA_TRY(cudaStreamSynchronize(st));
           tr_mark("extend: kernel done");
-          fgb_dfree(d_cells,st); fgb_dfree(d_stage,st);
+          fgb_dfree(d_cells,st); fgb_dfree(d_stage,st); fgb_dfree(d_big,st);
           out_used = ((u64) misc[5] << 32) | misc[4];
           unsigned nfailed = misc[2];
           if (out_used > out_cap)

@@ -187,12 +187,185 @@ sort_scatter_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, lon
     }
 }
 
+/***********************************************************************************************
+ *  Onesweep pass: one kernel per key byte reads every record once and writes it once.
+ *   - the GLOBAL digit histogram of a pass is produced by the previous pass (each tile counts
+ *     the next byte while it holds the records; the first pass has a small histogram kernel);
+ *   - the tile's base inside each digit bucket comes from a decoupled look-back over the
+ *     per-tile digit counts (status word = count | flag<<62; 1 = tile aggregate, 2 = inclusive
+ *     prefix), tiles being handed out by an atomic ticket so every predecessor is running.
+ **********************************************************************************************/
+
+#define ST_AGG  (1ull << 62)
+#define ST_INC  (2ull << 62)
+#define ST_MASK ((1ull << 62) - 1)
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_ghist_kernel(const rec128 *__restrict__ in, long long n, int byte, unsigned long long *__restrict__ ghist)
+{ __shared__ unsigned h[256];
+  int tid = threadIdx.x;
+  if (tid < 256) h[tid] = 0;
+  __syncthreads();
+  const unsigned long long *half = reinterpret_cast<const unsigned long long *>(in) + (byte >= 8);
+  int sh = 8*(byte & 7);
+  for (long long tile0 = (long long) blockIdx.x * SORT_TILE; tile0 < n; tile0 += (long long) gridDim.x * SORT_TILE)
+    {
+#pragma unroll
+      for (int it = 0; it < SORT_ITEMS; it++)
+        { long long idx = tile0 + it*SORT_THREADS + tid;
+          bool valid = idx < n;
+          unsigned d = 0x100u | (tid & 31);
+          if (valid) d = (unsigned) ((half[2*idx] >> sh) & 0xff);
+          unsigned peers = __match_any_sync(0xffffffffu,d);
+          if (valid && (tid & 31) == __ffs(peers)-1) atomicAdd(&h[d],__popc(peers));
+        }
+    }
+  __syncthreads();
+  if (tid < 256 && h[tid]) atomicAdd(&ghist[tid],(unsigned long long) h[tid]);
+}
+
+//  exclusive scan of a 256-bin global histogram -> bin bases; zeroes the histogram of the pass
+//  after it and the tile ticket.
+__global__ void sort_bins_kernel(const unsigned long long *__restrict__ ghist, unsigned long long *__restrict__ binbase,
+                                 unsigned long long *__restrict__ nexthist, unsigned *__restrict__ ticket)
+{ __shared__ unsigned long long ws[8];
+  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  unsigned long long v = ghist[tid], inc = v;
+  for (int o = 1; o < 32; o <<= 1)
+    { unsigned long long t = __shfl_up_sync(0xffffffffu,inc,o);
+      if (lane >= o) inc += t;
+    }
+  if (lane == 31) ws[w] = inc;
+  __syncthreads();
+  unsigned long long pre = 0;
+  for (int i = 0; i < w; i++) pre += ws[i];
+  binbase[tid] = pre + inc - v;
+  nexthist[tid] = 0;
+  if (tid == 0) *ticket = 0;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, long long n, int byte,
+                     int next_byte /* -1: none */, const unsigned long long *__restrict__ binbase,
+                     unsigned long long *__restrict__ nexthist, unsigned long long *status /* [ntiles][256] */,
+                     unsigned *__restrict__ ticket)
+{ extern __shared__ __align__(16) unsigned char smem_raw[];
+  rec128   *tile   = reinterpret_cast<rec128 *>(smem_raw);
+  unsigned *wcount = reinterpret_cast<unsigned *>(tile + SORT_TILE);   // [SORT_WARPS][256]
+  unsigned *bexcl  = wcount + SORT_WARPS*256;                           // [256]
+  unsigned *nhist  = bexcl + 256;                                       // [256] next byte
+  unsigned *wtot   = nhist + 256;                                       // [8]
+  unsigned long long *gbase = reinterpret_cast<unsigned long long *>(wtot + 8);   // [256]
+  __shared__ unsigned tile_s;
+
+  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) tile_s = atomicAdd(ticket,1u);
+  for (int i = tid; i < SORT_WARPS*256; i += SORT_THREADS) wcount[i] = 0;
+  if (tid < 256) nhist[tid] = 0;
+  __syncthreads();
+  const unsigned tileid = tile_s;
+  long long tile0 = (long long) tileid * SORT_TILE;
+  long long rem = n - tile0;
+  int cnt = rem < SORT_TILE ? (int) rem : SORT_TILE;
+
+  rec128   r[SORT_ITEMS];
+  unsigned rank[SORT_ITEMS];
+  int base = w*(32*SORT_ITEMS);
+  unsigned *myc = wcount + w*256;
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; it++)
+    { int idx = base + it*32 + lane;
+      bool valid = idx < cnt;
+      unsigned d = 0x100u | lane;
+      if (valid)
+        { r[it] = ld_rec(in + tile0 + idx);
+          d = rec_byte(r[it],byte);
+        }
+      unsigned peers = __match_any_sync(0xffffffffu,d);
+      int leader = __ffs(peers)-1;
+      unsigned b = 0;
+      if (valid && lane == leader)
+        { b = myc[d];
+          myc[d] = b + __popc(peers);
+        }
+      b = __shfl_sync(0xffffffffu,b,leader);
+      rank[it] = b + __popc(peers & lanemask_lt());
+      if (next_byte >= 0)
+        { unsigned d2 = valid ? rec_byte(r[it],next_byte) : (0x100u | lane);
+          unsigned p2 = __match_any_sync(0xffffffffu,d2);
+          if (valid && lane == __ffs(p2)-1) atomicAdd(&nhist[d2],__popc(p2));
+        }
+      __syncwarp();
+    }
+  __syncthreads();
+
+  unsigned c = 0, inc = 0;
+  if (tid < 256)
+    { unsigned sum = 0;
+#pragma unroll
+      for (int ww = 0; ww < SORT_WARPS; ww++)
+        { unsigned t = wcount[ww*256+tid];
+          wcount[ww*256+tid] = sum;
+          sum += t;
+        }
+      c = sum;
+      //  publish the tile aggregate, then look back for the exclusive prefix of this digit
+      volatile unsigned long long *stt = status;
+      unsigned long long *mine = status + (unsigned long long) tileid*256 + tid;
+      if (tileid == 0)
+        atomicExch(mine,ST_INC | c);
+      else
+        atomicExch(mine,ST_AGG | c);
+      unsigned long long excl = 0;
+      for (long long t = (long long) tileid - 1; t >= 0; )
+        { unsigned long long v = stt[(unsigned long long) t*256 + tid];
+          if ((v >> 62) == 0) continue;                        // predecessor not there yet: spin
+          excl += v & ST_MASK;
+          if (v & ST_INC) break;
+          t -= 1;
+        }
+      if (tileid != 0) atomicExch(mine,ST_INC | (excl + c));
+      inc = warp_incl_scan(c,lane);
+      if (lane == 31) wtot[w] = inc;
+      gbase[tid] = binbase[tid] + excl;                        // minus bexcl below
+      if (next_byte >= 0 && nhist[tid]) atomicAdd(&nexthist[tid],(unsigned long long) nhist[tid]);
+    }
+  __syncthreads();
+  if (tid < 256)
+    { unsigned pre = 0;
+      for (int i = 0; i < w; i++) pre += wtot[i];
+      unsigned ex = pre + inc - c;
+      bexcl[tid] = ex;
+      gbase[tid] -= ex;
+    }
+  __syncthreads();
+
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; it++)
+    { int idx = base + it*32 + lane;
+      if (idx < cnt)
+        { unsigned d = rec_byte(r[it],byte);
+          st_rec(tile + (bexcl[d] + myc[d] + rank[it]),r[it]);
+        }
+    }
+  __syncthreads();
+
+  for (int p = tid; p < cnt; p += SORT_THREADS)
+    { rec128 v = ld_rec(tile + p);
+      unsigned d = rec_byte(v,byte);
+      st_rec(out + (gbase[d] + p),v);
+    }
+}
+
+static const size_t ONESWEEP_SMEM = SORT_TILE*sizeof(rec128) + (SORT_WARPS*256 + 256 + 256 + 8)*sizeof(unsigned)
+                                    + 256*sizeof(unsigned long long);
+
 static const size_t SCATTER_SMEM = SORT_TILE*sizeof(rec128) + (SORT_WARPS*256 + 256 + 256 + 8)*sizeof(unsigned);
 
 extern "C" long long fgb_sort128_tmp_bytes(long long n)
 { long long ntiles = (n + SORT_TILE - 1) / SORT_TILE;
   if (ntiles < 1) ntiles = 1;
-  return (256*ntiles + 512) * (long long) sizeof(unsigned);
+  return 256*ntiles*8 + (3*256 + 16)*8;          // look-back status + 2 histograms + bin bases + ticket
 }
 
 //  Sorts n records on key bytes [byte_lo,byte_hi) of the 128-bit little-endian value, stable.
@@ -209,24 +382,32 @@ extern "C" int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo
   if (tmp_bytes < fgb_sort128_tmp_bytes(n)) return FGB_ERR_ARG;
 
   int ntiles = (int) ((n + SORT_TILE - 1) / SORT_TILE);
-  unsigned *blockhist = (unsigned *) d_tmp;
-  unsigned *rowtotal  = blockhist + 256ll*ntiles;
-  unsigned *binbase   = rowtotal + 256;
+  unsigned long long *status = (unsigned long long *) d_tmp;
+  unsigned long long *hist[2] = { status + 256ull*ntiles, status + 256ull*ntiles + 256 };
+  unsigned long long *binbase = status + 256ull*ntiles + 512;
+  unsigned *ticket = (unsigned *) (binbase + 256);
 
   static bool attr_set = false;
   if (!attr_set)
-    { CUDA_TRY(cudaFuncSetAttribute(sort_scatter_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int) SCATTER_SMEM));
+    { CUDA_TRY(cudaFuncSetAttribute(sort_onesweep_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int) ONESWEEP_SMEM));
       attr_set = true;
     }
 
   rec128 *src = (rec128 *) d_a, *dst = (rec128 *) d_b;
+  CUDA_TRY(cudaMemsetAsync(hist[0],0,256*8,st));
+  { int nb = ntiles < 1184 ? ntiles : 1184;
+    sort_ghist_kernel<<<nb,SORT_THREADS,0,st>>>(src,n,byte_lo,hist[0]);
+    fgb_count_launch(1);
+  }
+  int cur = 0;
   for (int b = byte_lo; b < byte_hi; b++)
-    { sort_hist_kernel<<<ntiles,SORT_THREADS,0,st>>>(src,n,b,blockhist,ntiles);
-      sort_rowscan_kernel<<<256,1024,0,st>>>(blockhist,ntiles,rowtotal);
-      sort_binbase_kernel<<<1,256,0,st>>>(rowtotal,binbase);
-      sort_scatter_kernel<<<ntiles,SORT_THREADS,SCATTER_SMEM,st>>>(src,dst,n,b,blockhist,binbase,ntiles);
-      fgb_count_launch(4);
+    { sort_bins_kernel<<<1,256,0,st>>>(hist[cur],binbase,hist[cur^1],ticket);
+      CUDA_TRY(cudaMemsetAsync(status,0,256ull*ntiles*8,st));
+      sort_onesweep_kernel<<<ntiles,SORT_THREADS,ONESWEEP_SMEM,st>>>(src,dst,n,b,(b+1 < byte_hi) ? b+1 : -1,
+                                                                   binbase,hist[cur^1],status,ticket);
+      fgb_count_launch(2);
+      cur ^= 1;
       rec128 *t = src; src = dst; dst = t;
       *result_in_b ^= 1;
     }

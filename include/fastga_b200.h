@@ -128,6 +128,14 @@ int  fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo, int byte
                         void *d_tmp, long long tmp_bytes, int *result_in_b, void *stream);
 long long fgb_sort128_tmp_bytes(long long n);
 
+/* ---- the reference's own extern sort entry points, same signatures, host byte records in
+ *      place (MSDsort.c:404 built -DLCPs, GIXmake.c:117; RSDsort.c:292, FastGA.c:149) ---- */
+typedef struct { int beg; int end; long long off; } fgb_range;      /* Range, RSDsort.c:254-258 */
+void fgb_msd_sort(unsigned char *array, long long nelem, int rsize, int ksize,
+                  long long *part, int beg, int end, int nthreads);
+int  fgb_rmsd_sort(unsigned char *array, long long nelem, int rsize, int ksize, int nparts,
+                   long long *part, int nthreads, fgb_range *range);
+
 /* ---- housekeeping ---- */
 int  fgb_device_ready(void);
 void fgb_release_cache(void);      /* return cached device blocks to the driver */

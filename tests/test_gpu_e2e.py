@@ -78,3 +78,42 @@ def test_example_hap1_hap2_bit_exact():
     assert alns.nraw == gold["alns"]
     assert len(alns) == gold["kept"]
     assert ol.md5_lines(alns.canonical_lines()) == gold["aln_md5"]
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
+def test_gix_files_match_reference_gixmake():
+    """the .ktab entry stream, the stub index and the part split produced from the
+    device table equal what the reference GIXmake writes (equal k-mers canonicalised), and the
+    reference's own GIX files import back into the identical device table."""
+    A, _ = synth.make_pair(17, 2_500_000, 5, 0.05, sv_every=100_000)
+    with tempfile.TemporaryDirectory() as wd:
+        formats.write_fasta(os.path.join(wd, "A.fasta"), synth.scaffolds_of(A, "sa", 2))
+        ol.run_ref(["GIXmake", "-T4", "-P" + wd, "A"], cwd=wd)
+        ref = formats.read_gix(os.path.join(wd, "A.gix"))
+    g = formats.genome_from_arrays(A)
+    dg = lib.DeviceGenome(g)
+    gx = lib.DeviceGix.build(dg)
+    tab, pstart, buck = gx.download()
+    assert gx.n == ref.n
+    pb, cb = formats.gix_bytes(g)
+    assert (pb, cb) == (ref.post_bytes, ref.cont_bytes) == (gx.post_bytes, max(gx.cont_bytes, cb))
+    assert np.array_equal(pstart[1:].astype(np.int64), ref.index)
+    assert np.array_equal(dg.perm, ref.perm[:g.ncontig])
+    # part split from the sampler histogram (GIXmake.c:655-691)
+    nparts = formats.gix_nparts(g.seqtot, max(g.ncontig, 4), pb, cb, nthreads=4)
+    assert nparts == ref.nparts
+    ks = formats.ksplit_from_buckets(buck, nparts)
+    part_first = np.array([int(pstart[k << 14]) for k in ks[:-1]], dtype=np.int64)
+    part_n = np.diff(np.concatenate([part_first, [gx.n]]))
+    assert list(part_n) == ref.part_n
+    ent = gx.export_ktab(part_first) if gx.cont_bytes == cb else None
+    if ent is None:     # device handle counts real contigs only; re-encode with the padded width
+        ent = formats.ktab_entries_from_table(tab, pb, cb, part_first)
+    E = ref.esize
+    assert np.array_equal(formats.canonical_ktab(ent, E, ref.index), formats.canonical_ktab(ref.entries, E, ref.index))
+    # and the reverse direction: reference files -> device table
+    imp = lib.DeviceGix.import_ktab(ref)
+    itab, ipstart, _ = imp.download()
+    assert np.array_equal(ipstart, pstart)
+    key = lambda t: np.lexsort((t[:, 0] & np.uint64(0xffffffffffff), t[:, 0] >> np.uint64(48), t[:, 1]))
+    assert np.array_equal(itab[key(itab)], tab[key(tab)])
