@@ -67,13 +67,25 @@ struct ext_params
   unsigned char *bigstate;                             // wide-band kernel: per-warp wave state in HBM
 };
 
+//  Mailbox of a warp pair in shared memory: the primary warp posts the reverse pass of a
+//  Local_Alignment as soon as its start diagonal is final; the helper warp runs the wave and
+//  returns the trim point (the pebble chain stays in the helper's arena).
+struct Mbox
+{ volatile int state;                    // 0 idle, 1 job posted, 2 done, 3 exit
+  int low, anti, minp, maxp, aoff;
+  int status, endx, endy, diffs, trimha;
+  int alen, blen;
+  const unsigned *A, *B;
+};
+
 struct Ctx
 { const unsigned *A, *B; int alen, blen; long long anw, bnw;
-  int *V, *HA, *HM, *NA; u64 *T; int *carry;
-  Peb *cells; int cmax, avail;
+  int *V, *HA, *HM, *NA, *RD; u64 *T; int *carry;
+  Mbox *mbox;                            // pair mailbox (primary -> helper warp), NULL = none
+  Peb *cells; const Peb *pcells; int cmax, avail;      // pcells: the partner warp's arena
   unsigned char *fstage, *rstage; int smax;
   int tspace, path_ave; const short *score, *table; const short2 *tt1, *tt2;
-  u64 nwaves, ncells, cyc_wave, cyc_extract;
+  u64 nwaves, ncells, cyc_wave, cyc_extract, njobs, nmiss, cyc_wait;
 };
 
 #define EX_WBIG      8192                // diagonals of wave state per warp in the wide-band retry kernel (HBM)
@@ -174,7 +186,8 @@ static __device__ __forceinline__ int warp_prefix_max_excl(int v, int lane)
 
 template<int s, int W>
 static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, int maxp,
-                           const int aoff, int &endx, int &endy, int &diffs, int &trimha_out)
+                           const int aoff, int &endx, int &endy, int &diffs, int &trimha_out,
+                           bool *posted = NULL)
 { const int lane = threadIdx.x & 31;
   const unsigned lt = lanemask_lt();
   const int FRESH = (s > 0) ? -1 : -INT_MAX;
@@ -189,7 +202,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
   int dif = 0, more = 1;
   int besta = s*mida, trima = besta, lasta = besta;
   int bestx = s*((mida+hgh)>>1), trimx = bestx;
-  int trimd = 0, trimha = 0;
+  int trimd = 0, trimha = 0, trimrd = 0;
   int aclip = INT_MAX, bclip = -INT_MAX;
   bool anyhit = false;
 
@@ -236,6 +249,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
           besta = trima = lasta = __shfl_sync(FULL,cc,L);
           bestx = trimx = __shfl_sync(FULL,xn,L);
           trimha = __shfl_sync(FULL,ha,L);
+          trimrd = top - L;                               // wave 0: the root is the diagonal itself
         }
       unsigned hb = __ballot_sync(FULL,act && flag == 1);
       unsigned hq = __ballot_sync(FULL,act && flag == 2);
@@ -243,7 +257,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
       if (hq) { anyhit = true; aclip = top - (31 - __clz(hq)); }
       if (act)
         { c.V[IX(kk)] = cc; c.T[IX(kk)] = PATH_INT; c.HA[IX(kk)] = ha; c.HM[IX(kk)] = hm;
-          c.NA[IX(kk)] = nan;
+          c.NA[IX(kk)] = nan; c.RD[IX(kk)] = kk;
         }
     }
   __syncwarp();
@@ -268,12 +282,12 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
       if (lane == 0)
         { c.V[IX(hghk+1)] = FRESH; c.V[IX(lowk-1)] = FRESH;
           c.carry[0] = FRESH; c.carry[1] = (int) (unsigned) PATH_INT;
-          c.carry[2] = (int) (PATH_INT >> 32); c.carry[3] = -1; c.carry[4] = 0;
+          c.carry[2] = (int) (PATH_INT >> 32); c.carry[3] = -1; c.carry[4] = 0; c.carry[5] = 0;
         }
       __syncwarp();
       c.nwaves += 1; c.ncells += (u64) (hghk - lowk + 1);
       const bool single = (hghk - lowk < 32);
-      int lastcc = 0, lasttop = hghk;
+      int lastcc = 0, lasttop = hghk, lastrd = 0;
 
       for (int top = hghk; top >= lowk; top -= 32)
         { int kk = top - lane;
@@ -284,24 +298,25 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
           int pred, cc;
           if (ac < am) { if (am < ap) { pred = 1; cc = ap+1; } else { pred = -1; cc = am+1; } }
           else         { if (ac < ap) { pred = 1; cc = ap+1; } else { pred = 0;  cc = ac+2; } }
-          u64 b; int ha, hm;
+          u64 b; int ha, hm, rd;
           if (pred == 1 && lane == 0)
             { b  = (u64) (unsigned) c.carry[1] | ((u64) (unsigned) c.carry[2] << 32);
-              ha = c.carry[3]; hm = c.carry[4];
+              ha = c.carry[3]; hm = c.carry[4]; rd = c.carry[5];
             }
           else
             { int si = IX(kk+pred);
-              b = c.T[si]; ha = c.HA[si]; hm = c.HM[si];
+              b = c.T[si]; ha = c.HA[si]; hm = c.HM[si]; rd = c.RD[si];
             }
           int nan = c.NA[IX(kk)];
           //  lane 31's own old state is the next chunk's "kk+1"
-          int  o_v = 0, o_ha = 0, o_hm = 0; u64 o_t = 0;
+          int  o_v = 0, o_ha = 0, o_hm = 0, o_rd = 0; u64 o_t = 0;
           const bool morechunks = (top - 32 >= lowk);
-          if (lane == 31 && morechunks) { o_v = ac; o_t = c.T[IX(kk)]; o_ha = c.HA[IX(kk)]; o_hm = c.HM[IX(kk)]; }
+          if (lane == 31 && morechunks)
+            { o_v = ac; o_t = c.T[IX(kk)]; o_ha = c.HA[IX(kk)]; o_hm = c.HM[IX(kk)]; o_rd = c.RD[IX(kk)]; }
           __syncwarp();                              // all reads of old state done
           if (lane == 31 && morechunks)
             { c.carry[0] = o_v; c.carry[1] = (int) (unsigned) o_t; c.carry[2] = (int) (o_t >> 32);
-              c.carry[3] = o_ha; c.carry[4] = o_hm;
+              c.carry[3] = o_ha; c.carry[4] = o_hm; c.carry[5] = o_rd;
             }
 
           b <<= 1;
@@ -344,6 +359,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
                 { lasta = mx; trima = mx; trimd = dif;
                   trimx  = __shfl_sync(FULL,xn,Lb);
                   trimha = __shfl_sync(FULL,ha,Lb);
+                  trimrd = __shfl_sync(FULL,rd,Lb);
                 }
               else
                 { int ex = max(warp_prefix_max_excl(cm,lane),besta);
@@ -355,6 +371,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
                       trima  = __shfl_sync(FULL,cc,L3);
                       trimx  = __shfl_sync(FULL,xn,L3);
                       trimha = __shfl_sync(FULL,ha,L3);
+                      trimrd = __shfl_sync(FULL,rd,L3);
                       trimd  = dif;
                     }
                 }
@@ -368,10 +385,10 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
               if (hb) { int v = top - (__ffs(hb)-1); if (bclip < v) bclip = v; }
               if (hq) aclip = top - (31 - __clz(hq));
             }
-          lastcc = cc; lasttop = top;
+          lastcc = cc; lasttop = top; lastrd = rd;
           if (act)
             { c.V[IX(kk)] = cc; c.T[IX(kk)] = b; c.HA[IX(kk)] = ha; c.HM[IX(kk)] = hm;
-              c.NA[IX(kk)] = nan;
+              c.NA[IX(kk)] = nan; c.RD[IX(kk)] = rd;
             }
           __syncwarp();
         }
@@ -389,6 +406,24 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
           unsigned m = __ballot_sync(FULL,kk >= lowk && kk <= hghk && lastcc >= n);
           if (m == 0) hghk = lowk-1;
           else { hghk = lasttop - (__ffs(m)-1); lowk = lasttop - (31 - __clz(m)); }
+          //  Reverse-pass hand-off: once every surviving diagonal and the trim point descend from
+          //  the same wave-0 diagonal, that diagonal is final (*mind of align.c:872) and the
+          //  reverse wave, which only needs it, can start on the partner warp right now.
+          if (s > 0 && posted != NULL && !*posted && c.mbox != NULL && m != 0 && (dif & 31) == 0)
+            { bool in = (m >> lane) & 1;
+              int rmin = __reduce_min_sync(FULL,in ? lastrd : INT_MAX);
+              int rmax = __reduce_max_sync(FULL,in ? lastrd : INT_MIN);
+              if (rmin == rmax && rmin == trimrd)
+                { if (lane == 0)
+                    { Mbox *mb = c.mbox;
+                      mb->low = rmin; mb->anti = mida; mb->minp = minp; mb->maxp = maxp; mb->aoff = aoff;
+                      mb->alen = c.alen; mb->blen = c.blen; mb->A = c.A; mb->B = c.B;
+                      __threadfence_block();
+                      mb->state = 1;
+                    }
+                  *posted = true;
+                }
+            }
         }
       else
       { int n = besta - WAVE_LAG, nh = lowk-1;
@@ -461,12 +496,12 @@ static __device__ int fwd_extract(Ctx &c, int trimha, int mida, int trimx, int t
 //  Reverse read-out (align.c:1334-1414): pairs in FINAL order (tip first) into c.rstage; the
 //  start-not-on-a-trace-point case folds its pair into the first forward pair (c.fstage[0..1]).
 
-static __device__ int rev_extract(Ctx &c, int trimha, int aoff, int trimx, int trimy, int trimd,
-                                  int ftlen, int &rtlen)
+static __device__ int rev_extract(Ctx &c, const Peb *cells, int trimha, int aoff, int trimx, int trimy,
+                                  int trimd, int ftlen, int &rtlen)
 { const int lane = threadIdx.x & 31;
   int n = 0, h, root = trimha;
-  for (h = trimha; h >= 0; h = c.cells[h].ptr) { n += 1; root = h; }
-  Peb r0 = c.cells[root];
+  for (h = trimha; h >= 0; h = cells[h].ptr) { n += 1; root = h; }
+  Peb r0 = cells[root];
   int b0 = r0.mark - r0.diag;
   bool offpt = ((b0 + r0.diag) % c.tspace != aoff);
   int wr = 0;                                        // bytes written to rstage so far
@@ -504,7 +539,7 @@ static __device__ int rev_extract(Ctx &c, int trimha, int aoff, int trimx, int t
 
   //  n >= 2: pairs i = n-1 .. 1 between chain cells c_i and c_(i-1); pair 1 is merged into the
   //  forward trace when the root is off a trace point and a forward trace exists.
-  Peb tip = c.cells[trimha];
+  Peb tip = cells[trimha];
   int kt = tip.diag, bt = tip.mark - kt, et = tip.diff;
   bool extra = (bt + kt != trimx);
   int addd = 0, addb = 0;
@@ -521,7 +556,7 @@ static __device__ int rev_extract(Ctx &c, int trimha, int aoff, int trimx, int t
   Peb cur = tip;
   int idx = n-1;
   while (cur.ptr >= 0)
-    { Peb prv = c.cells[cur.ptr];
+    { Peb prv = cells[cur.ptr];
       int a = cur.mark - cur.diag, d = cur.diff;
       int bp = prv.mark - prv.diag, ep = (prv.ptr < 0) ? 0 : prv.diff;
       int pd = d - ep, pb = bp - a;
@@ -558,22 +593,51 @@ static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int a
 
   R.ftlen = R.rtlen = 0; R.diffs = 0;
   long long tk = clock64();
-  st = wave<1,W>(c,low,hgh,anti,minp,maxp,aoff,ex,ey,df,tha);
-  if (st) return st;
+  bool posted = false;
+  st = wave<1,W>(c,low,hgh,anti,minp,maxp,aoff,ex,ey,df,tha,&posted);
   c.cyc_wave += (u64) (clock64() - tk); tk = clock64();
-  st = fwd_extract(c,tha,anti,ex,ey,df,R.ftlen,rootd);
-  if (st) return st;
+  int st2 = st ? 0 : fwd_extract(c,tha,anti,ex,ey,df,R.ftlen,rootd);
   c.cyc_extract += (u64) (clock64() - tk);
   __syncwarp();
-  R.aepos = ex; R.bepos = ey; R.diffs = df;
+  const Peb *rcells = c.cells;
+  bool have_rev = false;
+  if (posted)                                    // collect the partner's reverse wave
+    { Mbox *mb = c.mbox;
+      long long tw = clock64();
+      while (mb->state != 2) __nanosleep(100);
+      c.cyc_wait += (u64) (clock64() - tw);
+      c.njobs += 1;
+      __threadfence_block();
+      int hst = mb->status, hlow = mb->low;
+      int hx = mb->endx, hy = mb->endy, hd = mb->diffs, hh = mb->trimha;
+      __syncwarp();
+      if (threadIdx.x % 32 == 0) mb->state = 0;
+      __syncwarp();
+      if (st == ST_OK && st2 == ST_OK)
+        { if (hst) return hst;
+          if (hlow == rootd)                     // always, but the forward read-out is the authority
+            { have_rev = true;
+              R.aepos = ex; R.bepos = ey; R.diffs = df;
+              ex = hx; ey = hy; df = hd; tha = hh;
+              rcells = c.pcells;
+            }
+          else
+            c.nmiss += 1;
+        }
+    }
+  if (st) return st;
+  if (st2) return st2;
+  if (!have_rev) { R.aepos = ex; R.bepos = ey; R.diffs = df; }
   low = rootd;
   bool fshort = ((R.aepos + R.bepos) - anti < DUB_TRIM);
 
   tk = clock64();
-  st = wave<-1,W>(c,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
-  if (st) return st;
+  if (!have_rev)
+    { st = wave<-1,W>(c,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
+      if (st) return st;
+    }
   c.cyc_wave += (u64) (clock64() - tk); tk = clock64();
-  st = rev_extract(c,tha,aoff,ex,ey,df,R.ftlen,R.rtlen);
+  st = rev_extract(c,rcells,tha,aoff,ex,ey,df,R.ftlen,R.rtlen);
   if (st) return st;
   c.cyc_extract += (u64) (clock64() - tk);
   R.abpos = ex; R.bbpos = ey; R.diffs += df;
@@ -602,7 +666,7 @@ static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int a
       R.ftlen = R.rtlen = 0; R.diffs = 0;
       st = wave<-1,W>(c,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
       if (st) return st;
-      st = rev_extract(c,tha,aoff,ex,ey,df,0,R.rtlen);
+      st = rev_extract(c,c.cells,tha,aoff,ex,ey,df,0,R.rtlen);
       if (st) return st;
       R.abpos = ex; R.bbpos = ey; R.diffs += df;
     }
@@ -1093,10 +1157,12 @@ __global__ void prefilter_kernel(ext_params P, unsigned *__restrict__ work_long,
     work_short[atomicAdd(nwork+1,1u)] = j;
 }
 
-#define WSTATE_BYTES(W) ((W)*(4*4+8) + 32)
+#define WSTATE_BYTES(W) ((W)*(5*4+8) + 32)
 #define STATE_BYTES (WSTATE_BYTES(EX_W) + SCAN_SMEM)
 #define BIG_SMEM_PER_WARP (SCAN_SMEM)
 #define TT_BYTES    ((256+128)*4)
+#define MBOX_BYTES  ((EX_WARPS/2)*((int) sizeof(Mbox)))
+#define EX_PRIM     (EX_WARPS/2)        // warps 0..EX_PRIM-1 take triples, warp p+EX_PRIM is the helper of warp p
 
 template<int W>
 __global__ void __launch_bounds__(EX_WARPS*32)
@@ -1110,8 +1176,8 @@ extend_kernel(ext_params P)
   Ctx c;
   c.T  = (u64 *) sb;
   c.V  = (int *) (sb + W*8);
-  c.HA = c.V + W; c.HM = c.HA + W; c.NA = c.HM + W;
-  c.carry = c.NA + W;
+  c.HA = c.V + W; c.HM = c.HA + W; c.NA = c.HM + W; c.RD = c.NA + W;
+  c.carry = c.RD + W;
   rec128 *stagebuf = (W == EX_W) ? (rec128 *) (sb + WSTATE_BYTES(EX_W))
                                  : (rec128 *) (smem + (size_t) wp * BIG_SMEM_PER_WARP);
   { short2 *tt = (short2 *) (smem + (size_t) EX_WARPS * per_warp);
@@ -1125,18 +1191,50 @@ extend_kernel(ext_params P)
         tt[u] = make_short2((short) sc,(short) mxp);
       }
     c.tt1 = tt; c.tt2 = tt + 256;
+    Mbox *mb = (Mbox *) (smem + (size_t) EX_WARPS * per_warp + TT_BYTES) + (wp % EX_PRIM);
+    if (wp < EX_PRIM && lane == 0) mb->state = 0;
+    c.mbox = mb;
     __syncthreads();
   }
   long long t_start = clock64();
   c.cells = P.cells + gw * P.cells_per_warp;
+  c.pcells = P.cells + (gw + EX_PRIM) * P.cells_per_warp;
   c.cmax  = (int) P.cells_per_warp;
   c.avail = 0;
   c.fstage = P.stage + gw * 2ll * P.stage_bytes;
   c.rstage = c.fstage + P.stage_bytes;
   c.smax = P.stage_bytes;
   c.tspace = P.tspace; c.path_ave = P.path_ave; c.score = P.score; c.table = P.table;
-  c.nwaves = 0; c.ncells = 0; c.cyc_wave = 0; c.cyc_extract = 0;
+  c.nwaves = 0; c.ncells = 0; c.cyc_wave = 0; c.cyc_extract = 0; c.njobs = 0; c.nmiss = 0; c.cyc_wait = 0;
   u64 nla = 0, nhits = 0;
+
+  if (wp >= EX_PRIM)
+    { //  helper warp: runs the reverse waves its primary posts
+      Mbox *mb = c.mbox;
+      c.mbox = NULL;
+      while (true)
+        { int stt;
+          while ((stt = mb->state) != 1 && stt != 3) __nanosleep(200);
+          if (stt == 3) break;
+          __threadfence_block();
+          c.A = mb->A; c.B = mb->B; c.alen = mb->alen; c.blen = mb->blen;
+          int lowd = mb->low, ex = 0, ey = 0, df = 0, tha = 0;
+          int hst = wave<-1,W>(c,lowd,lowd,mb->anti,mb->minp,mb->maxp,mb->aoff,ex,ey,df,tha);
+          __syncwarp();
+          if (lane == 0)
+            { mb->status = hst; mb->endx = ex; mb->endy = ey; mb->diffs = df; mb->trimha = tha;
+              __threadfence_block();
+              __threadfence();                   // pebbles written to HBM are read by the primary
+              mb->state = 2;
+            }
+          __syncwarp();
+        }
+      if (lane == 0)
+        { atomicAdd(&P.counters[2],c.nwaves);
+          atomicAdd(&P.counters[3],c.ncells);
+        }
+      return;
+    }
 
   while (true)
     { unsigned w = 0;
@@ -1155,6 +1253,7 @@ extend_kernel(ext_params P)
         nhits += nh;
       __syncwarp();
     }
+  if (lane == 0) c.mbox->state = 3;            // release the helper
   if (lane == 0)
     { atomicAdd(&P.counters[0],nhits);
       atomicAdd(&P.counters[1],nla);
@@ -1163,6 +1262,10 @@ extend_kernel(ext_params P)
       atomicAdd(&P.counters[8],(u64) (clock64() - t_start));
       atomicAdd(&P.counters[9],c.cyc_wave);
       atomicAdd(&P.counters[10],c.cyc_extract);
+      atomicAdd(&P.counters[11],c.njobs);
+      atomicAdd(&P.counters[12],c.nmiss);
+      atomicAdd(&P.counters[13],c.cyc_wait);
+      atomicMax(&P.counters[14],(u64) (clock64() - t_start));
     }
 }
 
@@ -1306,14 +1409,14 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
     { int dev = 0, nsm = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&nsm,cudaDevAttrMultiProcessorCount,dev);
-      size_t smem = (size_t) EX_WARPS * STATE_BYTES + TT_BYTES;
-      size_t smem_big = (size_t) EX_WARPS * BIG_SMEM_PER_WARP + TT_BYTES;
+      size_t smem = (size_t) EX_WARPS * STATE_BYTES + TT_BYTES + MBOX_BYTES;
+      size_t smem_big = (size_t) EX_WARPS * BIG_SMEM_PER_WARP + TT_BYTES + MBOX_BYTES;
       CUDA_TRY(cudaFuncSetAttribute(extend_kernel<EX_W>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem));
       int bps = 0;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps,extend_kernel<EX_W>,EX_WARPS*32,smem));
       if (bps < 1) bps = 1;
       long long nblocks = (long long) nsm * bps;
-      long long want = ((long long) nwork + EX_WARPS - 1) / EX_WARPS;
+      long long want = ((long long) nwork + EX_PRIM - 1) / EX_PRIM;
       if (nblocks > want) nblocks = want;
       long long nwarps = nblocks * EX_WARPS;
 
@@ -1385,7 +1488,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           CUDA_TRY(cudaMemcpy(d_work2,f.data(),sizeof(unsigned)*nfailed,cudaMemcpyHostToDevice));
           d_list = d_work2; nlist = nfailed;
           cells_per_warp *= 8; stage_bytes *= 4;
-          long long nb2 = ((long long) nfailed + EX_WARPS - 1) / EX_WARPS;
+          long long nb2 = ((long long) nfailed + EX_PRIM - 1) / EX_PRIM;
           long long maxb = (24ll << 30) / ((long long) sizeof(Peb) * cells_per_warp * EX_WARPS);
           if (maxb < 1) maxb = 1;
           nblocks = nb2 < maxb ? nb2 : maxb;

@@ -31,6 +31,8 @@ static __host__ __device__ __forceinline__ int seed_key_bits(const seed_layout &
 #define MG_THREADS 256
 #define MG_WARPS   (MG_THREADS/32)
 #define MG_TILE    64                     // T1 entries per warp
+#define MG_T2CAP   1280                   // staged T2 entries per block (20 KB)
+#define MG_PCAP    1536                   // staged prefix-index entries per block (6 KB)
 
 //  lcp (in bases, 0..28) of two 56-bit suffixes
 static __device__ __forceinline__ int lcp56(u64 a, u64 b)
@@ -65,6 +67,9 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
                        rec128 *__restrict__ seeds, unsigned long long capacity,
                        unsigned long long *__restrict__ counters /* [0]=nseeds [1]=sum plen */)
 { __shared__ __align__(16) rec128 sbuf[MG_WARPS][MG_TILE];
+  __shared__ __align__(16) rec128 s_T2[MG_T2CAP];        // the block's slice of T2 ...
+  __shared__ unsigned s_ps[MG_PCAP];                      // ... and of its prefix index
+  __shared__ unsigned s_rng[4];
   __shared__ unsigned s_excl[MG_WARPS][33];
   __shared__ unsigned s_lowi[MG_WARPS][32];
   __shared__ unsigned s_plen[MG_WARPS][32];
@@ -75,6 +80,30 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
   const unsigned lt = lanemask_lt();
   unsigned long long base = ((unsigned long long) blockIdx.x * MG_WARPS + wp) * MG_TILE;
   unsigned long long sumlen = 0;
+
+  //  The block's 512 T1 entries are consecutive in k-mer order, so the T2 entries they can match
+  //  are one contiguous slice [pstart2[pA], pstart2[pB+1]).  When it fits, that slice and the
+  //  prefix-index range are staged in shared memory with coalesced loads and every search,
+  //  walk and payload read below hits shared memory instead of a dependent L2/HBM round trip.
+  { unsigned long long b0 = (unsigned long long) blockIdx.x * MG_WARPS * MG_TILE;
+    if (threadIdx.x == 0)
+      { unsigned long long b1 = b0 + MG_WARPS*MG_TILE - 1;
+        if (b1 >= n1) b1 = n1 - 1;
+        unsigned pA = KREC_PREFIX24(T1[b0].hi), pB = KREC_PREFIX24(T1[b1].hi);
+        unsigned lo2 = pstart2[pA], hi2 = pstart2[pB+1];
+        s_rng[0] = pA; s_rng[1] = pB - pA + 2; s_rng[2] = lo2; s_rng[3] = hi2 - lo2;
+      }
+    __syncthreads();
+  }
+  const unsigned pA = s_rng[0], lo2 = s_rng[2];
+  const bool staged = (s_rng[1] <= MG_PCAP && s_rng[3] <= MG_T2CAP);
+  if (staged)
+    { for (unsigned i = threadIdx.x; i < s_rng[1]; i += MG_THREADS) s_ps[i] = pstart2[pA + i];
+      for (unsigned i = threadIdx.x; i < s_rng[3]; i += MG_THREADS) st_rec(s_T2 + i,ld_rec(T2 + lo2 + i));
+    }
+  __syncthreads();
+  const rec128   *T2v = staged ? s_T2 : T2;     const unsigned t2off = staged ? lo2 : 0;
+  const unsigned *psv = staged ? s_ps : pstart2; const unsigned psoff = staged ? pA  : 0;
 
   if (base < n1)
     { unsigned i0 = (unsigned) base + lane, i1 = i0 + 32;
@@ -96,27 +125,27 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
           if (idx < nd)
             { r1 = ld_rec(&sbuf[wp][idx]);
               unsigned p  = KREC_PREFIX24(r1.hi);
-              unsigned lo = pstart2[p], hi = pstart2[p+1];
+              unsigned lo = psv[p - psoff], hi = psv[p + 1 - psoff];
               if (lo < hi)
                 { u64 s1 = KREC_SUFFIX56(r1);
                   unsigned a = lo, b = hi;                    // lower bound of s1 in T2[lo,hi)
                   while (a < b)
                     { unsigned m = (a + b) >> 1;
-                      if (suffix_of(T2,m) < s1) a = m+1; else b = m;
+                      if (suffix_of(T2v,m - t2off) < s1) a = m+1; else b = m;
                     }
-                  int ll = (a > lo) ? lcp56(s1,suffix_of(T2,a-1)) : -1;
-                  int lr = (a < hi) ? lcp56(s1,suffix_of(T2,a))   : -1;
+                  int ll = (a > lo) ? lcp56(s1,suffix_of(T2v,a-1 - t2off)) : -1;
+                  int lr = (a < hi) ? lcp56(s1,suffix_of(T2v,a - t2off))   : -1;
                   int m  = ll > lr ? ll : lr;
                   plen = 12 + m;
                   unsigned lft = a, rgt = a;
                   int sh = 56 - 2*m;
                   u64 key = s1 >> sh;
                   while (lft > lo && rgt - lft < (unsigned) freq)
-                    { if ((suffix_of(T2,lft-1) >> sh) != key) break;
+                    { if ((suffix_of(T2v,lft-1 - t2off) >> sh) != key) break;
                       lft -= 1;
                     }
                   while (rgt < hi && rgt - lft < (unsigned) freq)
-                    { if ((suffix_of(T2,rgt) >> sh) != key) break;
+                    { if ((suffix_of(T2v,rgt - t2off) >> sh) != key) break;
                       rgt += 1;
                     }
                   if (rgt - lft < (unsigned) freq)             // |R| < FREQ (:799-823)
@@ -149,7 +178,7 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
               for (int st = 16; st > 0; st >>= 1)
                 if (s_excl[wp][j + st] <= o) j += st;
               unsigned k = o - s_excl[wp][j];
-              rec128 r2 = ld_rec(T2 + s_lowi[wp][j] + k);
+              rec128 r2 = ld_rec(T2v + (s_lowi[wp][j] + k - t2off));
               unsigned long long pay = s_pay[wp][j];
               long long ipost = (long long) (unsigned) pay, jpost = (long long) (unsigned) r2.lo;
               unsigned icont = (unsigned) (pay >> 32) & 0x7fff;

@@ -303,3 +303,87 @@ def canonical_ktab(entries, esize, index):
     order = np.lexsort((pay, run))
     ent[:, 9:] = ent[order, 9:]
     return ent.reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------
+#  .1aln output (ONEcode, ASCII flavour -- the reference's tools read both flavours)
+# ------------------------------------------------------------------------------------------
+
+def _skeleton_lines(genome, prefix="s"):
+    """'g' group with S/G/C lines, as Write_Skeleton emits (GDB.c:2065-2092)"""
+    out = ["g"]
+    nscaf = int(genome.scaf.max()) + 1 if genome.scaf is not None and len(genome.scaf) else genome.ncontig
+    for s in range(nscaf):
+        if genome.scaf is not None:
+            ctgs = np.flatnonzero(genome.scaf == s)
+            name = genome.names[s]
+            slen = int(genome.slen[s])
+        else:
+            ctgs, name, slen = np.array([s]), "%s_%d" % (prefix, s + 1), int(genome.clen[s])
+        out.append("S %d %s" % (len(name), name))
+        pos = 0
+        for c in ctgs:
+            b = int(genome.sbeg[c]) if genome.sbeg is not None else 0
+            if b > pos:
+                out.append("G %d" % (b - pos))
+            out.append("C %d" % int(genome.clen[c]))
+            pos = b + int(genome.clen[c])
+        if slen > pos:
+            out.append("G %d" % (slen - pos))
+    return out
+
+
+# the .1aln schema as the file states it about itself (alncode.c:19-52); ONEcode ASCII files carry
+# their schema in '~' header lines, which is what lets generic readers (ONEview) parse them
+_ALN_SCHEMA = """~ D t 1 3 INT
+~ O g 0
+~ G S 0
+~ O S 1 6 STRING
+~ D G 1 3 INT
+~ D C 1 3 INT
+~ O a 0
+~ G A 0
+~ D p 2 3 INT 3 INT
+~ O A 6 3 INT 3 INT 3 INT 3 INT 3 INT 3 INT
+~ D L 2 3 INT 3 INT
+~ D R 0
+~ D D 1 3 INT
+~ D T 1 8 INT_LIST
+~ D X 1 8 INT_LIST
+~ D Q 1 3 INT
+~ D E 1 3 INT
+~ D Z 1 6 STRING
+~ D U 1 3 INT
+"""
+
+
+def write_1aln_ascii(path, alns, gA, gB, gdb1="./A.1gdb", gdb2="./B.1gdb", cwd=".", tspace=100,
+                     command="fastga_b200"):
+    """Writes the alignments as an ASCII ONEcode '.1aln' with the schema of alncode.c:19-52:
+    provenance, the two GDB references + cwd, 't' trace spacing, the GDB skeleton(s), then per
+    alignment  A aread abpos aepos bread bbpos bepos / R / D diffs / T b-advances / X diffs
+    (Write_Aln_Overlap, Write_Aln_Trace, alncode.c:272-305)."""
+    import datetime
+    stamp = datetime.datetime.now().strftime("%Y-%m-%d_%H:%M:%S")
+    with open(path, "w") as f:
+        f.write("1 3 aln 2 1\n")
+        f.write("! 4 %d %s 3 0.1 %d %s %d %s\n" % (len("fastga_b200"), "fastga_b200", len(command), command,
+                                                  len(stamp), stamp))
+        f.write("< %d %s 1\n" % (len(gdb1), gdb1))
+        if gdb2 is not None:
+            f.write("< %d %s 2\n" % (len(gdb2), gdb2))
+        f.write("< %d %s 3\n" % (len(cwd), cwd))
+        f.write(_ALN_SCHEMA)
+        f.write("t %d\n" % tspace)
+        f.write("\n".join(_skeleton_lines(gA, "a")) + "\n")
+        if gB is not None:
+            f.write("\n".join(_skeleton_lines(gB, "b")) + "\n")
+        for i in range(len(alns)):
+            comp, ar, br, ab, bb, ae, be, df, tl = (int(x) for x in alns.fields[i])
+            t = alns.trace(i)
+            f.write("A %d %d %d %d %d %d\n" % (ar, ab, ae, br, bb, be))
+            if comp:
+                f.write("R\n")
+            f.write("D %d\n" % df)
+            f.write("T %d%s\n" % (tl // 2, "".join(" %d" % v for v in t[1::2])))
+            f.write("X %d%s\n" % (tl // 2, "".join(" %d" % v for v in t[0::2])))

@@ -287,7 +287,8 @@ class DeviceOverlaps:
         L.fgb_overlaps_counters(self.h, out)
         v = list(out)
         return {"hits": v[0], "la_calls": v[1], "waves": v[2], "cells": v[3], "nseg": v[5], "nwork": v[6],
-                "warp_cycles": v[8], "wave_cycles": v[9], "extract_cycles": v[10]}
+                "warp_cycles": v[8], "wave_cycles": v[9], "extract_cycles": v[10], "jobs": v[11],
+                "job_miss": v[12], "wait_cycles": v[13], "max_warp_cycles": v[14]}
 
     def records(self):
         """(structured array sorted in reference discovery order, trace byte pool)"""

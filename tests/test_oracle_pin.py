@@ -150,3 +150,26 @@ def test_oracle_vs_live_reference_run(tmp_path):
     r = ol.oracle_pipeline(gA, gB)
     assert (r["nseeds"], r["nhit"], r["nraw"], len(r["lines"])) == (st["seeds"], st["hits"], st["alns"], st["kept"])
     assert r["lines"] == ref
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
+def test_written_1aln_is_read_by_reference_tools(tmp_path):
+    """a .1aln written by formats.write_1aln_ascii is accepted by the reference's
+    ONEview (same records back) and -- after ONEview -b adds the binary index the threaded readers
+    need -- by its ALNtoPAF next to the reference-made GDBs (same PAF as from the reference's own
+    .1aln)."""
+    A, B = synth.make_pair(41, 500_000, 3, 0.06, sv_every=40_000)
+    wd = str(tmp_path)
+    formats.write_fasta(os.path.join(wd, "A.fasta"), synth.scaffolds_of(A, "sa", 2))
+    formats.write_fasta(os.path.join(wd, "B.fasta"), synth.scaffolds_of(B, "sb", 1))
+    ol.ref_fastga(wd, "A", "B", threads=4)
+    gA = formats.genome_from_fasta(os.path.join(wd, "A.fasta"))
+    gB = formats.genome_from_fasta(os.path.join(wd, "B.fasta"))
+    r = ol.oracle_pipeline(gA, gB)
+    formats.write_1aln_ascii(os.path.join(wd, "mine.1aln"), r["alns"], gA, gB, "./A.1gdb", "./B.1gdb", wd)
+    assert ol.oneview_records(os.path.join(wd, "mine.1aln")) == ol.oneview_records(os.path.join(wd, "ref.1aln"))
+    paf_ref = sorted(ol.run_ref(["ALNtoPAF", "-T2", "ref"], cwd=wd).split("\n"))
+    # the threaded converters need ONEcode's binary index: ONEview -b turns the ASCII file into it
+    ol.run_ref(["ONEview", "-b", "-o", "mineb.1aln", "mine.1aln"], cwd=wd)
+    paf_mine = sorted(ol.run_ref(["ALNtoPAF", "-T2", "mineb"], cwd=wd).split("\n"))
+    assert len(paf_ref) > 3 and paf_mine == paf_ref
