@@ -187,7 +187,18 @@ def main():
         barrier()
         return float(ms.item()) / steps, outs
 
-    step = lambda: lib.align_resident(dA, dB, freqA)
+    if world > 1:
+        dev = torch.device("cuda", local_rank)
+
+        def step():
+            xA = lib.DeviceGix.build(dA)
+            xB = shard.build_table_cooperatively(dB, dist, dev)       # NCCL all-gather of sorted shares
+            out = lib.align_tables(dA, dB, xA, xB, freqA)
+            xA.close()
+            xB.close()
+            return out
+    else:
+        step = lambda: lib.align_resident(dA, dB, freqA)
     for _ in range(args.warmup):
         step()
 
@@ -238,7 +249,8 @@ def main():
                                    "every ~%d kbp, seed %d; FastGA defaults -f10 -c85 -s1000 -l100 -i.7; "
                                    "k-mer tables and seed sets are larger than L2 (no flush needed)"
                                    % (args.per_gpu_bp // 1_000_000, NCONTIG, SV_EVERY // 1000, SEED),
-                       "sharding": "genome-1 contigs by rank, genome 2 replicated", "alignments": nrec,
+                       "sharding": "genome-1 contigs by rank; genome-2 table built cooperatively (k-mer prefix "
+                                   "slices sorted per rank, NCCL all-gather)" if world > 1 else "single GPU", "alignments": nrec,
                        "seeds": stats["nseeds"], "kmers": [stats["nkmers1"], stats["nkmers2"]],
                        "hits": stats["nhits"], "la_calls": stats["nla"], "waves": stats["nwaves"],
                        "wave_cells": stats["ncells"], "stage_ms": dev_ms,

@@ -24,10 +24,11 @@ int fgb_syncmer_count_device(const void *d_seq, const long long *d_clen, const l
                              const int *d_crank, const int *d_tile_contig, const int *d_tile_start,
                              int ntiles, unsigned *d_tile_count, unsigned long long *d_buck1024,
                              unsigned long long *d_total, void *d_tmp, long long tmp_bytes,
-                             void *stream);
+                             unsigned plo, unsigned phi, void *stream);
 int fgb_syncmer_emit_device(const void *d_seq, const long long *d_clen, const long long *d_woff,
                             const int *d_crank, const int *d_tile_contig, const int *d_tile_start,
-                            int ntiles, unsigned *d_tile_offset, void *d_records, void *stream);
+                            int ntiles, unsigned *d_tile_offset, void *d_records, unsigned plo,
+                            unsigned phi, void *stream);
 int fgb_kix_index_device(const void *d_tab, long long n, unsigned *d_pstart, void *stream);
 int fgb_ktab_export_device(const void *d_tab, long long n, int pbytes, int cbytes,
                            const long long *d_part_first, int nparts, void *d_out, void *stream);
@@ -241,7 +242,20 @@ static void gix_bytes(const fgb_genome *g, fgb_gix *x)        // GIXmake.c:1888-
 //  K1..K4: syncmer scan -> 128-bit records -> 10-pass byte radix sort on the 80-bit k-mer ->
 //  2^24 prefix index.
 
+static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi, fgb_gix **out, void *stream);
+
 extern "C" int fgb_gix_build(const fgb_genome *g, fgb_gix **out, void *stream)
+{ return gix_build_range(g,0u,1u << 24,out,stream); }
+
+//  Only the k-mers whose 12-base prefix lies in [plo,phi): one rank's share of a table that is
+//  built cooperatively (every rank scans the genome, sorts 1/N of the records, the sorted shares
+//  concatenate in rank order -- fastga_b200/shard.py all-gathers them over NCCL).
+extern "C" int fgb_gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi, fgb_gix **out, void *stream)
+{ if (plo > phi || phi > (1u << 24)) return FGB_ERR_ARG;
+  return gix_build_range(g,plo,phi,out,stream);
+}
+
+static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi, fgb_gix **out, void *stream)
 { cudaStream_t st = (cudaStream_t) stream;
   int T = fgb_sc_tile();
   std::vector<int> tc, ts;
@@ -271,7 +285,7 @@ extern "C" int fgb_gix_build(const fgb_genome *g, fgb_gix **out, void *stream)
   u64 total = 0;
   { stage_timer t(&g_timings.scan_ms,st);
     rc = fgb_syncmer_count_device(g->d_seq,g->d_clen,g->d_woff,g->d_crank,d_tc,d_ts,ntiles,d_cnt,
-                                  d_buck,d_total,d_tmp,tmpb,st);
+                                  d_buck,d_total,d_tmp,tmpb,plo,phi,st);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(&total,d_total,8,cudaMemcpyDeviceToHost,st));
     CUDA_TRY(cudaMemcpyAsync(x->buck1024,d_buck,8*1024,cudaMemcpyDeviceToHost,st));
@@ -287,7 +301,7 @@ extern "C" int fgb_gix_build(const fgb_genome *g, fgb_gix **out, void *stream)
   CUDA_TRY(fgb_dmalloc((void **) &d_b,sizeof(rec128)*(n+1),st));
   CUDA_TRY(fgb_dmalloc((void **) &d_stmp,stmpb,st));
   { stage_timer t(&g_timings.scan_ms,st);
-    rc = fgb_syncmer_emit_device(g->d_seq,g->d_clen,g->d_woff,g->d_crank,d_tc,d_ts,ntiles,d_cnt,d_a,st);
+    rc = fgb_syncmer_emit_device(g->d_seq,g->d_clen,g->d_woff,g->d_crank,d_tc,d_ts,ntiles,d_cnt,d_a,plo,phi,st);
     if (rc) return rc;
   }
   int inb = 0;
@@ -309,6 +323,30 @@ extern "C" int fgb_gix_build(const fgb_genome *g, fgb_gix **out, void *stream)
 }
 
 extern "C" long long fgb_gix_size(const fgb_gix *x) { return x->n; }
+
+//  device-to-device copy of the sorted records into a caller-owned device buffer (n x 16 bytes)
+extern "C" int fgb_gix_copy_table(const fgb_gix *x, void *d_dst, void *stream)
+{ CUDA_TRY(cudaMemcpyAsync(d_dst,x->d_tab,sizeof(rec128)*x->n,cudaMemcpyDeviceToDevice,(cudaStream_t) stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t) stream));
+  return FGB_OK;
+}
+
+//  A GIX over sorted device-layout records that already sit in device memory (copied).
+extern "C" int fgb_gix_from_device(const void *d_tab, long long n, int post_bytes, int cont_bytes,
+                                   int ncontig, fgb_gix **out, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  if (n >= 0xfffffff0ll) return FGB_ERR_LIMIT;
+  fgb_gix *x = new fgb_gix();
+  x->n = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
+  CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
+  CUDA_TRY(cudaMemcpyAsync(x->d_tab,d_tab,sizeof(rec128)*n,cudaMemcpyDeviceToDevice,st));
+  int rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (rc) return rc;
+  *out = x;
+  return FGB_OK;
+}
 extern "C" int fgb_gix_post_bytes(const fgb_gix *x) { return x->post_bytes; }
 extern "C" int fgb_gix_cont_bytes(const fgb_gix *x) { return x->cont_bytes; }
 
@@ -496,19 +534,38 @@ struct fgb_run_stats
             nseg, nwork, warp_cycles, wave_cycles, extract_cycles,
             us_gix, us_seeds, us_extend, us_filter; };
 
+//  Merge + seed sort + extension + filter from prebuilt tables (x2 may have been assembled from
+//  shares built on several ranks).
+extern "C" int fgb_align_tables(const fgb_genome *A, const fgb_genome *B, const fgb_gix *x1,
+                                const fgb_gix *x2, const float *freqA,
+                                int freq, int chain_break, int chain_min, int align_min,
+                                double align_rate, fgb_alns **out, fgb_run_stats *stats, void *stream);
+
 //  Device-resident genomes in, final alignments out (the timed "step" of bench.py).
 extern "C" int fgb_align_resident(const fgb_genome *A, const fgb_genome *B, const float *freqA,
                                   int freq, int chain_break, int chain_min, int align_min,
                                   double align_rate, fgb_alns **out, fgb_run_stats *stats, void *stream)
-{ fgb_gix *x1 = NULL, *x2 = NULL; fgb_seeds *sd = NULL; fgb_overlaps *ov = NULL;
+{ fgb_gix *x1 = NULL, *x2 = NULL;
   int rc;
-  long long t0 = now_us(), t1, t2, t3, t4;
+  long long t0 = now_us();
   if ((rc = fgb_gix_build(A,&x1,stream))) return rc;
   if ((rc = fgb_gix_build(B,&x2,stream))) { fgb_gix_free(x1); return rc; }
-  t1 = now_us();
+  long long t1 = now_us();
+  rc = fgb_align_tables(A,B,x1,x2,freqA,freq,chain_break,chain_min,align_min,align_rate,out,stats,stream);
+  fgb_gix_free(x1); fgb_gix_free(x2);
+  if (stats) stats->us_gix = t1 - t0;
+  return rc;
+}
+
+extern "C" int fgb_align_tables(const fgb_genome *A, const fgb_genome *B, const fgb_gix *x1,
+                                const fgb_gix *x2, const float *freqA,
+                                int freq, int chain_break, int chain_min, int align_min,
+                                double align_rate, fgb_alns **out, fgb_run_stats *stats, void *stream)
+{ fgb_seeds *sd = NULL; fgb_overlaps *ov = NULL;
+  int rc;
+  long long t0 = now_us(), t1 = t0, t2, t3, t4;
   rc = fgb_seeds_find(x1,x2,A->maxlen,B->maxlen,freq,&sd,stream);
   long long n1 = x1->n, n2 = x2->n;
-  fgb_gix_free(x1); fgb_gix_free(x2);
   if (rc) return rc;
   t2 = now_us();
   short *tables = (short *) malloc(65536*sizeof(short));

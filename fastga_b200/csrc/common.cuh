@@ -60,3 +60,31 @@ void fgb_count_launch(int n);                 // kernels launched (bench.py gpu_
 //  stream-ordered device allocation from a retained pool (no cudaMalloc/cudaFree stalls per step)
 cudaError_t fgb_dmalloc(void **p, size_t bytes, cudaStream_t st);
 void fgb_dfree(void *p, cudaStream_t st);
+
+//  TMA 1-D bulk copy global -> shared (cp.async.bulk, SASS UBLKCP) completed on an mbarrier.
+//  dst/src 16-byte aligned, bytes a multiple of 16.  One elected thread issues; every thread of
+//  the CTA may wait on the barrier phase.
+static __device__ __forceinline__ unsigned smem_u32(const void *p)
+{ return (unsigned) __cvta_generic_to_shared(p); }
+
+static __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+static __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes,
+                                                   unsigned long long *bar)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+static __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase)
+{ unsigned ok;
+  do
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  while (!ok);
+}

@@ -272,19 +272,13 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
   while (more && lasta >= besta - TRIM_MLAG)
     { lowk -= 1; hghk += 1;
       if (hghk - lowk + 5 > W) return ST_BAND;
-      if (lane == 0)
-        { if (lowk >= minpn) { c.NA[IX(lowk)] = c.NA[IX(lowk+1)]; c.V[IX(lowk)] = FRESH; }
-          if (hghk <= maxpn) { c.NA[IX(hghk)] = c.NA[IX(hghk-1)]; c.V[IX(hghk)] = FRESH; }
-        }
-      if (lowk < minpn) lowk += 1;
-      if (hghk > maxpn) hghk -= 1;
+      if (dif > c.alen + c.blen + 1000) return ST_STAGE;     // cannot happen (every wave is one more difference): hang guard
+      //  new band edges (align.c:611-622): a fresh diagonal copies its neighbour's NA and counts as
+      //  FRESH; done with predicates on the owning lanes instead of stores + a warp barrier
+      const bool newlow = (lowk >= minpn), newhgh = (hghk <= maxpn);
+      if (!newlow) lowk += 1;
+      if (!newhgh) hghk -= 1;
       dif += 1;
-      if (lane == 0)
-        { c.V[IX(hghk+1)] = FRESH; c.V[IX(lowk-1)] = FRESH;
-          c.carry[0] = FRESH; c.carry[1] = (int) (unsigned) PATH_INT;
-          c.carry[2] = (int) (PATH_INT >> 32); c.carry[3] = -1; c.carry[4] = 0; c.carry[5] = 0;
-        }
-      __syncwarp();
       c.nwaves += 1; c.ncells += (u64) (hghk - lowk + 1);
       const bool single = (hghk - lowk < 32);
       int lastcc = 0, lasttop = hghk, lastrd = 0;
@@ -292,9 +286,12 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
       for (int top = hghk; top >= lowk; top -= 32)
         { int kk = top - lane;
           bool act = kk >= lowk;
-          int ap = (lane == 0) ? c.carry[0] : c.V[IX(kk+1)];
-          int ac = c.V[IX(kk)];
-          int am = c.V[IX(kk-1)];
+          const bool flo = newlow && kk == lowk, fhi = newhgh && kk == hghk;
+          //  a fresh edge diagonal is FRESH for itself AND for the neighbour that looks at it
+          int ap = (kk == hghk || (newhgh && kk+1 == hghk)) ? FRESH
+                                                            : ((lane == 0) ? c.carry[0] : c.V[IX(kk+1)]);
+          int ac = (flo || fhi) ? FRESH : c.V[IX(kk)];
+          int am = (kk == lowk || (newlow && kk-1 == lowk)) ? FRESH : c.V[IX(kk-1)];
           int pred, cc;
           if (ac < am) { if (am < ap) { pred = 1; cc = ap+1; } else { pred = -1; cc = am+1; } }
           else         { if (ac < ap) { pred = 1; cc = ap+1; } else { pred = 0;  cc = ac+2; } }
@@ -307,7 +304,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
             { int si = IX(kk+pred);
               b = c.T[si]; ha = c.HA[si]; hm = c.HM[si]; rd = c.RD[si];
             }
-          int nan = c.NA[IX(kk)];
+          int nan = c.NA[IX(flo ? kk+1 : (fhi ? kk-1 : kk))];
           //  lane 31's own old state is the next chunk's "kk+1"
           int  o_v = 0, o_ha = 0, o_hm = 0, o_rd = 0; u64 o_t = 0;
           const bool morechunks = (top - 32 >= lowk);
@@ -1214,7 +1211,7 @@ extend_kernel(ext_params P)
       c.mbox = NULL;
       while (true)
         { int stt;
-          while ((stt = mb->state) != 1 && stt != 3) __nanosleep(200);
+          while ((stt = mb->state) != 1 && stt != 3) __nanosleep(2000);
           if (stt == 3) break;
           __threadfence_block();
           c.A = mb->A; c.B = mb->B; c.alen = mb->alen; c.blen = mb->blen;

@@ -70,6 +70,7 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
   __shared__ __align__(16) rec128 s_T2[MG_T2CAP];        // the block's slice of T2 ...
   __shared__ unsigned s_ps[MG_PCAP];                      // ... and of its prefix index
   __shared__ unsigned s_rng[4];
+  __shared__ __align__(8) unsigned long long s_bar;
   __shared__ unsigned s_excl[MG_WARPS][33];
   __shared__ unsigned s_lowi[MG_WARPS][32];
   __shared__ unsigned s_plen[MG_WARPS][32];
@@ -92,6 +93,10 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
         unsigned pA = KREC_PREFIX24(T1[b0].hi), pB = KREC_PREFIX24(T1[b1].hi);
         unsigned lo2 = pstart2[pA], hi2 = pstart2[pB+1];
         s_rng[0] = pA; s_rng[1] = pB - pA + 2; s_rng[2] = lo2; s_rng[3] = hi2 - lo2;
+        mbar_init(&s_bar,1);
+        //  the T2 slice is one contiguous run of 128-bit records: a single TMA bulk copy
+        if (pB - pA + 2 <= MG_PCAP && hi2 - lo2 <= MG_T2CAP && hi2 > lo2)
+          tma_load_1d(s_T2,T2 + lo2,(hi2 - lo2) * 16u,&s_bar);
       }
     __syncthreads();
   }
@@ -99,7 +104,7 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
   const bool staged = (s_rng[1] <= MG_PCAP && s_rng[3] <= MG_T2CAP);
   if (staged)
     { for (unsigned i = threadIdx.x; i < s_rng[1]; i += MG_THREADS) s_ps[i] = pstart2[pA + i];
-      for (unsigned i = threadIdx.x; i < s_rng[3]; i += MG_THREADS) st_rec(s_T2 + i,ld_rec(T2 + lo2 + i));
+      if (s_rng[3] > 0) mbar_wait(&s_bar,0);
     }
   __syncthreads();
   const rec128   *T2v = staged ? s_T2 : T2;     const unsigned t2off = staged ? lo2 : 0;

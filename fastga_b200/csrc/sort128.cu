@@ -5,10 +5,11 @@
 //   rmsd_sort  (RSDsort.c:292)  -- adaptive-seed records, key = (jcont, band, anti, drem, lcp)
 // Both are in-place American-flag MSD sorts on byte-packed records (MSDsort.c:211-360); on the
 // device every record is widened to one 16-byte word so each pass is a perfectly coalesced
-// stream (read 16 B, write 16 B per record).  One pass = per-tile digit histogram, a row scan of
-// the (digit x tile) matrix, and a stable scatter that ranks records inside a 4096-record tile
-// with warp match-any multi-split, stages the tile in shared memory in digit order and writes
-// digit runs back coalesced.  HBM-bound integer work: no tensor cores.
+// stream (read 16 B, write 16 B per record).  One pass = one Onesweep kernel: a stable scatter
+// that ranks records inside a 4096-record tile with warp match-any multi-split, finds the tile's
+// bases by decoupled look-back, stages the tile in shared memory in digit order and writes digit
+// runs back coalesced, while counting the next pass's histogram.  HBM-bound integer work: no
+// tensor cores.
 #include "common.cuh"
 
 #define SORT_THREADS 512
@@ -24,167 +25,6 @@ static __device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane)
       if (lane >= o) v += t;
     }
   return v;
-}
-
-//  Per-tile histogram of one key byte.  blockhist is digit-major: [256][ntiles].
-
-__global__ void __launch_bounds__(SORT_THREADS)
-sort_hist_kernel(const rec128 *__restrict__ in, long long n, int byte,
-                 unsigned *__restrict__ blockhist, int ntiles)
-{ __shared__ unsigned h[256];
-  int tid = threadIdx.x;
-  if (tid < 256) h[tid] = 0;
-  __syncthreads();
-
-  long long tile0 = (long long) blockIdx.x * SORT_TILE;
-  const unsigned long long *half = reinterpret_cast<const unsigned long long *>(in) + (byte >= 8);
-  int sh = 8*(byte & 7);
-#pragma unroll
-  for (int it = 0; it < SORT_ITEMS; it++)
-    { long long idx = tile0 + it*SORT_THREADS + tid;
-      bool valid = idx < n;
-      unsigned d = 0x100u | (tid & 31);
-      if (valid)
-        d = (unsigned) ((half[2*idx] >> sh) & 0xff);
-      unsigned peers = __match_any_sync(0xffffffffu,d);
-      if (valid && (tid & 31) == __ffs(peers)-1)
-        atomicAdd(&h[d],__popc(peers));
-    }
-  __syncthreads();
-  if (tid < 256)
-    blockhist[(long long) tid*ntiles + blockIdx.x] = h[tid];
-}
-
-//  Exclusive scan of each digit row (one block per digit); row totals out.
-
-__global__ void __launch_bounds__(1024)
-sort_rowscan_kernel(unsigned *__restrict__ blockhist, int ntiles, unsigned *__restrict__ rowtotal)
-{ __shared__ unsigned wsum[32];
-  __shared__ unsigned carry_s;
-  unsigned *row = blockhist + (long long) blockIdx.x * ntiles;
-  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < ntiles; base += 1024)
-    { int i = base + tid;
-      unsigned v = (i < ntiles) ? row[i] : 0;
-      unsigned inc = warp_incl_scan(v,lane);
-      if (lane == 31) wsum[w] = inc;
-      __syncthreads();
-      if (w == 0)
-        { unsigned s = wsum[lane];
-          unsigned si = warp_incl_scan(s,lane);
-          wsum[lane] = si - s;
-        }
-      __syncthreads();
-      unsigned carry = carry_s;
-      unsigned ex = carry + wsum[w] + inc - v;
-      if (i < ntiles) row[i] = ex;
-      __syncthreads();
-      if (tid == 1023) carry_s = ex + v;
-      __syncthreads();
-    }
-  if (tid == 0) rowtotal[blockIdx.x] = carry_s;
-}
-
-__global__ void sort_binbase_kernel(const unsigned *__restrict__ rowtotal, unsigned *__restrict__ binbase)
-{ __shared__ unsigned wsum[8];
-  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  unsigned v = rowtotal[tid];
-  unsigned inc = warp_incl_scan(v,lane);
-  if (lane == 31) wsum[w] = inc;
-  __syncthreads();
-  unsigned pre = 0;
-  for (int i = 0; i < w; i++) pre += wsum[i];
-  binbase[tid] = pre + inc - v;
-}
-
-//  Stable scatter of one tile.
-
-__global__ void __launch_bounds__(SORT_THREADS)
-sort_scatter_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, long long n, int byte,
-                    const unsigned *__restrict__ blockhist, const unsigned *__restrict__ binbase,
-                    int ntiles)
-{ extern __shared__ __align__(16) unsigned char smem_raw[];
-  rec128   *tile   = reinterpret_cast<rec128 *>(smem_raw);
-  unsigned *wcount = reinterpret_cast<unsigned *>(tile + SORT_TILE);   // [SORT_WARPS][256]
-  unsigned *bexcl  = wcount + SORT_WARPS*256;                           // [256]
-  unsigned *gbase  = bexcl + 256;                                       // [256]
-  unsigned *wtot   = gbase + 256;                                       // [8]
-
-  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  long long tile0 = (long long) blockIdx.x * SORT_TILE;
-  long long rem = n - tile0;
-  int cnt = rem < SORT_TILE ? (int) rem : SORT_TILE;
-
-  for (int i = tid; i < SORT_WARPS*256; i += SORT_THREADS)
-    wcount[i] = 0;
-  __syncthreads();
-
-  rec128   r[SORT_ITEMS];
-  unsigned rank[SORT_ITEMS];
-  int base = w*(32*SORT_ITEMS);
-  unsigned *myc = wcount + w*256;
-#pragma unroll
-  for (int it = 0; it < SORT_ITEMS; it++)
-    { int idx = base + it*32 + lane;
-      bool valid = idx < cnt;
-      unsigned d = 0x100u | lane;
-      if (valid)
-        { r[it] = ld_rec(in + tile0 + idx);
-          d = rec_byte(r[it],byte);
-        }
-      unsigned peers = __match_any_sync(0xffffffffu,d);
-      int leader = __ffs(peers)-1;
-      unsigned b = 0;
-      if (valid && lane == leader)
-        { b = myc[d];
-          myc[d] = b + __popc(peers);
-        }
-      b = __shfl_sync(0xffffffffu,b,leader);
-      rank[it] = b + __popc(peers & lanemask_lt());
-      __syncwarp();
-    }
-  __syncthreads();
-
-  unsigned c = 0, inc = 0;
-  if (tid < 256)
-    { unsigned sum = 0;
-#pragma unroll
-      for (int ww = 0; ww < SORT_WARPS; ww++)
-        { unsigned t = wcount[ww*256+tid];
-          wcount[ww*256+tid] = sum;
-          sum += t;
-        }
-      c = sum;
-      inc = warp_incl_scan(c,lane);
-      if (lane == 31) wtot[w] = inc;
-    }
-  __syncthreads();
-  if (tid < 256)
-    { unsigned pre = 0;
-      for (int i = 0; i < w; i++) pre += wtot[i];
-      unsigned ex = pre + inc - c;
-      bexcl[tid] = ex;
-      gbase[tid] = binbase[tid] + blockhist[(long long) tid*ntiles + blockIdx.x] - ex;
-    }
-  __syncthreads();
-
-#pragma unroll
-  for (int it = 0; it < SORT_ITEMS; it++)
-    { int idx = base + it*32 + lane;
-      if (idx < cnt)
-        { unsigned d = rec_byte(r[it],byte);
-          st_rec(tile + (bexcl[d] + myc[d] + rank[it]),r[it]);
-        }
-    }
-  __syncthreads();
-
-  for (int p = tid; p < cnt; p += SORT_THREADS)
-    { rec128 v = ld_rec(tile + p);
-      unsigned d = rec_byte(v,byte);
-      st_rec(out + (unsigned) (gbase[d] + p),v);
-    }
 }
 
 /***********************************************************************************************
@@ -257,9 +97,19 @@ sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, lo
   unsigned *wtot   = nhist + 256;                                       // [8]
   unsigned long long *gbase = reinterpret_cast<unsigned long long *>(wtot + 8);   // [256]
   __shared__ unsigned tile_s;
+  __shared__ __align__(8) unsigned long long tbar;
 
   int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid == 0) tile_s = atomicAdd(ticket,1u);
+  if (tid == 0)
+    { unsigned t = atomicAdd(ticket,1u);
+      tile_s = t;
+      //  the tile is 4096 consecutive 128-bit records: fetched by one TMA bulk copy (UBLKCP)
+      //  into the staging buffer while the block zeroes its counters
+      long long t0 = (long long) t * SORT_TILE, rm = n - t0;
+      unsigned nb = (unsigned) (rm < SORT_TILE ? rm : SORT_TILE) * 16u;
+      mbar_init(&tbar,1);
+      tma_load_1d(tile,in + t0,nb,&tbar);
+    }
   for (int i = tid; i < SORT_WARPS*256; i += SORT_THREADS) wcount[i] = 0;
   if (tid < 256) nhist[tid] = 0;
   __syncthreads();
@@ -272,13 +122,14 @@ sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, lo
   unsigned rank[SORT_ITEMS];
   int base = w*(32*SORT_ITEMS);
   unsigned *myc = wcount + w*256;
+  mbar_wait(&tbar,0);
 #pragma unroll
   for (int it = 0; it < SORT_ITEMS; it++)
     { int idx = base + it*32 + lane;
       bool valid = idx < cnt;
       unsigned d = 0x100u | lane;
       if (valid)
-        { r[it] = ld_rec(in + tile0 + idx);
+        { r[it] = ld_rec(tile + idx);
           d = rec_byte(r[it],byte);
         }
       unsigned peers = __match_any_sync(0xffffffffu,d);
@@ -359,8 +210,6 @@ sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, lo
 
 static const size_t ONESWEEP_SMEM = SORT_TILE*sizeof(rec128) + (SORT_WARPS*256 + 256 + 256 + 8)*sizeof(unsigned)
                                     + 256*sizeof(unsigned long long);
-
-static const size_t SCATTER_SMEM = SORT_TILE*sizeof(rec128) + (SORT_WARPS*256 + 256 + 256 + 8)*sizeof(unsigned);
 
 extern "C" long long fgb_sort128_tmp_bytes(long long n)
 { long long ntiles = (n + SORT_TILE - 1) / SORT_TILE;

@@ -106,6 +106,28 @@ class DeviceGix:
         return cls(h)
 
     @classmethod
+    def build_range(cls, dgenome, plo, phi, stream=None):
+        L = load_library()
+        h = c_void_p()
+        L.fgb_gix_build_range.argtypes = [c_void_p, C.c_uint, C.c_uint, C.POINTER(c_void_p), c_void_p]
+        _check(L.fgb_gix_build_range(dgenome.h, plo, phi, C.byref(h), stream), "fgb_gix_build_range")
+        return cls(h)
+
+    @classmethod
+    def from_device(cls, dev_ptr, n, post_bytes, cont_bytes, ncontig, stream=None):
+        L = load_library()
+        h = c_void_p()
+        L.fgb_gix_from_device.argtypes = [c_void_p, c_ll, c_int, c_int, c_int, C.POINTER(c_void_p), c_void_p]
+        _check(L.fgb_gix_from_device(c_void_p(dev_ptr), n, post_bytes, cont_bytes, ncontig, C.byref(h), stream),
+               "fgb_gix_from_device")
+        return cls(h)
+
+    def copy_table_to(self, dev_ptr, stream=None):
+        L = load_library()
+        L.fgb_gix_copy_table.argtypes = [c_void_p, c_void_p, c_void_p]
+        _check(L.fgb_gix_copy_table(self.h, c_void_p(dev_ptr), stream), "fgb_gix_copy_table")
+
+    @classmethod
     def upload(cls, tab, post_bytes, cont_bytes, ncontig, stream=None):
         L = load_library()
         h = c_void_p()
@@ -423,6 +445,22 @@ def align_resident(dA, dB, freqA, stream=None, **kw):
     _check(L.fgb_align_resident(dA.h, dB.h, _ptr(f), p["freq"], p["chain_break"], p["chain_min"],
                                 p["align_min"], float(p["align_rate"]), C.byref(h), C.byref(st), stream),
            "fgb_align_resident")
+    return _alns_out(h), st.asdict()
+
+
+def align_tables(dA, dB, xA, xB, freqA, stream=None, **kw):
+    """merge + seed sort + extension + filter from prebuilt tables"""
+    p = dict(DEFAULTS)
+    p.update(kw)
+    L = load_library()
+    h = c_void_p()
+    st = RunStats()
+    f = np.ascontiguousarray(freqA, dtype=np.float32)
+    L.fgb_align_tables.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                   C.c_double, C.POINTER(c_void_p), C.POINTER(RunStats), c_void_p]
+    _check(L.fgb_align_tables(dA.h, dB.h, xA.h, xB.h, _ptr(f), p["freq"], p["chain_break"], p["chain_min"],
+                              p["align_min"], float(p["align_rate"]), C.byref(h), C.byref(st), stream),
+           "fgb_align_tables")
     return _alns_out(h), st.asdict()
 
 

@@ -64,6 +64,11 @@ int fgb_align_resident(const fgb_genome *A, const fgb_genome *B, const float *fr
                        int freq, int chain_break, int chain_min, int align_min, double align_rate,
                        fgb_alns **out, fgb_run_stats *stats, void *stream);
 
+/* Same from prebuilt tables (x2 possibly assembled from per-rank shares). */
+int fgb_align_tables(const fgb_genome *A, const fgb_genome *B, const fgb_gix *x1, const fgb_gix *x2,
+                     const float *freqA, int freq, int chain_break, int chain_min, int align_min,
+                     double align_rate, fgb_alns **out, fgb_run_stats *stats, void *stream);
+
 /* ---- genome (GDB.h:28-72; Get_Contig / Get_Contig_Piece GDB.c:1739,1841; Complement_Seq) ---- */
 int  fgb_genome_create(const unsigned char *bps, long long bps_bytes, int ncontig,
                        const long long *clen, const long long *boff, int want_revcomp,
@@ -75,6 +80,12 @@ long long fgb_genome_words(const fgb_genome *g);
 
 /* ---- GIX (GIXmake.c distribute + k_sort; MSDsort.c msd_sort; libfastk.c Kmer_Stream) ---- */
 int  fgb_gix_build(const fgb_genome *g, fgb_gix **out, void *stream);
+/* one rank's share (12-base prefix in [plo,phi)) of a cooperatively built table, and the pieces
+   to assemble the shares gathered over NCCL (fastga_b200/shard.py) */
+int  fgb_gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi, fgb_gix **out, void *stream);
+int  fgb_gix_copy_table(const fgb_gix *x, void *d_dst, void *stream);
+int  fgb_gix_from_device(const void *d_tab, long long n, int post_bytes, int cont_bytes, int ncontig,
+                         fgb_gix **out, void *stream);
 int  fgb_gix_upload(const void *tab, long long n, int post_bytes, int cont_bytes, int ncontig,
                     fgb_gix **out, void *stream);
 /* entries = concatenated .ktab parts, index = the stub's cumulative 2^24 table (libfastk.c:815-840) */
