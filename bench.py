@@ -85,6 +85,21 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes of one adaptamer_merge_kernel launch on this workload from the committed ncu
+    --set full capture (profiles/r01_ncu_merge_kernel.json); None if no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_merge_kernel.json")
+    try:
+        d = json.load(open(p))
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v, u = d[k].split()
+            tot += float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+        return tot
+    except Exception:
+        return None
+
+
 def run_reference_sample(sample_bp, ncontig, steps, warmup, threads):
     """times oracle/_ref/FastGA on a bounded sample of the workload; returns (Gbp/s, ms/step, info)"""
     from fastga_b200 import formats, synth
@@ -116,6 +131,21 @@ def run_reference_sample(sample_bp, ncontig, steps, warmup, threads):
 
 
 def main():
+    #  stdout carries exactly ONE line (the JSON): libraries that chat on fd 1 (NCCL prints its
+    #  version there) are pointed at stderr for the duration of the run
+    sys.stdout.flush()
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run()
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_out, 1)
+    if line is not None:
+        os.write(1, (json.dumps(line) + "\n").encode())
+
+
+def run():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -132,7 +162,7 @@ def main():
 
     if args.impl == "reference":
         if rank != 0:
-            return
+            return None
         threads = min(cores, 32)          # GIXmake refuses -T > 32 (GIXmake.c:1723)
         sample_bp = 20_000_000
         val, ms, info = run_reference_sample(sample_bp, 4, max(1, args.steps), min(args.warmup, 1), threads)
@@ -146,8 +176,7 @@ def main():
                 "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": threads, "kind": "reference",
                                  "sample": "%.3f Gbp pair, FastGA incl. FAtoGDB+GIXmake, tmp on /dev/shm" % info["sample_gbp"]},
                 "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return
+        return line
 
     import torch
     import torch.distributed as dist
@@ -227,7 +256,7 @@ def main():
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
+        return None
 
     steps = args.steps
     # roofline of the seed-merge kernel (the kernel north_star grades): algorithmic bytes on the
@@ -258,9 +287,12 @@ def main():
                        "host_wall_us": {k: stats[k] for k in ("us_gix", "us_seeds", "us_extend", "us_filter")},
                        "extend_cycles": {k: stats[k] for k in ("warp_cycles", "wave_cycles", "extract_cycles")}},
             "roofline": {"bound": "hbm", "kernel": "adaptamer_merge_kernel", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": ach / peak,
+                         "traffic": ncu_traffic_bytes() if (world == 1 and args.per_gpu_bp == PER_GPU_BP) else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes": algo, "kernel_ms": merge_ms},
-            "extend_kernel": {"ms": tm["extend_ms"] / steps, "cell_updates_per_s":
+            "extend_kernel": {"ms": tm["extend_ms"] / steps, "launches_per_step": tm["extend_launches"] / steps,
+                              "cell_updates_per_s":
                               stats["ncells"] / max(1e-9, tm["extend_ms"] / steps / 1000.0)},
             "clocks": sampler.summary(),
             "e2e": {"value": total_gbp / (ms_e2e / 1000.0), "unit": "Gbp/s",
@@ -278,9 +310,9 @@ def main():
         except Exception as ex:      # the reference arm must never sink the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "Gbp/s", "cores": cores, "kind": "reference",
                                     "sample": "failed: %s" % str(ex)[:200]}
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":

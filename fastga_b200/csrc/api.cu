@@ -311,10 +311,11 @@ static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi, fgb_
   }
   x->d_tab = inb ? d_b : d_a;
   CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
-  { stage_timer t(&g_timings.index_ms,st);
-    rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
-    if (rc) return rc;
-  }
+  if (plo == 0 && phi == (1u << 24))              // a share is indexed after assembly, not here
+    { stage_timer t(&g_timings.index_ms,st);
+      rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
+      if (rc) return rc;
+    }
   CUDA_TRY(cudaStreamSynchronize(st));
   fgb_dfree(inb ? d_a : d_b,st); fgb_dfree(d_stmp,st);
   fgb_dfree(d_tc,st); fgb_dfree(d_ts,st); fgb_dfree(d_cnt,st); fgb_dfree(d_buck,st); fgb_dfree(d_total,st); fgb_dfree(d_tmp,st);
@@ -341,7 +342,10 @@ extern "C" int fgb_gix_from_device(const void *d_tab, long long n, int post_byte
   CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
   CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
   CUDA_TRY(cudaMemcpyAsync(x->d_tab,d_tab,sizeof(rec128)*n,cudaMemcpyDeviceToDevice,st));
-  int rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
+  int rc;
+  { stage_timer t(&g_timings.index_ms,st);
+    rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
+  }
   CUDA_TRY(cudaStreamSynchronize(st));
   if (rc) return rc;
   *out = x;

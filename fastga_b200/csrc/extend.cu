@@ -1120,7 +1120,8 @@ __global__ void seg_fill2_kernel(const rec128 *__restrict__ seeds, long long n, 
 #define PREF_LONG 64
 
 __global__ void prefilter_kernel(ext_params P, unsigned *__restrict__ work_long, unsigned *__restrict__ work_short,
-                                 unsigned *__restrict__ nwork /* [0] long [1] short */)
+                                 unsigned *__restrict__ nwork /* [0] long [1] short */,
+                                 unsigned *__restrict__ long_size)
 { unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= (unsigned) P.nseg) return;
   const rec128 *S = P.seeds;
@@ -1145,7 +1146,9 @@ __global__ void prefilter_kernel(ext_params P, unsigned *__restrict__ work_long,
             isnew = false;
         }
       if (isnew || e != m)
-        work_long[atomicAdd(nwork,1u)] = j;
+        { unsigned o = atomicAdd(nwork,1u);
+          work_long[o] = j; long_size[o] = e - b;
+        }
       return;
     }
   Ctx c; u64 nla = 0; unsigned nh = 0;
@@ -1158,8 +1161,15 @@ __global__ void prefilter_kernel(ext_params P, unsigned *__restrict__ work_long,
 #define STATE_BYTES (WSTATE_BYTES(EX_W) + SCAN_SMEM)
 #define BIG_SMEM_PER_WARP (SCAN_SMEM)
 #define TT_BYTES    ((256+128)*4)
-#define MBOX_BYTES  ((EX_WARPS/2)*((int) sizeof(Mbox)))
-#define EX_PRIM     (EX_WARPS/2)        // warps 0..EX_PRIM-1 take triples, warp p+EX_PRIM is the helper of warp p
+#define MBOX_BYTES  (EX_WARPS*((int) sizeof(Mbox)))
+//  EX_HANDOFF 1: warps 0..EX_PRIM-1 take triples and warp p+EX_PRIM runs the reverse passes of
+//  warp p.  Measured on the 100 Mbp benchmark the reverse pass is short (tubes are entered 128
+//  anti-diagonals above their start, FastGA.c:3235), so pairing halves the number of triples in
+//  flight for a ~5 % gain on the longest one; with EX_HANDOFF 0 every warp takes triples.
+#ifndef EX_HANDOFF
+#define EX_HANDOFF 0
+#endif
+#define EX_PRIM     (EX_HANDOFF ? EX_WARPS/2 : EX_WARPS)
 
 template<int W>
 __global__ void __launch_bounds__(EX_WARPS*32)
@@ -1190,12 +1200,12 @@ extend_kernel(ext_params P)
     c.tt1 = tt; c.tt2 = tt + 256;
     Mbox *mb = (Mbox *) (smem + (size_t) EX_WARPS * per_warp + TT_BYTES) + (wp % EX_PRIM);
     if (wp < EX_PRIM && lane == 0) mb->state = 0;
-    c.mbox = mb;
+    c.mbox = EX_HANDOFF ? mb : NULL;
     __syncthreads();
   }
   long long t_start = clock64();
   c.cells = P.cells + gw * P.cells_per_warp;
-  c.pcells = P.cells + (gw + EX_PRIM) * P.cells_per_warp;
+  c.pcells = P.cells + (gw + (EX_HANDOFF ? EX_PRIM : 0)) * P.cells_per_warp;
   c.cmax  = (int) P.cells_per_warp;
   c.avail = 0;
   c.fstage = P.stage + gw * 2ll * P.stage_bytes;
@@ -1205,7 +1215,7 @@ extend_kernel(ext_params P)
   c.nwaves = 0; c.ncells = 0; c.cyc_wave = 0; c.cyc_extract = 0; c.njobs = 0; c.nmiss = 0; c.cyc_wait = 0;
   u64 nla = 0, nhits = 0;
 
-  if (wp >= EX_PRIM)
+  if (EX_HANDOFF && wp >= EX_PRIM)
     { //  helper warp: runs the reverse waves its primary posts
       Mbox *mb = c.mbox;
       c.mbox = NULL;
@@ -1250,7 +1260,7 @@ extend_kernel(ext_params P)
         nhits += nh;
       __syncwarp();
     }
-  if (lane == 0) c.mbox->state = 3;            // release the helper
+  if (EX_HANDOFF && lane == 0) c.mbox->state = 3;   // release the helper
   if (lane == 0)
     { atomicAdd(&P.counters[0],nhits);
       atomicAdd(&P.counters[1],nla);
@@ -1382,17 +1392,31 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       CUDA_TRY(cudaStreamSynchronize(st));
       nseg = (unsigned) tot;
       CUDA_TRY(fgb_dmalloc((void **) &d_seg,sizeof(unsigned)*(nseg+2),st));
-      CUDA_TRY(fgb_dmalloc((void **) &d_work,sizeof(unsigned)*(2ll*nseg+2),st));
+      CUDA_TRY(fgb_dmalloc((void **) &d_work,sizeof(unsigned)*(3ll*nseg+3),st));
       nb = (int) ((n + 1 + 255) / 256);
       seg_fill2_kernel<<<nb,256,0,st>>>(S->d_rec,n,P.p_band,d_flag,d_seg,nseg);
       P.seg_start = d_seg; P.nseg = (int) nseg;
-      prefilter_kernel<<<(nseg + 127)/128,128,0,st>>>(P,d_work,d_work + nseg + 1,d_misc + 6);
+      prefilter_kernel<<<(nseg + 127)/128,128,0,st>>>(P,d_work,d_work + nseg + 1,d_misc + 6,d_work + 2ll*nseg + 2);
       fgb_count_launch(3);
       CUDA_TRY(cudaGetLastError());
       unsigned nw2[2];
       CUDA_TRY(cudaMemcpyAsync(nw2,d_misc + 6,8,cudaMemcpyDeviceToHost,st));
       CUDA_TRY(cudaStreamSynchronize(st));
-      //  long triples first (they are the stragglers), then the exact short hits
+      //  long triples first, largest first (the kernel's makespan is its longest triple, so it
+      //  must not start late), then the exact short hits
+      if (nw2[0] > 1 && nw2[0] <= (1u << 20))
+        { std::vector<unsigned> lj(nw2[0]), ls(nw2[0]), ord(nw2[0]);
+          CUDA_TRY(cudaMemcpyAsync(lj.data(),d_work,4ull*nw2[0],cudaMemcpyDeviceToHost,st));
+          CUDA_TRY(cudaMemcpyAsync(ls.data(),d_work + 2ll*nseg + 2,4ull*nw2[0],cudaMemcpyDeviceToHost,st));
+          CUDA_TRY(cudaStreamSynchronize(st));
+          for (unsigned q = 0; q < nw2[0]; q++) ord[q] = q;
+          std::sort(ord.begin(),ord.end(),[&](unsigned a, unsigned b)
+                    { return ls[a] != ls[b] ? ls[a] > ls[b] : lj[a] < lj[b]; });
+          std::vector<unsigned> sj(nw2[0]);
+          for (unsigned q = 0; q < nw2[0]; q++) sj[q] = lj[ord[q]];
+          CUDA_TRY(cudaMemcpyAsync(d_work,sj.data(),4ull*nw2[0],cudaMemcpyHostToDevice,st));
+          CUDA_TRY(cudaStreamSynchronize(st));
+        }
       CUDA_TRY(cudaMemcpyAsync(d_work + nw2[0],d_work + nseg + 1,sizeof(unsigned)*nw2[1],
                                cudaMemcpyDeviceToDevice,st));
       nwork = nw2[0] + nw2[1];
