@@ -1273,6 +1273,10 @@ extend_kernel(ext_params P)
       atomicAdd(&P.counters[12],c.nmiss);
       atomicAdd(&P.counters[13],c.cyc_wait);
       atomicMax(&P.counters[14],(u64) (clock64() - t_start));
+      { u64 cy = (u64) (clock64() - t_start) >> 12, wv = c.nwaves > 0xffffff ? 0xffffff : c.nwaves;
+        u64 la = nla > 0xffff ? 0xffff : nla;
+        atomicMax(&P.counters[15],(cy << 40) | (wv << 16) | la);      // the slowest warp: cycles/4096, waves, LA calls
+      }
     }
 }
 

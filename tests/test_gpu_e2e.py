@@ -117,3 +117,25 @@ def test_gix_files_match_reference_gixmake():
     assert np.array_equal(ipstart, pstart)
     key = lambda t: np.lexsort((t[:, 0] & np.uint64(0xffffffffffff), t[:, 0] >> np.uint64(48), t[:, 1]))
     assert np.array_equal(itab[key(itab)], tab[key(tab)])
+
+
+# ---------------------------------------------------------------------------------------------
+#  edge cases (tests/edge_cases.py): ragged / degenerate inputs, against the reference
+# ---------------------------------------------------------------------------------------------
+
+import edge_cases  # noqa: E402
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", sorted(edge_cases.CASES))
+def test_edge_case_bit_exact_vs_reference(name):
+    A, B, threads, check = edge_cases.CASES[name]()
+    with tempfile.TemporaryDirectory() as wd:
+        formats.write_fasta(os.path.join(wd, "A.fasta"), synth.scaffolds_of(A, "sa", 1))
+        formats.write_fasta(os.path.join(wd, "B.fasta"), synth.scaffolds_of(B, "sb", 1))
+        st = ol.parse_fastga_log(ol.ref_fastga(wd, "A", "B", threads=threads))
+        ref = ol.oneview_records(os.path.join(wd, "ref.1aln"))
+    alns, stats = lib.fastga(formats.genome_from_arrays(A), formats.genome_from_arrays(B))
+    assert stats["nseeds"] == st.get("seeds", 0)
+    assert alns.canonical_lines() == ref
+    check(alns, stats["nhits"])

@@ -173,3 +173,22 @@ def test_written_1aln_is_read_by_reference_tools(tmp_path):
     ol.run_ref(["ONEview", "-b", "-o", "mineb.1aln", "mine.1aln"], cwd=wd)
     paf_mine = sorted(ol.run_ref(["ALNtoPAF", "-T2", "mineb"], cwd=wd).split("\n"))
     assert len(paf_ref) > 3 and paf_mine == paf_ref
+
+
+import edge_cases  # noqa: E402
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", sorted(edge_cases.CASES))
+def test_oracle_edge_cases_vs_live_reference(name, tmp_path):
+    """the oracle on the edge-case inputs of tests/edge_cases.py, against a live reference run"""
+    A, B, threads, check = edge_cases.CASES[name]()
+    wd = str(tmp_path)
+    formats.write_fasta(os.path.join(wd, "A.fasta"), synth.scaffolds_of(A, "sa", 1))
+    formats.write_fasta(os.path.join(wd, "B.fasta"), synth.scaffolds_of(B, "sb", 1))
+    st = ol.parse_fastga_log(ol.ref_fastga(wd, "A", "B", threads=threads))
+    ref = ol.oneview_records(os.path.join(wd, "ref.1aln"))
+    r = ol.oracle_pipeline(formats.genome_from_arrays(A), formats.genome_from_arrays(B))
+    assert r["nseeds"] == st.get("seeds", 0)
+    assert r["lines"] == ref
+    check(r["alns"], r["nhit"])
