@@ -27,7 +27,12 @@
 
 typedef unsigned long long u64;
 
+#ifndef EX_WARPS
 #define EX_WARPS     8
+#endif
+#ifndef EX_MINBLK
+#define EX_MINBLK    1
+#endif
 #define EX_W         256                 // diagonals of wave state per warp (shared memory)
 #define FULL         0xffffffffu
 
@@ -67,26 +72,62 @@ struct ext_params
   unsigned char *bigstate;                             // wide-band kernel: per-warp wave state in HBM
 };
 
-//  Mailbox of a warp pair in shared memory: the primary warp posts the reverse pass of a
-//  Local_Alignment as soon as its start diagonal is final; the helper warp runs the wave and
-//  returns the trim point (the pebble chain stays in the helper's arena).
-struct Mbox
-{ volatile int state;                    // 0 idle, 1 job posted, 2 done, 3 exit
-  int low, anti, minp, maxp, aoff;
-  int status, endx, endy, diffs, trimha;
-  int alen, blen;
-  const unsigned *A, *B;
-};
-
 struct Ctx
 { const unsigned *A, *B; int alen, blen; long long anw, bnw;
-  int *V, *HA, *HM, *NA, *RD; u64 *T; int *carry;
-  Mbox *mbox;                            // pair mailbox (primary -> helper warp), NULL = none
-  Peb *cells; const Peb *pcells; int cmax, avail;      // pcells: the partner warp's arena
+  int *V, *HA, *HM, *NA; u64 *T; int *carry;
+  Peb *cells; int cmax, avail;
   unsigned char *fstage, *rstage; int smax;
-  int tspace, path_ave; const short *score, *table; const short2 *tt1, *tt2;
-  u64 nwaves, ncells, cyc_wave, cyc_extract, njobs, nmiss, cyc_wait;
+  int tspace, path_ave; const short *score, *table; const short *ttab; int sc15;
+  u64 nwaves, ncells, cyc_wave, cyc_extract, pwaves, npairs, fwait, ftot, bwait, btot;
+  struct PairBox *box;                   // front/back warp pair mailbox (NULL: this warp runs waves alone)
 };
+
+//  Front/back pairing of a wave pass.  The recurrence that makes a pass serial is only the
+//  furthest-point recurrence V (three-way max + snake) and the band trim that follows from it;
+//  the match bit-vectors, the trim-point tests and the trace pebbles hang off it without feeding
+//  back, except for the loop's stop test.  So a pass is split over two warps of a block: the FRONT
+//  warp runs V and the band, and streams each wave (the 32 new V values + a header) through a ring
+//  in shared memory; the BACK warp replays the predecessor choice from the V values, carries
+//  T / HA / HM / NA in its registers, tests trim points, drops pebbles, and raises `stop` when
+//  lasta falls TRIM_MLAG behind.  The front may run ahead by at most EX_RING waves; what it
+//  computes past the stop wave is discarded.  Anything unusual (band wider than 31 diagonals,
+//  a wave that does not advance the best point, an empty band) is handed back: the back warp
+//  spills its state and the front warp finishes the pass alone on the code below.
+
+#ifndef EX_PAIR
+#define EX_PAIR 1
+#endif
+#define EX_RING 32
+
+struct __align__(16) RingEnt
+{ int cmd, top, lowk, mx;                // cmd 1 wave, 2 last wave (more == 0), 3 hand back; band [lowk,top] of the wave
+  int lowk_after, hghk_after, pad0, pad1;
+  int cc[32];
+};
+
+struct __align__(16) PairBox
+{ volatile int seq, cmd;                 // front -> back: seq bumps per request; cmd 1 / 2 = forward / reverse pass, 9 exit
+  volatile int head, tail;               // last wave pushed / consumed
+  volatile int stop;                     // back -> front: 0 running, 1 pass finished, 2 handed back
+  int lowk, hghk, besta, lasta, trima, trimx, trimd, trimha, avail;
+  int tspace, path_ave, cmax, wmask, dif0;
+  Peb *cells; int *V, *HA, *HM, *NA; u64 *T;
+  int status, r_lasta, r_trima, r_trimx, r_trimd, r_trimha, r_avail, r_dif; u64 r_ncell;
+  long long r_bwait, r_btot;             // diagnostics: back warp cycles waiting for the front / in the pass
+  RingEnt ring[EX_RING];
+};
+
+#define SPIN_LIMIT (1 << 27)
+#ifndef EX_DIAG
+#define EX_DIAG 0                        // 1: per-wave wait-cycle accounting of the pair (slows the waves by ~5 %)
+#endif
+#define DIAG_CLOCK() (EX_DIAG ? clock64() : 0ll)
+
+static __device__ __forceinline__ Peb ldpeb(const Peb *p)        // pebbles may have been written by the partner warp
+{ int4 v = __ldcg((const int4 *) p);
+  Peb r; r.ptr = v.x; r.diag = v.y; r.diff = v.z; r.mark = v.w;
+  return r;
+}
 
 #define EX_WBIG      8192                // diagonals of wave state per warp in the wide-band retry kernel (HBM)
 #define IX(k) ((k) & (W-1))
@@ -154,20 +195,14 @@ static __device__ __forceinline__ int snake(const Ctx &c, int xn, int kk, int &f
   return t;
 }
 
-//  TABLE[x] / SCORE[x] of align.c:207-220 for a 15-bit column pattern x, from two small shared
-//  tables instead of the 2 x 64 KB arrays: the pattern is scored MSB first with +mscore / -dscore;
-//  SCORE = final score, TABLE = final score - max over the proper prefixes (incl. the empty one).
-//  tt1[u] (first 8 columns): x = score after them, y = max prefix score before each of them;
-//  tt2[v] (last 7 columns):  x = their score, y = max partial score before each of them (>= 0).
+//  TABLE[x] / SCORE[x] of align.c:207-220 for a 15-bit column pattern x.  TABLE (64 KB of int16)
+//  is staged in shared memory once per block; SCORE[x] = popc(x)*1000 - 15*dscore needs no table.
 
 static __device__ __forceinline__ bool trim_ok(const Ctx &c, u64 b)
 { int lo15 = (int) (b & TRIM_MASK), hi15 = (int) ((b >> TRIM_LEN) & TRIM_MASK);
-  short2 l1 = c.tt1[lo15 >> 7], l2 = c.tt2[lo15 & 127];
-  int ltot = l1.x + l2.x, lmax = max((int) l1.y,l1.x + l2.y);
-  if (ltot - lmax < 0) return false;                       // TABLE[b & MASK] >= 0
-  short2 h1 = c.tt1[hi15 >> 7], h2 = c.tt2[hi15 & 127];
-  int htot = h1.x + h2.x, hmax = max((int) h1.y,h1.x + h2.y);
-  return (htot - hmax) + ltot >= 0;                        // TABLE[hi] + SCORE[lo] >= 0
+  int tl = c.ttab[lo15], th = c.ttab[hi15];
+  int sl = __popc(lo15)*1000 - c.sc15;
+  return tl >= 0 && th + sl >= 0;                        // TABLE[lo] >= 0 && TABLE[hi] + SCORE[lo] >= 0
 }
 
 static __device__ __forceinline__ int warp_prefix_max_excl(int v, int lane)
@@ -183,11 +218,158 @@ static __device__ __forceinline__ int warp_prefix_max_excl(int v, int lane)
 
 //  One wave pass (direction s) from anti-diagonal mida over diagonals [low,hgh].
 //  Outputs the trim point (original coordinates), its diffs and the pebble chain head.
+//
+//  Wave state per diagonal: V (furthest anti-diagonal), T (match bit-vector of the last 64
+//  columns), HA/HM (head pebble and its mark), NA (next trace-point anti-diagonal).  While the
+//  band fits one warp (<= 32 diagonals, the normal case: the WAVE_LAG trim keeps ~8) the state
+//  lives in REGISTERS of the lane that owns the diagonal (lane = -kk mod 32, fixed for the whole
+//  pass), neighbours are read with shuffles and a wave is one straight-line pass with no shared
+//  memory traffic and no barrier.  Wider bands spill to the arrays in c (shared memory, or HBM in
+//  the wide-band retry kernel) and are processed in 32-diagonal chunks.
+
+static __device__ __forceinline__ unsigned rotr32(unsigned x, int r) { return __funnelshift_r(x,x,r); }
+
+//  BACK warp of a pair: one wave pass (direction s) from the state the front warp left after
+//  wave 0.  Returns when the pass is finished (stop = 1) or handed back (stop = 2).
+
+static __device__ __forceinline__ void back_results(PairBox *bx, int status, int lasta, int trima, int trimx,
+                                                    int trimd, int trimha, int avail, int dif, u64 ncell, int stop)
+{ __syncwarp();
+  if ((threadIdx.x & 31) == 0)
+    { bx->status = status; bx->r_lasta = lasta; bx->r_trima = trima; bx->r_trimx = trimx; bx->r_trimd = trimd;
+      bx->r_trimha = trimha; bx->r_avail = avail; bx->r_dif = dif; bx->r_ncell = ncell;
+      __threadfence();                               // pebbles (HBM) before the flag
+      bx->stop = stop;
+    }
+  __syncwarp();
+}
+
+template<int s>
+static __device__ void wave_back(const Ctx &c, PairBox *bx)
+{ const int lane = threadIdx.x & 31;
+  const unsigned lt = lanemask_lt();
+  const int FRESH = (s > 0) ? -1 : -INT_MAX;
+  const int lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;
+  int lowk = bx->lowk, hghk = bx->hghk, besta = bx->besta, lasta = bx->lasta, trima = bx->trima;
+  int trimx = bx->trimx, trimd = bx->trimd, trimha = bx->trimha, avail = bx->avail;
+  const int tspace = bx->tspace, path_ave = bx->path_ave, cmax = bx->cmax, wmask = bx->wmask, dif0 = bx->dif0;
+  Peb *cells = bx->cells;
+  u64 ncell = 0;
+  int rV, rHA, rHM, rNA; u64 rT;
+  { const int kk = hghk - ((lane - ((-hghk) & 31)) & 31);
+    const int ix = kk & wmask;
+    rV = (kk >= lowk) ? bx->V[ix] : FRESH;
+    rT = bx->T[ix]; rHA = bx->HA[ix]; rHM = bx->HM[ix]; rNA = bx->NA[ix];
+  }
+  int d = 0, head_seen = 0;
+  long long bwait = 0; const long long bt0 = DIAG_CLOCK();
+  while (true)
+    { d += 1;
+      if (d > head_seen)
+        { int spin = 0;
+          long long w0 = DIAG_CLOCK();
+          if (EX_DIAG && lane == 0) { bx->r_bwait = bwait; bx->r_btot = w0 - bt0; }
+          while ((head_seen = bx->head) < d)
+            if (++spin > SPIN_LIMIT)
+              { back_results(bx,ST_STAGE,lasta,trima,trimx,trimd,trimha,avail,dif0+d-1,ncell,1); return; }
+          bwait += DIAG_CLOCK() - w0;
+          __threadfence_block();
+        }
+      const RingEnt *e = &bx->ring[d & (EX_RING-1)];
+      const int4 hd = *(const int4 *) e;                       // cmd, top, lowk, mx
+      if (hd.x == 3)
+        { //  hand back: the band of the last wave goes to the front warp's arrays
+          const int kk = hghk - ((lane - ((-hghk) & 31)) & 31);
+          if (kk >= lowk)
+            { const int ix = kk & wmask;
+              bx->V[ix] = rV; bx->T[ix] = rT; bx->HA[ix] = rHA; bx->HM[ix] = rHM; bx->NA[ix] = rNA;
+            }
+          back_results(bx,ST_OK,lasta,trima,trimx,trimd,trimha,avail,dif0+d-1,ncell,2);
+          return;
+        }
+      const int top = hd.y, lowb = hd.z, mx = hd.w;
+      const int la = e->lowk_after, ha_ = e->hghk_after;
+      int cc = e->cc[lane];
+      const int ltop = (-top) & 31;
+      const int kk = top - ((lane - ltop) & 31);
+      const bool act = kk >= lowb;
+      const bool fresh = (kk == top || kk == lowb);
+      //  replay the predecessor choice (align.c:625-660): out-of-band lanes hold FRESH
+      const int ap = __shfl_sync(FULL,rV,lane_up), am = __shfl_sync(FULL,rV,lane_dn), ac = rV;
+      int pred, cp;
+      if (ap > max(ac,am)) { pred = 1;  cp = ap+1; }
+      else if (am > ac)    { pred = -1; cp = am+1; }
+      else                 { pred = 0;  cp = ac+2; }
+      const int src = (lane - pred) & 31;
+      u64 b  = __shfl_sync(FULL,rT,src);
+      int ha = __shfl_sync(FULL,rHA,src), hm = __shfl_sync(FULL,rHM,src);
+      int nn = __shfl_sync(FULL,rNA,src);
+      int nan = fresh ? nn : rNA;
+      const int xn = (cc + kk) >> 1, k = s*kk;
+      { int t = xn - ((cp + kk) >> 1);                        // matches the snake slid over
+        b <<= 1;
+        b = (t >= 64) ? ~0ull : ((b << t) | ((1ull << t) - 1));
+      }
+
+      bool need = act && xn >= nan;
+      while (__any_sync(FULL,need))
+        { bool create = need && (s*hm < nan);
+          if (avail + 32 > cmax)
+            { back_results(bx,ST_CELLS,lasta,trima,trimx,trimd,trimha,avail,dif0+d-1,ncell,1); return; }
+          unsigned m = __ballot_sync(FULL,create);
+          int idx = avail + __popc(m & lt);
+          avail += __popc(m);
+          if (create)
+            { Peb p; p.ptr = ha; p.diag = k; p.diff = dif0+d; p.mark = s*nan;
+              cells[idx] = p;
+              ha = idx; hm = s*nan;
+            }
+          if (need) nan += tspace;
+          need = act && xn >= nan;
+        }
+
+      //  the front warp only pushes waves that advance the best point (mx > besta)
+      { const int cm = act ? cc : INT_MIN;
+        unsigned eq = rotr32(__ballot_sync(FULL,cm == mx),ltop);
+        int Lb = (ltop + __ffs(eq) - 1) & 31;
+        bool qual = act && cc > besta && __popcll(b & PATH_WIN) >= path_ave;
+        bool tq = qual && trim_ok(c,b);
+        unsigned ql = __ballot_sync(FULL,qual), tl = __ballot_sync(FULL,tq);
+        if ((tl >> Lb) & 1)
+          { lasta = mx; trima = mx; trimd = dif0+d;
+            trimx  = __shfl_sync(FULL,xn,Lb);
+            trimha = __shfl_sync(FULL,ha,Lb);
+          }
+        else
+          { int cpos = __shfl_sync(FULL,cm,(ltop + lane) & 31);   // value at position = lane
+            int ex = max(warp_prefix_max_excl(cpos,lane),besta);
+            unsigned rm = __ballot_sync(FULL,cpos > ex);
+            unsigned qm = rm & rotr32(ql,ltop), tm = rm & rotr32(tl,ltop);
+            if (qm) lasta = __shfl_sync(FULL,cc,(ltop + 31 - __clz(qm)) & 31);
+            if (tm)
+              { int L3 = (ltop + 31 - __clz(tm)) & 31;
+                trima  = __shfl_sync(FULL,cc,L3);
+                trimx  = __shfl_sync(FULL,xn,L3);
+                trimha = __shfl_sync(FULL,ha,L3);
+                trimd  = dif0+d;
+              }
+          }
+        besta = mx;
+      }
+      if (act) { rT = b; rHA = ha; rHM = hm; rNA = nan; }
+      rV = (kk >= la && kk <= ha_ && act) ? cc : FRESH;
+      lowk = la; hghk = ha_;
+      ncell += (u64) (top - lowb + 1);
+      __syncwarp();
+      if (lane == 0) bx->tail = d;
+      if (hd.x == 2 || lasta < besta - TRIM_MLAG)
+        { back_results(bx,ST_OK,lasta,trima,trimx,trimd,trimha,avail,dif0+d,ncell,1); return; }
+    }
+}
 
 template<int s, int W>
 static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, int maxp,
-                           const int aoff, int &endx, int &endy, int &diffs, int &trimha_out,
-                           bool *posted = NULL)
+                           const int aoff, int &endx, int &endy, int &diffs, int &trimha_out)
 { const int lane = threadIdx.x & 31;
   const unsigned lt = lanemask_lt();
   const int FRESH = (s > 0) ? -1 : -INT_MAX;
@@ -202,9 +384,10 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
   int dif = 0, more = 1;
   int besta = s*mida, trima = besta, lasta = besta;
   int bestx = s*((mida+hgh)>>1), trimx = bestx;
-  int trimd = 0, trimha = 0, trimrd = 0;
+  int trimd = 0, trimha = 0;
   int aclip = INT_MAX, bclip = -INT_MAX;
   bool anyhit = false;
+  u64 ncell = 0;
 
   //  wave 0 (align.c:426-507 / :956-1036)
   for (int top = hghk; top >= lowk; top -= 32)
@@ -249,7 +432,6 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
           besta = trima = lasta = __shfl_sync(FULL,cc,L);
           bestx = trimx = __shfl_sync(FULL,xn,L);
           trimha = __shfl_sync(FULL,ha,L);
-          trimrd = top - L;                               // wave 0: the root is the diagonal itself
         }
       unsigned hb = __ballot_sync(FULL,act && flag == 1);
       unsigned hq = __ballot_sync(FULL,act && flag == 2);
@@ -257,7 +439,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
       if (hq) { anyhit = true; aclip = top - (31 - __clz(hq)); }
       if (act)
         { c.V[IX(kk)] = cc; c.T[IX(kk)] = PATH_INT; c.HA[IX(kk)] = ha; c.HM[IX(kk)] = hm;
-          c.NA[IX(kk)] = nan; c.RD[IX(kk)] = kk;
+          c.NA[IX(kk)] = nan;
         }
     }
   __syncwarp();
@@ -269,8 +451,129 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
     }
 
   //  successive waves (align.c:546-800 / :1077-1330)
+  bool inreg = false;                          // state of the band is in the r* registers
+  int rV = 0, rHA = 0, rHM = 0, rNA = 0; u64 rT = 0;
+  const int lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;      // owners of kk+1 / kk-1
+
+  bool pair_ok = EX_PAIR && c.box != NULL && minp == -INT_MAX && maxp == INT_MAX;
   while (more && lasta >= besta - TRIM_MLAG)
-    { lowk -= 1; hghk += 1;
+    {
+      //  ---- front/back pairing (see PairBox): this warp keeps only V and the band ----
+      if (EX_PAIR && pair_ok && hghk >= lowk && hghk - lowk <= 24)
+        { PairBox *bx = c.box;
+          if (inreg)                                   // the band of the last wave goes to the arrays
+            { const int kk = hghk - ((lane - ((-hghk) & 31)) & 31);
+              if (kk >= lowk)
+                { c.V[IX(kk)] = rV; c.T[IX(kk)] = rT; c.HA[IX(kk)] = rHA; c.HM[IX(kk)] = rHM; c.NA[IX(kk)] = rNA; }
+              inreg = false;
+            }
+          __syncwarp();
+          if (lane == 0)
+            { bx->lowk = lowk; bx->hghk = hghk; bx->besta = besta; bx->lasta = lasta; bx->trima = trima;
+              bx->trimx = trimx; bx->trimd = trimd; bx->trimha = trimha; bx->avail = c.avail;
+              bx->tspace = tspace; bx->path_ave = c.path_ave; bx->cmax = c.cmax; bx->wmask = W-1; bx->dif0 = dif;
+              bx->cells = c.cells; bx->V = c.V; bx->HA = c.HA; bx->HM = c.HM; bx->NA = c.NA; bx->T = c.T;
+              bx->head = 0; bx->tail = 0; bx->stop = 0;
+              bx->cmd = (s > 0) ? 1 : 2;
+              __threadfence_block();
+              bx->seq = bx->seq + 1;
+            }
+          __syncwarp();
+          { const int kk = hghk - ((lane - ((-hghk) & 31)) & 31);
+            rV = (kk >= lowk) ? c.V[IX(kk)] : FRESH;
+          }
+          int d = 0, stp = 0, tail_seen = 0;
+          long long fwait = 0; const long long ft0 = DIAG_CLOCK();
+          while (true)
+            { const int lowk0 = lowk, hghk0 = hghk;
+              lowk -= 1; hghk += 1;
+              const int top = hghk, ltop = (-top) & 31;
+              const int kk = top - ((lane - ltop) & 31);
+              const bool act = kk >= lowk;
+              bool bail = (hghk - lowk > 30);
+              const bool wide = bail;
+              int cc = 0, xn = 0, flag = 0, mx = 0;
+              unsigned m = 0;
+              int nlow = lowk, nhgh = hghk, nmore = 1;
+              if (!bail)
+                { int vp = __shfl_sync(FULL,rV,lane_up), vm = __shfl_sync(FULL,rV,lane_dn);
+                  cc = max(max(vp,vm)+1,rV+2);
+                  xn = (cc + kk) >> 1;
+                  if (act) xn += snake<s>(c,xn,kk,flag);
+                  cc = 2*xn - kk;
+                  mx = __reduce_max_sync(FULL,act ? cc : INT_MIN);
+                  if (mx <= besta) bail = true;
+                }
+              if (!bail)
+                { if (__any_sync(FULL,act && flag != 0))
+                    { unsigned hb = rotr32(__ballot_sync(FULL,act && flag == 1),ltop);
+                      unsigned hq = rotr32(__ballot_sync(FULL,act && flag == 2),ltop);
+                      unsigned eq = rotr32(__ballot_sync(FULL,act && cc == mx),ltop);
+                      int bx_ = __shfl_sync(FULL,xn,(ltop + __ffs(eq) - 1) & 31);
+                      int acl = INT_MAX, bcl = -INT_MAX;
+                      if (hb) bcl = top - (__ffs(hb)-1);
+                      if (hq) acl = top - (31 - __clz(hq));
+                      nmore = (b_at<s>(c,mx-bx_) != 4 && a_at<s>(c,bx_) != 4);
+                      if (nhgh >= acl) nhgh = acl-1;
+                      if (nlow <= bcl) nlow = bcl+1;
+                    }
+                  m = rotr32(__ballot_sync(FULL,kk >= nlow && kk <= nhgh && cc >= mx - WAVE_LAG),ltop);
+                  if (m == 0) bail = true;
+                }
+              if (bail)
+                { //  not a plain wave: undo it, let the back warp spill, finish alone below
+                  lowk = lowk0; hghk = hghk0;
+                  if (!wide) pair_ok = false;                  // pathological wave: stay alone for the rest of the pass
+                  int spin = 0;
+                  while (d + 1 - bx->tail > EX_RING-1 && bx->stop == 0) if (++spin > SPIN_LIMIT) break;
+                  __syncwarp();
+                  if (lane == 0)
+                    { bx->ring[(d+1) & (EX_RING-1)].cmd = 3;
+                      __threadfence_block();
+                      bx->head = d+1;
+                    }
+                  break;
+                }
+              d += 1;
+              besta = mx;
+              hghk = top - (__ffs(m)-1); lowk = top - (31 - __clz(m));
+              rV = (kk >= lowk && kk <= hghk) ? cc : FRESH;
+              if (d - tail_seen > EX_RING-1)
+                { int spin = 0; long long w0 = DIAG_CLOCK();
+                  while (d - (tail_seen = bx->tail) > EX_RING-1 && bx->stop == 0) if (++spin > SPIN_LIMIT) break;
+                  fwait += DIAG_CLOCK() - w0;
+                }
+              RingEnt *e = &bx->ring[d & (EX_RING-1)];
+              e->cc[lane] = cc;
+              if (lane == 0)
+                { *(int4 *) e = make_int4(nmore ? 1 : 2,top,lowk0-1,mx);
+                  e->lowk_after = lowk; e->hghk_after = hghk;
+                }
+              if (!nmore || (d & 1) == 0)                        // publish every other wave
+                { __syncwarp();
+                  if (lane == 0) { __threadfence_block(); bx->head = d; }
+                }
+              if (!nmore || ((d & 7) == 0 && bx->stop != 0)) break;
+            }
+          { int spin = 0; long long w0 = DIAG_CLOCK();
+            while ((stp = bx->stop) == 0) if (++spin > SPIN_LIMIT) { stp = 1; break; }
+            fwait += DIAG_CLOCK() - w0;
+            c.fwait += (u64) fwait; c.ftot += (u64) (DIAG_CLOCK() - ft0);
+          }
+          __threadfence_block();
+          const int bst = bx->status;
+          lasta = bx->r_lasta; trima = bx->r_trima; trimx = bx->r_trimx; trimd = bx->r_trimd; trimha = bx->r_trimha;
+          if (EX_DIAG) { c.bwait += (u64) bx->r_bwait; c.btot += (u64) bx->r_btot; }
+          c.avail = bx->r_avail; c.pwaves += (u64) (bx->r_dif - dif); c.npairs += 1; dif = bx->r_dif; ncell += bx->r_ncell;
+          __syncwarp();
+          if (bst != ST_OK) return bst;
+          if (stp == 1) more = 0;                        // the pass ended in the back warp
+          //  stp == 2: handed back after wave dif; lowk/hghk/besta are this warp's own
+          continue;
+        }
+
+
+      lowk -= 1; hghk += 1;
       if (hghk - lowk + 5 > W) return ST_BAND;
       if (dif > c.alen + c.blen + 1000) return ST_STAGE;     // cannot happen (every wave is one more difference): hang guard
       //  new band edges (align.c:611-622): a fresh diagonal copies its neighbour's NA and counts as
@@ -279,15 +582,122 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
       if (!newlow) lowk += 1;
       if (!newhgh) hghk -= 1;
       dif += 1;
-      c.nwaves += 1; c.ncells += (u64) (hghk - lowk + 1);
-      const bool single = (hghk - lowk < 32);
-      int lastcc = 0, lasttop = hghk, lastrd = 0;
+      ncell += (u64) (hghk - lowk + 1);
 
+      if (hghk - lowk < 32)
+        { //  ---- register path: lane (-kk & 31) owns diagonal kk ----
+          const int top = hghk, ltop = (-top) & 31;
+          const int kk = top - ((lane - ltop) & 31);
+          const bool act = kk >= lowk;
+          if (!inreg)
+            { rV = c.V[IX(kk)]; rT = c.T[IX(kk)]; rHA = c.HA[IX(kk)]; rHM = c.HM[IX(kk)]; rNA = c.NA[IX(kk)];
+              inreg = true;
+            }
+          const bool flo = newlow && kk == lowk, fhi = newhgh && kk == top;
+          int vp = __shfl_sync(FULL,rV,lane_up), vm = __shfl_sync(FULL,rV,lane_dn);
+          //  a fresh edge diagonal is FRESH for itself AND for the neighbour that looks at it
+          int ap = (kk == top  || (newhgh && kk+1 == top))  ? FRESH : vp;
+          int ac = (flo || fhi) ? FRESH : rV;
+          int am = (kk == lowk || (newlow && kk-1 == lowk)) ? FRESH : vm;
+          int pred, cc;
+          if (ac < am) { if (am < ap) { pred = 1; cc = ap+1; } else { pred = -1; cc = am+1; } }
+          else         { if (ac < ap) { pred = 1; cc = ap+1; } else { pred = 0;  cc = ac+2; } }
+          const int src = (lane - pred) & 31;
+          u64 b  = __shfl_sync(FULL,rT,src);
+          int ha = __shfl_sync(FULL,rHA,src), hm = __shfl_sync(FULL,rHM,src);
+          int nn = __shfl_sync(FULL,rNA,src);            // a fresh edge always descends from its one neighbour
+          int nan = (flo || fhi) ? nn : rNA;
+
+          b <<= 1;
+          int xn = (cc + kk) >> 1, flag = 0, k = s*kk;
+          if (act)
+            { int t = snake<s>(c,xn,kk,flag);
+              xn += t;
+              b = (t >= 64) ? ~0ull : ((b << t) | ((1ull << t) - 1));
+            }
+          cc = 2*xn - kk;
+
+          bool need = act && xn >= nan;
+          while (__any_sync(FULL,need))
+            { bool create = need && (s*hm < nan);
+              if (c.avail + 32 > c.cmax) return ST_CELLS;
+              unsigned m = __ballot_sync(FULL,create);
+              int idx = c.avail + __popc(m & lt);
+              c.avail += __popc(m);
+              if (create)
+                { Peb p; p.ptr = ha; p.diag = k; p.diff = dif; p.mark = s*nan;
+                  c.cells[idx] = p;
+                  ha = idx; hm = s*nan;
+                }
+              if (need) nan += tspace;
+              need = act && xn >= nan;
+            }
+          if (act) { rV = cc; rT = b; rHA = ha; rHM = hm; rNA = nan; }
+
+          //  masks below are rotated into "position" space: bit p = diagonal top-p
+          int cm = act ? cc : INT_MIN;
+          int mx = __reduce_max_sync(FULL,cm);
+          if (mx > besta)
+            { //  Pb = highest diagonal reaching the wave maximum = the last record setter of the
+              //  sequential scan.  If it passes both quality tests it alone decides lasta and the
+              //  trim point; otherwise fall back to the full prefix-max.
+              unsigned eq = rotr32(__ballot_sync(FULL,cm == mx),ltop);
+              int Lb = (ltop + __ffs(eq) - 1) & 31;
+              bool qual = act && cc > besta && __popcll(b & PATH_WIN) >= c.path_ave;
+              bool tq = qual && trim_ok(c,b);
+              unsigned ql = __ballot_sync(FULL,qual), tl = __ballot_sync(FULL,tq);
+              if ((tl >> Lb) & 1)
+                { lasta = mx; trima = mx; trimd = dif;
+                  trimx  = __shfl_sync(FULL,xn,Lb);
+                  trimha = __shfl_sync(FULL,ha,Lb);
+                }
+              else
+                { int cp = __shfl_sync(FULL,cm,(ltop + lane) & 31);      // value at position = lane
+                  int ex = max(warp_prefix_max_excl(cp,lane),besta);
+                  unsigned rm = __ballot_sync(FULL,cp > ex);
+                  unsigned qm = rm & rotr32(ql,ltop), tm = rm & rotr32(tl,ltop);
+                  if (qm) lasta = __shfl_sync(FULL,cc,(ltop + 31 - __clz(qm)) & 31);
+                  if (tm)
+                    { int L3 = (ltop + 31 - __clz(tm)) & 31;
+                      trima  = __shfl_sync(FULL,cc,L3);
+                      trimx  = __shfl_sync(FULL,xn,L3);
+                      trimha = __shfl_sync(FULL,ha,L3);
+                      trimd  = dif;
+                    }
+                }
+              besta = mx;
+              bestx = __shfl_sync(FULL,xn,Lb);
+            }
+          if (__any_sync(FULL,act && flag != 0))
+            { unsigned hb = rotr32(__ballot_sync(FULL,act && flag == 1),ltop);
+              unsigned hq = rotr32(__ballot_sync(FULL,act && flag == 2),ltop);
+              if (hb) { int v = top - (__ffs(hb)-1); if (bclip < v) bclip = v; }
+              if (hq) aclip = top - (31 - __clz(hq));
+              more = (b_at<s>(c,besta-bestx) != 4 && a_at<s>(c,bestx) != 4);
+              if (hghk >= aclip) hghk = aclip-1;
+              if (lowk <= bclip) lowk = bclip+1;
+              aclip = INT_MAX; bclip = -INT_MAX;
+            }
+          //  trim the band to points within WAVE_LAG of the best (align.c:782-790)
+          unsigned m = rotr32(__ballot_sync(FULL,kk >= lowk && kk <= hghk && cc >= besta - WAVE_LAG),ltop);
+          if (m == 0) hghk = lowk-1;
+          else { hghk = top - (__ffs(m)-1); lowk = top - (31 - __clz(m)); }
+          continue;
+        }
+
+      //  ---- wide band: state in the arrays of c, 32-diagonal chunks ----
+      if (inreg)
+        { const int otop = hghk - (newhgh ? 1 : 0), olow = lowk + (newlow ? 1 : 0);   // band of the last wave
+          const int kk = otop - ((lane - ((-otop) & 31)) & 31);
+          if (kk >= olow)
+            { c.V[IX(kk)] = rV; c.T[IX(kk)] = rT; c.HA[IX(kk)] = rHA; c.HM[IX(kk)] = rHM; c.NA[IX(kk)] = rNA; }
+          inreg = false;
+          __syncwarp();
+        }
       for (int top = hghk; top >= lowk; top -= 32)
         { int kk = top - lane;
           bool act = kk >= lowk;
           const bool flo = newlow && kk == lowk, fhi = newhgh && kk == hghk;
-          //  a fresh edge diagonal is FRESH for itself AND for the neighbour that looks at it
           int ap = (kk == hghk || (newhgh && kk+1 == hghk)) ? FRESH
                                                             : ((lane == 0) ? c.carry[0] : c.V[IX(kk+1)]);
           int ac = (flo || fhi) ? FRESH : c.V[IX(kk)];
@@ -295,25 +705,25 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
           int pred, cc;
           if (ac < am) { if (am < ap) { pred = 1; cc = ap+1; } else { pred = -1; cc = am+1; } }
           else         { if (ac < ap) { pred = 1; cc = ap+1; } else { pred = 0;  cc = ac+2; } }
-          u64 b; int ha, hm, rd;
+          u64 b; int ha, hm;
           if (pred == 1 && lane == 0)
             { b  = (u64) (unsigned) c.carry[1] | ((u64) (unsigned) c.carry[2] << 32);
-              ha = c.carry[3]; hm = c.carry[4]; rd = c.carry[5];
+              ha = c.carry[3]; hm = c.carry[4];
             }
           else
             { int si = IX(kk+pred);
-              b = c.T[si]; ha = c.HA[si]; hm = c.HM[si]; rd = c.RD[si];
+              b = c.T[si]; ha = c.HA[si]; hm = c.HM[si];
             }
           int nan = c.NA[IX(flo ? kk+1 : (fhi ? kk-1 : kk))];
           //  lane 31's own old state is the next chunk's "kk+1"
-          int  o_v = 0, o_ha = 0, o_hm = 0, o_rd = 0; u64 o_t = 0;
+          int  o_v = 0, o_ha = 0, o_hm = 0; u64 o_t = 0;
           const bool morechunks = (top - 32 >= lowk);
           if (lane == 31 && morechunks)
-            { o_v = ac; o_t = c.T[IX(kk)]; o_ha = c.HA[IX(kk)]; o_hm = c.HM[IX(kk)]; o_rd = c.RD[IX(kk)]; }
+            { o_v = ac; o_t = c.T[IX(kk)]; o_ha = c.HA[IX(kk)]; o_hm = c.HM[IX(kk)]; }
           __syncwarp();                              // all reads of old state done
           if (lane == 31 && morechunks)
             { c.carry[0] = o_v; c.carry[1] = (int) (unsigned) o_t; c.carry[2] = (int) (o_t >> 32);
-              c.carry[3] = o_ha; c.carry[4] = o_hm; c.carry[5] = o_rd;
+              c.carry[3] = o_ha; c.carry[4] = o_hm;
             }
 
           b <<= 1;
@@ -344,10 +754,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
           int cm = act ? cc : INT_MIN;
           int mx = __reduce_max_sync(FULL,cm);
           if (mx > besta)
-            { //  Lb = first lane (highest diagonal) reaching the wave maximum = the last record
-              //  setter of the sequential scan.  If it passes both quality tests it alone decides
-              //  lasta and the trim point; otherwise fall back to the full prefix-max.
-              unsigned eq = __ballot_sync(FULL,cm == mx);
+            { unsigned eq = __ballot_sync(FULL,cm == mx);
               int Lb = __ffs(eq) - 1;
               bool qual = act && cc > besta && __popcll(b & PATH_WIN) >= c.path_ave;
               bool tq = qual && trim_ok(c,b);
@@ -356,7 +763,6 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
                 { lasta = mx; trima = mx; trimd = dif;
                   trimx  = __shfl_sync(FULL,xn,Lb);
                   trimha = __shfl_sync(FULL,ha,Lb);
-                  trimrd = __shfl_sync(FULL,rd,Lb);
                 }
               else
                 { int ex = max(warp_prefix_max_excl(cm,lane),besta);
@@ -368,7 +774,6 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
                       trima  = __shfl_sync(FULL,cc,L3);
                       trimx  = __shfl_sync(FULL,xn,L3);
                       trimha = __shfl_sync(FULL,ha,L3);
-                      trimrd = __shfl_sync(FULL,rd,L3);
                       trimd  = dif;
                     }
                 }
@@ -382,10 +787,9 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
               if (hb) { int v = top - (__ffs(hb)-1); if (bclip < v) bclip = v; }
               if (hq) aclip = top - (31 - __clz(hq));
             }
-          lastcc = cc; lasttop = top; lastrd = rd;
           if (act)
             { c.V[IX(kk)] = cc; c.T[IX(kk)] = b; c.HA[IX(kk)] = ha; c.HM[IX(kk)] = hm;
-              c.NA[IX(kk)] = nan; c.RD[IX(kk)] = rd;
+              c.NA[IX(kk)] = nan;
             }
           __syncwarp();
         }
@@ -398,31 +802,6 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
         }
 
       //  trim the band to points within WAVE_LAG of the best (align.c:782-790)
-      if (single)
-        { int n = besta - WAVE_LAG, kk = lasttop - lane;
-          unsigned m = __ballot_sync(FULL,kk >= lowk && kk <= hghk && lastcc >= n);
-          if (m == 0) hghk = lowk-1;
-          else { hghk = lasttop - (__ffs(m)-1); lowk = lasttop - (31 - __clz(m)); }
-          //  Reverse-pass hand-off: once every surviving diagonal and the trim point descend from
-          //  the same wave-0 diagonal, that diagonal is final (*mind of align.c:872) and the
-          //  reverse wave, which only needs it, can start on the partner warp right now.
-          if (s > 0 && posted != NULL && !*posted && c.mbox != NULL && m != 0 && (dif & 31) == 0)
-            { bool in = (m >> lane) & 1;
-              int rmin = __reduce_min_sync(FULL,in ? lastrd : INT_MAX);
-              int rmax = __reduce_max_sync(FULL,in ? lastrd : INT_MIN);
-              if (rmin == rmax && rmin == trimrd)
-                { if (lane == 0)
-                    { Mbox *mb = c.mbox;
-                      mb->low = rmin; mb->anti = mida; mb->minp = minp; mb->maxp = maxp; mb->aoff = aoff;
-                      mb->alen = c.alen; mb->blen = c.blen; mb->A = c.A; mb->B = c.B;
-                      __threadfence_block();
-                      mb->state = 1;
-                    }
-                  *posted = true;
-                }
-            }
-        }
-      else
       { int n = besta - WAVE_LAG, nh = lowk-1;
         for (int top = hghk; top >= lowk; top -= 32)
           { int kk = top - lane;
@@ -438,6 +817,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
       }
     }
 
+  c.nwaves += (u64) dif; c.ncells += ncell;
   endx = s*trimx;
   endy = s*(trima - trimx);
   diffs = trimd;
@@ -451,8 +831,8 @@ static __device__ int fwd_extract(Ctx &c, int trimha, int mida, int trimx, int t
                                   int &tlen, int &root_diag)
 { const int lane = threadIdx.x & 31;
   int n = 0, h;
-  for (h = trimha; h >= 0; h = c.cells[h].ptr) n += 1;
-  Peb tip = c.cells[trimha];
+  for (h = trimha; h >= 0; h = ldpeb(c.cells+h).ptr) n += 1;
+  Peb tip = ldpeb(c.cells+trimha);
   int kt = tip.diag, bt, et;
   if (tip.ptr < 0) { bt = (mida - kt) >> 1; et = 0; }
   else             { bt = tip.mark - kt;    et = tip.diff; }
@@ -472,7 +852,7 @@ static __device__ int fwd_extract(Ctx &c, int trimha, int mida, int trimx, int t
   Peb cur = tip;
   root_diag = kt;
   while (cur.ptr >= 0)
-    { Peb prv = c.cells[cur.ptr];
+    { Peb prv = ldpeb(c.cells+cur.ptr);
       int a = cur.mark - cur.diag, d = cur.diff, bp, ep;
       if (prv.ptr < 0) { bp = (mida - prv.diag) >> 1; ep = 0; }
       else             { bp = prv.mark - prv.diag;    ep = prv.diff; }
@@ -497,8 +877,8 @@ static __device__ int rev_extract(Ctx &c, const Peb *cells, int trimha, int aoff
                                   int trimd, int ftlen, int &rtlen)
 { const int lane = threadIdx.x & 31;
   int n = 0, h, root = trimha;
-  for (h = trimha; h >= 0; h = cells[h].ptr) { n += 1; root = h; }
-  Peb r0 = cells[root];
+  for (h = trimha; h >= 0; h = ldpeb(cells+h).ptr) { n += 1; root = h; }
+  Peb r0 = ldpeb(cells+root);
   int b0 = r0.mark - r0.diag;
   bool offpt = ((b0 + r0.diag) % c.tspace != aoff);
   int wr = 0;                                        // bytes written to rstage so far
@@ -536,7 +916,7 @@ static __device__ int rev_extract(Ctx &c, const Peb *cells, int trimha, int aoff
 
   //  n >= 2: pairs i = n-1 .. 1 between chain cells c_i and c_(i-1); pair 1 is merged into the
   //  forward trace when the root is off a trace point and a forward trace exists.
-  Peb tip = cells[trimha];
+  Peb tip = ldpeb(cells+trimha);
   int kt = tip.diag, bt = tip.mark - kt, et = tip.diff;
   bool extra = (bt + kt != trimx);
   int addd = 0, addb = 0;
@@ -553,7 +933,7 @@ static __device__ int rev_extract(Ctx &c, const Peb *cells, int trimha, int aoff
   Peb cur = tip;
   int idx = n-1;
   while (cur.ptr >= 0)
-    { Peb prv = cells[cur.ptr];
+    { Peb prv = ldpeb(cells+cur.ptr);
       int a = cur.mark - cur.diag, d = cur.diff;
       int bp = prv.mark - prv.diag, ep = (prv.ptr < 0) ? 0 : prv.diff;
       int pd = d - ep, pb = bp - a;
@@ -590,51 +970,22 @@ static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int a
 
   R.ftlen = R.rtlen = 0; R.diffs = 0;
   long long tk = clock64();
-  bool posted = false;
-  st = wave<1,W>(c,low,hgh,anti,minp,maxp,aoff,ex,ey,df,tha,&posted);
+  st = wave<1,W>(c,low,hgh,anti,minp,maxp,aoff,ex,ey,df,tha);
   c.cyc_wave += (u64) (clock64() - tk); tk = clock64();
   int st2 = st ? 0 : fwd_extract(c,tha,anti,ex,ey,df,R.ftlen,rootd);
   c.cyc_extract += (u64) (clock64() - tk);
   __syncwarp();
-  const Peb *rcells = c.cells;
-  bool have_rev = false;
-  if (posted)                                    // collect the partner's reverse wave
-    { Mbox *mb = c.mbox;
-      long long tw = clock64();
-      while (mb->state != 2) __nanosleep(100);
-      c.cyc_wait += (u64) (clock64() - tw);
-      c.njobs += 1;
-      __threadfence_block();
-      int hst = mb->status, hlow = mb->low;
-      int hx = mb->endx, hy = mb->endy, hd = mb->diffs, hh = mb->trimha;
-      __syncwarp();
-      if (threadIdx.x % 32 == 0) mb->state = 0;
-      __syncwarp();
-      if (st == ST_OK && st2 == ST_OK)
-        { if (hst) return hst;
-          if (hlow == rootd)                     // always, but the forward read-out is the authority
-            { have_rev = true;
-              R.aepos = ex; R.bepos = ey; R.diffs = df;
-              ex = hx; ey = hy; df = hd; tha = hh;
-              rcells = c.pcells;
-            }
-          else
-            c.nmiss += 1;
-        }
-    }
   if (st) return st;
   if (st2) return st2;
-  if (!have_rev) { R.aepos = ex; R.bepos = ey; R.diffs = df; }
+  R.aepos = ex; R.bepos = ey; R.diffs = df;
   low = rootd;
   bool fshort = ((R.aepos + R.bepos) - anti < DUB_TRIM);
 
   tk = clock64();
-  if (!have_rev)
-    { st = wave<-1,W>(c,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
-      if (st) return st;
-    }
+  st = wave<-1,W>(c,low,low,anti,minp,maxp,aoff,ex,ey,df,tha);
+  if (st) return st;
   c.cyc_wave += (u64) (clock64() - tk); tk = clock64();
-  st = rev_extract(c,rcells,tha,aoff,ex,ey,df,R.ftlen,R.rtlen);
+  st = rev_extract(c,c.cells,tha,aoff,ex,ey,df,R.ftlen,R.rtlen);
   if (st) return st;
   c.cyc_extract += (u64) (clock64() - tk);
   R.abpos = ex; R.bbpos = ey; R.diffs += df;
@@ -1157,22 +1508,15 @@ __global__ void prefilter_kernel(ext_params P, unsigned *__restrict__ work_long,
     work_short[atomicAdd(nwork+1,1u)] = j;
 }
 
-#define WSTATE_BYTES(W) ((W)*(5*4+8) + 32)
+#define WSTATE_BYTES(W) ((W)*(4*4+8) + 32)
 #define STATE_BYTES (WSTATE_BYTES(EX_W) + SCAN_SMEM)
 #define BIG_SMEM_PER_WARP (SCAN_SMEM)
-#define TT_BYTES    ((256+128)*4)
-#define MBOX_BYTES  (EX_WARPS*((int) sizeof(Mbox)))
-//  EX_HANDOFF 1: warps 0..EX_PRIM-1 take triples and warp p+EX_PRIM runs the reverse passes of
-//  warp p.  Measured on the 100 Mbp benchmark the reverse pass is short (tubes are entered 128
-//  anti-diagonals above their start, FastGA.c:3235), so pairing halves the number of triples in
-//  flight for a ~5 % gain on the longest one; with EX_HANDOFF 0 every warp takes triples.
-#ifndef EX_HANDOFF
-#define EX_HANDOFF 0
-#endif
-#define EX_PRIM     (EX_HANDOFF ? EX_WARPS/2 : EX_WARPS)
+#define TT_BYTES    (32768*2)
+#define EX_NFRONT   (EX_PAIR ? EX_WARPS/2 : EX_WARPS)       // warps of a block that take triples
+#define BOX_BYTES   (EX_PAIR ? (EX_WARPS/2)*((int) sizeof(PairBox)) : 0)
 
 template<int W>
-__global__ void __launch_bounds__(EX_WARPS*32)
+__global__ void __launch_bounds__(EX_WARPS*32,EX_MINBLK)
 extend_kernel(ext_params P)
 { extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -1183,65 +1527,47 @@ extend_kernel(ext_params P)
   Ctx c;
   c.T  = (u64 *) sb;
   c.V  = (int *) (sb + W*8);
-  c.HA = c.V + W; c.HM = c.HA + W; c.NA = c.HM + W; c.RD = c.NA + W;
-  c.carry = c.RD + W;
+  c.HA = c.V + W; c.HM = c.HA + W; c.NA = c.HM + W;
+  c.carry = c.NA + W;
   rec128 *stagebuf = (W == EX_W) ? (rec128 *) (sb + WSTATE_BYTES(EX_W))
                                  : (rec128 *) (smem + (size_t) wp * BIG_SMEM_PER_WARP);
-  { short2 *tt = (short2 *) (smem + (size_t) EX_WARPS * per_warp);
-    int msc = 1000 - P.dscore, dsc = P.dscore;
-    for (int u = threadIdx.x; u < 384; u += blockDim.x)
-      { int nb = (u < 256) ? 8 : 7, x = (u < 256) ? u : u - 256, sc = 0, mxp = 0;
-        for (int i = nb-1; i >= 0; i--)
-          { if (sc > mxp) mxp = sc;
-            sc += ((x >> i) & 1) ? msc : -dsc;
-          }
-        tt[u] = make_short2((short) sc,(short) mxp);
+  { short *tt = (short *) (smem + (size_t) EX_WARPS * per_warp);
+    const int4 *src = (const int4 *) P.table;               // 64 KB, 16-byte aligned (fgb_dmalloc)
+    for (int u = threadIdx.x; u < TT_BYTES/16; u += blockDim.x) ((int4 *) tt)[u] = src[u];
+    c.ttab = tt; c.sc15 = TRIM_LEN * P.dscore;
+    c.box = NULL;
+    if (EX_PAIR)
+      { c.box = (PairBox *) (smem + (size_t) EX_WARPS * per_warp + TT_BYTES) + (wp >> 1);
+        if ((wp & 1) == 0 && lane == 0) { c.box->seq = 0; c.box->cmd = 0; c.box->stop = 0; }
       }
-    c.tt1 = tt; c.tt2 = tt + 256;
-    Mbox *mb = (Mbox *) (smem + (size_t) EX_WARPS * per_warp + TT_BYTES) + (wp % EX_PRIM);
-    if (wp < EX_PRIM && lane == 0) mb->state = 0;
-    c.mbox = EX_HANDOFF ? mb : NULL;
     __syncthreads();
   }
+  if (EX_PAIR && (wp & 1))
+    { //  back warp of pair wp/2: serves the passes its front warp (wp-1) starts
+      PairBox *bx = c.box;
+      int myseq = 0;
+      while (true)
+        { int sq;
+          while ((sq = bx->seq) == myseq) __nanosleep(200);
+          myseq = sq;
+          __threadfence_block();
+          int cm = bx->cmd;
+          if (cm == 9) break;
+          if (cm == 1) wave_back<1>(c,bx); else wave_back<-1>(c,bx);
+          __syncwarp();
+        }
+      return;
+    }
   long long t_start = clock64();
   c.cells = P.cells + gw * P.cells_per_warp;
-  c.pcells = P.cells + (gw + (EX_HANDOFF ? EX_PRIM : 0)) * P.cells_per_warp;
   c.cmax  = (int) P.cells_per_warp;
   c.avail = 0;
   c.fstage = P.stage + gw * 2ll * P.stage_bytes;
   c.rstage = c.fstage + P.stage_bytes;
   c.smax = P.stage_bytes;
   c.tspace = P.tspace; c.path_ave = P.path_ave; c.score = P.score; c.table = P.table;
-  c.nwaves = 0; c.ncells = 0; c.cyc_wave = 0; c.cyc_extract = 0; c.njobs = 0; c.nmiss = 0; c.cyc_wait = 0;
+  c.nwaves = 0; c.ncells = 0; c.cyc_wave = 0; c.cyc_extract = 0; c.pwaves = 0; c.npairs = 0; c.fwait = 0; c.ftot = 0; c.bwait = 0; c.btot = 0;
   u64 nla = 0, nhits = 0;
-
-  if (EX_HANDOFF && wp >= EX_PRIM)
-    { //  helper warp: runs the reverse waves its primary posts
-      Mbox *mb = c.mbox;
-      c.mbox = NULL;
-      while (true)
-        { int stt;
-          while ((stt = mb->state) != 1 && stt != 3) __nanosleep(2000);
-          if (stt == 3) break;
-          __threadfence_block();
-          c.A = mb->A; c.B = mb->B; c.alen = mb->alen; c.blen = mb->blen;
-          int lowd = mb->low, ex = 0, ey = 0, df = 0, tha = 0;
-          int hst = wave<-1,W>(c,lowd,lowd,mb->anti,mb->minp,mb->maxp,mb->aoff,ex,ey,df,tha);
-          __syncwarp();
-          if (lane == 0)
-            { mb->status = hst; mb->endx = ex; mb->endy = ey; mb->diffs = df; mb->trimha = tha;
-              __threadfence_block();
-              __threadfence();                   // pebbles written to HBM are read by the primary
-              mb->state = 2;
-            }
-          __syncwarp();
-        }
-      if (lane == 0)
-        { atomicAdd(&P.counters[2],c.nwaves);
-          atomicAdd(&P.counters[3],c.ncells);
-        }
-      return;
-    }
 
   while (true)
     { unsigned w = 0;
@@ -1260,7 +1586,11 @@ extend_kernel(ext_params P)
         nhits += nh;
       __syncwarp();
     }
-  if (EX_HANDOFF && lane == 0) c.mbox->state = 3;   // release the helper
+  if (EX_PAIR && lane == 0)
+    { c.box->cmd = 9;                              // release the back warp
+      __threadfence_block();
+      c.box->seq = c.box->seq + 1;
+    }
   if (lane == 0)
     { atomicAdd(&P.counters[0],nhits);
       atomicAdd(&P.counters[1],nla);
@@ -1269,9 +1599,10 @@ extend_kernel(ext_params P)
       atomicAdd(&P.counters[8],(u64) (clock64() - t_start));
       atomicAdd(&P.counters[9],c.cyc_wave);
       atomicAdd(&P.counters[10],c.cyc_extract);
-      atomicAdd(&P.counters[11],c.njobs);
-      atomicAdd(&P.counters[12],c.nmiss);
-      atomicAdd(&P.counters[13],c.cyc_wait);
+      atomicAdd(&P.counters[11],c.pwaves);
+      atomicAdd(&P.counters[12],c.npairs);
+      atomicAdd(&P.counters[4],c.fwait); atomicAdd(&P.counters[7],c.ftot);
+      atomicAdd(&P.counters[13],c.bwait);
       atomicMax(&P.counters[14],(u64) (clock64() - t_start));
       { u64 cy = (u64) (clock64() - t_start) >> 12, wv = c.nwaves > 0xffffff ? 0xffffff : c.nwaves;
         u64 la = nla > 0xffff ? 0xffff : nla;
@@ -1434,14 +1765,15 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
     { int dev = 0, nsm = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&nsm,cudaDevAttrMultiProcessorCount,dev);
-      size_t smem = (size_t) EX_WARPS * STATE_BYTES + TT_BYTES + MBOX_BYTES;
-      size_t smem_big = (size_t) EX_WARPS * BIG_SMEM_PER_WARP + TT_BYTES + MBOX_BYTES;
+      size_t smem = (size_t) EX_WARPS * STATE_BYTES + TT_BYTES + BOX_BYTES;
+      size_t smem_big = (size_t) EX_WARPS * BIG_SMEM_PER_WARP + TT_BYTES + BOX_BYTES;
       CUDA_TRY(cudaFuncSetAttribute(extend_kernel<EX_W>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem));
+      CUDA_TRY(cudaFuncSetAttribute(extend_kernel<EX_WBIG>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem_big));
       int bps = 0;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps,extend_kernel<EX_W>,EX_WARPS*32,smem));
       if (bps < 1) bps = 1;
       long long nblocks = (long long) nsm * bps;
-      long long want = ((long long) nwork + EX_PRIM - 1) / EX_PRIM;
+      long long want = ((long long) nwork + EX_NFRONT - 1) / EX_NFRONT;
       if (nblocks > want) nblocks = want;
       long long nwarps = nblocks * EX_WARPS;
 
@@ -1513,7 +1845,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           CUDA_TRY(cudaMemcpy(d_work2,f.data(),sizeof(unsigned)*nfailed,cudaMemcpyHostToDevice));
           d_list = d_work2; nlist = nfailed;
           cells_per_warp *= 8; stage_bytes *= 4;
-          long long nb2 = ((long long) nfailed + EX_PRIM - 1) / EX_PRIM;
+          long long nb2 = ((long long) nfailed + EX_NFRONT - 1) / EX_NFRONT;
           long long maxb = (24ll << 30) / ((long long) sizeof(Peb) * cells_per_warp * EX_WARPS);
           if (maxb < 1) maxb = 1;
           nblocks = nb2 < maxb ? nb2 : maxb;

@@ -309,8 +309,9 @@ class DeviceOverlaps:
         L.fgb_overlaps_counters(self.h, out)
         v = list(out)
         return {"hits": v[0], "la_calls": v[1], "waves": v[2], "cells": v[3], "nseg": v[5], "nwork": v[6],
-                "warp_cycles": v[8], "wave_cycles": v[9], "extract_cycles": v[10], "jobs": v[11],
-                "job_miss": v[12], "wait_cycles": v[13], "max_warp_cycles": v[14],
+                "warp_cycles": v[8], "wave_cycles": v[9], "extract_cycles": v[10], "paired_waves": v[11], "pairings": v[12],
+                "front_wait": v[4], "front_total": v[7], "back_wait": v[13],
+                "max_warp_cycles": v[14],
                 "slowest_warp": {"cycles": (v[15] >> 40) << 12, "waves": (v[15] >> 16) & 0xffffff, "la_calls": v[15] & 0xffff}}
 
     def records(self):
