@@ -14,6 +14,8 @@ static inline long long now_us()
 { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 extern "C" {
+int fgb_kmer_sort_device(void *d_a, void *d_b, long long n, void *d_tmp, long long tmp_bytes,
+                         int *result_in_b, void *stream);
 int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo, int byte_hi,
                        void *d_tmp, long long tmp_bytes, int *result_in_b, void *stream);
 long long fgb_sort128_tmp_bytes(long long n);
@@ -306,7 +308,7 @@ static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi, fgb_
   }
   int inb = 0;
   { stage_timer t(&g_timings.ksort_ms,st);
-    rc = fgb_sort128_device(d_a,d_b,n,6,16,d_stmp,stmpb,&inb,st);
+    rc = fgb_kmer_sort_device(d_a,d_b,n,d_stmp,stmpb,&inb,st);
     if (rc) return rc;
   }
   x->d_tab = inb ? d_b : d_a;

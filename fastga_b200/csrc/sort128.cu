@@ -11,6 +11,7 @@
 // runs back coalesced, while counting the next pass's histogram.  HBM-bound integer work: no
 // tensor cores.
 #include "common.cuh"
+#include <vector>
 
 #define SORT_THREADS 512
 #define SORT_ITEMS   8
@@ -25,6 +26,21 @@ static __device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane)
       if (lane >= o) v += t;
     }
   return v;
+}
+
+
+//  Lanes of the warp holding the same 8-bit digit as this lane (among valid lanes).  MATCH.ANY
+//  costs one internal round per distinct value in the warp (~30 for random digits); nine ballots
+//  are a fixed, much smaller cost.
+static __device__ __forceinline__ unsigned match_digit(unsigned d, bool valid)
+{ unsigned peers = __ballot_sync(0xffffffffu,valid);
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    { bool bit = (d >> k) & 1;
+      unsigned bk = __ballot_sync(0xffffffffu,bit);
+      peers &= bit ? bk : ~bk;
+    }
+  return peers;
 }
 
 /***********************************************************************************************
@@ -127,13 +143,13 @@ sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, lo
   for (int it = 0; it < SORT_ITEMS; it++)
     { int idx = base + it*32 + lane;
       bool valid = idx < cnt;
-      unsigned d = 0x100u | lane;
+      unsigned d = 0;
       if (valid)
         { r[it] = ld_rec(tile + idx);
           d = rec_byte(r[it],byte);
         }
-      unsigned peers = __match_any_sync(0xffffffffu,d);
-      int leader = __ffs(peers)-1;
+      unsigned peers = match_digit(d,valid);
+      int leader = valid ? __ffs(peers)-1 : lane;
       unsigned b = 0;
       if (valid && lane == leader)
         { b = myc[d];
@@ -141,11 +157,7 @@ sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, lo
         }
       b = __shfl_sync(0xffffffffu,b,leader);
       rank[it] = b + __popc(peers & lanemask_lt());
-      if (next_byte >= 0)
-        { unsigned d2 = valid ? rec_byte(r[it],next_byte) : (0x100u | lane);
-          unsigned p2 = __match_any_sync(0xffffffffu,d2);
-          if (valid && lane == __ffs(p2)-1) atomicAdd(&nhist[d2],__popc(p2));
-        }
+      if (next_byte >= 0 && valid) atomicAdd(&nhist[rec_byte(r[it],next_byte)],1u);
       __syncwarp();
     }
   __syncthreads();
@@ -261,6 +273,294 @@ extern "C" int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo
       *result_in_b ^= 1;
     }
   CUDA_TRY(cudaGetLastError());
+  return FGB_OK;
+}
+
+/***********************************************************************************************
+ *  k-mer table sort (msd_sort's job in GIXmake.c:1436): by the 40-mer (bytes 6..15), equal
+ *  k-mers by (strand|contig rank, post), i.e. by the whole 128-bit value.
+ *
+ *  Ten full Onesweep passes move 10 x 32 bytes per record through HBM.  Instead:
+ *    1. two Onesweep passes on the two MOST significant key bytes (byte 14 then 15) leave the
+ *       records partitioned into 65536 prefix bins;
+ *    2. consecutive bins are packed into groups of at most BK_CAP records and BK_SPAN bins; one
+ *       CTA per group pulls the group into shared memory with one TMA bulk copy, sorts it there
+ *       (kmer_bucket_sort_kernel) and writes it back once;
+ *    3. bins larger than BK_CAP (repeats) are compacted, sorted with the generic Onesweep sort and
+ *       copied back.
+ *  HBM traffic per record: 2 x 32 + 32 bytes instead of 10 x 32.
+ **********************************************************************************************/
+
+#define BK_THREADS SORT_THREADS
+#define BK_ITEMS   SORT_ITEMS
+#define BK_CAP     SORT_TILE
+#define BK_WARPS   SORT_WARPS
+#define BK_SPAN    4                     // a group covers at most this many consecutive 16-bit bins
+#define BK_SUBBITS 10
+#define BK_NSUB    (BK_SPAN << BK_SUBBITS)
+#define BK_MAXSUB  32                    // a sub-bin longer than this sends the group down the LSD path
+
+//  bin_start[p] = first record whose top 16 key bits are >= p, p in [0,65536]
+__global__ void kmer_bins_kernel(const rec128 *__restrict__ tab, long long n, unsigned *__restrict__ bin_start)
+{ long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  long long lo = (i == 0) ? -1 : (long long) (tab[i-1].hi >> 48);
+  long long hi = (i == n) ? 65536 : (long long) (tab[i].hi >> 48);
+  for (long long p = lo+1; p <= hi; p++) bin_start[p] = (unsigned) i;
+}
+
+//  One CTA sorts one group (<= BK_CAP records of <= BK_SPAN consecutive bins) by the full 128-bit
+//  value.  Fast path: a counting split on the next 10 key bits (shared-memory atomics) leaves
+//  sub-bins of one or two records, and every record finds its place by comparing itself with its
+//  sub-bin.  A group with a crowded sub-bin (repeats) runs sixteen LSD byte passes instead.
+
+__global__ void __launch_bounds__(BK_THREADS)
+kmer_bucket_sort_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out,
+                        const uint2 *__restrict__ groups /* start, count */)
+{ extern __shared__ __align__(16) unsigned char smem_raw[];
+  rec128   *tile   = reinterpret_cast<rec128 *>(smem_raw);
+  unsigned *cnt    = reinterpret_cast<unsigned *>(tile + BK_CAP);        // [BK_NSUB+1]; LSD path: wcount[BK_WARPS][256]
+  unsigned *bexcl  = cnt + BK_NSUB + 32;                                  // [256]
+  unsigned *wtot   = bexcl + 256;                                         // [BK_WARPS]
+  __shared__ __align__(8) unsigned long long tbar;
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint2 g = groups[blockIdx.x];
+  const int count = (int) g.y;
+  if (tid == 0)
+    { mbar_init(&tbar,1);
+      tma_load_1d(tile,in + g.x,(unsigned) count * 16u,&tbar);
+    }
+  for (int i = tid; i <= BK_NSUB; i += BK_THREADS) cnt[i] = 0;
+  __syncthreads();
+  mbar_wait(&tbar,0);
+
+  rec128   r[BK_ITEMS];
+  unsigned sub[BK_ITEMS], off[BK_ITEMS];
+  const int base = w*(32*BK_ITEMS);
+  const unsigned b0 = (unsigned) (tile[0].hi >> 48);
+#pragma unroll
+  for (int it = 0; it < BK_ITEMS; it++)
+    { int idx = base + it*32 + lane;
+      if (idx < count)
+        { r[it] = ld_rec(tile + idx);
+          sub[it] = ((((unsigned) (r[it].hi >> 48)) - b0) << BK_SUBBITS) | ((unsigned) (r[it].hi >> (48-BK_SUBBITS)) & ((1u << BK_SUBBITS)-1));
+          off[it] = atomicAdd(&cnt[sub[it]],1u);
+        }
+    }
+  __syncthreads();
+  //  exclusive scan of the sub-bin counts (8 per thread), crowded sub-bin detection
+  bool big = false;
+  { unsigned v[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { v[i] = cnt[8*tid+i]; big |= (v[i] > BK_MAXSUB); sum += v[i]; }
+    unsigned inc = warp_incl_scan(sum,lane);
+    if (lane == 31) wtot[w] = inc;
+    __syncthreads();
+    unsigned pre = inc - sum;
+    for (int i = 0; i < w; i++) pre += wtot[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { cnt[8*tid+i] = pre; pre += v[i]; }
+    if (tid == BK_THREADS-1) cnt[BK_NSUB] = pre;
+  }
+  big = __syncthreads_or(big);
+
+  if (!big)
+    {
+#pragma unroll
+      for (int it = 0; it < BK_ITEMS; it++)
+        { int idx = base + it*32 + lane;
+          if (idx < count) st_rec(tile + (cnt[sub[it]] + off[it]),r[it]);
+        }
+      __syncthreads();
+      for (int p = tid; p < count; p += BK_THREADS)
+        { rec128 R = ld_rec(tile + p);
+          unsigned sb = ((((unsigned) (R.hi >> 48)) - b0) << BK_SUBBITS) | ((unsigned) (R.hi >> (48-BK_SUBBITS)) & ((1u << BK_SUBBITS)-1));
+          int s = (int) cnt[sb], e = (int) cnt[sb+1], rank = 0;
+          for (int q = s; q < e; q++)
+            { rec128 Q = ld_rec(tile + q);
+              bool less = (Q.hi < R.hi) || (Q.hi == R.hi && (Q.lo < R.lo || (Q.lo == R.lo && q < p)));
+              rank += less;
+            }
+          st_rec(out + (g.x + s + rank),R);
+        }
+      return;
+    }
+
+  //  LSD path: all sixteen bytes, records still in registers in load order
+  unsigned *wcount = cnt;
+  unsigned *myc = wcount + w*256;
+  unsigned rank[BK_ITEMS];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; i++) myc[i*32 + lane] = 0;
+  __syncwarp();
+  for (int byte = 0; byte < 16; byte++)
+    {
+#pragma unroll
+      for (int it = 0; it < BK_ITEMS; it++)
+        { int idx = base + it*32 + lane;
+          bool valid = idx < count;
+          unsigned d = valid ? rec_byte(r[it],byte) : 0;
+          unsigned peers = match_digit(d,valid);
+          int leader = valid ? __ffs(peers)-1 : lane;
+          unsigned b = 0;
+          if (valid && lane == leader)
+            { b = myc[d];
+              myc[d] = b + __popc(peers);
+            }
+          b = __shfl_sync(0xffffffffu,b,leader);
+          rank[it] = b + __popc(peers & lanemask_lt());
+          __syncwarp();
+        }
+      __syncthreads();
+      unsigned c = 0, inc = 0;
+      if (tid < 256)
+        { unsigned sum = 0;
+#pragma unroll
+          for (int ww = 0; ww < BK_WARPS; ww++)
+            { unsigned t = wcount[ww*256+tid];
+              wcount[ww*256+tid] = sum;
+              sum += t;
+            }
+          c = sum;
+          inc = warp_incl_scan(c,lane);
+          if (lane == 31) wtot[w] = inc;
+        }
+      __syncthreads();
+      if (tid < 256)
+        { unsigned pre = 0;
+          for (int i = 0; i < w; i++) pre += wtot[i];
+          bexcl[tid] = pre + inc - c;
+        }
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < BK_ITEMS; it++)
+        { int idx = base + it*32 + lane;
+          if (idx < count)
+            { unsigned d = rec_byte(r[it],byte);
+              st_rec(tile + (bexcl[d] + myc[d] + rank[it]),r[it]);
+            }
+        }
+      __syncthreads();
+      if (byte + 1 < 16)
+        {
+#pragma unroll
+          for (int it = 0; it < BK_ITEMS; it++)
+            { int idx = base + it*32 + lane;
+              if (idx < count) r[it] = ld_rec(tile + idx);
+            }
+#pragma unroll
+          for (int i = 0; i < 8; i++) myc[i*32 + lane] = 0;
+          __syncwarp();
+        }
+    }
+  for (int p = tid; p < count; p += BK_THREADS)
+    st_rec(out + (g.x + p),ld_rec(tile + p));
+}
+
+//  copies record segments: src[sfrom[k] .. +len[k]) -> dst[dfrom[k] ..); pre[] = prefix sums of len
+__global__ void kmer_copy_segments_kernel(const rec128 *__restrict__ src, rec128 *__restrict__ dst,
+                                          const unsigned *__restrict__ sfrom, const unsigned *__restrict__ dfrom,
+                                          const unsigned *__restrict__ pre, int nseg, long long total)
+{ for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long) gridDim.x * blockDim.x)
+    { int lo = 0, hi = nseg;                                  // last k with pre[k] <= i
+      while (hi - lo > 1) { int md = (lo+hi) >> 1; if (pre[md] <= i) lo = md; else hi = md; }
+      unsigned o = (unsigned) (i - pre[lo]);
+      st_rec(dst + (dfrom[lo] + o),ld_rec(src + (sfrom[lo] + o)));
+    }
+}
+
+static const size_t BUCKET_SMEM = BK_CAP*sizeof(rec128) + (BK_NSUB + 32 + 256 + BK_WARPS)*sizeof(unsigned);
+
+//  d_a: n records in emit order; d_b: scratch of the same size.  Sorted table lands in d_a or d_b
+//  (*result_in_b).  d_tmp as for fgb_sort128_device.  Synchronises the stream once (the bin
+//  boundaries come to the host to pack the groups).
+
+extern "C" int fgb_kmer_sort_device(void *d_a, void *d_b, long long n, void *d_tmp, long long tmp_bytes,
+                                    int *result_in_b, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  *result_in_b = 0;
+  if (n <= 1) return FGB_OK;
+  if (n >= 0xffffffffll) return FGB_ERR_LIMIT;
+  int inb = 0;
+  int rc = fgb_sort128_device(d_a,d_b,n,14,16,d_tmp,tmp_bytes,&inb,st);
+  if (rc) return rc;
+  rec128 *src = (rec128 *) (inb ? d_b : d_a), *dst = (rec128 *) (inb ? d_a : d_b);
+
+  static bool attr_set = false;
+  if (!attr_set)
+    { CUDA_TRY(cudaFuncSetAttribute(kmer_bucket_sort_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int) BUCKET_SMEM));
+      attr_set = true;
+    }
+
+  unsigned *d_bins = NULL;
+  CUDA_TRY(fgb_dmalloc((void **) &d_bins,sizeof(unsigned)*65537,st));
+  { int nb = (int) ((n + 1 + 255) / 256);
+    kmer_bins_kernel<<<nb,256,0,st>>>(src,n,d_bins);
+    fgb_count_launch(1);
+  }
+  std::vector<unsigned> bins(65537);
+  CUDA_TRY(cudaMemcpyAsync(bins.data(),d_bins,sizeof(unsigned)*65537,cudaMemcpyDeviceToHost,st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+
+  std::vector<uint2> groups;
+  std::vector<unsigned> ofrom, opre;                    // oversized bins: start, prefix of lengths
+  unsigned ototal = 0;
+  { unsigned gs = bins[0], gc = 0; int gp = 0;                 // group start record, size, first bin
+    for (int p = 0; p < 65536; p++)
+      { unsigned len = bins[p+1] - bins[p];
+        if (len == 0) continue;
+        if (len > BK_CAP)
+          { if (gc) { groups.push_back(make_uint2(gs,gc)); gc = 0; }
+            ofrom.push_back(bins[p]); opre.push_back(ototal); ototal += len;
+            continue;
+          }
+        if (gc != 0 && (gc + len > BK_CAP || p - gp >= BK_SPAN))
+          { groups.push_back(make_uint2(gs,gc)); gc = 0; }
+        if (gc == 0) { gs = bins[p]; gp = p; }
+        gc += len;
+      }
+    if (gc) groups.push_back(make_uint2(gs,gc));
+  }
+
+  uint2 *d_groups = NULL;
+  if (!groups.empty())
+    { CUDA_TRY(fgb_dmalloc((void **) &d_groups,sizeof(uint2)*groups.size(),st));
+      CUDA_TRY(cudaMemcpyAsync(d_groups,groups.data(),sizeof(uint2)*groups.size(),cudaMemcpyHostToDevice,st));
+      kmer_bucket_sort_kernel<<<(unsigned) groups.size(),BK_THREADS,BUCKET_SMEM,st>>>(src,dst,d_groups);
+      fgb_count_launch(1);
+      CUDA_TRY(cudaGetLastError());
+    }
+  if (ototal > 0)
+    { int nseg = (int) ofrom.size();
+      opre.push_back(ototal);
+      std::vector<unsigned> cfrom(opre.begin(),opre.end()-1);            // position in the compact array
+      rec128 *d_c1 = NULL, *d_c2 = NULL; void *d_ctmp = NULL; unsigned *d_seg = NULL;
+      long long ctb = fgb_sort128_tmp_bytes(ototal);
+      CUDA_TRY(fgb_dmalloc((void **) &d_c1,sizeof(rec128)*((size_t) ototal+1),st));
+      CUDA_TRY(fgb_dmalloc((void **) &d_c2,sizeof(rec128)*((size_t) ototal+1),st));
+      CUDA_TRY(fgb_dmalloc(&d_ctmp,ctb,st));
+      CUDA_TRY(fgb_dmalloc((void **) &d_seg,sizeof(unsigned)*(3*(size_t) nseg+1),st));
+      CUDA_TRY(cudaMemcpyAsync(d_seg,ofrom.data(),sizeof(unsigned)*nseg,cudaMemcpyHostToDevice,st));
+      CUDA_TRY(cudaMemcpyAsync(d_seg+nseg,cfrom.data(),sizeof(unsigned)*nseg,cudaMemcpyHostToDevice,st));
+      CUDA_TRY(cudaMemcpyAsync(d_seg+2*nseg,opre.data(),sizeof(unsigned)*(nseg+1),cudaMemcpyHostToDevice,st));
+      int nb = (int) ((ototal + 255) / 256); if (nb > 4736) nb = 4736;
+      kmer_copy_segments_kernel<<<nb,256,0,st>>>(src,d_c1,d_seg,d_seg+nseg,d_seg+2*nseg,nseg,ototal);
+      int cinb = 0;
+      rc = fgb_sort128_device(d_c1,d_c2,ototal,0,16,d_ctmp,ctb,&cinb,st);
+      if (rc) return rc;
+      kmer_copy_segments_kernel<<<nb,256,0,st>>>(cinb ? d_c2 : d_c1,dst,d_seg+nseg,d_seg,d_seg+2*nseg,nseg,ototal);
+      fgb_count_launch(2);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(st));                // the staging vectors above must outlive the copies
+      fgb_dfree(d_c1,st); fgb_dfree(d_c2,st); fgb_dfree(d_ctmp,st); fgb_dfree(d_seg,st);
+    }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  fgb_dfree(d_bins,st); if (d_groups) fgb_dfree(d_groups,st);
+  *result_in_b = inb ^ 1;
   return FGB_OK;
 }
 

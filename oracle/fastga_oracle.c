@@ -90,11 +90,12 @@ int64_t orc_syncmers(const uint8_t *seq, int64_t len, int64_t *out /* >= len ent
   return n;
 }
 
-static int KCMP(const void *l, const void *r)      /* by 80-bit k-mer, then input order (stable) */
+static int KCMP(const void *l, const void *r)
+/* by 80-bit k-mer, then (strand|contig rank, post): the reference leaves the order of equal
+   k-mers to its thread schedule (MSDsort.c, unstable); the device table fixes it by value */
 { const rec128 *a = *(const rec128 * const *) l, *b = *(const rec128 * const *) r;
   if (a->hi != b->hi) return a->hi < b->hi ? -1 : 1;
-  uint64_t x = a->lo >> 48, y = b->lo >> 48;
-  if (x != y) return x < y ? -1 : 1;
+  if (a->lo != b->lo) return a->lo < b->lo ? -1 : 1;
   return a < b ? -1 : (a > b);
 }
 

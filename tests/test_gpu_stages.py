@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as ol
-from fastga_b200 import lib
+from fastga_b200 import formats, lib
 
 pytestmark = pytest.mark.gpu
 
@@ -60,6 +60,24 @@ def test_gix_build_matches_oracle(small_pair):
         assert gx.n == len(want)
         assert np.array_equal(tab, want)
         assert np.array_equal(pstart, wstart)
+
+
+def test_gix_build_with_heavy_repeats_matches_oracle():
+    """exact tandem repeats put > 4096 records into one 16-bit prefix bin: the oversized-bin path
+    of the bucketed k-mer sort (compaction + generic sort + copy back) and the packed groups"""
+    rng = np.random.default_rng(77)
+    unit = rng.integers(0, 4, 37, dtype=np.uint8)
+    contigs = [rng.integers(0, 4, 300_000, dtype=np.uint8), np.tile(unit, 8000),
+               np.zeros(50_000, dtype=np.uint8), rng.integers(0, 4, 150_001, dtype=np.uint8)]
+    g = formats.genome_from_arrays(contigs)
+    dg = lib.DeviceGenome(g)
+    perm, rank = ol.contig_rank(g.clen)
+    want, wstart = ol.gix_build(g, rank)
+    gx = lib.DeviceGix.build(dg)
+    tab, pstart, _ = gx.download()
+    assert gx.n == len(want)
+    assert np.array_equal(tab, want)
+    assert np.array_equal(pstart, wstart)
 
 
 def test_merge_and_seed_sort_match_oracle(small_pair):
