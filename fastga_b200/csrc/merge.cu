@@ -52,13 +52,141 @@ struct seed_pack                          // kernel-uniform packing constants
   long long amxpos, bmxpos, maxdag;
 };
 
-//  One warp owns MG_TILE consecutive T1 entries:
-//   1. two coalesced 512-byte loads; forward-strand entries (the only ones that seed,
+struct blk_stage                          // the block's staging of T2
+{ rec128 t2[MG_T2CAP];                    // the slice of T2 the block's tile can match (TMA destination),
+                                          //   then rewritten in place as (56-bit suffix, payload) pairs
+  unsigned ps[MG_PCAP];                   // the prefix-index range
+  unsigned rng[4];
+  unsigned wtot[MG_WARPS], wsum[MG_WARPS];
+  unsigned long long gbase;
+  unsigned long long bar;
+};
+
+struct warp_stage                         // one warp's private buffers
+{ rec128 t1[MG_TILE];                     // forward-strand T1 entries of the warp's tile, compacted
+  unsigned excl[MG_TILE+1], lowi[MG_TILE], plen[MG_TILE];
+  u64    ipay[MG_TILE];
+};
+
+//  The two table views of the search: staged (shared memory, suffixes precomputed once per T2
+//  entry) or direct (global memory, when a tile's slice does not fit the staging buffers).
+struct view_staged
+{ const blk_stage *S; unsigned t2off, psoff;
+  __device__ __forceinline__ unsigned ps(unsigned p)  const { return S->ps[p - psoff]; }
+  __device__ __forceinline__ u64 suf(unsigned i)      const { return reinterpret_cast<const u64 *>(S->t2)[2*(i - t2off)]; }
+  __device__ __forceinline__ u64 pay(unsigned i)      const { return reinterpret_cast<const u64 *>(S->t2)[2*(i - t2off)+1]; }
+};
+struct view_direct
+{ const rec128 *T2; const unsigned *pstart;
+  __device__ __forceinline__ unsigned ps(unsigned p)  const { return pstart[p]; }
+  __device__ __forceinline__ u64 suf(unsigned i)      const { return suffix_of(T2,i); }
+  __device__ __forceinline__ u64 pay(unsigned i)      const { return T2[i].lo & 0xffffffffffffull; }
+};
+
+//  the adaptamer of one T1 entry: |R| (0 if no seed), first T2 index of R, plen
+template<class View>
+static __device__ __forceinline__ unsigned adaptamer(const View &V, const rec128 &r1, int freq,
+                                                     unsigned &lowi, int &plen)
+{ unsigned p  = KREC_PREFIX24(r1.hi);
+  unsigned lo = V.ps(p), hi = V.ps(p+1);
+  lowi = 0; plen = 0;
+  if (lo >= hi) return 0;
+  u64 s1 = KREC_SUFFIX56(r1);
+  unsigned a = lo, b = hi;                                    // lower bound of s1 in T2[lo,hi)
+  while (a < b)
+    { unsigned m = (a + b) >> 1;
+      if (V.suf(m) < s1) a = m+1; else b = m;
+    }
+  int ll = (a > lo) ? lcp56(s1,V.suf(a-1)) : -1;
+  int lr = (a < hi) ? lcp56(s1,V.suf(a))   : -1;
+  int m  = ll > lr ? ll : lr;
+  plen = 12 + m;
+  unsigned lft = a, rgt = a;
+  int sh = 56 - 2*m;
+  u64 key = s1 >> sh;
+  while (lft > lo && rgt - lft < (unsigned) freq)
+    { if ((V.suf(lft-1) >> sh) != key) break;
+      lft -= 1;
+    }
+  while (rgt < hi && rgt - lft < (unsigned) freq)
+    { if ((V.suf(rgt) >> sh) != key) break;
+      rgt += 1;
+    }
+  if (rgt - lft >= (unsigned) freq) return 0;                 // |R| < FREQ (:799-823)
+  lowi = lft;
+  return rgt - lft;
+}
+
+//  One warp owns MG_TILE consecutive T1 entries; the block shares the staged slice of T2:
+//   1. two coalesced 512-byte loads of the tile; forward-strand entries (the only ones that seed,
 //      FastGA.c:921-928) are compacted into shared memory by ballot so the search lanes are dense;
-//   2. each lane searches its entry in the T2 panel (binary search + bounded walk);
-//   3. the seeds of the 32 lanes are expanded load-balanced: output slot o is built by lane
-//      o mod 32 (prefix sums in shared memory), so every lane builds one seed per step and the
-//      128-bit stores of a step are contiguous.
+//   2. the block's tiles are consecutive in k-mer order, so the T2 entries they can match are ONE
+//      contiguous slice [pstart2[pA], pstart2[pB+1]): fetched with one TMA bulk copy together with
+//      the prefix-index range, suffixes and payloads split once per staged entry;
+//   3. each lane searches its entries in the slice (binary search + bounded walk);
+//   4. the seeds of the tile are expanded load-balanced: output slot o is built by lane o mod 32
+//      (prefix sums in shared memory), so every lane builds one seed per step and the 128-bit
+//      stores of a step are contiguous; one atomic per tile reserves the output run.
+
+template<class View>
+static __device__ __forceinline__ unsigned merge_search(const View &V, warp_stage *S, int nd, int freq,
+                                                        unsigned &sumlen, int lane)
+{ unsigned run = 0, sl = 0;
+  for (int r0 = 0; r0 < nd; r0 += 32)
+    { int idx = r0 + lane;
+      unsigned cnt = 0, lowi = 0; int plen = 0;
+      u64 pay = 0;
+      if (idx < nd)
+        { rec128 r1 = ld_rec(&S->t1[idx]);
+          cnt = adaptamer(V,r1,freq,lowi,plen);
+          pay = r1.lo & 0xffffffffffffull;
+        }
+      unsigned inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+        { unsigned t = __shfl_up_sync(0xffffffffu,inc,o);
+          if (lane >= o) inc += t;
+        }
+      if (idx < MG_TILE)
+        { S->excl[idx] = run + inc - cnt; S->lowi[idx] = lowi; S->plen[idx] = (unsigned) plen; S->ipay[idx] = pay; }
+      run += __shfl_sync(0xffffffffu,inc,31);
+      sl  += cnt * (unsigned) plen;
+    }
+  const int nslot = (nd + 31) & ~31;                           // entries idx >= nd hold cnt 0
+  if (lane == 0) S->excl[nslot] = run;
+  sumlen = __reduce_add_sync(0xffffffffu,sl);
+  __syncwarp();
+  return run;
+}
+
+template<class View>
+static __device__ __forceinline__ void merge_expand(const View &V, const warp_stage *S, int nd, unsigned total,
+                                                    unsigned long long gbase, const seed_pack &K,
+                                                    rec128 *__restrict__ seeds, unsigned long long capacity,
+                                                    int lane)
+{ const int nslot = (nd + 31) & ~31;
+  for (unsigned o = lane; o < total; o += 32)
+    { int j = 0;                                               // last slot with excl <= o
+      for (int st = nslot >> 1; st > 0; st >>= 1)
+        if (S->excl[j + st] <= o) j += st;
+      unsigned k = o - S->excl[j];
+      u64 p2 = V.pay(S->lowi[j] + k), pay = S->ipay[j];
+      long long ipost = (long long) (unsigned) pay, jpost = (long long) (unsigned) p2;
+      unsigned icont = (unsigned) (pay >> 32) & 0x7fff;
+      unsigned cs = (unsigned) (p2 >> 32) & 0xffff;
+      unsigned comp = cs >> 15, jcont = cs & 0x7fff;
+      long long diag, anti;
+      if (comp) { diag = K.maxdag - (ipost + jpost); anti = K.amxpos - (ipost - jpost); }
+      else      { diag = K.bmxpos + (ipost - jpost); anti = ipost + jpost; }
+      u64 X = (u64) S->plen[j] | ((u64) (diag & 63) << 6) | ((u64) anti << 12);
+      u64 Y = (u64) (diag >> 6) | ((u64) jcont << K.s_jc) | ((u64) icont << K.s_ic)
+                                | ((u64) comp << K.s_cp);
+      rec128 sd;
+      sd.lo = X | (Y << K.p_band);
+      sd.hi = Y >> (64 - K.p_band);
+      if (gbase + o < capacity) st_rec(seeds + gbase + o,sd);
+    }
+}
 
 __global__ void __launch_bounds__(MG_THREADS)
 adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
@@ -66,151 +194,90 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
                        int freq, seed_pack K,
                        rec128 *__restrict__ seeds, unsigned long long capacity,
                        unsigned long long *__restrict__ counters /* [0]=nseeds [1]=sum plen */)
-{ __shared__ __align__(16) rec128 sbuf[MG_WARPS][MG_TILE];
-  __shared__ __align__(16) rec128 s_T2[MG_T2CAP];        // the block's slice of T2 ...
-  __shared__ unsigned s_ps[MG_PCAP];                      // ... and of its prefix index
-  __shared__ unsigned s_rng[4];
-  __shared__ __align__(8) unsigned long long s_bar;
-  __shared__ unsigned s_excl[MG_WARPS][33];
-  __shared__ unsigned s_lowi[MG_WARPS][32];
-  __shared__ unsigned s_plen[MG_WARPS][32];
-  __shared__ unsigned long long s_pay[MG_WARPS][32];
-  __shared__ unsigned long long s_sum[MG_WARPS];
-
+{ extern __shared__ __align__(16) unsigned char mg_smem[];
+  blk_stage  *B = reinterpret_cast<blk_stage *>(mg_smem);
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  warp_stage *S = reinterpret_cast<warp_stage *>(mg_smem + sizeof(blk_stage)) + wp;
   const unsigned lt = lanemask_lt();
-  unsigned long long base = ((unsigned long long) blockIdx.x * MG_WARPS + wp) * MG_TILE;
-  unsigned long long sumlen = 0;
+  const unsigned long long b0 = (unsigned long long) blockIdx.x * MG_WARPS * MG_TILE;
+  const unsigned long long base = b0 + (unsigned long long) wp * MG_TILE;
+
+  //  every warp's tile loads are in flight before the block waits for its T2 slice
+  unsigned i0 = (unsigned) base + lane, i1 = i0 + 32;
+  rec128 e0, e1;
+  e0.lo = e0.hi = e1.lo = e1.hi = 0;
+  bool f0 = false, f1 = false;
+  if (base < n1)
+    { if (i0 < n1) { e0 = ld_rec(T1 + i0); f0 = ((e0.lo >> 47) & 1) == 0; }
+      if (i1 < n1) { e1 = ld_rec(T1 + i1); f1 = ((e1.lo >> 47) & 1) == 0; }
+    }
 
   //  The block's 512 T1 entries are consecutive in k-mer order, so the T2 entries they can match
   //  are one contiguous slice [pstart2[pA], pstart2[pB+1]).  When it fits, that slice and the
-  //  prefix-index range are staged in shared memory with coalesced loads and every search,
-  //  walk and payload read below hits shared memory instead of a dependent L2/HBM round trip.
-  { unsigned long long b0 = (unsigned long long) blockIdx.x * MG_WARPS * MG_TILE;
-    if (threadIdx.x == 0)
-      { unsigned long long b1 = b0 + MG_WARPS*MG_TILE - 1;
-        if (b1 >= n1) b1 = n1 - 1;
-        unsigned pA = KREC_PREFIX24(T1[b0].hi), pB = KREC_PREFIX24(T1[b1].hi);
-        unsigned lo2 = pstart2[pA], hi2 = pstart2[pB+1];
-        s_rng[0] = pA; s_rng[1] = pB - pA + 2; s_rng[2] = lo2; s_rng[3] = hi2 - lo2;
-        mbar_init(&s_bar,1);
-        //  the T2 slice is one contiguous run of 128-bit records: a single TMA bulk copy
-        if (pB - pA + 2 <= MG_PCAP && hi2 - lo2 <= MG_T2CAP && hi2 > lo2)
-          tma_load_1d(s_T2,T2 + lo2,(hi2 - lo2) * 16u,&s_bar);
-      }
-    __syncthreads();
-  }
-  const unsigned pA = s_rng[0], lo2 = s_rng[2];
-  const bool staged = (s_rng[1] <= MG_PCAP && s_rng[3] <= MG_T2CAP);
-  if (staged)
-    { for (unsigned i = threadIdx.x; i < s_rng[1]; i += MG_THREADS) s_ps[i] = pstart2[pA + i];
-      if (s_rng[3] > 0) mbar_wait(&s_bar,0);
-    }
-  __syncthreads();
-  const rec128   *T2v = staged ? s_T2 : T2;     const unsigned t2off = staged ? lo2 : 0;
-  const unsigned *psv = staged ? s_ps : pstart2; const unsigned psoff = staged ? pA  : 0;
-
-  if (base < n1)
-    { unsigned i0 = (unsigned) base + lane, i1 = i0 + 32;
-      rec128 e0, e1;
-      bool f0 = false, f1 = false;
-      if (i0 < n1) { e0 = ld_rec(T1 + i0); f0 = ((e0.lo >> 47) & 1) == 0; }
-      if (i1 < n1) { e1 = ld_rec(T1 + i1); f1 = ((e1.lo >> 47) & 1) == 0; }
-      unsigned m0 = __ballot_sync(0xffffffffu,f0), m1 = __ballot_sync(0xffffffffu,f1);
-      int n0 = __popc(m0), nd = n0 + __popc(m1);
-      if (f0) st_rec(&sbuf[wp][__popc(m0 & lt)],e0);
-      if (f1) st_rec(&sbuf[wp][n0 + __popc(m1 & lt)],e1);
-      __syncwarp();
-
-      for (int r0 = 0; r0 < nd; r0 += 32)
-        { int idx = r0 + lane;
-          unsigned cnt = 0, lowi = 0;
-          int plen = 0;
-          rec128 r1; r1.lo = r1.hi = 0;
-          if (idx < nd)
-            { r1 = ld_rec(&sbuf[wp][idx]);
-              unsigned p  = KREC_PREFIX24(r1.hi);
-              unsigned lo = psv[p - psoff], hi = psv[p + 1 - psoff];
-              if (lo < hi)
-                { u64 s1 = KREC_SUFFIX56(r1);
-                  unsigned a = lo, b = hi;                    // lower bound of s1 in T2[lo,hi)
-                  while (a < b)
-                    { unsigned m = (a + b) >> 1;
-                      if (suffix_of(T2v,m - t2off) < s1) a = m+1; else b = m;
-                    }
-                  int ll = (a > lo) ? lcp56(s1,suffix_of(T2v,a-1 - t2off)) : -1;
-                  int lr = (a < hi) ? lcp56(s1,suffix_of(T2v,a - t2off))   : -1;
-                  int m  = ll > lr ? ll : lr;
-                  plen = 12 + m;
-                  unsigned lft = a, rgt = a;
-                  int sh = 56 - 2*m;
-                  u64 key = s1 >> sh;
-                  while (lft > lo && rgt - lft < (unsigned) freq)
-                    { if ((suffix_of(T2v,lft-1 - t2off) >> sh) != key) break;
-                      lft -= 1;
-                    }
-                  while (rgt < hi && rgt - lft < (unsigned) freq)
-                    { if ((suffix_of(T2v,rgt - t2off) >> sh) != key) break;
-                      rgt += 1;
-                    }
-                  if (rgt - lft < (unsigned) freq)             // |R| < FREQ (:799-823)
-                    { cnt = rgt - lft; lowi = lft; }
-                }
-            }
-
-          unsigned inc = cnt;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1)
-            { unsigned t = __shfl_up_sync(0xffffffffu,inc,o);
-              if (lane >= o) inc += t;
-            }
-          unsigned total = __shfl_sync(0xffffffffu,inc,31);
-          if (total == 0) continue;
-          sumlen += (unsigned long long) __reduce_add_sync(0xffffffffu,cnt * (unsigned) plen);
-          unsigned long long gbase = 0;
-          if (lane == 0) gbase = atomicAdd(&counters[0],(unsigned long long) total);
-          gbase = __shfl_sync(0xffffffffu,gbase,0);
-          s_excl[wp][lane] = inc - cnt;
-          if (lane == 31) s_excl[wp][32] = total;
-          s_lowi[wp][lane] = lowi;
-          s_plen[wp][lane] = (unsigned) plen;
-          s_pay[wp][lane]  = r1.lo & 0xffffffffffffull;
-          __syncwarp();
-
-          for (unsigned o = lane; o < total; o += 32)
-            { int j = 0;                                       // last lane with s_excl <= o
-#pragma unroll
-              for (int st = 16; st > 0; st >>= 1)
-                if (s_excl[wp][j + st] <= o) j += st;
-              unsigned k = o - s_excl[wp][j];
-              rec128 r2 = ld_rec(T2v + (s_lowi[wp][j] + k - t2off));
-              unsigned long long pay = s_pay[wp][j];
-              long long ipost = (long long) (unsigned) pay, jpost = (long long) (unsigned) r2.lo;
-              unsigned icont = (unsigned) (pay >> 32) & 0x7fff;
-              unsigned cs = (unsigned) (r2.lo >> 32) & 0xffff;
-              unsigned comp = cs >> 15, jcont = cs & 0x7fff;
-              long long diag, anti;
-              if (comp) { diag = K.maxdag - (ipost + jpost); anti = K.amxpos - (ipost - jpost); }
-              else      { diag = K.bmxpos + (ipost - jpost); anti = ipost + jpost; }
-              u64 X = (u64) s_plen[wp][j] | ((u64) (diag & 63) << 6) | ((u64) anti << 12);
-              u64 Y = (u64) (diag >> 6) | ((u64) jcont << K.s_jc) | ((u64) icont << K.s_ic)
-                                        | ((u64) comp << K.s_cp);
-              rec128 sd;
-              sd.lo = X | (Y << K.p_band);
-              sd.hi = Y >> (64 - K.p_band);
-              if (gbase + o < capacity) st_rec(seeds + gbase + o,sd);
-            }
-          __syncwarp();
+  //  prefix-index range are staged in shared memory (one TMA bulk copy + coalesced loads) and
+  //  every search, walk and payload read hits shared memory instead of a dependent L2/HBM trip.
+  if (wp == 0)
+    { unsigned long long b1 = b0 + MG_WARPS*MG_TILE - 1;
+      if (b1 >= n1) b1 = n1 - 1;
+      unsigned long long hv = 0;
+      if (lane == 0) hv = T1[b0].hi;                       // (warp 0's own lane-0 load again: L1 hit)
+      if (lane == 1) hv = T1[b1].hi;
+      unsigned pfx = KREC_PREFIX24(hv);
+      unsigned pA = __shfl_sync(0xffffffffu,pfx,0), pB = __shfl_sync(0xffffffffu,pfx,1);
+      unsigned q = 0;
+      if (lane == 0) q = pstart2[pA];
+      if (lane == 1) q = pstart2[pB+1];
+      unsigned lo2 = __shfl_sync(0xffffffffu,q,0), hi2 = __shfl_sync(0xffffffffu,q,1);
+      if (lane == 0)
+        { B->rng[0] = pA; B->rng[1] = pB - pA + 2; B->rng[2] = lo2; B->rng[3] = hi2 - lo2;
+          mbar_init(&B->bar,1);
+          if (pB - pA + 2 <= MG_PCAP && hi2 - lo2 <= MG_T2CAP && hi2 > lo2)
+            tma_load_1d(B->t2,T2 + lo2,(hi2 - lo2) * 16u,&B->bar);
         }
     }
-
-  if (lane == 0) s_sum[wp] = sumlen;
+  //  forward-strand compaction of the warp's tile while the slice is in flight
+  unsigned m0 = __ballot_sync(0xffffffffu,f0), m1 = __ballot_sync(0xffffffffu,f1);
+  int n0 = __popc(m0), nd = n0 + __popc(m1);
+  if (f0) st_rec(&S->t1[__popc(m0 & lt)],e0);
+  if (f1) st_rec(&S->t1[n0 + __popc(m1 & lt)],e1);
+  __syncthreads();
+  const unsigned pA = B->rng[0], nps = B->rng[1], lo2 = B->rng[2], nsl = B->rng[3];
+  const bool staged = (nps <= MG_PCAP && nsl <= MG_T2CAP);
+  if (staged)
+    { for (unsigned i = threadIdx.x; i < nps; i += MG_THREADS) B->ps[i] = pstart2[pA + i];
+      if (nsl > 0)
+        { mbar_wait(&B->bar,0);
+          for (unsigned j = threadIdx.x; j < nsl; j += MG_THREADS)
+            { rec128 r = ld_rec(&B->t2[j]), c;
+              c.lo = KREC_SUFFIX56(r);                       // first word: suffix, second: payload
+              c.hi = r.lo & 0xffffffffffffull;
+              st_rec(&B->t2[j],c);
+            }
+        }
+    }
+  __syncthreads();
+  //  search, then ONE atomic per block reserves the output run of its eight tiles (a per-tile
+  //  atomic on the single counter serialises in L2: 1.2 M same-address atomics cost > 1.5 ms)
+  unsigned total = 0, sl = 0;
+  view_staged Vs; Vs.S = B; Vs.t2off = lo2; Vs.psoff = pA;
+  view_direct Vd; Vd.T2 = T2; Vd.pstart = pstart2;
+  if (nd > 0)
+    total = staged ? merge_search(Vs,S,nd,freq,sl,lane) : merge_search(Vd,S,nd,freq,sl,lane);
+  if (lane == 0) { B->wtot[wp] = total; B->wsum[wp] = sl; }
   __syncthreads();
   if (threadIdx.x == 0)
-    { unsigned long long t = 0;
-      for (int k = 0; k < MG_WARPS; k++) t += s_sum[k];
-      if (t) atomicAdd(&counters[1],t);
+    { unsigned long long t = 0, q = 0;
+      for (int k = 0; k < MG_WARPS; k++) { t += B->wtot[k]; q += B->wsum[k]; }
+      unsigned long long g = 0;
+      if (t) { g = atomicAdd(&counters[0],t); atomicAdd(&counters[1],q); }
+      B->gbase = g;
     }
+  __syncthreads();
+  if (total == 0) return;
+  unsigned long long gbase = B->gbase;
+  for (int k = 0; k < wp; k++) gbase += B->wtot[k];
+  if (staged) merge_expand(Vs,S,nd,total,gbase,K,seeds,capacity,lane);
+  else        merge_expand(Vd,S,nd,total,gbase,K,seeds,capacity,lane);
 }
 
 //  T1/T2: sorted device tables; pstart2: [2^24+1] lower-bound index of T2.  Appends seed
@@ -242,7 +309,13 @@ extern "C" int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2
       cudaEvent_t ea, eb;
       cudaEventCreate(&ea); cudaEventCreate(&eb);
       cudaEventRecord(ea,st);
-      adaptamer_merge_kernel<<<nb,MG_THREADS,0,st>>>((const rec128 *) d_T1,(unsigned) n1,
+      static bool attr_set = false;
+      if (!attr_set)
+        { CUDA_TRY(cudaFuncSetAttribute(adaptamer_merge_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int) (sizeof(blk_stage) + MG_WARPS*sizeof(warp_stage))));
+          attr_set = true;
+        }
+      adaptamer_merge_kernel<<<nb,MG_THREADS,sizeof(blk_stage) + MG_WARPS*sizeof(warp_stage),st>>>((const rec128 *) d_T1,(unsigned) n1,
                                                      (const rec128 *) d_T2,d_pstart2,freq,K,
                                                      (rec128 *) d_seeds,(unsigned long long) capacity,
                                                      d_counters);
