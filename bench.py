@@ -85,6 +85,24 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def other_kernels(stats, dev_ms, peak, seed_passes):
+    """achieved HBM GB/s of the sort stages from their CUDA-event times (bytes = records x 16 B x 2 per pass)"""
+    out = []
+    nk = stats["nkmers1"] + stats["nkmers2"]
+    if dev_ms.get("ksort_ms", 0) > 0:
+        b = nk * 32 * 3
+        out.append({"stage": "k-mer table sort (sort_onesweep_kernel x2 + kmer_bucket_sort_kernel)", "bound": "hbm",
+                    "bytes": b, "ms": dev_ms["ksort_ms"], "achieved": b / dev_ms["ksort_ms"] / 1e6,
+                    "frac": b / dev_ms["ksort_ms"] / 1e6 / peak})
+    if dev_ms.get("ssort_ms", 0) > 0:
+        passes = seed_passes
+        b = stats["nseeds"] * 32 * passes
+        out.append({"stage": "seed sort (sort_onesweep_kernel, %d byte passes)" % passes, "bound": "hbm",
+                    "bytes": b, "ms": dev_ms["ssort_ms"], "achieved": b / dev_ms["ssort_ms"] / 1e6,
+                    "frac": b / dev_ms["ssort_ms"] / 1e6 / peak})
+    return out
+
+
 def ncu_traffic_bytes():
     """DRAM bytes of one adaptamer_merge_kernel launch on this workload from the committed ncu
     --set full capture (profiles/r01_ncu_merge_kernel.json); None if no capture is committed."""
@@ -240,8 +258,18 @@ def run():
     sampler.join(timeout=2)
     alns, stats = outs[-1]
 
-    # end to end through the reference-facing call on host buffers
-    e2e_step = lambda: lib.fastga(gA, gB)
+    # end to end through the reference-facing call on HOST buffers: the .bps images sit in pinned
+    # host memory (what a caller that wants full PCIe rate does), every step copies them to the
+    # device and reads the alignment records back
+    def pinned(g):
+        t = torch.empty(g.bps.size, dtype=torch.uint8).pin_memory()
+        t.numpy()[:] = g.bps
+        q = formats.Genome(g.clen, t.numpy())
+        q._pin = t
+        q._freq = g.freq
+        return q
+    pA, pB = pinned(gA), pinned(gB)
+    e2e_step = lambda: lib.fastga(pA, pB)
     e2e_step()
     ms_e2e, outs2 = timed(e2e_step, max(1, min(args.steps, 3)))
     st2 = outs2[-1][1]
@@ -266,6 +294,10 @@ def run():
     R = 1 + 2 * (pb + 1)
     algo = (stats["nkmers1"] + stats["nkmers2"]) * E1 + stats["nseeds"] * R
     merge_ms = tm["merge_ms"] / max(1, tm["merge_launches"])
+    # byte passes of the seed sort: key = lcp(6) drem(6) anti band jcont icont strand (api.cu:fgb_seeds_find)
+    abits = int(gA.clen.max() + gB.clen.max()).bit_length()
+    kb = 12 + abits + max(1, abits - 6) + max(1, (gB.ncontig - 1).bit_length()) + max(1, (gA.ncontig - 1).bit_length()) + 1
+    seed_passes = (kb + 7) // 8
     peak, peak_src = measured_peak_hbm()
     ach = algo / (merge_ms * 1e-3) / 1e9 if merge_ms > 0 else 0.0
     dev_ms = {k: v / steps for k, v in tm.items() if k.endswith("_ms")}
@@ -291,6 +323,9 @@ def run():
                          "traffic": ncu_traffic_bytes() if (world == 1 and args.per_gpu_bp == PER_GPU_BP) else None,
                          "peak_source": peak_src,
                          "algorithmic_bytes": algo, "kernel_ms": merge_ms},
+            # the other HBM-side stages against the same measured peak (16-byte device records;
+            # k-mer sort = 2 Onesweep passes + 1 shared-memory bucket pass, seed sort = ceil(keybits/8) passes)
+            "other_kernels": other_kernels(stats, dev_ms, peak, seed_passes),
             "extend_kernel": {"ms": tm["extend_ms"] / steps, "launches_per_step": tm["extend_launches"] / steps,
                               "cell_updates_per_s":
                               stats["ncells"] / max(1e-9, tm["extend_ms"] / steps / 1000.0)},

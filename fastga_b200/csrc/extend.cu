@@ -167,10 +167,10 @@ template<int S>
 static __device__ __forceinline__ int snake(const Ctx &c, int xn, int kk, int &flag)
 { int yn = xn - kk, t = 0, tmax;
   if (S > 0)
-    { int x = xn, y = yn;
-      if (y < 0 || y >= c.blen) { flag = 1; return 0; }
-      if (x < 0 || x >= c.alen) { flag = 2; return 0; }
+    { const int x = xn, y = yn;
       tmax = min(c.alen - x,c.blen - y);
+      if ((x | y) < 0 || tmax <= 0)                        // off a sequence end (rare): B first, then A
+        { flag = (y < 0 || y >= c.blen) ? 1 : 2; return 0; }
       while (t < tmax)
         { u64 d = win(c.A,x+t) ^ win(c.B,y+t);
           if (d) { t += (__ffsll((long long) d)-1) >> 1; break; }
@@ -180,10 +180,10 @@ static __device__ __forceinline__ int snake(const Ctx &c, int xn, int kk, int &f
       else flag = 0;
     }
   else
-    { int x = -xn, y = -yn;
-      if (y-1 < 0 || y-1 >= c.blen) { flag = 1; return 0; }
-      if (x-1 < 0 || x-1 >= c.alen) { flag = 2; return 0; }
+    { const int x = -xn, y = -yn;
       tmax = min(x,y);
+      if (tmax <= 0 || y > c.blen || x > c.alen)
+        { flag = (y <= 0 || y > c.blen) ? 1 : 2; return 0; }
       while (t < tmax)
         { u64 d = win(c.A,x-t-32) ^ win(c.B,y-t-32);
           if (d) { t += __clzll((long long) d) >> 1; break; }

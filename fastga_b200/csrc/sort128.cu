@@ -29,6 +29,15 @@ static __device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane)
 }
 
 
+/***********************************************************************************************
+ *  Onesweep pass: one kernel per key byte reads every record once and writes it once.
+ *   - the GLOBAL digit histogram of a pass is produced by the previous pass (each tile counts
+ *     the next byte while it holds the records; the first pass has a small histogram kernel);
+ *   - the tile's base inside each digit bucket comes from a decoupled look-back over the
+ *     per-tile digit counts (status word = count | flag<<62; 1 = tile aggregate, 2 = inclusive
+ *     prefix), tiles being handed out by an atomic ticket so every predecessor is running.
+ **********************************************************************************************/
+
 //  Lanes of the warp holding the same 8-bit digit as this lane (among valid lanes).  MATCH.ANY
 //  costs one internal round per distinct value in the warp (~30 for random digits); nine ballots
 //  are a fixed, much smaller cost.
@@ -43,14 +52,6 @@ static __device__ __forceinline__ unsigned match_digit(unsigned d, bool valid)
   return peers;
 }
 
-/***********************************************************************************************
- *  Onesweep pass: one kernel per key byte reads every record once and writes it once.
- *   - the GLOBAL digit histogram of a pass is produced by the previous pass (each tile counts
- *     the next byte while it holds the records; the first pass has a small histogram kernel);
- *   - the tile's base inside each digit bucket comes from a decoupled look-back over the
- *     per-tile digit counts (status word = count | flag<<62; 1 = tile aggregate, 2 = inclusive
- *     prefix), tiles being handed out by an atomic ticket so every predecessor is running.
- **********************************************************************************************/
 
 #define ST_AGG  (1ull << 62)
 #define ST_INC  (2ull << 62)
@@ -70,9 +71,8 @@ sort_ghist_kernel(const rec128 *__restrict__ in, long long n, int byte, unsigned
       for (int it = 0; it < SORT_ITEMS; it++)
         { long long idx = tile0 + it*SORT_THREADS + tid;
           bool valid = idx < n;
-          unsigned d = 0x100u | (tid & 31);
-          if (valid) d = (unsigned) ((half[2*idx] >> sh) & 0xff);
-          unsigned peers = __match_any_sync(0xffffffffu,d);
+          unsigned d = valid ? (unsigned) ((half[2*idx] >> sh) & 0xff) : 0;
+          unsigned peers = match_digit(d,valid);             // one atomic per distinct digit of the warp
           if (valid && (tid & 31) == __ffs(peers)-1) atomicAdd(&h[d],__popc(peers));
         }
     }
