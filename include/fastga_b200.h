@@ -78,7 +78,10 @@ int  fgb_genome_perm(const fgb_genome *g, int *perm_out);   /* Perm of GIXmake.c
 int  fgb_genome_download(const fgb_genome *g, int rev, unsigned long long *words, long long *woff_out);
 long long fgb_genome_words(const fgb_genome *g);
 
-/* ---- GIX (GIXmake.c distribute + k_sort; MSDsort.c msd_sort; libfastk.c Kmer_Stream) ---- */
+/* ---- GIX (GIXmake.c distribute + k_sort; MSDsort.c msd_sort; libfastk.c Kmer_Stream) ----
+ * The table is sorted by the 40-mer; entries with EQUAL k-mers follow each other by
+ * (strand|contig rank, post).  msd_sort leaves that order to its unstable in-place permutation
+ * (MSDsort.c:211-360); no consumer depends on it (seeds are fully re-sorted, FastGA.c:4320). */
 int  fgb_gix_build(const fgb_genome *g, fgb_gix **out, void *stream);
 /* one rank's share (12-base prefix in [plo,phi)) of a cooperatively built table, and the pieces
    to assemble the shares gathered over NCCL (fastga_b200/shard.py) */
