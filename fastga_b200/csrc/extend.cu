@@ -97,6 +97,9 @@ struct Ctx
 #ifndef EX_PAIR
 #define EX_PAIR 1
 #endif
+#ifndef EX_NOREG
+#define EX_NOREG 0                       // 1 (debug): never use the register path of the single-warp waves
+#endif
 #define EX_RING 32
 
 struct __align__(16) RingEnt
@@ -584,7 +587,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
       dif += 1;
       ncell += (u64) (hghk - lowk + 1);
 
-      if (hghk - lowk < 32)
+      if (!EX_NOREG && hghk - lowk < 32)
         { //  ---- register path: lane (-kk & 31) owns diagonal kk ----
           const int top = hghk, ltop = (-top) & 31;
           const int kk = top - ((lane - ltop) & 31);
@@ -715,15 +718,18 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
               b = c.T[si]; ha = c.HA[si]; hm = c.HM[si];
             }
           int nan = c.NA[IX(flo ? kk+1 : (fhi ? kk-1 : kk))];
+          //  the fresh low edge copies the OLD NA of the diagonal above it (align.c:611-613, before
+          //  the wave): if that diagonal closed the previous chunk it has been updated already
+          if (flo && lane == 0 && top != hghk) nan = c.carry[5];
           //  lane 31's own old state is the next chunk's "kk+1"
-          int  o_v = 0, o_ha = 0, o_hm = 0; u64 o_t = 0;
+          int  o_v = 0, o_ha = 0, o_hm = 0, o_na = 0; u64 o_t = 0;
           const bool morechunks = (top - 32 >= lowk);
           if (lane == 31 && morechunks)
-            { o_v = ac; o_t = c.T[IX(kk)]; o_ha = c.HA[IX(kk)]; o_hm = c.HM[IX(kk)]; }
+            { o_v = ac; o_t = c.T[IX(kk)]; o_ha = c.HA[IX(kk)]; o_hm = c.HM[IX(kk)]; o_na = c.NA[IX(kk)]; }
           __syncwarp();                              // all reads of old state done
           if (lane == 31 && morechunks)
             { c.carry[0] = o_v; c.carry[1] = (int) (unsigned) o_t; c.carry[2] = (int) (o_t >> 32);
-              c.carry[3] = o_ha; c.carry[4] = o_hm;
+              c.carry[3] = o_ha; c.carry[4] = o_hm; c.carry[5] = o_na;
             }
 
           b <<= 1;
