@@ -14,8 +14,8 @@ static inline long long now_us()
 { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 extern "C" {
-int fgb_kmer_sort_device(void *d_a, void *d_b, long long n, void *d_tmp, long long tmp_bytes,
-                         int *result_in_b, void *stream);
+int fgb_kmer_sort_range_device(void *d_a, void *d_b, long long n, unsigned plo, unsigned phi,
+                               void *d_tmp, long long tmp_bytes, int *result_in_b, void *stream);
 int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo, int byte_hi,
                        void *d_tmp, long long tmp_bytes, int *result_in_b, void *stream);
 long long fgb_sort128_tmp_bytes(long long n);
@@ -37,7 +37,7 @@ int fgb_ktab_export_device(const void *d_tab, long long n, int pbytes, int cbyte
 int fgb_ktab_import_device(const void *d_ent, long long n, int pbytes, int cbytes,
                            const long long *d_index, void *d_tab, void *stream);
 int fgb_sc_tile();
-int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2, const unsigned *d_pstart2,
+int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2, long long n2, const unsigned *d_pstart2,
                      int freq, int anti_bits, int band_bits, int jc_bits, int ic_bits,
                      long long amxpos, long long bmxpos, void *d_seeds, long long capacity,
                      unsigned long long *d_counters, unsigned long long *h_nseeds,
@@ -308,7 +308,7 @@ static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi, fgb_
   }
   int inb = 0;
   { stage_timer t(&g_timings.ksort_ms,st);
-    rc = fgb_kmer_sort_device(d_a,d_b,n,d_stmp,stmpb,&inb,st);
+    rc = fgb_kmer_sort_range_device(d_a,d_b,n,plo,phi,d_stmp,stmpb,&inb,st);
     if (rc) return rc;
   }
   x->d_tab = inb ? d_b : d_a;
@@ -457,7 +457,7 @@ extern "C" int fgb_seeds_find(const fgb_gix *x1, const fgb_gix *x2, long long am
   for (int attempt = 0; ; attempt++)
     { CUDA_TRY(fgb_dmalloc((void **) &d_a,sizeof(rec128)*(cap+1),st));
       int rc;
-      rc = fgb_merge_device(x1->d_tab,x1->n,x2->d_tab,x2->d_pstart,freq,s->anti_bits,s->band_bits,
+      rc = fgb_merge_device(x1->d_tab,x1->n,x2->d_tab,x2->n,x2->d_pstart,freq,s->anti_bits,s->band_bits,
                             s->jc_bits,s->ic_bits,amxpos,bmxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
       if (rc == FGB_OK) break;
       fgb_dfree(d_a,st); d_a = NULL;

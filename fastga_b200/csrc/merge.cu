@@ -30,7 +30,7 @@ static __host__ __device__ __forceinline__ int seed_key_bits(const seed_layout &
 
 #define MG_THREADS 256
 #define MG_WARPS   (MG_THREADS/32)
-#define MG_TILE    64                     // T1 entries per warp
+#define MG_TILE    64                     // T1 entries per warp (32 / 16 when T2 is much denser than T1)
 #define MG_T2CAP   1280                   // staged T2 entries per block (20 KB)
 #define MG_PCAP    1536                   // staged prefix-index entries per block (6 KB)
 
@@ -188,6 +188,7 @@ static __device__ __forceinline__ void merge_expand(const View &V, const warp_st
     }
 }
 
+template<int TILE>
 __global__ void __launch_bounds__(MG_THREADS)
 adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
                        const rec128 *__restrict__ T2, const unsigned *__restrict__ pstart2,
@@ -199,8 +200,8 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   warp_stage *S = reinterpret_cast<warp_stage *>(mg_smem + sizeof(blk_stage)) + wp;
   const unsigned lt = lanemask_lt();
-  const unsigned long long b0 = (unsigned long long) blockIdx.x * MG_WARPS * MG_TILE;
-  const unsigned long long base = b0 + (unsigned long long) wp * MG_TILE;
+  const unsigned long long b0 = (unsigned long long) blockIdx.x * MG_WARPS * TILE;
+  const unsigned long long base = b0 + (unsigned long long) wp * TILE;
 
   //  every warp's tile loads are in flight before the block waits for its T2 slice
   unsigned i0 = (unsigned) base + lane, i1 = i0 + 32;
@@ -208,8 +209,8 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
   e0.lo = e0.hi = e1.lo = e1.hi = 0;
   bool f0 = false, f1 = false;
   if (base < n1)
-    { if (i0 < n1) { e0 = ld_rec(T1 + i0); f0 = ((e0.lo >> 47) & 1) == 0; }
-      if (i1 < n1) { e1 = ld_rec(T1 + i1); f1 = ((e1.lo >> 47) & 1) == 0; }
+    { if (lane < TILE && i0 < n1) { e0 = ld_rec(T1 + i0); f0 = ((e0.lo >> 47) & 1) == 0; }
+      if (TILE > 32 && i1 < n1)   { e1 = ld_rec(T1 + i1); f1 = ((e1.lo >> 47) & 1) == 0; }
     }
 
   //  The block's 512 T1 entries are consecutive in k-mer order, so the T2 entries they can match
@@ -217,7 +218,7 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
   //  prefix-index range are staged in shared memory (one TMA bulk copy + coalesced loads) and
   //  every search, walk and payload read hits shared memory instead of a dependent L2/HBM trip.
   if (wp == 0)
-    { unsigned long long b1 = b0 + MG_WARPS*MG_TILE - 1;
+    { unsigned long long b1 = b0 + MG_WARPS*TILE - 1;
       if (b1 >= n1) b1 = n1 - 1;
       unsigned long long hv = 0;
       if (lane == 0) hv = T1[b0].hi;                       // (warp 0's own lane-0 load again: L1 hit)
@@ -285,7 +286,7 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
 //  On return *h_nseeds is the number of seeds FOUND; if it exceeds capacity the buffer
 //  content is incomplete and the caller must retry with a larger buffer (FGB_ERR_OVERFLOW).
 
-extern "C" int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2,
+extern "C" int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2, long long n2,
                                 const unsigned *d_pstart2, int freq,
                                 int anti_bits, int band_bits, int jc_bits, int ic_bits,
                                 long long amxpos, long long bmxpos,
@@ -305,20 +306,29 @@ extern "C" int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2
   K.amxpos = amxpos; K.bmxpos = bmxpos; K.maxdag = amxpos + bmxpos;
   if (K.s_cp + 1 > 64 || K.p_band >= 64 || K.p_band < 13) return FGB_ERR_LIMIT;
   if (n1 > 0)
-    { unsigned nb = (unsigned) ((n1 + MG_WARPS*MG_TILE - 1) / (MG_WARPS*MG_TILE));
+    { //  T2 denser than T1 (a shard of genome 1 against all of genome 2): smaller tiles keep the
+      //  block's T2 slice inside the staging buffer
+      int tile = MG_TILE;
+      if (n2 > 0 && n1 > 0)
+        { double ratio = (double) n2 / (double) n1;
+          if (ratio > 3.2) tile = 16; else if (ratio > 1.6) tile = 32;
+        }
+      unsigned nb = (unsigned) ((n1 + MG_WARPS*tile - 1) / (MG_WARPS*tile));
       cudaEvent_t ea, eb;
       cudaEventCreate(&ea); cudaEventCreate(&eb);
-      cudaEventRecord(ea,st);
       static bool attr_set = false;
+      const int smem = (int) (sizeof(blk_stage) + MG_WARPS*sizeof(warp_stage));
       if (!attr_set)
-        { CUDA_TRY(cudaFuncSetAttribute(adaptamer_merge_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int) (sizeof(blk_stage) + MG_WARPS*sizeof(warp_stage))));
+        { CUDA_TRY(cudaFuncSetAttribute(adaptamer_merge_kernel<64>,cudaFuncAttributeMaxDynamicSharedMemorySize,smem));
+          CUDA_TRY(cudaFuncSetAttribute(adaptamer_merge_kernel<32>,cudaFuncAttributeMaxDynamicSharedMemorySize,smem));
+          CUDA_TRY(cudaFuncSetAttribute(adaptamer_merge_kernel<16>,cudaFuncAttributeMaxDynamicSharedMemorySize,smem));
           attr_set = true;
         }
-      adaptamer_merge_kernel<<<nb,MG_THREADS,sizeof(blk_stage) + MG_WARPS*sizeof(warp_stage),st>>>((const rec128 *) d_T1,(unsigned) n1,
-                                                     (const rec128 *) d_T2,d_pstart2,freq,K,
-                                                     (rec128 *) d_seeds,(unsigned long long) capacity,
-                                                     d_counters);
+      cudaEventRecord(ea,st);
+#define MG_LAUNCH(T) adaptamer_merge_kernel<T><<<nb,MG_THREADS,smem,st>>>((const rec128 *) d_T1,(unsigned) n1, \
+                       (const rec128 *) d_T2,d_pstart2,freq,K,(rec128 *) d_seeds,(unsigned long long) capacity,d_counters)
+      if (tile == 64) MG_LAUNCH(64); else if (tile == 32) MG_LAUNCH(32); else MG_LAUNCH(16);
+#undef MG_LAUNCH
       cudaEventRecord(eb,st);
       cudaEventSynchronize(eb);
       float ms = 0; cudaEventElapsedTime(&ms,ea,eb);

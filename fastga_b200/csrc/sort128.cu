@@ -300,12 +300,14 @@ extern "C" int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo
 #define BK_NSUB    (BK_SPAN << BK_SUBBITS)
 #define BK_MAXSUB  32                    // a sub-bin longer than this sends the group down the LSD path
 
-//  bin_start[p] = first record whose top 16 key bits are >= p, p in [0,65536]
-__global__ void kmer_bins_kernel(const rec128 *__restrict__ tab, long long n, unsigned *__restrict__ bin_start)
+//  bin_start[p] = first record whose bin ((hi >> binshift) - base) is >= p, p in [0,65536]
+__global__ void kmer_bins_kernel(const rec128 *__restrict__ tab, long long n, int binshift, unsigned long long base,
+                                 unsigned *__restrict__ bin_start)
 { long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
-  long long lo = (i == 0) ? -1 : (long long) (tab[i-1].hi >> 48);
-  long long hi = (i == n) ? 65536 : (long long) (tab[i].hi >> 48);
+  long long lo = (i == 0) ? -1 : (long long) ((tab[i-1].hi >> binshift) - base);
+  long long hi = (i == n) ? 65536 : (long long) ((tab[i].hi >> binshift) - base);
+  if (hi > 65536) hi = 65536;
   for (long long p = lo+1; p <= hi; p++) bin_start[p] = (unsigned) i;
 }
 
@@ -316,7 +318,7 @@ __global__ void kmer_bins_kernel(const rec128 *__restrict__ tab, long long n, un
 
 __global__ void __launch_bounds__(BK_THREADS)
 kmer_bucket_sort_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out,
-                        const uint2 *__restrict__ groups /* start, count */)
+                        const uint2 *__restrict__ groups /* start, count */, int binshift)
 { extern __shared__ __align__(16) unsigned char smem_raw[];
   rec128   *tile   = reinterpret_cast<rec128 *>(smem_raw);
   unsigned *cnt    = reinterpret_cast<unsigned *>(tile + BK_CAP);        // [BK_NSUB+1]; LSD path: wcount[BK_WARPS][256]
@@ -338,13 +340,14 @@ kmer_bucket_sort_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out,
   rec128   r[BK_ITEMS];
   unsigned sub[BK_ITEMS], off[BK_ITEMS];
   const int base = w*(32*BK_ITEMS);
-  const unsigned b0 = (unsigned) (tile[0].hi >> 48);
+  const unsigned b0 = (unsigned) (tile[0].hi >> binshift);
+  const int subshift = binshift - BK_SUBBITS;
 #pragma unroll
   for (int it = 0; it < BK_ITEMS; it++)
     { int idx = base + it*32 + lane;
       if (idx < count)
         { r[it] = ld_rec(tile + idx);
-          sub[it] = ((((unsigned) (r[it].hi >> 48)) - b0) << BK_SUBBITS) | ((unsigned) (r[it].hi >> (48-BK_SUBBITS)) & ((1u << BK_SUBBITS)-1));
+          sub[it] = ((((unsigned) (r[it].hi >> binshift)) - b0) << BK_SUBBITS) | ((unsigned) (r[it].hi >> subshift) & ((1u << BK_SUBBITS)-1));
           off[it] = atomicAdd(&cnt[sub[it]],1u);
         }
     }
@@ -375,7 +378,7 @@ kmer_bucket_sort_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out,
       __syncthreads();
       for (int p = tid; p < count; p += BK_THREADS)
         { rec128 R = ld_rec(tile + p);
-          unsigned sb = ((((unsigned) (R.hi >> 48)) - b0) << BK_SUBBITS) | ((unsigned) (R.hi >> (48-BK_SUBBITS)) & ((1u << BK_SUBBITS)-1));
+          unsigned sb = ((((unsigned) (R.hi >> binshift)) - b0) << BK_SUBBITS) | ((unsigned) (R.hi >> subshift) & ((1u << BK_SUBBITS)-1));
           int s = (int) cnt[sb], e = (int) cnt[sb+1], rank = 0;
           for (int q = s; q < e; q++)
             { rec128 Q = ld_rec(tile + q);
@@ -478,14 +481,24 @@ static const size_t BUCKET_SMEM = BK_CAP*sizeof(rec128) + (BK_NSUB + 32 + 256 + 
 //  (*result_in_b).  d_tmp as for fgb_sort128_device.  Synchronises the stream once (the bin
 //  boundaries come to the host to pack the groups).
 
-extern "C" int fgb_kmer_sort_device(void *d_a, void *d_b, long long n, void *d_tmp, long long tmp_bytes,
-                                    int *result_in_b, void *stream)
+//  [plo,phi): the range of 12-base prefixes the records come from (the whole space, or one
+//  rank's share of a cooperatively built table).  The 65536 bins always tile THAT range, so a share
+//  is binned as finely as a whole table of the same size (bins of 16 + log2(2^24/range) top bits;
+//  one more partition pass when that exceeds two bytes).
+
+extern "C" int fgb_kmer_sort_range_device(void *d_a, void *d_b, long long n, unsigned plo, unsigned phi,
+                                          void *d_tmp, long long tmp_bytes, int *result_in_b, void *stream)
 { cudaStream_t st = (cudaStream_t) stream;
   *result_in_b = 0;
   if (n <= 1) return FGB_OK;
   if (n >= 0xffffffffll) return FGB_ERR_LIMIT;
+  if (phi <= plo || phi > (1u << 24)) return FGB_ERR_ARG;
+  int sh = 0;                                            // bins = ((prefix24 - plo') >> sh), plo' = plo rounded down
+  while ((((unsigned long long) (phi - 1) >> sh) - ((unsigned long long) plo >> sh)) >= 65536) sh += 1;
+  const int binshift = 40 + sh;                          // prefix24 = hi >> 40
+  const unsigned long long base = (unsigned long long) plo >> sh;
   int inb = 0;
-  int rc = fgb_sort128_device(d_a,d_b,n,14,16,d_tmp,tmp_bytes,&inb,st);
+  int rc = fgb_sort128_device(d_a,d_b,n,(24 - sh > 16) ? 13 : 14,16,d_tmp,tmp_bytes,&inb,st);
   if (rc) return rc;
   rec128 *src = (rec128 *) (inb ? d_b : d_a), *dst = (rec128 *) (inb ? d_a : d_b);
 
@@ -499,7 +512,7 @@ extern "C" int fgb_kmer_sort_device(void *d_a, void *d_b, long long n, void *d_t
   unsigned *d_bins = NULL;
   CUDA_TRY(fgb_dmalloc((void **) &d_bins,sizeof(unsigned)*65537,st));
   { int nb = (int) ((n + 1 + 255) / 256);
-    kmer_bins_kernel<<<nb,256,0,st>>>(src,n,d_bins);
+    kmer_bins_kernel<<<nb,256,0,st>>>(src,n,binshift,base,d_bins);
     fgb_count_launch(1);
   }
   std::vector<unsigned> bins(65537);
@@ -530,7 +543,7 @@ extern "C" int fgb_kmer_sort_device(void *d_a, void *d_b, long long n, void *d_t
   if (!groups.empty())
     { CUDA_TRY(fgb_dmalloc((void **) &d_groups,sizeof(uint2)*groups.size(),st));
       CUDA_TRY(cudaMemcpyAsync(d_groups,groups.data(),sizeof(uint2)*groups.size(),cudaMemcpyHostToDevice,st));
-      kmer_bucket_sort_kernel<<<(unsigned) groups.size(),BK_THREADS,BUCKET_SMEM,st>>>(src,dst,d_groups);
+      kmer_bucket_sort_kernel<<<(unsigned) groups.size(),BK_THREADS,BUCKET_SMEM,st>>>(src,dst,d_groups,binshift);
       fgb_count_launch(1);
       CUDA_TRY(cudaGetLastError());
     }
@@ -563,6 +576,10 @@ extern "C" int fgb_kmer_sort_device(void *d_a, void *d_b, long long n, void *d_t
   *result_in_b = inb ^ 1;
   return FGB_OK;
 }
+
+extern "C" int fgb_kmer_sort_device(void *d_a, void *d_b, long long n, void *d_tmp, long long tmp_bytes,
+                                    int *result_in_b, void *stream)
+{ return fgb_kmer_sort_range_device(d_a,d_b,n,0,1u << 24,d_tmp,tmp_bytes,result_in_b,stream); }
 
 /***********************************************************************************************
  *  Generic exclusive scan of a u32 array (reduce / scan-of-sums / downsweep), used for stream

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as ol
-from fastga_b200 import formats, lib
+from fastga_b200 import formats, lib, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -80,6 +80,25 @@ def test_gix_build_with_heavy_repeats_matches_oracle():
     assert np.array_equal(pstart, wstart)
 
 
+def test_gix_shares_of_the_prefix_space_concatenate_to_the_full_table(small_pair):
+    """one rank's share of a cooperatively built table (fgb_gix_build_range) is binned relative to
+    its own prefix range; uneven shares must concatenate to exactly the single-GPU table"""
+    g = small_pair[1]
+    dg = lib.DeviceGenome(g)
+    full, _, _ = lib.DeviceGix.build(dg).download()
+    cuts = [0, 1 << 21, (1 << 23) + 12345, (3 << 22) + 7, 1 << 24]
+    parts = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        sh = lib.DeviceGix.build_range(dg, lo, hi)
+        tab = sh.download()[0]
+        assert len(tab) == sh.n
+        if sh.n:
+            pre = (tab[:, 1] >> np.uint64(40)).astype(np.int64)
+            assert pre.min() >= lo and pre.max() < hi
+        parts.append(tab)
+    assert np.array_equal(np.concatenate(parts), full)
+
+
 def test_merge_and_seed_sort_match_oracle(small_pair):
     gA, gB = small_pair
     dA, dB = lib.DeviceGenome(gA), lib.DeviceGenome(gB)
@@ -93,6 +112,28 @@ def test_merge_and_seed_sort_match_oracle(small_pair):
     want = ol.seed_records(seeds, ds.layout + (amx, bmx), sort=True)
     got = ds.download()
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("copies", [2, 5])
+def test_merge_against_a_denser_second_table(copies):
+    """a shard of genome 1 against all of genome 2 (multi-GPU): T2 is several times denser than T1,
+    the merge switches to 32- / 16-entry tiles so that the block's T2 slice still fits its staging"""
+    rng = np.random.default_rng(90 + copies)
+    a = rng.integers(0, 4, 400_000, dtype=np.uint8)
+    B = [synth.diverged_copy(rng, a, 0.03 + 0.01 * k, sv_every=60_000) for k in range(copies)]
+    B = [b[:len(b) - 7 * k] for k, b in enumerate(B)]
+    gA, gB = formats.genome_from_arrays([a]), formats.genome_from_arrays(B)
+    dA, dB = lib.DeviceGenome(gA), lib.DeviceGenome(gB)
+    xA, xB = lib.DeviceGix.build(dA), lib.DeviceGix.build(dB)
+    assert xB.n > 1.6 * xA.n
+    amx, bmx = int(gA.clen.max()), int(gB.clen.max())
+    ds = lib.DeviceSeeds.find(xA, xB, amx, bmx, 10)
+    tA, _, _ = xA.download(False)
+    tB, pB, _ = xB.download()
+    seeds, sumlen = ol.merge(tA, tB, pB, 10)
+    assert ds.n == len(seeds) and ds.sumlen == sumlen
+    want = ol.seed_records(seeds, ds.layout + (amx, bmx), sort=True)
+    assert np.array_equal(ds.download(), want)
 
 
 def _canon(recs, pool, aread=None, bread=None, comp=None):
