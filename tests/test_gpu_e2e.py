@@ -80,6 +80,20 @@ def test_example_hap1_hap2_bit_exact():
     assert ol.md5_lines(alns.canonical_lines()) == gold["aln_md5"]
 
 
+def test_example_regions_wide_band_chunks_bit_exact_vs_oracle():
+    """ten 25-40 kbp regions of EXAMPLE (tests/golden/example_regions.npz) whose alignments run
+    through bands wider than one 32-lane chunk with the fresh low edge alone in the last chunk: the
+    case where the edge must copy the OLD trace-point counter of the diagonal that closed the
+    previous chunk (a missing trace point otherwise; found on the full EXAMPLE)"""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "example_regions.npz"))
+    gA = formats.genome_from_arrays([z["a%d" % i] for i in range(10)])
+    gB = formats.genome_from_arrays([z["b%d" % i] for i in range(10)])
+    want = ol.oracle_pipeline(gA, gB)
+    alns, stats = lib.fastga(gA, gB)
+    assert stats["nseeds"] == want["nseeds"] and stats["nhits"] == want["nhit"]
+    assert alns.canonical_lines() == want["lines"]
+
+
 @pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
 def test_gix_files_match_reference_gixmake():
     """the .ktab entry stream, the stub index and the part split produced from the

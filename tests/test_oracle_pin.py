@@ -192,3 +192,19 @@ def test_oracle_edge_cases_vs_live_reference(name, tmp_path):
     assert r["nseeds"] == st.get("seeds", 0)
     assert r["lines"] == ref
     check(r["alns"], r["nhit"])
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
+def test_oracle_on_example_regions_vs_live_reference(tmp_path):
+    """the EXAMPLE regions fixture of the GPU regression test, oracle against a live reference run"""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "example_regions.npz"))
+    A = [z["a%d" % i] for i in range(10)]
+    B = [z["b%d" % i] for i in range(10)]
+    wd = str(tmp_path)
+    formats.write_fasta(os.path.join(wd, "A.fasta"), synth.scaffolds_of(A, "sa", 1))
+    formats.write_fasta(os.path.join(wd, "B.fasta"), synth.scaffolds_of(B, "sb", 1))
+    st = ol.parse_fastga_log(ol.ref_fastga(wd, "A", "B", threads=4))
+    ref = ol.oneview_records(os.path.join(wd, "ref.1aln"))
+    r = ol.oracle_pipeline(formats.genome_from_arrays(A), formats.genome_from_arrays(B))
+    assert r["nseeds"] == st.get("seeds", 0)
+    assert r["lines"] == ref
