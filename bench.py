@@ -2,14 +2,18 @@
 """bench.py -- Gbp aligned/s of the FastGA seed-and-extend hot path on B200 (BASELINE.json metric).
 
 One "step" = one pass of the whole path over one synthetic genome pair:
-  GIX build of both genomes (syncmer scan, record build, radix sort, prefix index) -> adaptamer
-  merge -> seed sort -> chain scan + wave extension -> D2H of the raw alignments -> host
+  GIX build of both genomes (syncmer scan, record build, bucketed k-mer sort, prefix index) ->
+  adaptamer merge -> seed sort -> chain scan + wave extension -> D2H of the raw alignments -> host
   redundancy filter.
 `value`  : inputs (the staged 2-bit genomes) already resident in HBM when the timed region starts.
-`e2e`    : the reference-facing C-ABI call fgb_fastga on HOST buffers (.bps images), H2D and D2H
-           inside the timed region.
-N > 1    : genome-1 contigs are sharded over the ranks (no data-path collective; every rank holds
-           all of genome 2), per-rank results are gathered to rank 0 with torch.distributed.
+`e2e`    : the reference-facing C-ABI call fgb_fastga on HOST buffers (.bps images in pinned
+           memory), H2D of both images and D2H of the records inside the timed region.
+`roofline`: the seed-merge kernel (the kernel SURVEY 8d grades), algorithmic bytes on the on-disk
+           widths over its own CUDA-event time; `other_kernels` the sort stages; the extension
+           kernel is latency-bound and reported as cell updates/s.
+N > 1    : genome-1 contigs are sharded over the ranks; the table of genome 2 is built
+           cooperatively (each rank sorts one slice of the k-mer prefix space, NCCL all-gather);
+           per-rank results are gathered to rank 0 with torch.distributed.
 --impl reference : the UNMODIFIED reference (oracle/_ref/FastGA -T<cores>) on a bounded sample of
            the same workload, on the box's host cores.
 """

@@ -6,7 +6,7 @@
 // Both are in-place American-flag MSD sorts on byte-packed records (MSDsort.c:211-360); on the
 // device every record is widened to one 16-byte word so each pass is a perfectly coalesced
 // stream (read 16 B, write 16 B per record).  One pass = one Onesweep kernel: a stable scatter
-// that ranks records inside a 4096-record tile with warp match-any multi-split, finds the tile's
+// that ranks records inside a 4096-record tile with a warp multi-split (ballots), finds the tile's
 // bases by decoupled look-back, stages the tile in shared memory in digit order and writes digit
 // runs back coalesced, while counting the next pass's histogram.  HBM-bound integer work: no
 // tensor cores.
