@@ -836,25 +836,27 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
 static __device__ int fwd_extract(Ctx &c, int trimha, int mida, int trimx, int trimy, int trimd,
                                   int &tlen, int &root_diag)
 { const int lane = threadIdx.x & 31;
-  int n = 0, h;
-  for (h = trimha; h >= 0; h = ldpeb(c.cells+h).ptr) n += 1;
+  //  ONE walk of the pebble chain (each hop is a dependent L2 round trip): the pairs come out last
+  //  to first, so they are written downwards from the top of the staging buffer and moved to its
+  //  start afterwards (warp-parallel) instead of counting the chain first.
   Peb tip = ldpeb(c.cells+trimha);
   int kt = tip.diag, bt, et;
   if (tip.ptr < 0) { bt = (mida - kt) >> 1; et = 0; }
   else             { bt = tip.mark - kt;    et = tip.diff; }
   int extra = (bt + kt != trimx);
-  int len = 2*(n-1) + (extra ? 2 : 0);
-  if (len > c.smax) return ST_STAGE;
+  int pos = c.smax & ~1;                                  // next pair goes to [pos-2,pos)
   int addd = 0, addb = 0;                                 // adjustment of the last pair
   if (extra)
-    { if (lane == 0)
-        { c.fstage[len-2] = (unsigned char) (trimd - et);
-          c.fstage[len-1] = (unsigned char) (trimy - bt);
+    { if (pos < 2) return ST_STAGE;
+      if (lane == 0)
+        { c.fstage[pos-2] = (unsigned char) (trimd - et);
+          c.fstage[pos-1] = (unsigned char) (trimy - bt);
         }
+      pos -= 2;
     }
   else if (bt != trimy)
     { addd = trimd - et; addb = trimy - bt; }
-  int idx = n-1;
+  bool first = true;
   Peb cur = tip;
   root_diag = kt;
   while (cur.ptr >= 0)
@@ -863,15 +865,26 @@ static __device__ int fwd_extract(Ctx &c, int trimha, int mida, int trimx, int t
       if (prv.ptr < 0) { bp = (mida - prv.diag) >> 1; ep = 0; }
       else             { bp = prv.mark - prv.diag;    ep = prv.diff; }
       int pd = d - ep, pb = a - bp;
-      if (idx == n-1) { pd += addd; pb += addb; }
+      if (first) { pd += addd; pb += addb; first = false; }
+      if (pos < 2) return ST_STAGE;
       if (lane == 0)
-        { c.fstage[2*(idx-1)]   = (unsigned char) pd;
-          c.fstage[2*(idx-1)+1] = (unsigned char) pb;
+        { c.fstage[pos-2] = (unsigned char) pd;
+          c.fstage[pos-1] = (unsigned char) pb;
         }
-      idx -= 1;
+      pos -= 2;
       cur = prv;
       root_diag = cur.diag;
     }
+  const int top = c.smax & ~1, len = top - pos;
+  __syncwarp();
+  if (pos > 0)
+    for (int o = 0; o < len; o += 32)                     // move down; reads stay ahead of writes
+      { unsigned char v = 0;
+        if (o + lane < len) v = c.fstage[pos + o + lane];
+        __syncwarp();
+        if (o + lane < len) c.fstage[o + lane] = v;
+        __syncwarp();
+      }
   tlen = len;
   return ST_OK;
 }
