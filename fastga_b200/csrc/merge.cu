@@ -188,11 +188,25 @@ static __device__ __forceinline__ void merge_expand(const View &V, const warp_st
     }
 }
 
+//  Per block of the merge: the prefix range of its T1 tile and the T2 slice it can match, found
+//  ahead of the merge with full parallelism (inside the merge this is a chain of two dependent HBM
+//  round trips made by one lane while 255 threads wait).
+__global__ void merge_ranges_kernel(const rec128 *__restrict__ T1, unsigned n1, const unsigned *__restrict__ pstart2,
+                                    unsigned per_block, unsigned nblocks, uint4 *__restrict__ rng)
+{ unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  unsigned long long b0 = (unsigned long long) b * per_block, b1 = b0 + per_block - 1;
+  if (b1 >= n1) b1 = n1 - 1;
+  unsigned pA = KREC_PREFIX24(T1[b0].hi), pB = KREC_PREFIX24(T1[b1].hi);
+  unsigned lo2 = pstart2[pA], hi2 = pstart2[pB+1];
+  rng[b] = make_uint4(pA,pB - pA + 2,lo2,hi2 - lo2);
+}
+
 template<int TILE>
 __global__ void __launch_bounds__(MG_THREADS)
 adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
                        const rec128 *__restrict__ T2, const unsigned *__restrict__ pstart2,
-                       int freq, seed_pack K,
+                       const uint4 *__restrict__ rng, int freq, seed_pack K,
                        rec128 *__restrict__ seeds, unsigned long long capacity,
                        unsigned long long *__restrict__ counters /* [0]=nseeds [1]=sum plen */)
 { extern __shared__ __align__(16) unsigned char mg_smem[];
@@ -217,24 +231,12 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
   //  are one contiguous slice [pstart2[pA], pstart2[pB+1]).  When it fits, that slice and the
   //  prefix-index range are staged in shared memory (one TMA bulk copy + coalesced loads) and
   //  every search, walk and payload read hits shared memory instead of a dependent L2/HBM trip.
-  if (wp == 0)
-    { unsigned long long b1 = b0 + MG_WARPS*TILE - 1;
-      if (b1 >= n1) b1 = n1 - 1;
-      unsigned long long hv = 0;
-      if (lane == 0) hv = T1[b0].hi;                       // (warp 0's own lane-0 load again: L1 hit)
-      if (lane == 1) hv = T1[b1].hi;
-      unsigned pfx = KREC_PREFIX24(hv);
-      unsigned pA = __shfl_sync(0xffffffffu,pfx,0), pB = __shfl_sync(0xffffffffu,pfx,1);
-      unsigned q = 0;
-      if (lane == 0) q = pstart2[pA];
-      if (lane == 1) q = pstart2[pB+1];
-      unsigned lo2 = __shfl_sync(0xffffffffu,q,0), hi2 = __shfl_sync(0xffffffffu,q,1);
-      if (lane == 0)
-        { B->rng[0] = pA; B->rng[1] = pB - pA + 2; B->rng[2] = lo2; B->rng[3] = hi2 - lo2;
-          mbar_init(&B->bar,1);
-          if (pB - pA + 2 <= MG_PCAP && hi2 - lo2 <= MG_T2CAP && hi2 > lo2)
-            tma_load_1d(B->t2,T2 + lo2,(hi2 - lo2) * 16u,&B->bar);
-        }
+  if (threadIdx.x == 0)
+    { const uint4 r = rng[blockIdx.x];                      // pA, #prefixes+1, first T2 entry, #T2 entries
+      B->rng[0] = r.x; B->rng[1] = r.y; B->rng[2] = r.z; B->rng[3] = r.w;
+      mbar_init(&B->bar,1);
+      if (r.y <= MG_PCAP && r.w <= MG_T2CAP && r.w > 0)
+        tma_load_1d(B->t2,T2 + r.z,r.w * 16u,&B->bar);
     }
   //  forward-strand compaction of the warp's tile while the slice is in flight
   unsigned m0 = __ballot_sync(0xffffffffu,f0), m1 = __ballot_sync(0xffffffffu,f1);
@@ -324,17 +326,22 @@ extern "C" int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2
           CUDA_TRY(cudaFuncSetAttribute(adaptamer_merge_kernel<16>,cudaFuncAttributeMaxDynamicSharedMemorySize,smem));
           attr_set = true;
         }
+      uint4 *d_rng = NULL;
+      CUDA_TRY(fgb_dmalloc((void **) &d_rng,sizeof(uint4)*(size_t) nb,st));
       cudaEventRecord(ea,st);
+      merge_ranges_kernel<<<(nb + 255)/256,256,0,st>>>((const rec128 *) d_T1,(unsigned) n1,d_pstart2,
+                                                      (unsigned) (MG_WARPS*tile),nb,d_rng);
 #define MG_LAUNCH(T) adaptamer_merge_kernel<T><<<nb,MG_THREADS,smem,st>>>((const rec128 *) d_T1,(unsigned) n1, \
-                       (const rec128 *) d_T2,d_pstart2,freq,K,(rec128 *) d_seeds,(unsigned long long) capacity,d_counters)
+                       (const rec128 *) d_T2,d_pstart2,d_rng,freq,K,(rec128 *) d_seeds,(unsigned long long) capacity,d_counters)
       if (tile == 64) MG_LAUNCH(64); else if (tile == 32) MG_LAUNCH(32); else MG_LAUNCH(16);
 #undef MG_LAUNCH
       cudaEventRecord(eb,st);
       cudaEventSynchronize(eb);
       float ms = 0; cudaEventElapsedTime(&ms,ea,eb);
       fgb_timing_add(3,ms);
-      fgb_count_launch(1);
+      fgb_count_launch(2);
       cudaEventDestroy(ea); cudaEventDestroy(eb);
+      fgb_dfree(d_rng,st);
     }
   CUDA_TRY(cudaGetLastError());
   unsigned long long h[2];

@@ -316,7 +316,7 @@ __global__ void kmer_bins_kernel(const rec128 *__restrict__ tab, long long n, in
 //  sub-bins of one or two records, and every record finds its place by comparing itself with its
 //  sub-bin.  A group with a crowded sub-bin (repeats) runs sixteen LSD byte passes instead.
 
-__global__ void __launch_bounds__(BK_THREADS)
+__global__ void __launch_bounds__(BK_THREADS,2)
 kmer_bucket_sort_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out,
                         const uint2 *__restrict__ groups /* start, count */, int binshift)
 { extern __shared__ __align__(16) unsigned char smem_raw[];
