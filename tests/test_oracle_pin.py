@@ -91,6 +91,19 @@ def _mutate(rng, a, rate):
 @pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_local_alignment_bit_exact_vs_reference_library(seed):
+    _la_compare(seed, borders=False)
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", [11, 12])
+def test_local_alignment_with_band_borders_vs_reference_library(seed):
+    """lbord / hbord >= 0 confine the band to [low-lbord, hgh+hbord] (align.c:1466-1481): what
+    align_contigs passes for a contig against itself (FastGA.c:3247-3262); the CUDA waves take the
+    same minp/maxp arguments but FastGA's non-self mode never sets them"""
+    _la_compare(seed, borders=True)
+
+
+def _la_compare(seed, borders):
     ref = C.CDLL(ol.REF_SO)
     orc = ol.orc()
     ref.New_Work_Data.restype = C.c_void_p
@@ -121,18 +134,22 @@ def test_local_alignment_bit_exact_vs_reference_library(seed):
         xa, xb = len(fa) + L // 2, len(fb) + L // 2
         d, anti = xa - xb, xa + xb + int(rng.integers(-100, 100))
         low, hgh = d - int(rng.integers(0, 80)), d + int(rng.integers(0, 80))
+        lb = hb = -1
+        if borders:
+            lb = int(rng.integers(0, 40)) if rng.random() < 0.7 else -1
+            hb = int(rng.integers(0, 40)) if rng.random() < 0.7 else -1
         p = Path()
         al = Alignment(C.pointer(p), 2 if acomp else 0, ab.ctypes.data + 1, bb.ctypes.data + 1, len(a), len(b))
-        assert ref.Local_Alignment(C.byref(al), work, spec, low, hgh, anti, -1, -1) == 0
+        assert ref.Local_Alignment(C.byref(al), work, spec, low, hgh, anti, lb, hb) == 0
         rt = np.ctypeslib.as_array(C.cast(p.trace, C.POINTER(C.c_uint16)), shape=(max(p.tlen, 1),))[:p.tlen]
         rt = rt.astype(np.uint8)
         op = OPath()
         orc.orc_local_alignment(owork, C.byref(ospec), ab.ctypes.data + 1, len(a), bb.ctypes.data + 1, len(b),
-                                acomp, low, hgh, anti, -1, -1, C.byref(op))
+                                acomp, low, hgh, anti, lb, hb, C.byref(op))
         ot = np.ctypeslib.as_array(op.trace, shape=(max(op.tlen, 1),))[:op.tlen] if op.tlen else np.zeros(0, np.uint8)
         assert (p.abpos, p.bbpos, p.aepos, p.bepos, p.diffs, p.tlen) == \
-               (op.abpos, op.bbpos, op.aepos, op.bepos, op.diffs, op.tlen), (it, L, rate, acomp)
-        assert np.array_equal(rt, ot), (it, L, rate, acomp)
+               (op.abpos, op.bbpos, op.aepos, op.bepos, op.diffs, op.tlen), (it, L, rate, acomp, lb, hb)
+        assert np.array_equal(rt, ot), (it, L, rate, acomp, lb, hb)
 
 
 @pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
