@@ -271,6 +271,47 @@ int64_t orc_merge(const rec128 *T1, int64_t n1, const rec128 *T2, int64_t n2,
   return nh;
 }
 
+/*  SELF mode (FastGA A): new_self_merge_thread (FastGA.c:1616-1909).  T2 is T1.  EVERY entry,
+    either strand, is an i: plen = its longest prefix shared with another entry of its 12-base
+    panel (max of the LCPs with its two neighbours), block = the run of entries sharing those plen
+    bases, entry included; if the block has < freq members, one pair (i, p) for every OTHER member
+    p, strand C iff the signs differ (:1801-1860).  Both orders of a pair come out; the reference
+    reports half the count (:1907).  Declarative restatement of the (plen, vlcp[], rend, eorun)
+    machine at :1707-1790.  */
+
+int64_t orc_self_merge(const rec128 *T, int64_t n, const uint32_t *pstart, int freq,
+                       orc_seed *out, int64_t *sumlen)
+{ int64_t nh = 0, ts = 0, i;
+  for (i = 0; i < n; i++)
+    { int64_t pre  = (int64_t) (T[i].hi >> 40);
+      int64_t cbeg = pstart[pre], cend = pstart[pre+1];
+      int lp = (i > cbeg)   ? klcp(T+i-1,T+i) : 11;
+      int ls = (i+1 < cend) ? klcp(T+i,T+i+1) : 11;
+      int plen = lp > ls ? lp : ls;
+      int64_t lo = i, hi = i+1, p;
+      if (plen < 12) continue;                              /* alone in its panel: block = itself */
+      while (lo > cbeg && klcp(T+lo-1,T+lo) >= plen) lo -= 1;
+      while (hi < cend && hi - lo < freq && klcp(T+hi-1,T+hi) >= plen) hi += 1;
+      if (hi - lo >= freq) continue;
+      for (p = lo; p < hi; p++)
+        { if (p == i) continue;
+          if (out)
+            { orc_seed *s = out+nh;
+              s->plen  = (uint8_t) plen;
+              s->comp  = (uint8_t) ((((T[i].lo >> 47) ^ (T[p].lo >> 47)) & 1));
+              s->icont = (uint16_t) ((T[i].lo >> 32) & 0x7fff);
+              s->jcont = (uint16_t) ((T[p].lo >> 32) & 0x7fff);
+              s->ipost = (uint32_t) T[i].lo;
+              s->jpost = (uint32_t) T[p].lo;
+            }
+          nh += 1;
+          ts += plen;
+        }
+    }
+  if (sumlen) *sumlen = ts;
+  return nh;
+}
+
 /***********************************************************************************************
  *  C.  Seed records (reimport_thread, FastGA.c:2703-2721) and their order (RSDsort.c: key read
  *      from the last byte backwards = jcont, band, anti, diag&63, lcp), here with strand and
@@ -849,6 +890,13 @@ uint8_t *orc_result_traces(orc_result *R) { return R->tpool; }
 #define BUCK_WIDTH 64
 #define BUCK_ANTI  128
 
+/*  SELF mode of align_contigs (FastGA.c:3030, :3247-3262): a contig against itself, forward
+    strand, is aligned strictly above or strictly below the main diagonal and not at all across
+    it.  In that last branch the reference only clears abpos/aepos, so the tube advances with the
+    bepos of the previous alignment (the orc_path below persists across calls, as Path does).  */
+static int g_self = 0;
+void orc_set_self(int on) { g_self = on; }
+
 /* aseq[c], bseq[c]: contig c (ORIGINAL numbering), one base per byte with a sentinel 4 at [-1]
    and [len]; acseq[c]: reverse complement of A contig c, same framing (Complement_Seq). */
 
@@ -963,8 +1011,19 @@ int64_t orc_search(const rec128 *seeds, int64_t n, const orc_layout *L, const or
                                             if (dgmin > dgmax) break;
                                           }
                                       }
-                                    orc_local_alignment(work,spec,as,(int) alen,bs,(int) blen,comp,
-                                                        dgmin,dgmax,(int) amid,-1,-1,&path);
+                                    if (g_self && ctg1 == ctg2 && !comp)
+                                      { if (dgmin > 0)
+                                          orc_local_alignment(work,spec,as,(int) alen,bs,(int) blen,comp,
+                                                              dgmin,dgmax,(int) amid,dgmin-1,-1,&path);
+                                        else if (dgmax < 0)
+                                          orc_local_alignment(work,spec,as,(int) alen,bs,(int) blen,comp,
+                                                              dgmin,dgmax,(int) amid,-1,-(dgmax+1),&path);
+                                        else
+                                          path.abpos = path.aepos = 0;
+                                      }
+                                    else
+                                      orc_local_alignment(work,spec,as,(int) alen,bs,(int) blen,comp,
+                                                          dgmin,dgmax,(int) amid,-1,-1,&path);
                                     rlen = path.aepos - path.abpos;
                                     if (rlen >= alnMin && alnRate*rlen >= path.diffs)
                                       { orc_ovl o;

@@ -89,6 +89,19 @@ def merge(T1, T2, pstart2, freq=10):
     return seeds, sl.value
 
 
+def self_merge(T, pstart, freq=10):
+    """SELF mode (FastGA A): every entry of the one table against its own block (orc_self_merge)"""
+    o = orc()
+    T = np.ascontiguousarray(T, dtype=np.uint64)
+    sl = C.c_int64()
+    args = [T.ctypes.data_as(C.c_void_p), C.c_int64(len(T)), pstart.ctypes.data_as(C.c_void_p), C.c_int(freq)]
+    o.orc_self_merge.restype = C.c_int64
+    n = o.orc_self_merge(*args, None, C.byref(sl))
+    seeds = np.zeros(n, dtype=SEED_DT)
+    o.orc_self_merge(*args, seeds.ctypes.data_as(C.c_void_p), C.byref(sl))
+    return seeds, sl.value
+
+
 def seed_records(seeds, layout, sort=True):
     o = orc()
     out = np.zeros((len(seeds), 2), dtype=np.uint64)
@@ -117,9 +130,9 @@ def run_ref(args, cwd, timeout=3600):
 
 
 def ref_fastga(workdir, a, b, out="ref", threads=8, extra=()):
-    """FastGA -v -k -T<n> -1:<out> a b in workdir; returns the -v log"""
-    return run_ref(["FastGA", "-v", "-k", "-T%d" % threads, "-P" + workdir, "-1:" + out] + list(extra) + [a, b],
-                   cwd=workdir)
+    """FastGA -v -k -T<n> -1:<out> a [b] in workdir (b None: SELF mode); returns the -v log"""
+    return run_ref(["FastGA", "-v", "-k", "-T%d" % threads, "-P" + workdir, "-1:" + out] + list(extra) +
+                   ([a, b] if b is not None else [a]), cwd=workdir)
 
 
 def parse_fastga_log(log):
@@ -302,3 +315,23 @@ def oracle_pipeline(gA, gB, **kw):
     al = lib.filter_overlaps(O.h, pa, pb, layout[2], layout[3])
     return dict(tabA=tA, tabB=tB, pstartA=sA, pstartB=sB, nseeds=len(seeds), sumlen=sumlen, seedrecs=recs,
                 nhit=nhit, nraw=len(ov), alns=al, lines=al.canonical_lines(), perm1=pa, perm2=pb)
+
+
+def oracle_pipeline_self(g, **kw):
+    """SELF mode (FastGA A) through the CPU oracle + the product's host filter (groundwork for
+    SURVEY row a-7; no CUDA path uses it yet)."""
+    from fastga_b200 import lib
+    pa, ra = contig_rank(g.clen)
+    t, s = gix_build(g, ra)
+    seeds, sumlen = self_merge(t, s, kw.get("freq", 10))
+    layout = seed_layout(g, g)
+    recs = seed_records(seeds, layout)
+    o = orc()
+    o.orc_set_self(1)
+    try:
+        ov, tp, nhit = search(recs, layout, g, g, pa, pa, g.freq)
+    finally:
+        o.orc_set_self(0)
+    O = pack_overlaps(ov, tp, ra, ra, layout[2], layout[3])
+    al = lib.filter_overlaps(O.h, pa, pa, layout[2], layout[3])
+    return dict(nseeds=len(seeds), sumlen=sumlen, nhit=nhit, nraw=len(ov), alns=al, lines=al.canonical_lines())

@@ -225,3 +225,44 @@ def test_oracle_on_example_regions_vs_live_reference(tmp_path):
     r = ol.oracle_pipeline(formats.genome_from_arrays(A), formats.genome_from_arrays(B))
     assert r["nseeds"] == st.get("seeds", 0)
     assert r["lines"] == ref
+
+
+def _self_genomes():
+    """genomes with internal homology for SELF mode (FastGA A): a diverged duplication inside and
+    across contigs plus an inverted copy, and two tandem-repeat genomes (near-diagonal chains: the
+    'nothing across the main diagonal' branch and the band borders of align_contigs)"""
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 4, 300_000, dtype=np.uint8)
+    dup = synth.diverged_copy(rng, a[50_000:150_000], 0.05, sv_every=40_000)
+    c0 = np.concatenate([a, dup, rng.integers(0, 4, 20_000, dtype=np.uint8)])
+    c1 = np.concatenate([rng.integers(0, 4, 100_000, dtype=np.uint8),
+                         synth.diverged_copy(rng, a[200_000:280_000], 0.04, sv_every=30_000),
+                         (3 - a[10_000:60_000][::-1]).astype(np.uint8)])
+    out = {"dup": [c0, c1[:len(c1) - 3]]}
+    for seed in (61, 62):
+        rng = np.random.default_rng(seed)
+        parts = []
+        while sum(len(p) for p in parts) < 500_000:
+            parts.append(rng.integers(0, 4, int(rng.integers(20_000, 60_000)), dtype=np.uint8))
+            unit = rng.integers(0, 4, int(rng.integers(150, 1200)), dtype=np.uint8)
+            parts.append(np.concatenate([synth._small_mutations(rng, unit, 0.03)
+                                         for _ in range(int(rng.integers(8, 60)))]))
+        g = np.concatenate(parts)[:500_000]
+        cut = int(rng.integers(200_000, 300_000))
+        out["tandem%d" % seed] = [g[:cut], g[cut:]]
+    return out
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", ["dup", "tandem61", "tandem62"])
+def test_oracle_self_mode_vs_live_reference(name, tmp_path):
+    """SURVEY row a-7 groundwork: the oracle's SELF mode (self block rule, band borders for a contig
+    against itself) against `FastGA A` of the reference"""
+    G = _self_genomes()[name]
+    wd = str(tmp_path)
+    formats.write_fasta(os.path.join(wd, "A.fasta"), synth.scaffolds_of(G, "sa", 1))
+    st = ol.parse_fastga_log(ol.ref_fastga(wd, "A", None, threads=4))
+    ref = ol.oneview_records(os.path.join(wd, "ref.1aln"))
+    r = ol.oracle_pipeline_self(formats.genome_from_arrays(G))
+    assert r["nseeds"] // 2 == st["seeds"] and r["nhit"] == st["hits"] and r["nraw"] == st["alns"]
+    assert r["lines"] == ref
