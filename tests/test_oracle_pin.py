@@ -264,5 +264,7 @@ def test_oracle_self_mode_vs_live_reference(name, tmp_path):
     st = ol.parse_fastga_log(ol.ref_fastga(wd, "A", None, threads=4))
     ref = ol.oneview_records(os.path.join(wd, "ref.1aln"))
     r = ol.oracle_pipeline_self(formats.genome_from_arrays(G))
-    assert r["nseeds"] // 2 == st["seeds"] and r["nhit"] == st["hits"] and r["nraw"] == st["alns"]
+    # every thread of the reference halves its own pair count (FastGA.c:1907): off by < #threads
+    assert abs(r["nseeds"] // 2 - st["seeds"]) < 4
+    assert r["nhit"] == st["hits"] and r["nraw"] == st["alns"]
     assert r["lines"] == ref
