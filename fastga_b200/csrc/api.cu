@@ -37,6 +37,11 @@ int fgb_ktab_export_device(const void *d_tab, long long n, int pbytes, int cbyte
 int fgb_ktab_import_device(const void *d_ent, long long n, int pbytes, int cbytes,
                            const long long *d_index, void *d_tab, void *stream);
 int fgb_sc_tile();
+int fgb_self_merge_device(const void *d_T, long long n, const unsigned *d_pstart, int freq,
+                          int anti_bits, int band_bits, int jc_bits, int ic_bits,
+                          long long amxpos, void *d_seeds, long long capacity,
+                          unsigned long long *d_counters, unsigned long long *h_nseeds,
+                          unsigned long long *h_sumlen, void *stream);
 int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2, long long n2, const unsigned *d_pstart2,
                      int freq, int anti_bits, int band_bits, int jc_bits, int ic_bits,
                      long long amxpos, long long bmxpos, void *d_seeds, long long capacity,
@@ -437,10 +442,22 @@ extern "C" void fgb_seeds_free(fgb_seeds *s)
   delete s;
 }
 
+static int seeds_find_impl(const fgb_gix *x1, const fgb_gix *x2, long long amxpos,
+                           long long bmxpos, int freq, bool self, fgb_seeds **out, void *stream);
+
 extern "C" int fgb_seeds_find(const fgb_gix *x1, const fgb_gix *x2, long long amxpos,
                               long long bmxpos, int freq, fgb_seeds **out, void *stream)
+{ return seeds_find_impl(x1,x2,amxpos,bmxpos,freq,false,out,stream); }
+
+//  SELF mode (FastGA A): the table against itself (new_self_merge_thread, FastGA.c:1616)
+extern "C" int fgb_seeds_find_self(const fgb_gix *x, long long amxpos, int freq, fgb_seeds **out, void *stream)
+{ return seeds_find_impl(x,x,amxpos,amxpos,freq,true,out,stream); }
+
+static int seeds_find_impl(const fgb_gix *x1, const fgb_gix *x2, long long amxpos,
+                           long long bmxpos, int freq, bool self, fgb_seeds **out, void *stream)
 { cudaStream_t st = (cudaStream_t) stream;
   fgb_seeds *s = new fgb_seeds();
+  s->self_mode = self ? 1 : 0;
   s->anti_bits = bitlen(amxpos + bmxpos);
   s->band_bits = s->anti_bits > 6 ? s->anti_bits - 6 : 1;
   s->jc_bits   = bitlen(x2->ncontig > 1 ? x2->ncontig-1 : 1);
@@ -451,14 +468,18 @@ extern "C" int fgb_seeds_find(const fgb_gix *x1, const fgb_gix *x2, long long am
 
   u64 *d_counters = NULL;
   CUDA_TRY(fgb_dmalloc((void **) &d_counters,16,st));
-  long long cap = x1->n + (x1->n >> 2) + 1024;
+  long long cap = (self ? 2*x1->n : x1->n + (x1->n >> 2)) + 1024;
   rec128 *d_a = NULL;
   u64 nseeds = 0, sumlen = 0;
   for (int attempt = 0; ; attempt++)
     { CUDA_TRY(fgb_dmalloc((void **) &d_a,sizeof(rec128)*(cap+1),st));
       int rc;
-      rc = fgb_merge_device(x1->d_tab,x1->n,x2->d_tab,x2->n,x2->d_pstart,freq,s->anti_bits,s->band_bits,
-                            s->jc_bits,s->ic_bits,amxpos,bmxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
+      if (self)
+        rc = fgb_self_merge_device(x1->d_tab,x1->n,x1->d_pstart,freq,s->anti_bits,s->band_bits,
+                                   s->jc_bits,s->ic_bits,amxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
+      else
+        rc = fgb_merge_device(x1->d_tab,x1->n,x2->d_tab,x2->n,x2->d_pstart,freq,s->anti_bits,s->band_bits,
+                              s->jc_bits,s->ic_bits,amxpos,bmxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
       if (rc == FGB_OK) break;
       fgb_dfree(d_a,st); d_a = NULL;
       if (rc != FGB_ERR_OVERFLOW || attempt > 0) { fgb_dfree(d_counters,st); return rc; }
@@ -607,6 +628,43 @@ extern "C" int fgb_align_tables(const fgb_genome *A, const fgb_genome *B, const 
 
 //  The reference-facing call: host .bps images + contig tables in, alignments out; every
 //  host<->device copy happens inside.
+//  SELF mode: `FastGA A` (one source).  Same path with T2 = T1, BMXPOS = AMXPOS, the self block rule
+//  in the merge and the band borders of align_contigs for a contig against itself.
+extern "C" int fgb_fastga_self(const unsigned char *bps, long long nb, int nc, const long long *clen,
+                               const long long *boff, const float *freq4,
+                               int freq, int chain_break, int chain_min, int align_min, double align_rate,
+                               fgb_alns **out, fgb_run_stats *stats, void *stream)
+{ fgb_genome *A = NULL; fgb_gix *x = NULL; fgb_seeds *sd = NULL; fgb_overlaps *ov = NULL;
+  int rc;
+  if ((rc = fgb_genome_create(bps,nb,nc,clen,boff,1,&A,stream))) return rc;
+  if ((rc = fgb_gix_build(A,&x,stream))) { fgb_genome_free(A); return rc; }
+  rc = fgb_seeds_find_self(x,A->maxlen,freq,&sd,stream);
+  long long n1 = x->n;
+  fgb_gix_free(x);
+  if (rc) { fgb_genome_free(A); return rc; }
+  short *tables = (short *) malloc(65536*sizeof(short));
+  int ave = 0;
+  fgb_align_spec(1.-align_rate,freq4,tables,&ave);
+  rc = fgb_extend(sd,A,A,chain_break,chain_min,align_min,align_rate,tables,ave,100,&ov,stream);
+  free(tables);
+  long long nseeds = sd->n, sumlen = sd->sumlen;
+  int jb = sd->jc_bits, ib = sd->ic_bits;
+  fgb_seeds_free(sd);
+  if (rc) { fgb_genome_free(A); return rc; }
+  rc = fgb_filter(ov,A->perm.data(),A->perm.data(),jb,ib,1,out);
+  if (stats)
+    { memset(stats,0,sizeof(*stats));
+      unsigned long long c[16];
+      fgb_overlaps_counters(ov,c);
+      stats->nkmers1 = stats->nkmers2 = n1; stats->nseeds = nseeds; stats->sumlen = sumlen;
+      stats->nhits = (long long) c[0]; stats->nla = (long long) c[1]; stats->nwaves = (long long) c[2];
+      stats->ncells = (long long) c[3];
+    }
+  fgb_overlaps_free(ov);
+  fgb_genome_free(A);
+  return rc;
+}
+
 extern "C" int fgb_fastga(const unsigned char *bpsA, long long nbA, int ncA, const long long *clenA,
                           const long long *boffA, const float *freqA,
                           const unsigned char *bpsB, long long nbB, int ncB, const long long *clenB,

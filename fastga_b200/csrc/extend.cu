@@ -70,6 +70,7 @@ struct ext_params
   u64 *counters;                                       // 0 hits 1 LA calls 2 waves 3 cells 4 records
   unsigned *failed; unsigned *nfailed;                 // triples that overflowed an arena
   unsigned char *bigstate;                             // wide-band kernel: per-warp wave state in HBM
+  int self_mode;                                       // FastGA A: genome against itself (align_contigs :3030)
 };
 
 struct Ctx
@@ -979,13 +980,17 @@ struct LAres { int abpos, bbpos, aepos, bepos, diffs, ftlen, rtlen; };
 
 //  Local_Alignment (align.c:1423-1576), lbord = hbord = -1 and A != B (non-self).
 
+//  lbord / hbord >= 0 confine the band to [low-lbord, hgh+hbord] (align.c:1466-1481; aseq != bseq
+//  always here, so the "selfie" defaults never apply): used for a contig against itself.
 template<int W>
-static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int anti, LAres &R)
-{ int minp = -INT_MAX, maxp = INT_MAX;
-  int aoff = acomp ? (c.alen % c.tspace) : 0;
+static __device__ int local_alignment(Ctx &c, int acomp, int low, int hgh, int anti, LAres &R,
+                                      int lbord = -1, int hbord = -1)
+{ int aoff = acomp ? (c.alen % c.tspace) : 0;
   int ex, ey, df, tha, st, rootd = 0;
 
   while (((anti-hgh)>>1) < 0) hgh -= 1;
+  const int minp = (lbord < 0) ? -INT_MAX : low - lbord;
+  const int maxp = (hbord < 0) ?  INT_MAX : hgh + hbord;
 
   R.ftlen = R.rtlen = 0; R.diffs = 0;
   long long tk = clock64();
@@ -1242,7 +1247,7 @@ static __device__ int scan_triple(const ext_params &P, Ctx &c, unsigned j, unsig
  **********************************************************************************************/
 
 struct TripleCtx
-{ unsigned j, pairkey; int comp, seq; bool isnew;
+{ unsigned j, pairkey; int comp, seq; bool isnew, selfpair;
   long long cdiag, alen, blen, mlen, doffset, aoffset, alast;
 };
 
@@ -1269,7 +1274,17 @@ static __device__ int handle_hit(const ext_params &P, Ctx &c, TripleCtx &T, long
                 }
             }
           LAres R;
-          int st = local_alignment<W>(c,T.comp,dgmin,dgmax,(int) amid,R);
+          int st = ST_OK;
+          if (T.selfpair)
+            { //  a contig against itself, forward strand: strictly above or strictly below the main
+              //  diagonal, nothing across it (FastGA.c:3247-3262; there the tube then advances with
+              //  the stale bepos of the previous alignment of the thread -- here with 0)
+              if (dgmin > 0)      st = local_alignment<W>(c,T.comp,dgmin,dgmax,(int) amid,R,dgmin-1,-1);
+              else if (dgmax < 0) st = local_alignment<W>(c,T.comp,dgmin,dgmax,(int) amid,R,-1,-(dgmax+1));
+              else { R.abpos = R.aepos = R.bbpos = R.bepos = 0; R.diffs = 0; R.ftlen = R.rtlen = 0; }
+            }
+          else
+            st = local_alignment<W>(c,T.comp,dgmin,dgmax,(int) amid,R);
           if (st) return st;
           nla += 1;
           int rlen = R.aepos - R.abpos;                    // same after the ACOMP flip
@@ -1323,6 +1338,7 @@ static __device__ int scan_triple_warp(const ext_params &P, Ctx &c, unsigned j, 
   T.pairkey = (unsigned) grp;
   { int ctg1 = P.aperm[get_bits(r0,P.p_ic,P.ic_bits)];
     int ctg2 = P.bperm[get_bits(r0,P.p_jc,P.jc_bits)];
+    T.selfpair = (P.self_mode != 0 && ctg1 == ctg2 && T.comp == 0);
     T.alen = P.aclen[ctg1]; T.blen = P.bclen[ctg2]; T.mlen = T.alen + T.blen;
     T.doffset = T.alen - (P.amxpos + P.bmxpos); T.aoffset = T.alen - P.amxpos;
     c.A = (const unsigned *) ((T.comp ? P.arseq : P.aseq) + P.awoff[ctg1]);
@@ -1715,6 +1731,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
   P.chain_break = chain_break; P.chain_min = chain_min;
   P.aln_min = align_min - 50; P.aln_rate = align_rate + .05;      // FastGA.c:3013-3014
   P.tspace = tspace; P.path_ave = ave_path;
+  P.self_mode = S->self_mode;
   P.dscore = -tables[0] / TRIM_LEN;                     // SCORE[0] = -15 * dscore
 
   short *d_tables = NULL;

@@ -31,4 +31,5 @@ struct fgb_seeds
   struct rec128 *d_rec = nullptr;          // sorted seed records
   int anti_bits = 0, band_bits = 0, jc_bits = 0, ic_bits = 0;
   long long amxpos = 0, bmxpos = 0;
+  int self_mode = 0;                       // seeds of a genome against itself (FastGA A)
 };

@@ -283,6 +283,120 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
   else        merge_expand(Vd,S,nd,total,gbase,K,seeds,capacity,lane);
 }
 
+/***********************************************************************************************
+ *  SELF mode (FastGA A): new_self_merge_thread (FastGA.c:1616-1909).  One table; EVERY entry,
+ *  either strand, is an i.  plen = its longest prefix shared with another entry of its 12-base
+ *  panel = max of the LCPs with its two neighbours; block = the run of entries sharing those plen
+ *  bases, the entry included; if the block has < FREQ members, one seed (i, p) for every OTHER
+ *  member p, strand C iff the signs differ.  One thread per entry: no search, its own index is
+ *  the insertion point.  Output run of a block reserved with one atomic.
+ **********************************************************************************************/
+
+static __device__ __forceinline__ int lcp_full(const rec128 &a, const rec128 &b)      // bases, 0..40
+{ u64 x = a.hi ^ b.hi;
+  if (x) return __clzll(x) >> 1;
+  unsigned y = (unsigned) ((a.lo ^ b.lo) >> 48);
+  if (y) return 32 + ((__clz(y) - 16) >> 1);
+  return 40;
+}
+
+__global__ void __launch_bounds__(256)
+self_merge_kernel(const rec128 *__restrict__ T, unsigned n, const unsigned *__restrict__ pstart,
+                  int freq, seed_pack K, rec128 *__restrict__ seeds, unsigned long long capacity,
+                  unsigned long long *__restrict__ counters)
+{ __shared__ unsigned s_w[8], s_l[8];
+  __shared__ unsigned long long s_base;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const unsigned i = blockIdx.x * 256u + threadIdx.x;
+  unsigned lo = i, hi = i, cnt = 0;
+  int plen = 0;
+  rec128 e; e.lo = e.hi = 0;
+  if (i < n)
+    { e = ld_rec(T + i);
+      unsigned p = KREC_PREFIX24(e.hi);
+      unsigned cbeg = pstart[p], cend = pstart[p+1];
+      int lp = (i > cbeg)   ? lcp_full(ld_rec(T + i - 1),e) : 11;
+      int ls = (i+1 < cend) ? lcp_full(e,ld_rec(T + i + 1)) : 11;
+      plen = lp > ls ? lp : ls;
+      if (plen >= 12)
+        { lo = i; hi = i+1;
+          while (lo > cbeg && i - lo < (unsigned) freq && lcp_full(ld_rec(T + lo - 1),ld_rec(T + lo)) >= plen) lo -= 1;
+          while (hi < cend && hi - lo < (unsigned) freq && lcp_full(ld_rec(T + hi - 1),ld_rec(T + hi)) >= plen) hi += 1;
+          if (hi - lo < (unsigned) freq) cnt = hi - lo - 1;
+        }
+    }
+  unsigned inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+    { unsigned t = __shfl_up_sync(0xffffffffu,inc,o);
+      if (lane >= o) inc += t;
+    }
+  unsigned slen = __reduce_add_sync(0xffffffffu,cnt * (unsigned) plen);
+  if (lane == 31) { s_w[wp] = inc; s_l[wp] = slen; }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    { unsigned long long t = 0, q = 0;
+      for (int k = 0; k < 8; k++) { t += s_w[k]; q += s_l[k]; }
+      s_base = t ? atomicAdd(&counters[0],t) : 0ull;
+      if (q) atomicAdd(&counters[1],q);
+    }
+  __syncthreads();
+  if (cnt == 0) return;
+  unsigned long long o = s_base + (inc - cnt);
+  for (int k = 0; k < wp; k++) o += s_w[k];
+  const long long ipost = (long long) (unsigned) e.lo;
+  const unsigned icont = (unsigned) (e.lo >> 32) & 0x7fff, isign = (unsigned) (e.lo >> 47) & 1;
+  for (unsigned q = lo; q < hi; q++)
+    { if (q == i) continue;
+      rec128 r2 = ld_rec(T + q);
+      long long jpost = (long long) (unsigned) r2.lo;
+      unsigned cs = (unsigned) (r2.lo >> 32) & 0xffff;
+      unsigned comp = (cs >> 15) ^ isign, jcont = cs & 0x7fff;
+      long long diag, anti;
+      if (comp) { diag = K.maxdag - (ipost + jpost); anti = K.amxpos - (ipost - jpost); }
+      else      { diag = K.bmxpos + (ipost - jpost); anti = ipost + jpost; }
+      u64 X = (u64) (unsigned) plen | ((u64) (diag & 63) << 6) | ((u64) anti << 12);
+      u64 Y = (u64) (diag >> 6) | ((u64) jcont << K.s_jc) | ((u64) icont << K.s_ic)
+                                | ((u64) comp << K.s_cp);
+      rec128 sd;
+      sd.lo = X | (Y << K.p_band);
+      sd.hi = Y >> (64 - K.p_band);
+      if (o < capacity) st_rec(seeds + o,sd);
+      o += 1;
+    }
+}
+
+extern "C" int fgb_self_merge_device(const void *d_T, long long n, const unsigned *d_pstart, int freq,
+                                     int anti_bits, int band_bits, int jc_bits, int ic_bits,
+                                     long long amxpos, void *d_seeds, long long capacity,
+                                     unsigned long long *d_counters, unsigned long long *h_nseeds,
+                                     unsigned long long *h_sumlen, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  seed_layout L;
+  L.anti_bits = anti_bits; L.band_bits = band_bits; L.jc_bits = jc_bits; L.ic_bits = ic_bits;
+  L.amxpos = amxpos; L.bmxpos = amxpos;
+  if (seed_key_bits(L) > 128 || freq < 1 || freq > 255) return FGB_ERR_LIMIT;
+  if (n >= 0xffffffffll) return FGB_ERR_LIMIT;
+  CUDA_TRY(cudaMemsetAsync(d_counters,0,16,st));
+  seed_pack K;
+  K.p_band = 12 + anti_bits;
+  K.s_jc = band_bits; K.s_ic = band_bits + jc_bits; K.s_cp = band_bits + jc_bits + ic_bits;
+  K.amxpos = amxpos; K.bmxpos = amxpos; K.maxdag = 2*amxpos;
+  if (K.s_cp + 1 > 64 || K.p_band >= 64 || K.p_band < 13) return FGB_ERR_LIMIT;
+  if (n > 0)
+    { self_merge_kernel<<<(unsigned) ((n + 255) / 256),256,0,st>>>((const rec128 *) d_T,(unsigned) n,d_pstart,freq,K,
+                                                                  (rec128 *) d_seeds,(unsigned long long) capacity,d_counters);
+      fgb_count_launch(1);
+    }
+  CUDA_TRY(cudaGetLastError());
+  unsigned long long h[2];
+  CUDA_TRY(cudaMemcpyAsync(h,d_counters,16,cudaMemcpyDeviceToHost,st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *h_nseeds = h[0];
+  if (h_sumlen) *h_sumlen = h[1];
+  return (h[0] > (unsigned long long) capacity) ? FGB_ERR_OVERFLOW : FGB_OK;
+}
+
 //  T1/T2: sorted device tables; pstart2: [2^24+1] lower-bound index of T2.  Appends seed
 //  records to d_seeds (capacity records).  d_counters: 2 x u64 on the device, zeroed here.
 //  On return *h_nseeds is the number of seeds FOUND; if it exceeds capacity the buffer

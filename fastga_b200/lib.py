@@ -466,6 +466,23 @@ def align_tables(dA, dB, xA, xB, freqA, stream=None, **kw):
     return _alns_out(h), st.asdict()
 
 
+def fastga_self(g, stream=None, **kw):
+    """SELF mode, `FastGA A` with one source (formats.Genome) -> (Alignments, stats)"""
+    p = dict(DEFAULTS)
+    p.update(kw)
+    L = load_library()
+    h = c_void_p()
+    st = RunStats()
+    f = np.ascontiguousarray(g.freq, dtype=np.float32)
+    L.fgb_fastga_self.argtypes = [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_int, c_int, c_int, c_int, C.c_double,
+                                  C.POINTER(c_void_p), C.POINTER(RunStats), c_void_p]
+    _check(L.fgb_fastga_self(_ptr(g.bps), g.bps.size, g.ncontig, _ptr(g.clen), _ptr(g.boff), _ptr(f),
+                             p["freq"], p["chain_break"], p["chain_min"], p["align_min"], float(p["align_rate"]),
+                             C.byref(h), C.byref(st), stream), "fgb_fastga_self")
+    return _alns_out(h), st.asdict()
+
+
 def fastga(gA, gB, stream=None, **kw):
     """The reference-facing call on host buffers (formats.Genome x2) -> (Alignments, stats)"""
     p = dict(DEFAULTS)

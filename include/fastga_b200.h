@@ -59,6 +59,15 @@ int fgb_fastga(const unsigned char *bpsA, long long bps_bytesA, int ncontigA, co
                int freq, int chain_break, int chain_min, int align_min, double align_rate,
                fgb_alns **out, fgb_run_stats *stats, void *stream);
 
+/* SELF mode, `FastGA A` with one source (FastGA.c:4867-4931): T2 = T1 and BMXPOS = AMXPOS; the
+ * merge follows new_self_merge_thread (FastGA.c:1616: every entry, both strands, against the other
+ * members of its own block); a contig against itself, forward strand, is aligned strictly above or
+ * strictly below the main diagonal (Local_Alignment's lbord / hbord, FastGA.c:3247-3262). */
+int fgb_fastga_self(const unsigned char *bps, long long bps_bytes, int ncontig, const long long *clen,
+                    const long long *boff, const float *freq4,
+                    int freq, int chain_break, int chain_min, int align_min, double align_rate,
+                    fgb_alns **out, fgb_run_stats *stats, void *stream);
+
 /* Same from device-resident genomes (bench.py's timed step). */
 int fgb_align_resident(const fgb_genome *A, const fgb_genome *B, const float *freqA,
                        int freq, int chain_break, int chain_min, int align_min, double align_rate,
@@ -107,6 +116,9 @@ void fgb_gix_free(fgb_gix *x);
  *             rmsd_sort RSDsort.c:292) ---- */
 int  fgb_seeds_find(const fgb_gix *x1, const fgb_gix *x2, long long amxpos, long long bmxpos,
                     int freq, fgb_seeds **out, void *stream);
+/* SELF mode: the table against itself (self_adaptamer_merge FastGA.c:2496, new_self_merge_thread :1616);
+   fgb_extend on these seeds applies the self rules of align_contigs */
+int  fgb_seeds_find_self(const fgb_gix *x, long long amxpos, int freq, fgb_seeds **out, void *stream);
 long long fgb_seeds_size(const fgb_seeds *s);
 long long fgb_seeds_sumlen(const fgb_seeds *s);
 int  fgb_seeds_layout(const fgb_seeds *s, int *bits /* anti, band, jcont, icont */);
