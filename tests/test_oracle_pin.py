@@ -250,11 +250,27 @@ def _self_genomes():
         g = np.concatenate(parts)[:500_000]
         cut = int(rng.integers(200_000, 300_000))
         out["tandem%d" % seed] = [g[:cut], g[cut:]]
+    # C-strand self pairs, identical contigs, a palindrome, a long near-diagonal repeat array
+    rng = np.random.default_rng(101)
+    a = rng.integers(0, 4, 200_000, dtype=np.uint8)
+    inv = (3 - a[30_000:90_000][::-1]).astype(np.uint8)
+    out["inverted_dup"] = [np.concatenate([a, rng.integers(0, 4, 5000, dtype=np.uint8),
+                                           synth._small_mutations(rng, inv, 0.03)])]
+    out["identical_contigs"] = [a.copy(), a.copy()[:199_990], rng.integers(0, 4, 50_000, dtype=np.uint8)]
+    out["palindrome"] = [np.concatenate([a[:60_000], (3 - a[:60_000][::-1]).astype(np.uint8)]),
+                         rng.integers(0, 4, 30_001, dtype=np.uint8)]
+    rng = np.random.default_rng(102)
+    unit = rng.integers(0, 4, 5000, dtype=np.uint8)
+    out["near_diagonal_repeats"] = [np.concatenate(
+        [rng.integers(0, 4, 50_000, dtype=np.uint8)] +
+        [synth._small_mutations(rng, unit, 0.04) for _ in range(30)] +
+        [rng.integers(0, 4, 50_000, dtype=np.uint8)])]
     return out
 
 
 @pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("name", ["dup", "tandem61", "tandem62"])
+@pytest.mark.parametrize("name", ["dup", "tandem61", "tandem62", "inverted_dup", "identical_contigs",
+                                  "palindrome", "near_diagonal_repeats"])
 def test_oracle_self_mode_vs_live_reference(name, tmp_path):
     """SURVEY row a-7 groundwork: the oracle's SELF mode (self block rule, band borders for a contig
     against itself) against `FastGA A` of the reference"""
