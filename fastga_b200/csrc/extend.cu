@@ -8,14 +8,18 @@
 // Unit of parallel work = one TRIPLE (two adjacent 64-wide diagonal bands of one
 // (strand, A-contig, B-contig) group): inside a triple the reference carries `alast` from chain
 // to chain and the next Local_Alignment starts where the previous ended, so a triple is a
-// sequential program; triples are independent (FastGA.c:3087).  One warp owns one triple:
-//   * the chain scan runs warp-uniformly (every lane executes the same scalar code);
-//   * a wave is data-parallel over its diagonals: lane l owns diagonal top-l of each 32-wide
-//     chunk; per-diagonal state (V, T, HA, HM, NA) lives in shared memory, indexed circularly;
+// sequential program; triples are independent (FastGA.c:3087).  One warp PAIR owns one triple:
+//   * the chain scan is warp-parallel on the front warp (32 merged seeds per step);
+//   * a wave is data-parallel over its diagonals.  While the band fits a warp the state
+//     (V, T, HA, HM, NA) lives in registers of the lane owning the diagonal and the pass is split
+//     between the front warp (V recurrence, snake, band trim) and the back warp (bit-vectors, trim
+//     tests, pebbles) through a ring in shared memory (struct PairBox); wider or bordered bands run
+//     on the front warp alone, in 32-diagonal chunks over circular arrays in shared memory / HBM;
 //   * the running maxima besta/lasta/trim* (strict '>' in descending-k order) are reproduced
-//     with a warp prefix-max and ballots;
+//     with redux.max + ballots, a warp prefix-max when the best cell fails its quality test;
 //   * pebbles (trace-point crossings) go to a per-warp arena in HBM, allocated by ballot;
-//   * the two wave routines are one direction-normalised routine (see oracle/fastga_oracle.c D).
+//   * the two wave routines are one direction-normalised routine (see oracle/fastga_oracle.c D);
+//   * SELF mode (a genome against itself): band borders for a contig against itself (handle_hit).
 // Sequences are the 2-bit staged contigs (gix.cu); a snake step compares 32 bases per 64-bit XOR.
 // Integer / branch work: no tensor cores.
 #include "common.cuh"
