@@ -14,8 +14,14 @@ One "step" = one pass of the whole path over one synthetic genome pair:
 N > 1    : genome-1 contigs are sharded over the ranks; the table of genome 2 is built
            cooperatively (each rank sorts one slice of the k-mer prefix space, NCCL all-gather);
            per-rank results are gathered to rank 0 with torch.distributed.
---impl reference : the UNMODIFIED reference (oracle/_ref/FastGA -T<cores>) on a bounded sample of
-           the same workload, on the box's host cores.
+--impl reference : the UNMODIFIED reference (oracle/_ref: GIXmake x2 + FastGA -T<cores>) on the
+           IDENTICAL pair the GPU arm runs at this N (same generator, same seed, same size), from
+           the .1gdb/.bps the reference's own FAtoGDB wrote (FASTA parsing is outside both arms'
+           timed regions) to the .1aln, temp files on /dev/shm.  One run takes 10 s .. minutes, so
+           the number of timed runs is capped (config.reference_runs says how many).
+Parity on the bench pair: both arms put the canonical md5 of their alignment records
+           (ONEview form, sorted) into the line; at N=1 the GPU arm's cpu_baseline leg runs the
+           reference once on the same pair and records whether the two md5s are equal.
 """
 import argparse
 import json
@@ -89,13 +95,14 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def other_kernels(stats, dev_ms, peak, seed_passes):
-    """achieved HBM GB/s of the sort stages from their CUDA-event times (bytes = records x 16 B x 2 per pass)"""
+def other_kernels(stats, dev_ms, peak, seed_passes, nk_sorted):
+    """achieved HBM GB/s of the sort stages from their CUDA-event times on THIS rank
+    (bytes = records this rank sorted x 16 B x 2 per pass)"""
     out = []
-    nk = stats["nkmers1"] + stats["nkmers2"]
     if dev_ms.get("ksort_ms", 0) > 0:
-        b = nk * 32 * 3
-        out.append({"stage": "k-mer table sort (sort_onesweep_kernel x2 + kmer_bucket_sort_kernel)", "bound": "hbm",
+        b = nk_sorted * 32 * 3
+        out.append({"stage": "k-mer table sort (sort_onesweep_kernel x2 + kmer_bucket_sort_kernel), records sorted "
+                             "by this rank: %d" % nk_sorted, "bound": "hbm",
                     "bytes": b, "ms": dev_ms["ksort_ms"], "achieved": b / dev_ms["ksort_ms"] / 1e6,
                     "frac": b / dev_ms["ksort_ms"] / 1e6 / peak})
     if dev_ms.get("ssort_ms", 0) > 0:
@@ -109,8 +116,9 @@ def other_kernels(stats, dev_ms, peak, seed_passes):
 
 def ncu_traffic_bytes():
     """DRAM bytes of one adaptamer_merge_kernel launch on this workload from the committed ncu
-    --set full capture (profiles/r01_ncu_merge_kernel.json); None if no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_merge_kernel.json")
+    --set full capture of the CURRENT kernel (profiles/r02_ncu_merge_kernel.json); None if no
+    capture of this round's kernel is committed."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_merge_kernel.json")
     try:
         d = json.load(open(p))
         tot = 0.0
@@ -122,34 +130,109 @@ def ncu_traffic_bytes():
         return None
 
 
-def run_reference_sample(sample_bp, ncontig, steps, warmup, threads):
-    """times oracle/_ref/FastGA on a bounded sample of the workload; returns (Gbp/s, ms/step, info)"""
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def canonical_md5(lines):
+    import hashlib
+    h = hashlib.md5()
+    for l in sorted(lines):
+        h.update(l.encode() + b"\n")
+    return h.hexdigest()
+
+
+def oneview_lines(path):
+    """one text line per alignment of a .1aln ('A .. | R | D .. | T .. | X ..'), through the
+    reference's own ONEview (SURVEY 8c canonical form)"""
+    out = subprocess.run([os.path.join(REF_DIR, "ONEview"), path], stdout=subprocess.PIPE, text=True,
+                         check=True).stdout
+    recs, cur = [], None
+    for line in out.split("\n"):
+        if line.startswith("A "):
+            if cur is not None:
+                recs.append(cur)
+            cur = line
+        elif cur is not None and line[:1] in ("R", "D", "T", "X") and (len(line) == 1 or line[1] == " "):
+            cur += " | " + line
+    if cur is not None:
+        recs.append(cur)
+    return recs
+
+
+def run_reference(A, B, threads, max_runs, warmup, budget_s=240.0):
+    """times the unmodified reference on the pair (A, B): FAtoGDB once (untimed, like the staging of
+    the .bps images on the GPU side), then per run GIXmake A, GIXmake B, FastGA -1:ref A B from the
+    .1gdb.  Returns a dict with the per-run wall seconds, the phase split and the canonical md5."""
+    import re
     from fastga_b200 import formats, synth
-    ref = os.path.join(ROOT, "oracle", "_ref")
-    if not os.path.exists(os.path.join(ref, "FastGA")):
+    if not os.path.exists(os.path.join(REF_DIR, "FastGA")):
         raise RuntimeError("oracle/_ref/FastGA missing: run __graft_entry__.build() where /root/reference exists")
-    A, B = synth.make_pair(SEED, sample_bp, ncontig, DIV, sv_every=SV_EVERY)
-    gbp = (sum(len(a) for a in A) + sum(len(b) for b in B)) / 1e9
     env = dict(os.environ)
-    env["PATH"] = ref + os.pathsep + env.get("PATH", "")
-    times = []
+    env["PATH"] = REF_DIR + os.pathsep + env.get("PATH", "")
+    gbp = (sum(len(a) for a in A) + sum(len(b) for b in B)) / 1e9
+    times, gix_s, proper_s = [], [], []
+    info = {}
+
+    def sh(cmd, wd):
+        r = subprocess.run(cmd, cwd=wd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("reference command failed: %s\n%s" % (" ".join(cmd), r.stdout[-2000:]))
+        return r.stdout
+
     with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as wd:
         formats.write_fasta(os.path.join(wd, "A.fasta"), synth.scaffolds_of(A, "sa", 1))
         formats.write_fasta(os.path.join(wd, "B.fasta"), synth.scaffolds_of(B, "sb", 1))
-        for s in range(warmup + steps):
+        sh(["FAtoGDB", "A.fasta"], wd)
+        sh(["FAtoGDB", "B.fasta"], wd)
+        os.remove(os.path.join(wd, "A.fasta"))
+        os.remove(os.path.join(wd, "B.fasta"))
+        run = 0
+        while True:
             for f in os.listdir(wd):
-                if not f.endswith(".fasta"):
+                if ".ktab." in f or f.endswith(".gix") or f.endswith(".1aln"):
                     os.remove(os.path.join(wd, f))
             t0 = time.time()
-            r = subprocess.run(["FastGA", "-T%d" % threads, "-P" + wd, "-1:ref", "A.fasta", "B.fasta"], cwd=wd,
-                               env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-            dt = time.time() - t0
-            if r.returncode != 0:
-                raise RuntimeError("reference FastGA failed:\n" + r.stdout[-2000:])
-            if s >= warmup:
-                times.append(dt)
-    ms = 1000.0 * float(np.mean(times))
-    return gbp / (ms / 1000.0), ms, {"sample_gbp": gbp, "threads": threads}
+            sh(["GIXmake", "-T%d" % threads, "-P" + wd, "A"], wd)
+            sh(["GIXmake", "-T%d" % threads, "-P" + wd, "B"], wd)
+            t1 = time.time()
+            log = sh(["FastGA", "-v", "-T%d" % threads, "-P" + wd, "-1:ref", "A", "B"], wd)
+            t2 = time.time()
+            timed = run >= warmup
+            if timed:
+                times.append(t2 - t0)
+                gix_s.append(t1 - t0)
+                proper_s.append(t2 - t1)
+            run += 1
+            ntimed = len(times)
+            if ntimed >= max_runs:
+                break
+            if timed and (ntimed + 1) * (t2 - t0) > budget_s:
+                break
+            if not timed and (t2 - t0) > budget_s / 3:      # a single run is already long: count it
+                times.append(t2 - t0); gix_s.append(t1 - t0); proper_s.append(t2 - t1)
+                break
+        log = log.replace("\r", "\n")
+        m = re.search(r"Total seeds = ([\d,]+)", log)
+        if m:
+            info["seeds"] = int(m.group(1).replace(",", ""))
+        m = re.search(r"Total hits over \d+bp = (\d+), (\d+) aln's, (\d+) non-redundant", log)
+        if m:
+            info["hits"], info["alns"], info["kept"] = int(m.group(1)), int(m.group(2)), int(m.group(3))
+        lines = oneview_lines(os.path.join(wd, "ref.1aln"))
+        info["alignments"] = len(lines)
+        info["aln_md5"] = canonical_md5(lines)
+    s = float(np.mean(times))
+    info.update({"gbp": gbp, "threads": threads, "runs": len(times), "s_per_run": s,
+                 "gix_s": float(np.mean(gix_s)), "fastga_proper_s": float(np.mean(proper_s)),
+                 "value": gbp / s, "value_proper": gbp / float(np.mean(proper_s))})
+    return info
+
+
+def workload_text(per_gpu_bp, n):
+    return ("synthetic %d Mbp genome (%d contigs) vs 5%%-diverged copy%s, SV breaks every ~%d kbp, seed %d; "
+            "FastGA defaults -f10 -c85 -s1000 -l100 -i.7"
+            % (per_gpu_bp * n // 1_000_000, NCONTIG * n, " (100 Mbp per GPU x %d GPUs)" % n if n > 1 else "",
+               SV_EVERY // 1000, SEED))
 
 
 def main():
@@ -186,17 +269,24 @@ def run():
         if rank != 0:
             return None
         threads = min(cores, 32)          # GIXmake refuses -T > 32 (GIXmake.c:1723)
-        sample_bp = 20_000_000
-        val, ms, info = run_reference_sample(sample_bp, 4, max(1, args.steps), min(args.warmup, 1), threads)
+        A, B = workload(args.gpus, args.per_gpu_bp)
+        info = run_reference(A, B, threads, max(1, args.steps), min(args.warmup, 1))
+        val, ms = info["value"], 1000.0 * info["s_per_run"]
         line = {"impl": "reference", "metric": "Gbp aligned/sec (genome x genome)", "value": val,
                 "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic",
-                "config": {"workload": "synthetic %d Mbp genome vs 5%%-diverged copy (bounded sample of the "
-                                       "100 Mbp/GPU workload), reference FastGA -T%d end to end from FASTA"
-                                       % (sample_bp // 1_000_000, threads)},
+                "config": {"workload": workload_text(args.per_gpu_bp, args.gpus),
+                           "scope": "from the .1gdb/.bps (FAtoGDB outside the timed region) to the .1aln: "
+                                    "GIXmake -T%d x2 + FastGA -T%d, temp on /dev/shm" % (threads, threads),
+                           "reference_runs": info["runs"],
+                           "phase_s": {"gix_build": info["gix_s"], "fastga_proper": info["fastga_proper_s"]},
+                           "value_fastga_proper": info["value_proper"],
+                           "alignments": info.get("alignments"), "aln_md5": info.get("aln_md5"),
+                           "seeds": info.get("seeds"), "hits": info.get("hits")},
                 "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": threads, "kind": "reference",
-                                 "sample": "%.3f Gbp pair, FastGA incl. FAtoGDB+GIXmake, tmp on /dev/shm" % info["sample_gbp"]},
+                                 "sample": "the whole %.3f Gbp pair (same config as the GPU arm), %d run(s) of %.1f s"
+                                           % (info["gbp"], info["runs"], info["s_per_run"])},
                 "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         return line
 
@@ -224,17 +314,22 @@ def run():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    per_step_ms = []
+
+    def timed(fn, steps, keep=None):
         barrier()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        outs = [fn() for _ in range(steps)]
-        e1.record()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record()
+        outs = []
+        for i in range(steps):
+            outs.append(fn())
+            evs[i + 1].record()
         torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        ms = torch.tensor([evs[0].elapsed_time(evs[steps])], device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if keep is not None:
+            keep.extend(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
         barrier()
         return float(ms.item()) / steps, outs
 
@@ -242,7 +337,7 @@ def run():
         dev = torch.device("cuda", local_rank)
 
         def step():
-            xA = lib.DeviceGix.build(dA)
+            xA = lib.DeviceGix.build_forward(dA)
             xB = shard.build_table_cooperatively(dB, dist, dev)       # NCCL all-gather of sorted shares
             out = lib.align_tables(dA, dB, xA, xB, freqA)
             xA.close()
@@ -256,7 +351,7 @@ def run():
     sampler = ClockSampler(local_rank)
     sampler.start()
     lib.timings_reset()
-    ms_step, outs = timed(step, args.steps)
+    ms_step, outs = timed(step, args.steps, per_step_ms)
     tm = lib.timings_get()
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -280,23 +375,30 @@ def run():
 
     # gather the per-rank record streams on rank 0 (variable length; the path's only collective)
     nrec = len(alns)
+    final = alns
     if world > 1:
         merged = shard.gather_alignments(alns, np.array(mine, dtype=np.int32), dist, torch.device("cuda", local_rank))
         if rank == 0:
             nrec = len(merged)
+            final = merged
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return None
 
+    gpu_md5 = canonical_md5(final.canonical_lines_unsorted())
     steps = args.steps
     # roofline of the seed-merge kernel (the kernel north_star grades): algorithmic bytes on the
-    # on-disk widths, B = (N1+N2)*E + H*R  
+    # on-disk widths, B = (N1 + N2)*E + H*R with N1 = the entries of table 1 the merge
+    # has to see: its forward-strand entries (reverse entries never seed, FastGA.c:921-928, and the
+    # fused path does not build them).  `frac_ondisk_n1` is the same time against the both-strand
+    # table the reference keeps on disk.
     pb = max(1, (int(max(gA.clen.max(), gB.clen.max())).bit_length() + 7) // 8)
     E1 = 9 + pb + 1
     R = 1 + 2 * (pb + 1)
-    algo = (stats["nkmers1"] + stats["nkmers2"]) * E1 + stats["nseeds"] * R
+    algo = (stats["nkmers1_fwd"] + stats["nkmers2"]) * E1 + stats["nseeds"] * R
+    algo_ondisk = (stats["nkmers1"] + stats["nkmers2"]) * E1 + stats["nseeds"] * R
     merge_ms = tm["merge_ms"] / max(1, tm["merge_launches"])
     # byte passes of the seed sort: key = lcp(6) drem(6) anti band jcont icont strand (api.cu:fgb_seeds_find)
     abits = int(gA.clen.max() + gB.clen.max()).bit_length()
@@ -305,20 +407,24 @@ def run():
     peak, peak_src = measured_peak_hbm()
     ach = algo / (merge_ms * 1e-3) / 1e9 if merge_ms > 0 else 0.0
     dev_ms = {k: v / steps for k, v in tm.items() if k.endswith("_ms")}
+    # records this rank's k-mer sorts handled per step: table 1 forward-only + its share of table 2
+    nk_sorted = stats["nkmers1_fwd"] + (stats["nkmers2"] // world if world > 1 else stats["nkmers2"])
+    step_ms = sorted(per_step_ms)
 
     line = {"metric": "Gbp aligned/sec (genome x genome)", "value": total_gbp / (ms_step / 1000.0),
             "unit": "Gbp/s", "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
-            "config": {"workload": "synthetic %d Mbp genome (%d contigs) vs 5%%-diverged copy per GPU, SV breaks "
-                                   "every ~%d kbp, seed %d; FastGA defaults -f10 -c85 -s1000 -l100 -i.7; "
-                                   "k-mer tables and seed sets are larger than L2 (no flush needed)"
-                                   % (args.per_gpu_bp // 1_000_000, NCONTIG, SV_EVERY // 1000, SEED),
+            "config": {"workload": workload_text(args.per_gpu_bp, world) +
+                                   "; k-mer tables and seed sets are larger than L2 (no flush needed)",
                        "sharding": "genome-1 contigs by rank; genome-2 table built cooperatively (k-mer prefix "
-                                   "slices sorted per rank, NCCL all-gather)" if world > 1 else "single GPU", "alignments": nrec,
+                                   "slices sorted per rank, NCCL all-gather)" if world > 1 else "single GPU",
+                       "alignments": nrec, "aln_md5": gpu_md5,
                        "seeds": stats["nseeds"], "kmers": [stats["nkmers1"], stats["nkmers2"]],
+                       "kmers1_forward": stats["nkmers1_fwd"],
                        "hits": stats["nhits"], "la_calls": stats["nla"], "waves": stats["nwaves"],
                        "wave_cells": stats["ncells"], "stage_ms": dev_ms,
+                       "step_ms_min_med_max": [step_ms[0], step_ms[len(step_ms) // 2], step_ms[-1]],
                        "triples": [stats["nseg"], stats["nwork"]],
                        "host_wall_us": {k: stats[k] for k in ("us_gix", "us_seeds", "us_extend", "us_filter")},
                        "extend_cycles": {k: stats[k] for k in ("warp_cycles", "wave_cycles", "extract_cycles")}},
@@ -326,10 +432,11 @@ def run():
                          "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic_bytes() if (world == 1 and args.per_gpu_bp == PER_GPU_BP) else None,
                          "peak_source": peak_src,
-                         "algorithmic_bytes": algo, "kernel_ms": merge_ms},
+                         "algorithmic_bytes": algo, "kernel_ms": merge_ms,
+                         "frac_ondisk_n1": (algo_ondisk / (merge_ms * 1e-3) / 1e9 / peak) if merge_ms > 0 else 0.0},
             # the other HBM-side stages against the same measured peak (16-byte device records;
             # k-mer sort = 2 Onesweep passes + 1 shared-memory bucket pass, seed sort = ceil(keybits/8) passes)
-            "other_kernels": other_kernels(stats, dev_ms, peak, seed_passes),
+            "other_kernels": other_kernels(stats, dev_ms, peak, seed_passes, nk_sorted),
             "extend_kernel": {"ms": tm["extend_ms"] / steps, "launches_per_step": tm["extend_launches"] / steps,
                               "cell_updates_per_s":
                               stats["ncells"] / max(1e-9, tm["extend_ms"] / steps / 1000.0)},
@@ -340,12 +447,20 @@ def run():
             "gpu_launches": tm["launches"]}
 
     if not args.no_cpu_baseline and world == 1:
+        # the reference on the SAME pair (one run, ~10-20 s at -T32): baseline and parity in one go
         try:
             threads = min(cores, 32)
-            val, ms, info = run_reference_sample(10_000_000, 4, 1, 0, threads)
-            line["cpu_baseline"] = {"value": val, "unit": "Gbp/s", "cores": threads, "kind": "reference",
-                                    "sample": "%.3f Gbp pair of the same generator (10 Mbp/genome), reference "
-                                              "FastGA -T%d end to end from FASTA, %.1f s" % (info["sample_gbp"], threads, ms / 1000)}
+            info = run_reference(A, B, threads, 1, 0)
+            line["cpu_baseline"] = {"value": info["value"], "unit": "Gbp/s", "cores": threads, "kind": "reference",
+                                    "sample": "the whole %.3f Gbp pair (same config): GIXmake x2 %.1f s + FastGA "
+                                              "-T%d %.1f s from the .1gdb, 1 run"
+                                              % (info["gbp"], info["gix_s"], threads, info["fastga_proper_s"]),
+                                    "value_fastga_proper": info["value_proper"]}
+            line["parity"] = {"pair": "the bench pair itself", "reference_md5": info["aln_md5"], "gpu_md5": gpu_md5,
+                              "equal": info["aln_md5"] == gpu_md5,
+                              "reference_counts": {k: info.get(k) for k in ("seeds", "hits", "alns", "kept")},
+                              "gpu_counts": {"seeds": stats["nseeds"], "hits": stats["nhits"],
+                                             "alns": final.nraw, "kept": nrec}}
         except Exception as ex:      # the reference arm must never sink the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "Gbp/s", "cores": cores, "kind": "reference",
                                     "sample": "failed: %s" % str(ex)[:200]}

@@ -42,6 +42,7 @@ int fgb_self_merge_device(const void *d_T, long long n, const unsigned *d_pstart
                           long long amxpos, void *d_seeds, long long capacity,
                           unsigned long long *d_counters, unsigned long long *h_nseeds,
                           unsigned long long *h_sumlen, void *stream);
+int fgb_forward_view_device(const void *d_T, long long n, void *d_out, long long *h_nfwd, void *stream);
 int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2, long long n2, const unsigned *d_pstart2,
                      int freq, int anti_bits, int band_bits, int jc_bits, int ic_bits,
                      long long amxpos, long long bmxpos, void *d_seeds, long long capacity,
@@ -249,10 +250,17 @@ static void gix_bytes(const fgb_genome *g, fgb_gix *x)        // GIXmake.c:1888-
 //  K1..K4: syncmer scan -> 128-bit records -> 10-pass byte radix sort on the 80-bit k-mer ->
 //  2^24 prefix index.
 
+#define GIX_FWD_ONLY 0x80000000u     // flag bit carried in `phi` down to syncmer_kernel
+
 static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi, fgb_gix **out, void *stream);
 
 extern "C" int fgb_gix_build(const fgb_genome *g, fgb_gix **out, void *stream)
 { return gix_build_range(g,0u,1u << 24,out,stream); }
+
+//  Forward-strand entries only: the table of the genome that supplies the adaptamers.  Reverse
+//  entries of T1 never seed (FastGA.c:921-928), so the fused path does not build, sort or read them.
+extern "C" int fgb_gix_build_forward(const fgb_genome *g, fgb_gix **out, void *stream)
+{ return gix_build_range(g,0u,(1u << 24) | GIX_FWD_ONLY,out,stream); }
 
 //  Only the k-mers whose 12-base prefix lies in [plo,phi): one rank's share of a table that is
 //  built cooperatively (every rank scans the genome, sorts 1/N of the records, the sorted shares
@@ -262,8 +270,9 @@ extern "C" int fgb_gix_build_range(const fgb_genome *g, unsigned plo, unsigned p
   return gix_build_range(g,plo,phi,out,stream);
 }
 
-static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi, fgb_gix **out, void *stream)
+static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi_flags, fgb_gix **out, void *stream)
 { cudaStream_t st = (cudaStream_t) stream;
+  const unsigned phi = phi_flags & ~GIX_FWD_ONLY;
   int T = fgb_sc_tile();
   std::vector<int> tc, ts;
   for (int c = 0; c < g->ncontig; c++)
@@ -282,25 +291,28 @@ static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi, fgb_
   CUDA_TRY(fgb_dmalloc((void **) &d_tc,sizeof(int)*(ntiles+1),st));
   CUDA_TRY(fgb_dmalloc((void **) &d_ts,sizeof(int)*(ntiles+1),st));
   CUDA_TRY(fgb_dmalloc((void **) &d_cnt,sizeof(unsigned)*(ntiles+1),st));
-  CUDA_TRY(fgb_dmalloc((void **) &d_buck,8*1024,st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_buck,8*1025,st));
   CUDA_TRY(fgb_dmalloc((void **) &d_total,8,st));
   CUDA_TRY(fgb_dmalloc((void **) &d_tmp,tmpb,st));
   CUDA_TRY(cudaMemcpyAsync(d_tc,tc.data(),sizeof(int)*ntiles,cudaMemcpyHostToDevice,st));
   CUDA_TRY(cudaMemcpyAsync(d_ts,ts.data(),sizeof(int)*ntiles,cudaMemcpyHostToDevice,st));
 
   int rc;
-  u64 total = 0;
+  u64 total = 0, rdropped = 0;
   { stage_timer t(&g_timings.scan_ms,st);
     rc = fgb_syncmer_count_device(g->d_seq,g->d_clen,g->d_woff,g->d_crank,d_tc,d_ts,ntiles,d_cnt,
-                                  d_buck,d_total,d_tmp,tmpb,plo,phi,st);
+                                  d_buck,d_total,d_tmp,tmpb,plo,phi_flags,st);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(&total,d_total,8,cudaMemcpyDeviceToHost,st));
     CUDA_TRY(cudaMemcpyAsync(x->buck1024,d_buck,8*1024,cudaMemcpyDeviceToHost,st));
+    CUDA_TRY(cudaMemcpyAsync(&rdropped,d_buck + 1024,8,cudaMemcpyDeviceToHost,st));
     CUDA_TRY(cudaStreamSynchronize(st));
   }
   if (total >= 0xfffffff0ull) return FGB_ERR_LIMIT;
   long long n = (long long) total;
   x->n = n;
+  x->fwd_only = (phi_flags & GIX_FWD_ONLY) ? 1 : 0;
+  x->n_both = n + (long long) rdropped;
 
   rec128 *d_a = NULL, *d_b = NULL; void *d_stmp = NULL;
   long long stmpb = fgb_sort128_tmp_bytes(n);
@@ -308,7 +320,7 @@ static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi, fgb_
   CUDA_TRY(fgb_dmalloc((void **) &d_b,sizeof(rec128)*(n+1),st));
   CUDA_TRY(fgb_dmalloc((void **) &d_stmp,stmpb,st));
   { stage_timer t(&g_timings.scan_ms,st);
-    rc = fgb_syncmer_emit_device(g->d_seq,g->d_clen,g->d_woff,g->d_crank,d_tc,d_ts,ntiles,d_cnt,d_a,plo,phi,st);
+    rc = fgb_syncmer_emit_device(g->d_seq,g->d_clen,g->d_woff,g->d_crank,d_tc,d_ts,ntiles,d_cnt,d_a,plo,phi_flags,st);
     if (rc) return rc;
   }
   int inb = 0;
@@ -345,7 +357,7 @@ extern "C" int fgb_gix_from_device(const void *d_tab, long long n, int post_byte
 { cudaStream_t st = (cudaStream_t) stream;
   if (n >= 0xfffffff0ll) return FGB_ERR_LIMIT;
   fgb_gix *x = new fgb_gix();
-  x->n = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
+  x->n = n; x->n_both = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
   CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
   CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
   CUDA_TRY(cudaMemcpyAsync(x->d_tab,d_tab,sizeof(rec128)*n,cudaMemcpyDeviceToDevice,st));
@@ -375,7 +387,7 @@ extern "C" int fgb_gix_upload(const void *tab, long long n, int post_bytes, int 
 { cudaStream_t st = (cudaStream_t) stream;
   if (n >= 0xfffffff0ll) return FGB_ERR_LIMIT;
   fgb_gix *x = new fgb_gix();
-  x->n = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
+  x->n = n; x->n_both = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
   CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
   CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
   CUDA_TRY(cudaMemcpyAsync(x->d_tab,tab,sizeof(rec128)*n,cudaMemcpyHostToDevice,st));
@@ -394,7 +406,7 @@ extern "C" int fgb_gix_import_ktab(const unsigned char *entries, long long n, in
 { cudaStream_t st = (cudaStream_t) stream;
   if (n >= 0xfffffff0ll || post_bytes > 4 || cont_bytes > 2) return FGB_ERR_LIMIT;
   fgb_gix *x = new fgb_gix();
-  x->n = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
+  x->n = n; x->n_both = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
   long long E = 9 + post_bytes + cont_bytes;
   unsigned char *d_ent = NULL; long long *d_index = NULL;
   CUDA_TRY(fgb_dmalloc((void **) &d_ent,E*n + 16,st));
@@ -456,52 +468,69 @@ extern "C" int fgb_seeds_find_self(const fgb_gix *x, long long amxpos, int freq,
 static int seeds_find_impl(const fgb_gix *x1, const fgb_gix *x2, long long amxpos,
                            long long bmxpos, int freq, bool self, fgb_seeds **out, void *stream)
 { cudaStream_t st = (cudaStream_t) stream;
-  fgb_seeds *s = new fgb_seeds();
-  s->self_mode = self ? 1 : 0;
-  s->anti_bits = bitlen(amxpos + bmxpos);
-  s->band_bits = s->anti_bits > 6 ? s->anti_bits - 6 : 1;
-  s->jc_bits   = bitlen(x2->ncontig > 1 ? x2->ncontig-1 : 1);
-  s->ic_bits   = bitlen(x1->ncontig > 1 ? x1->ncontig-1 : 1);
-  s->amxpos = amxpos; s->bmxpos = bmxpos;
-  int keybits  = 12 + s->anti_bits + s->band_bits + s->jc_bits + s->ic_bits + 1;
+  const int anti_bits = bitlen(amxpos + bmxpos);
+  const int band_bits = anti_bits > 6 ? anti_bits - 6 : 1;
+  const int jc_bits   = bitlen(x2->ncontig > 1 ? x2->ncontig-1 : 1);
+  const int ic_bits   = bitlen(x1->ncontig > 1 ? x1->ncontig-1 : 1);
+  const int keybits   = 12 + anti_bits + band_bits + jc_bits + ic_bits + 1;
   if (keybits > 128) return FGB_ERR_LIMIT;
+  if (self && x1->fwd_only) return FGB_ERR_ARG;                // SELF mode needs both strands
 
-  u64 *d_counters = NULL;
-  CUDA_TRY(fgb_dmalloc((void **) &d_counters,16,st));
-  long long cap = (self ? 2*x1->n : x1->n + (x1->n >> 2)) + 1024;
-  rec128 *d_a = NULL;
+  //  every device block of this call is released on every exit path
+  u64 *d_counters = NULL; rec128 *d_fwd = NULL, *d_a = NULL, *d_b = NULL; void *d_tmp = NULL;
+  fgb_seeds *s = NULL;
+  int rc = FGB_OK;
   u64 nseeds = 0, sumlen = 0;
-  for (int attempt = 0; ; attempt++)
-    { CUDA_TRY(fgb_dmalloc((void **) &d_a,sizeof(rec128)*(cap+1),st));
-      int rc;
-      if (self)
-        rc = fgb_self_merge_device(x1->d_tab,x1->n,x1->d_pstart,freq,s->anti_bits,s->band_bits,
-                                   s->jc_bits,s->ic_bits,amxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
-      else
-        rc = fgb_merge_device(x1->d_tab,x1->n,x2->d_tab,x2->n,x2->d_pstart,freq,s->anti_bits,s->band_bits,
-                              s->jc_bits,s->ic_bits,amxpos,bmxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
-      if (rc == FGB_OK) break;
-      fgb_dfree(d_a,st); d_a = NULL;
-      if (rc != FGB_ERR_OVERFLOW || attempt > 0) { fgb_dfree(d_counters,st); return rc; }
-      cap = (long long) nseeds + 1024;
-      g_timings.merge_ms = 0; g_timings.merge_launches = 0;   // only the successful launch is reported
-    }
-  fgb_dfree(d_counters,st);
-  if (nseeds >= 0xfffffff0ull) return FGB_ERR_LIMIT;
-  s->n = (long long) nseeds; s->sumlen = (long long) sumlen;
+#define SF_TRY(call) do { if ((call) != cudaSuccess) { rc = FGB_ERR_CUDA; goto done; } } while (0)
 
-  rec128 *d_b = NULL; void *d_tmp = NULL;
-  long long tmpb = fgb_sort128_tmp_bytes(s->n);
-  CUDA_TRY(fgb_dmalloc((void **) &d_b,sizeof(rec128)*(s->n+1),st));
-  CUDA_TRY(fgb_dmalloc((void **) &d_tmp,tmpb,st));
-  int inb = 0, rc;
-  { stage_timer t(&g_timings.ssort_ms,st);
-    rc = fgb_sort128_device(d_a,d_b,s->n,0,(keybits+7)/8,d_tmp,tmpb,&inb,st);
+  SF_TRY(fgb_dmalloc((void **) &d_counters,16,st));
+  { //  the adaptamer side must be a forward-strand table (reverse entries never seed): a both-strand
+    //  table (imported .ktab, fgb_gix_build) is compacted once; the fused path builds it forward-only
+    const rec128 *t1 = x1->d_tab; long long n1 = x1->n;
+    if (!self && !x1->fwd_only && n1 > 0)
+      { SF_TRY(fgb_dmalloc((void **) &d_fwd,sizeof(rec128)*(n1+1),st));
+        if ((rc = fgb_forward_view_device(x1->d_tab,n1,d_fwd,&n1,st))) goto done;
+        t1 = d_fwd;
+      }
+    long long cap = (self ? 2*x1->n : 2*n1 + (n1 >> 1)) + 1024;
+    for (int attempt = 0; ; attempt++)
+      { SF_TRY(fgb_dmalloc((void **) &d_a,sizeof(rec128)*(cap+1),st));
+        if (self)
+          rc = fgb_self_merge_device(x1->d_tab,x1->n,x1->d_pstart,freq,anti_bits,band_bits,
+                                     jc_bits,ic_bits,amxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
+        else
+          rc = fgb_merge_device(t1,n1,x2->d_tab,x2->n,x2->d_pstart,freq,anti_bits,band_bits,
+                                jc_bits,ic_bits,amxpos,bmxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
+        if (rc == FGB_OK) break;
+        fgb_dfree(d_a,st); d_a = NULL;
+        if (rc != FGB_ERR_OVERFLOW || attempt > 0) goto done;
+        cap = (long long) nseeds + 1024;
+        g_timings.merge_ms = 0; g_timings.merge_launches = 0;   // only the successful launch is reported
+      }
+    fgb_dfree(d_fwd,st); d_fwd = NULL;
+    if (nseeds >= 0xfffffff0ull) { rc = FGB_ERR_LIMIT; goto done; }
+    s = new fgb_seeds();
+    s->self_mode = self ? 1 : 0;
+    s->anti_bits = anti_bits; s->band_bits = band_bits; s->jc_bits = jc_bits; s->ic_bits = ic_bits;
+    s->amxpos = amxpos; s->bmxpos = bmxpos;
+    s->n = (long long) nseeds; s->sumlen = (long long) sumlen; s->n1_merged = n1;
   }
-  CUDA_TRY(cudaStreamSynchronize(st));
-  s->d_rec = inb ? d_b : d_a;
-  fgb_dfree(inb ? d_a : d_b,st); fgb_dfree(d_tmp,st);
-  if (rc) return rc;
+  { long long tmpb = fgb_sort128_tmp_bytes(s->n);
+    SF_TRY(fgb_dmalloc((void **) &d_b,sizeof(rec128)*(s->n+1),st));
+    SF_TRY(fgb_dmalloc((void **) &d_tmp,tmpb,st));
+    int inb = 0;
+    { stage_timer t(&g_timings.ssort_ms,st);
+      rc = fgb_sort128_device(d_a,d_b,s->n,0,(keybits+7)/8,d_tmp,tmpb,&inb,st);
+    }
+    if (rc == FGB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = FGB_ERR_CUDA;
+    if (rc) goto done;
+    s->d_rec = inb ? d_b : d_a;
+    if (inb) d_b = NULL; else d_a = NULL;                       // ownership moved to the handle
+  }
+done:
+#undef SF_TRY
+  fgb_dfree(d_counters,st); fgb_dfree(d_fwd,st); fgb_dfree(d_a,st); fgb_dfree(d_b,st); fgb_dfree(d_tmp,st);
+  if (rc) { delete s; return rc; }
   *out = s;
   return FGB_OK;
 }
@@ -559,7 +588,7 @@ int fgb_filter(const fgb_overlaps *O, const int *perm1, const int *perm2, int jc
 struct fgb_run_stats
 { long long nkmers1, nkmers2, nseeds, sumlen, nhits, nla, nwaves, ncells, nraw, h2d_bytes, d2h_bytes,
             nseg, nwork, warp_cycles, wave_cycles, extract_cycles,
-            us_gix, us_seeds, us_extend, us_filter; };
+            us_gix, us_seeds, us_extend, us_filter, nkmers1_fwd; };
 
 //  Merge + seed sort + extension + filter from prebuilt tables (x2 may have been assembled from
 //  shares built on several ranks).
@@ -575,7 +604,7 @@ extern "C" int fgb_align_resident(const fgb_genome *A, const fgb_genome *B, cons
 { fgb_gix *x1 = NULL, *x2 = NULL;
   int rc;
   long long t0 = now_us();
-  if ((rc = fgb_gix_build(A,&x1,stream))) return rc;
+  if ((rc = fgb_gix_build_forward(A,&x1,stream))) return rc;     // adaptamer side: forward strand only
   if ((rc = fgb_gix_build(B,&x2,stream))) { fgb_gix_free(x1); return rc; }
   long long t1 = now_us();
   rc = fgb_align_tables(A,B,x1,x2,freqA,freq,chain_break,chain_min,align_min,align_rate,out,stats,stream);
@@ -592,8 +621,9 @@ extern "C" int fgb_align_tables(const fgb_genome *A, const fgb_genome *B, const 
   int rc;
   long long t0 = now_us(), t1 = t0, t2, t3, t4;
   rc = fgb_seeds_find(x1,x2,A->maxlen,B->maxlen,freq,&sd,stream);
-  long long n1 = x1->n, n2 = x2->n;
+  long long n1 = x1->n_both, n2 = x2->n;
   if (rc) return rc;
+  const long long n1f = sd->n1_merged;
   t2 = now_us();
   short *tables = (short *) malloc(65536*sizeof(short));
   int ave = 0;
@@ -605,15 +635,13 @@ extern "C" int fgb_align_tables(const fgb_genome *A, const fgb_genome *B, const 
   int jb = sd->jc_bits, ib = sd->ic_bits;
   fgb_seeds_free(sd);
   if (rc) return rc;
-  { cudaEvent_t a, b;                                         // host filter: wall time, not device
-    (void) a; (void) b;
-  }
   rc = fgb_filter(ov,A->perm.data(),B->perm.data(),jb,ib,1,out);
   t4 = now_us();
   if (stats)
     { stats->us_gix = t1-t0; stats->us_seeds = t2-t1; stats->us_extend = t3-t2; stats->us_filter = t4-t3; unsigned long long c[16];
       fgb_overlaps_counters(ov,c);
       stats->nkmers1 = n1; stats->nkmers2 = n2; stats->nseeds = nseeds; stats->sumlen = sumlen;
+      stats->nkmers1_fwd = n1f;
       stats->nhits = (long long) c[0]; stats->nla = (long long) c[1]; stats->nwaves = (long long) c[2];
       stats->ncells = (long long) c[3]; stats->nraw = 0;
       stats->nseg = (long long) c[5]; stats->nwork = (long long) c[6];

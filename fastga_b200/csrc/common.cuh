@@ -81,6 +81,18 @@ static __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *g
                :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+//  several bulk copies completing on ONE barrier phase: announce the byte total once, then issue the copies
+static __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+static __device__ __forceinline__ void tma_copy_1d(void *smem_dst, const void *gmem_src, unsigned bytes,
+                                                   unsigned long long *bar)
+{ asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 static __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase)
 { unsigned ok;
   do

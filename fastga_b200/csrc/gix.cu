@@ -182,12 +182,16 @@ syncmer_kernel(const u64 *__restrict__ seq, const long long *__restrict__ clen,
                const int *__restrict__ tile_contig, const int *__restrict__ tile_start,
                unsigned *__restrict__ tile_count,       // EMIT=0: out counts; EMIT=1: in offsets
                unsigned long long *__restrict__ buck1024,
-               rec128 *__restrict__ out, unsigned plo, unsigned phi)
+               rec128 *__restrict__ out, unsigned plo, unsigned phi_flags)
 { __shared__ u64 sw[SC_WORDS+1];
   __shared__ unsigned char tn[256], tc[256];
   __shared__ unsigned wsum[SC_THREADS/32];
   __shared__ unsigned hist[1024];
 
+  //  bit 31 of phi_flags: forward-strand entries only (the table is only ever the adaptamer side
+  //  of a merge, where reverse entries never seed, FastGA.c:921-928)
+  const unsigned phi = phi_flags & 0x7fffffffu;
+  const bool fwd_only = (phi_flags >> 31) != 0;
   int tid = threadIdx.x;
   int c   = tile_contig[blockIdx.x];
   int t0  = tile_start[blockIdx.x];
@@ -237,6 +241,8 @@ syncmer_kernel(const u64 *__restrict__ seq, const long long *__restrict__ clen,
             }
         }
     }
+  unsigned rdropped = 0;                       // reverse entries a forward-only table leaves out
+  if (fwd_only) { rdropped = __popc(rmask); rmask = 0; }
   unsigned cnt = __popc(fmask) + __popc(rmask);
 
   int lane = tid & 31, wp = tid >> 5;
@@ -276,6 +282,10 @@ syncmer_kernel(const u64 *__restrict__ seq, const long long *__restrict__ clen,
       __syncthreads();
       for (int i = tid; i < 1024; i += SC_THREADS)
         if (hist[i]) atomicAdd(&buck1024[i],(unsigned long long) hist[i]);
+      if (fwd_only)                            // slot 1024: size of the both-strand table minus this one
+        { rdropped = __reduce_add_sync(0xffffffffu,rdropped);
+          if (lane == 0 && rdropped) atomicAdd(&buck1024[1024],(unsigned long long) rdropped);
+        }
       if (tid == 0) tile_count[blockIdx.x] = tot;
       return;
     }
@@ -432,7 +442,7 @@ extern "C" int fgb_syncmer_count_device(const void *d_seq, const long long *d_cl
 { cudaStream_t st = (cudaStream_t) stream;
   int rc = init_tables();
   if (rc) return rc;
-  CUDA_TRY(cudaMemsetAsync(d_buck1024,0,1024*8,st));
+  CUDA_TRY(cudaMemsetAsync(d_buck1024,0,1025*8,st));
   if (ntiles > 0)
     syncmer_kernel<0><<<ntiles,SC_THREADS,0,st>>>((const u64 *) d_seq,d_clen,d_woff,d_crank,
                                                    d_tile_contig,d_tile_start,d_tile_count,

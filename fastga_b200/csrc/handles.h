@@ -24,6 +24,8 @@ struct fgb_gix
   unsigned *d_pstart = nullptr;            // [2^24+1] lower-bound index by 12-base prefix
   unsigned long long buck1024[1024] = {0}; // sampler histogram (decides the .ktab part split)
   int post_bytes = 0, cont_bytes = 0, ncontig = 0;
+  int fwd_only = 0;                        // forward-strand entries only (adaptamer side of a merge)
+  long long n_both = 0;                    // entries of the both-strand table (= n unless fwd_only)
 };
 
 struct fgb_seeds
@@ -32,4 +34,5 @@ struct fgb_seeds
   int anti_bits = 0, band_bits = 0, jc_bits = 0, ic_bits = 0;
   long long amxpos = 0, bmxpos = 0;
   int self_mode = 0;                       // seeds of a genome against itself (FastGA A)
+  long long n1_merged = 0;                 // forward-strand T1 entries the merge consumed
 };

@@ -8,11 +8,17 @@
 //     plen  = max over the panel of LCP(e1,e2)            (12..40)
 //     R(e1) = the block of T2 entries with LCP(e1,e2) >= plen
 //     if |R| < FREQ emit (plen, e1, e2) for every e2 in R, strand C iff e2 is a reverse entry.
-// Here one thread owns one T1 entry: it binary-searches its 56-bit suffix in the T2 panel
-// (located through the 2^24 prefix index), takes plen from the two neighbours of the insertion
-// point, and walks at most FREQ entries either side.  T1 is streamed with coalesced 128-bit
-// loads; the T2 panel of neighbouring threads is the same few cache lines, so T2 is read from
-// HBM once.  Seeds of a block are compacted with a block scan and appended with one atomic.
+//
+// Tiled co-scan: T1 is a FORWARD-STRAND-ONLY table (reverse entries never seed; the fused path
+// builds it that way, any other table is compacted once).  A CTA owns TILE consecutive T1 entries;
+// because both tables are sorted, the T2 entries they can match are ONE contiguous slice.  Both the
+// tile and the slice arrive by TMA bulk copy on one mbarrier and stay in record form (the 128-bit
+// record orders as (k-mer, payload), so a probe is one 128-bit shared-memory load and compare);
+// every T1 entry finds its insertion point with a few probes inside its panel (bounds from the
+// 2^24 prefix index, read through L1); a neighbour sharing fewer than 12 bases is "no partner".
+// Seeds are expanded load-balanced: each entry drops one 32-bit descriptor per seed into shared
+// memory, then every thread builds one 128-bit seed record per step and the stores of the CTA are
+// one contiguous run reserved with ONE atomic.
 #include "common.cuh"
 
 typedef unsigned long long u64;
@@ -30,14 +36,20 @@ static __host__ __device__ __forceinline__ int seed_key_bits(const seed_layout &
 
 #define MG_THREADS 256
 #define MG_WARPS   (MG_THREADS/32)
-#define MG_TILE    64                     // T1 entries per warp (32 / 16 when T2 is much denser than T1)
-#define MG_T2CAP   1280                   // staged T2 entries per block (20 KB)
-#define MG_PCAP    1536                   // staged prefix-index entries per block (6 KB)
-
+#define MG_T2CAP   1536                   // staged T2 entries per CTA (24 KB)
+#define MG_DCAP    4608                   // seed descriptors per CTA (512 entries x (FREQ-1 = 9))
 //  lcp (in bases, 0..28) of two 56-bit suffixes
 static __device__ __forceinline__ int lcp56(u64 a, u64 b)
 { u64 x = a ^ b;
   return x ? ((__clzll(x) - 8) >> 1) : 28;
+}
+
+//  lcp (in bases, 0..40) of the k-mers of two records
+static __device__ __forceinline__ int lcp_rec(const rec128 &a, const rec128 &b)
+{ u64 x = a.hi ^ b.hi;
+  if (x) return __clzll(x) >> 1;
+  unsigned y = (unsigned) ((a.lo ^ b.lo) >> 48);
+  return y ? 32 + ((__clz(y) - 16) >> 1) : 40;
 }
 
 static __device__ __forceinline__ u64 suffix_of(const rec128 *__restrict__ T, unsigned i)
@@ -52,144 +64,104 @@ struct seed_pack                          // kernel-uniform packing constants
   long long amxpos, bmxpos, maxdag;
 };
 
-struct blk_stage                          // the block's staging of T2
-{ rec128 t2[MG_T2CAP];                    // the slice of T2 the block's tile can match (TMA destination),
-                                          //   then rewritten in place as (56-bit suffix, payload) pairs
-  unsigned ps[MG_PCAP];                   // the prefix-index range
+//  seed record of (plen, T1 payload, T2 payload); payload = post | (contig rank | strand<<15) << 32
+//  (reimport_thread, FastGA.c:2703-2721)
+static __device__ __forceinline__ rec128 make_seed(unsigned plen, u64 pay, u64 p2, const seed_pack &K)
+{ long long ipost = (long long) (unsigned) pay, jpost = (long long) (unsigned) p2;
+  unsigned icont = (unsigned) (pay >> 32) & 0x7fff;
+  unsigned cs = (unsigned) (p2 >> 32) & 0xffff;
+  unsigned comp = cs >> 15, jcont = cs & 0x7fff;
+  long long diag, anti;
+  if (comp) { diag = K.maxdag - (ipost + jpost); anti = K.amxpos - (ipost - jpost); }
+  else      { diag = K.bmxpos + (ipost - jpost); anti = ipost + jpost; }
+  u64 X = (u64) plen | ((u64) (diag & 63) << 6) | ((u64) anti << 12);
+  u64 Y = (u64) (diag >> 6) | ((u64) jcont << K.s_jc) | ((u64) icont << K.s_ic)
+                            | ((u64) comp << K.s_cp);
+  rec128 sd;
+  sd.lo = X | (Y << K.p_band);
+  sd.hi = Y >> (64 - K.p_band);
+  return sd;
+}
+
+template<int TILE> struct mg_stage
+{ rec128   t2[MG_T2CAP];                  // the T2 slice (TMA destination)
+  rec128   t1[TILE];                      // the T1 tile (TMA destination)
+  unsigned desc[MG_DCAP];                 // per seed: T2 slot (11) | T1 slot (9) << 11 | (plen-12) << 20
+  unsigned wtot[2*MG_WARPS], wsum[2*MG_WARPS];
   unsigned rng[4];
-  unsigned wtot[MG_WARPS], wsum[MG_WARPS];
   unsigned long long gbase;
   unsigned long long bar;
 };
 
-struct warp_stage                         // one warp's private buffers
-{ rec128 t1[MG_TILE];                     // forward-strand T1 entries of the warp's tile, compacted
-  unsigned excl[MG_TILE+1], lowi[MG_TILE], plen[MG_TILE];
-  u64    ipay[MG_TILE];
-};
-
-//  The two table views of the search: staged (shared memory, suffixes precomputed once per T2
-//  entry) or direct (global memory, when a tile's slice does not fit the staging buffers).
-struct view_staged
-{ const blk_stage *S; unsigned t2off, psoff;
-  __device__ __forceinline__ unsigned ps(unsigned p)  const { return S->ps[p - psoff]; }
-  __device__ __forceinline__ u64 suf(unsigned i)      const { return reinterpret_cast<const u64 *>(S->t2)[2*(i - t2off)]; }
-  __device__ __forceinline__ u64 pay(unsigned i)      const { return reinterpret_cast<const u64 *>(S->t2)[2*(i - t2off)+1]; }
-};
-struct view_direct
-{ const rec128 *T2; const unsigned *pstart;
-  __device__ __forceinline__ unsigned ps(unsigned p)  const { return pstart[p]; }
-  __device__ __forceinline__ u64 suf(unsigned i)      const { return suffix_of(T2,i); }
-  __device__ __forceinline__ u64 pay(unsigned i)      const { return T2[i].lo & 0xffffffffffffull; }
-};
-
-//  the adaptamer of one T1 entry: |R| (0 if no seed), first T2 index of R, plen
-template<class View>
-static __device__ __forceinline__ unsigned adaptamer(const View &V, const rec128 &r1, int freq,
-                                                     unsigned &lowi, int &plen)
-{ unsigned p  = KREC_PREFIX24(r1.hi);
-  unsigned lo = V.ps(p), hi = V.ps(p+1);
-  lowi = 0; plen = 0;
-  if (lo >= hi) return 0;
-  u64 s1 = KREC_SUFFIX56(r1);
-  unsigned a = lo, b = hi;                                    // lower bound of s1 in T2[lo,hi)
+//  Adaptamer of one T1 entry against the staged slice: |R| (0 if no seed), first slice slot of R, plen.
+static __device__ __forceinline__ unsigned adaptamer_staged(const rec128 *__restrict__ t2, unsigned nsl,
+                                                            const rec128 &r1, unsigned lo, unsigned hi, int freq,
+                                                            unsigned &lowi, int &plen)
+{ const u64 k1 = r1.lo >> 48;
+  unsigned a = lo, b = hi;                                    // lower bound of r1's k-mer inside its panel [lo,hi)
   while (a < b)
     { unsigned m = (a + b) >> 1;
-      if (V.suf(m) < s1) a = m+1; else b = m;
+      rec128 q = ld_rec(t2 + m);
+      if (q.hi < r1.hi || (q.hi == r1.hi && (q.lo >> 48) < k1)) a = m+1; else b = m;
     }
-  int ll = (a > lo) ? lcp56(s1,V.suf(a-1)) : -1;
-  int lr = (a < hi) ? lcp56(s1,V.suf(a))   : -1;
+  //  the neighbours of the insertion point decide plen; a neighbour in another panel (the slice only
+  //  holds the tile's panels, so this covers the slice ends too) shares fewer than 12 bases
+  int ll = (a > 0)   ? lcp_rec(r1,ld_rec(t2 + a - 1)) : 0;
+  int lr = (a < nsl) ? lcp_rec(r1,ld_rec(t2 + a))     : 0;
   int m  = ll > lr ? ll : lr;
-  plen = 12 + m;
+  lowi = 0; plen = 0;
+  if (m < 12) return 0;
+  plen = m;
   unsigned lft = a, rgt = a;
-  int sh = 56 - 2*m;
-  u64 key = s1 >> sh;
-  while (lft > lo && rgt - lft < (unsigned) freq)
-    { if ((V.suf(lft-1) >> sh) != key) break;
-      lft -= 1;
+  if (ll == m)
+    { lft = a-1;
+      while (lft > 0 && rgt - lft < (unsigned) freq && lcp_rec(r1,ld_rec(t2 + lft - 1)) >= m) lft -= 1;
     }
-  while (rgt < hi && rgt - lft < (unsigned) freq)
-    { if ((V.suf(rgt) >> sh) != key) break;
-      rgt += 1;
+  if (lr == m)
+    { rgt = a+1;
+      while (rgt < nsl && rgt - lft < (unsigned) freq && lcp_rec(r1,ld_rec(t2 + rgt)) >= m) rgt += 1;
     }
   if (rgt - lft >= (unsigned) freq) return 0;                 // |R| < FREQ (:799-823)
   lowi = lft;
   return rgt - lft;
 }
 
-//  One warp owns MG_TILE consecutive T1 entries; the block shares the staged slice of T2:
-//   1. two coalesced 512-byte loads of the tile; forward-strand entries (the only ones that seed,
-//      FastGA.c:921-928) are compacted into shared memory by ballot so the search lanes are dense;
-//   2. the block's tiles are consecutive in k-mer order, so the T2 entries they can match are ONE
-//      contiguous slice [pstart2[pA], pstart2[pB+1]): fetched with one TMA bulk copy together with
-//      the prefix-index range, suffixes and payloads split once per staged entry;
-//   3. each lane searches its entries in the slice (binary search + bounded walk);
-//   4. the seeds of the tile are expanded load-balanced: output slot o is built by lane o mod 32
-//      (prefix sums in shared memory), so every lane builds one seed per step and the 128-bit
-//      stores of a step are contiguous; one atomic per tile reserves the output run.
-
-template<class View>
-static __device__ __forceinline__ unsigned merge_search(const View &V, warp_stage *S, int nd, int freq,
-                                                        unsigned &sumlen, int lane)
-{ unsigned run = 0, sl = 0;
-  for (int r0 = 0; r0 < nd; r0 += 32)
-    { int idx = r0 + lane;
-      unsigned cnt = 0, lowi = 0; int plen = 0;
-      u64 pay = 0;
-      if (idx < nd)
-        { rec128 r1 = ld_rec(&S->t1[idx]);
-          cnt = adaptamer(V,r1,freq,lowi,plen);
-          pay = r1.lo & 0xffffffffffffull;
-        }
-      unsigned inc = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1)
-        { unsigned t = __shfl_up_sync(0xffffffffu,inc,o);
-          if (lane >= o) inc += t;
-        }
-      if (idx < MG_TILE)
-        { S->excl[idx] = run + inc - cnt; S->lowi[idx] = lowi; S->plen[idx] = (unsigned) plen; S->ipay[idx] = pay; }
-      run += __shfl_sync(0xffffffffu,inc,31);
-      sl  += cnt * (unsigned) plen;
+//  Same straight from HBM (a tile whose slice does not fit the staging buffers: long repeats).
+static __device__ __forceinline__ unsigned adaptamer_direct(const rec128 *__restrict__ T2,
+                                                            const unsigned *__restrict__ pstart, const rec128 &r1,
+                                                            int freq, unsigned &lowi, int &plen)
+{ unsigned p  = KREC_PREFIX24(r1.hi);
+  unsigned lo = pstart[p], hi = pstart[p+1];
+  lowi = 0; plen = 0;
+  if (lo >= hi) return 0;
+  u64 s1 = KREC_SUFFIX56(r1);
+  unsigned a = lo, b = hi;
+  while (a < b)
+    { unsigned m = (a + b) >> 1;
+      if (suffix_of(T2,m) < s1) a = m+1; else b = m;
     }
-  const int nslot = (nd + 31) & ~31;                           // entries idx >= nd hold cnt 0
-  if (lane == 0) S->excl[nslot] = run;
-  sumlen = __reduce_add_sync(0xffffffffu,sl);
-  __syncwarp();
-  return run;
+  int ll = (a > lo) ? lcp56(s1,suffix_of(T2,a-1)) : -1;
+  int lr = (a < hi) ? lcp56(s1,suffix_of(T2,a))   : -1;
+  int m  = ll > lr ? ll : lr;
+  plen = 12 + m;
+  unsigned lft = a, rgt = a;
+  int sh = 56 - 2*m;
+  u64 key = s1 >> sh;
+  while (lft > lo && rgt - lft < (unsigned) freq)
+    { if ((suffix_of(T2,lft-1) >> sh) != key) break;
+      lft -= 1;
+    }
+  while (rgt < hi && rgt - lft < (unsigned) freq)
+    { if ((suffix_of(T2,rgt) >> sh) != key) break;
+      rgt += 1;
+    }
+  if (rgt - lft >= (unsigned) freq) return 0;
+  lowi = lft;
+  return rgt - lft;
 }
 
-template<class View>
-static __device__ __forceinline__ void merge_expand(const View &V, const warp_stage *S, int nd, unsigned total,
-                                                    unsigned long long gbase, const seed_pack &K,
-                                                    rec128 *__restrict__ seeds, unsigned long long capacity,
-                                                    int lane)
-{ const int nslot = (nd + 31) & ~31;
-  for (unsigned o = lane; o < total; o += 32)
-    { int j = 0;                                               // last slot with excl <= o
-      for (int st = nslot >> 1; st > 0; st >>= 1)
-        if (S->excl[j + st] <= o) j += st;
-      unsigned k = o - S->excl[j];
-      u64 p2 = V.pay(S->lowi[j] + k), pay = S->ipay[j];
-      long long ipost = (long long) (unsigned) pay, jpost = (long long) (unsigned) p2;
-      unsigned icont = (unsigned) (pay >> 32) & 0x7fff;
-      unsigned cs = (unsigned) (p2 >> 32) & 0xffff;
-      unsigned comp = cs >> 15, jcont = cs & 0x7fff;
-      long long diag, anti;
-      if (comp) { diag = K.maxdag - (ipost + jpost); anti = K.amxpos - (ipost - jpost); }
-      else      { diag = K.bmxpos + (ipost - jpost); anti = ipost + jpost; }
-      u64 X = (u64) S->plen[j] | ((u64) (diag & 63) << 6) | ((u64) anti << 12);
-      u64 Y = (u64) (diag >> 6) | ((u64) jcont << K.s_jc) | ((u64) icont << K.s_ic)
-                                | ((u64) comp << K.s_cp);
-      rec128 sd;
-      sd.lo = X | (Y << K.p_band);
-      sd.hi = Y >> (64 - K.p_band);
-      if (gbase + o < capacity) st_rec(seeds + gbase + o,sd);
-    }
-}
-
-//  Per block of the merge: the prefix range of its T1 tile and the T2 slice it can match, found
-//  ahead of the merge with full parallelism (inside the merge this is a chain of two dependent HBM
+//  Per CTA of the merge: the prefix span of its T1 tile and the T2 slice it can match, found ahead
+//  of the merge with full parallelism (inside the merge this would be a chain of two dependent HBM
 //  round trips made by one lane while 255 threads wait).
 __global__ void merge_ranges_kernel(const rec128 *__restrict__ T1, unsigned n1, const unsigned *__restrict__ pstart2,
                                     unsigned per_block, unsigned nblocks, uint4 *__restrict__ rng)
@@ -199,7 +171,7 @@ __global__ void merge_ranges_kernel(const rec128 *__restrict__ T1, unsigned n1, 
   if (b1 >= n1) b1 = n1 - 1;
   unsigned pA = KREC_PREFIX24(T1[b0].hi), pB = KREC_PREFIX24(T1[b1].hi);
   unsigned lo2 = pstart2[pA], hi2 = pstart2[pB+1];
-  rng[b] = make_uint4(pA,pB - pA + 2,lo2,hi2 - lo2);
+  rng[b] = make_uint4(pA,pB - pA,lo2,hi2 - lo2);
 }
 
 template<int TILE>
@@ -210,77 +182,150 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
                        rec128 *__restrict__ seeds, unsigned long long capacity,
                        unsigned long long *__restrict__ counters /* [0]=nseeds [1]=sum plen */)
 { extern __shared__ __align__(16) unsigned char mg_smem[];
-  blk_stage  *B = reinterpret_cast<blk_stage *>(mg_smem);
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  warp_stage *S = reinterpret_cast<warp_stage *>(mg_smem + sizeof(blk_stage)) + wp;
-  const unsigned lt = lanemask_lt();
-  const unsigned long long b0 = (unsigned long long) blockIdx.x * MG_WARPS * TILE;
-  const unsigned long long base = b0 + (unsigned long long) wp * TILE;
+  mg_stage<TILE> *S = reinterpret_cast<mg_stage<TILE> *>(mg_smem);
+  constexpr int ROUNDS = (TILE >= MG_THREADS) ? TILE/MG_THREADS : 1;
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  const unsigned long long b0 = (unsigned long long) blockIdx.x * TILE;
+  const unsigned nt1 = (n1 - b0 < (unsigned long long) TILE) ? (unsigned) (n1 - b0) : (unsigned) TILE;
 
-  //  every warp's tile loads are in flight before the block waits for its T2 slice
-  unsigned i0 = (unsigned) base + lane, i1 = i0 + 32;
-  rec128 e0, e1;
-  e0.lo = e0.hi = e1.lo = e1.hi = 0;
-  bool f0 = false, f1 = false;
-  if (base < n1)
-    { if (lane < TILE && i0 < n1) { e0 = ld_rec(T1 + i0); f0 = ((e0.lo >> 47) & 1) == 0; }
-      if (TILE > 32 && i1 < n1)   { e1 = ld_rec(T1 + i1); f1 = ((e1.lo >> 47) & 1) == 0; }
+  if (tid == 0)
+    { const uint4 r = rng[blockIdx.x];                      // pA, pB-pA, first T2 entry, #T2 entries
+      S->rng[0] = r.x; S->rng[1] = r.y; S->rng[2] = r.z; S->rng[3] = r.w;
+      mbar_init(&S->bar,1);
+      const bool st = (r.w <= MG_T2CAP);
+      mbar_expect_tx(&S->bar,nt1*16u + ((st && r.w) ? r.w*16u : 0u));
+      tma_copy_1d(S->t1,T1 + b0,nt1*16u,&S->bar);
+      if (st && r.w) tma_copy_1d(S->t2,T2 + r.z,r.w*16u,&S->bar);
     }
-
-  //  The block's 512 T1 entries are consecutive in k-mer order, so the T2 entries they can match
-  //  are one contiguous slice [pstart2[pA], pstart2[pB+1]).  When it fits, that slice and the
-  //  prefix-index range are staged in shared memory (one TMA bulk copy + coalesced loads) and
-  //  every search, walk and payload read hits shared memory instead of a dependent L2/HBM trip.
-  if (threadIdx.x == 0)
-    { const uint4 r = rng[blockIdx.x];                      // pA, #prefixes+1, first T2 entry, #T2 entries
-      B->rng[0] = r.x; B->rng[1] = r.y; B->rng[2] = r.z; B->rng[3] = r.w;
-      mbar_init(&B->bar,1);
-      if (r.y <= MG_PCAP && r.w <= MG_T2CAP && r.w > 0)
-        tma_load_1d(B->t2,T2 + r.z,r.w * 16u,&B->bar);
-    }
-  //  forward-strand compaction of the warp's tile while the slice is in flight
-  unsigned m0 = __ballot_sync(0xffffffffu,f0), m1 = __ballot_sync(0xffffffffu,f1);
-  int n0 = __popc(m0), nd = n0 + __popc(m1);
-  if (f0) st_rec(&S->t1[__popc(m0 & lt)],e0);
-  if (f1) st_rec(&S->t1[n0 + __popc(m1 & lt)],e1);
   __syncthreads();
-  const unsigned pA = B->rng[0], nps = B->rng[1], lo2 = B->rng[2], nsl = B->rng[3];
-  const bool staged = (nps <= MG_PCAP && nsl <= MG_T2CAP);
-  if (staged)
-    { for (unsigned i = threadIdx.x; i < nps; i += MG_THREADS) B->ps[i] = pstart2[pA + i];
-      if (nsl > 0)
-        { mbar_wait(&B->bar,0);
-          for (unsigned j = threadIdx.x; j < nsl; j += MG_THREADS)
-            { rec128 r = ld_rec(&B->t2[j]), c;
-              c.lo = KREC_SUFFIX56(r);                       // first word: suffix, second: payload
-              c.hi = r.lo & 0xffffffffffffull;
-              st_rec(&B->t2[j],c);
+  const unsigned lo2 = S->rng[2], nsl = S->rng[3];
+  const bool staged = (nsl <= MG_T2CAP);
+  mbar_wait(&S->bar,0);
+
+  //  search: thread tid owns tile entries tid, tid+256, ...
+  const u64 *t2k = reinterpret_cast<const u64 *>(S->t2);
+  const u64 *t1k = reinterpret_cast<const u64 *>(S->t1);
+  const u64 PAY = 0xffffffffffffull;
+  unsigned cnt[ROUNDS], lowi[ROUNDS], excl[ROUNDS]; int plen[ROUNDS];
+#pragma unroll
+  for (int r = 0; r < ROUNDS; r++)
+    { const unsigned j = r*MG_THREADS + tid;
+      cnt[r] = 0; lowi[r] = 0; plen[r] = 0;
+      if (j < nt1)
+        { const rec128 r1 = ld_rec(&S->t1[j]);
+          if (staged)
+            { const unsigned p = KREC_PREFIX24(r1.hi);
+              const unsigned lo = __ldg(pstart2 + p) - lo2, hi = __ldg(pstart2 + p + 1) - lo2;
+              if (lo < hi) cnt[r] = adaptamer_staged(S->t2,nsl,r1,lo,hi,freq,lowi[r],plen[r]);
             }
+          else
+            cnt[r] = adaptamer_direct(T2,pstart2,r1,freq,lowi[r],plen[r]);
+        }
+      unsigned inc = cnt[r];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+        { unsigned t = __shfl_up_sync(0xffffffffu,inc,o);
+          if (lane >= o) inc += t;
+        }
+      excl[r] = inc - cnt[r];
+      const unsigned sl = __reduce_add_sync(0xffffffffu,cnt[r] * (unsigned) plen[r]);
+      if (lane == 31) S->wtot[r*MG_WARPS + wp] = inc;
+      if (lane == 0)  S->wsum[r*MG_WARPS + wp] = sl;
+    }
+  __syncthreads();
+  unsigned total = 0;
+  { unsigned pre[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) pre[r] = 0;
+#pragma unroll
+    for (int q = 0; q < ROUNDS*MG_WARPS; q++)
+      { const unsigned v = S->wtot[q];
+#pragma unroll
+        for (int r = 0; r < ROUNDS; r++) if (q < r*MG_WARPS + wp) pre[r] += v;
+        total += v;
+      }
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) excl[r] += pre[r];
+  }
+  const bool fast = staged && total <= MG_DCAP;
+  if (fast)
+    {
+#pragma unroll
+      for (int r = 0; r < ROUNDS; r++)
+        { const unsigned d = lowi[r] | ((unsigned) (r*MG_THREADS + tid) << 11) | ((unsigned) (plen[r] - 12) << 20);
+          for (unsigned k = 0; k < cnt[r]; k++) S->desc[excl[r] + k] = d + k;
         }
     }
-  __syncthreads();
-  //  search, then ONE atomic per block reserves the output run of its eight tiles (a per-tile
-  //  atomic on the single counter serialises in L2: 1.2 M same-address atomics cost > 1.5 ms)
-  unsigned total = 0, sl = 0;
-  view_staged Vs; Vs.S = B; Vs.t2off = lo2; Vs.psoff = pA;
-  view_direct Vd; Vd.T2 = T2; Vd.pstart = pstart2;
-  if (nd > 0)
-    total = staged ? merge_search(Vs,S,nd,freq,sl,lane) : merge_search(Vd,S,nd,freq,sl,lane);
-  if (lane == 0) { B->wtot[wp] = total; B->wsum[wp] = sl; }
-  __syncthreads();
-  if (threadIdx.x == 0)
-    { unsigned long long t = 0, q = 0;
-      for (int k = 0; k < MG_WARPS; k++) { t += B->wtot[k]; q += B->wsum[k]; }
-      unsigned long long g = 0;
-      if (t) { g = atomicAdd(&counters[0],t); atomicAdd(&counters[1],q); }
-      B->gbase = g;
+  //  ONE atomic per CTA reserves its output run (per-warp atomics on the single counter serialise in L2)
+  if (tid == 0)
+    { unsigned long long q = 0, g = 0;
+      for (int k = 0; k < ROUNDS*MG_WARPS; k++) q += S->wsum[k];
+      if (total) { g = atomicAdd(&counters[0],(unsigned long long) total); atomicAdd(&counters[1],q); }
+      S->gbase = g;
     }
   __syncthreads();
   if (total == 0) return;
-  unsigned long long gbase = B->gbase;
-  for (int k = 0; k < wp; k++) gbase += B->wtot[k];
-  if (staged) merge_expand(Vs,S,nd,total,gbase,K,seeds,capacity,lane);
-  else        merge_expand(Vd,S,nd,total,gbase,K,seeds,capacity,lane);
+  const unsigned long long gbase = S->gbase;
+  if (fast)
+    { for (unsigned o = tid; o < total; o += MG_THREADS)
+        { const unsigned d = S->desc[o];
+          const u64 p2 = t2k[2*(d & 2047u)] & PAY, p1 = t1k[2*((d >> 11) & 511u)] & PAY;
+          if (gbase + o < capacity) st_rec(seeds + gbase + o,make_seed(12u + (d >> 20),p1,p2,K));
+        }
+      return;
+    }
+  //  slow path (unstaged tile or more seeds than descriptors): every entry writes its own seeds
+#pragma unroll
+  for (int r = 0; r < ROUNDS; r++)
+    { const unsigned j = r*MG_THREADS + tid;
+      if (cnt[r] == 0) continue;
+      const u64 p1 = t1k[2*j] & PAY;
+      for (unsigned k = 0; k < cnt[r]; k++)
+        { const u64 p2 = staged ? t2k[2*(lowi[r]+k)+1] : (T2[lowi[r]+k].lo & 0xffffffffffffull);
+          const unsigned long long o = gbase + excl[r] + k;
+          if (o < capacity) st_rec(seeds + o,make_seed((unsigned) plen[r],p1,p2,K));
+        }
+    }
+}
+
+//  Forward-strand view of a both-strand table (order kept): flags -> exclusive scan -> scatter.
+__global__ void fwd_flag_kernel(const rec128 *__restrict__ T, long long n, unsigned *__restrict__ flag)
+{ long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (unsigned) (((T[i].lo >> 47) & 1) ^ 1);
+}
+__global__ void fwd_scatter_kernel(const rec128 *__restrict__ T, long long n, const unsigned *__restrict__ pos,
+                                   rec128 *__restrict__ out)
+{ long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rec128 r = ld_rec(T + i);
+  if (((r.lo >> 47) & 1) == 0) st_rec(out + pos[i],r);
+}
+
+//  d_out: room for n records.  *h_nfwd = number of forward-strand entries written.
+extern "C" int fgb_forward_view_device(const void *d_T, long long n, void *d_out, long long *h_nfwd, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  *h_nfwd = 0;
+  if (n <= 0) return FGB_OK;
+  unsigned *d_flag = NULL; void *d_tmp = NULL; unsigned long long *d_total = NULL;
+  long long tmpb = fgb_dev_scan_tmp_bytes(n);
+  cudaError_t e;
+  if ((e = fgb_dmalloc((void **) &d_flag,sizeof(unsigned)*(n+1),st)) != cudaSuccess ||
+      (e = fgb_dmalloc(&d_tmp,tmpb,st)) != cudaSuccess ||
+      (e = fgb_dmalloc((void **) &d_total,8,st)) != cudaSuccess)
+    { fgb_dfree(d_flag,st); fgb_dfree(d_tmp,st); fgb_dfree(d_total,st); return FGB_ERR_CUDA; }
+  int nb = (int) ((n + 255) / 256);
+  fwd_flag_kernel<<<nb,256,0,st>>>((const rec128 *) d_T,n,d_flag);
+  int rc = fgb_dev_exclusive_scan_u32(d_flag,n,d_total,d_tmp,tmpb,st);
+  unsigned long long tot = 0;
+  if (!rc)
+    { fwd_scatter_kernel<<<nb,256,0,st>>>((const rec128 *) d_T,n,d_flag,(rec128 *) d_out);
+      fgb_count_launch(2);
+      if (cudaMemcpyAsync(&tot,d_total,8,cudaMemcpyDeviceToHost,st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess) rc = FGB_ERR_CUDA;
+    }
+  fgb_dfree(d_flag,st); fgb_dfree(d_tmp,st); fgb_dfree(d_total,st);
+  *h_nfwd = (long long) tot;
+  return rc;
 }
 
 /***********************************************************************************************
@@ -397,10 +442,35 @@ extern "C" int fgb_self_merge_device(const void *d_T, long long n, const unsigne
   return (h[0] > (unsigned long long) capacity) ? FGB_ERR_OVERFLOW : FGB_OK;
 }
 
-//  T1/T2: sorted device tables; pstart2: [2^24+1] lower-bound index of T2.  Appends seed
-//  records to d_seeds (capacity records).  d_counters: 2 x u64 on the device, zeroed here.
-//  On return *h_nseeds is the number of seeds FOUND; if it exceeds capacity the buffer
-//  content is incomplete and the caller must retry with a larger buffer (FGB_ERR_OVERFLOW).
+//  T1: sorted FORWARD-STRAND-ONLY device table; T2: sorted device table, pstart2: its [2^24+1]
+//  lower-bound index.  Appends seed records to d_seeds (capacity records).  d_counters: 2 x u64 on
+//  the device, zeroed here.  On return *h_nseeds is the number of seeds FOUND; if it exceeds
+//  capacity the buffer content is incomplete and the caller must retry with a larger buffer
+//  (FGB_ERR_OVERFLOW).
+
+template<int TILE>
+static int merge_launch(const rec128 *T1, unsigned n1, const rec128 *T2, const unsigned *pstart2, int freq,
+                        const seed_pack &K, rec128 *seeds, unsigned long long capacity,
+                        unsigned long long *counters, cudaStream_t st)
+{ const int smem = (int) sizeof(mg_stage<TILE>);
+  CUDA_TRY(cudaFuncSetAttribute(adaptamer_merge_kernel<TILE>,cudaFuncAttributeMaxDynamicSharedMemorySize,smem));
+  unsigned nb = (unsigned) (((unsigned long long) n1 + TILE - 1) / TILE);
+  uint4 *d_rng = NULL;
+  CUDA_TRY(fgb_dmalloc((void **) &d_rng,sizeof(uint4)*(size_t) nb,st));
+  cudaEvent_t ea, eb;
+  cudaEventCreate(&ea); cudaEventCreate(&eb);
+  cudaEventRecord(ea,st);
+  merge_ranges_kernel<<<(nb + 255)/256,256,0,st>>>(T1,n1,pstart2,(unsigned) TILE,nb,d_rng);
+  adaptamer_merge_kernel<TILE><<<nb,MG_THREADS,smem,st>>>(T1,n1,T2,pstart2,d_rng,freq,K,seeds,capacity,counters);
+  cudaEventRecord(eb,st);
+  cudaEventSynchronize(eb);
+  float ms = 0; cudaEventElapsedTime(&ms,ea,eb);
+  fgb_timing_add(3,ms);
+  fgb_count_launch(2);
+  cudaEventDestroy(ea); cudaEventDestroy(eb);
+  fgb_dfree(d_rng,st);
+  return FGB_OK;
+}
 
 extern "C" int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2, long long n2,
                                 const unsigned *d_pstart2, int freq,
@@ -422,40 +492,18 @@ extern "C" int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2
   K.amxpos = amxpos; K.bmxpos = bmxpos; K.maxdag = amxpos + bmxpos;
   if (K.s_cp + 1 > 64 || K.p_band >= 64 || K.p_band < 13) return FGB_ERR_LIMIT;
   if (n1 > 0)
-    { //  T2 denser than T1 (a shard of genome 1 against all of genome 2): smaller tiles keep the
-      //  block's T2 slice inside the staging buffer
-      int tile = MG_TILE;
-      if (n2 > 0 && n1 > 0)
-        { double ratio = (double) n2 / (double) n1;
-          if (ratio > 3.2) tile = 16; else if (ratio > 1.6) tile = 32;
-        }
-      unsigned nb = (unsigned) ((n1 + MG_WARPS*tile - 1) / (MG_WARPS*tile));
-      cudaEvent_t ea, eb;
-      cudaEventCreate(&ea); cudaEventCreate(&eb);
-      static bool attr_set = false;
-      const int smem = (int) (sizeof(blk_stage) + MG_WARPS*sizeof(warp_stage));
-      if (!attr_set)
-        { CUDA_TRY(cudaFuncSetAttribute(adaptamer_merge_kernel<64>,cudaFuncAttributeMaxDynamicSharedMemorySize,smem));
-          CUDA_TRY(cudaFuncSetAttribute(adaptamer_merge_kernel<32>,cudaFuncAttributeMaxDynamicSharedMemorySize,smem));
-          CUDA_TRY(cudaFuncSetAttribute(adaptamer_merge_kernel<16>,cudaFuncAttributeMaxDynamicSharedMemorySize,smem));
-          attr_set = true;
-        }
-      uint4 *d_rng = NULL;
-      CUDA_TRY(fgb_dmalloc((void **) &d_rng,sizeof(uint4)*(size_t) nb,st));
-      cudaEventRecord(ea,st);
-      merge_ranges_kernel<<<(nb + 255)/256,256,0,st>>>((const rec128 *) d_T1,(unsigned) n1,d_pstart2,
-                                                      (unsigned) (MG_WARPS*tile),nb,d_rng);
-#define MG_LAUNCH(T) adaptamer_merge_kernel<T><<<nb,MG_THREADS,smem,st>>>((const rec128 *) d_T1,(unsigned) n1, \
-                       (const rec128 *) d_T2,d_pstart2,d_rng,freq,K,(rec128 *) d_seeds,(unsigned long long) capacity,d_counters)
-      if (tile == 64) MG_LAUNCH(64); else if (tile == 32) MG_LAUNCH(32); else MG_LAUNCH(16);
-#undef MG_LAUNCH
-      cudaEventRecord(eb,st);
-      cudaEventSynchronize(eb);
-      float ms = 0; cudaEventElapsedTime(&ms,ea,eb);
-      fgb_timing_add(3,ms);
-      fgb_count_launch(2);
-      cudaEventDestroy(ea); cudaEventDestroy(eb);
-      fgb_dfree(d_rng,st);
+    { //  tile = T1 entries per CTA: the denser T2 is relative to T1 (a shard of genome 1 against
+      //  all of genome 2), the smaller the tile, so that the CTA's T2 slice fits the staging buffer
+      double ratio = (double) (n2 > 0 ? n2 : 1) / (double) n1;
+      int rc;
+#define MG_ARGS (const rec128 *) d_T1,(unsigned) n1,(const rec128 *) d_T2,d_pstart2,freq,K,(rec128 *) d_seeds, \
+                (unsigned long long) capacity,d_counters,st
+      if (ratio <= 2.5)       rc = merge_launch<512>(MG_ARGS);
+      else if (ratio <= 5.0)  rc = merge_launch<256>(MG_ARGS);
+      else if (ratio <= 10.0) rc = merge_launch<128>(MG_ARGS);
+      else                    rc = merge_launch<64>(MG_ARGS);
+#undef MG_ARGS
+      if (rc) return rc;
     }
   CUDA_TRY(cudaGetLastError());
   unsigned long long h[2];

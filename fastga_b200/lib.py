@@ -106,6 +106,15 @@ class DeviceGix:
         return cls(h)
 
     @classmethod
+    def build_forward(cls, dgenome, stream=None):
+        """forward-strand entries only (the adaptamer side of a merge)"""
+        L = load_library()
+        h = c_void_p()
+        L.fgb_gix_build_forward.argtypes = [c_void_p, C.POINTER(c_void_p), c_void_p]
+        _check(L.fgb_gix_build_forward(dgenome.h, C.byref(h), stream), "fgb_gix_build_forward")
+        return cls(h)
+
+    @classmethod
     def build_range(cls, dgenome, plo, phi, stream=None):
         L = load_library()
         h = c_void_p()
@@ -409,7 +418,8 @@ def overlaps_from_buffer(buf):
 class RunStats(C.Structure):
     _fields_ = [(n, c_ll) for n in ("nkmers1", "nkmers2", "nseeds", "sumlen", "nhits", "nla", "nwaves",
                                     "ncells", "nraw", "h2d_bytes", "d2h_bytes", "nseg", "nwork", "warp_cycles",
-                                    "wave_cycles", "extract_cycles", "us_gix", "us_seeds", "us_extend", "us_filter")]
+                                    "wave_cycles", "extract_cycles", "us_gix", "us_seeds", "us_extend", "us_filter",
+                                    "nkmers1_fwd")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

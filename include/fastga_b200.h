@@ -35,7 +35,8 @@ typedef struct fgb_alns     fgb_alns;      /* final alignments in .1aln order, h
 typedef struct
 { long long nkmers1, nkmers2, nseeds, sumlen, nhits, nla, nwaves, ncells, nraw, h2d_bytes, d2h_bytes,
             nseg, nwork, warp_cycles, wave_cycles, extract_cycles,
-            us_gix, us_seeds, us_extend, us_filter;      /* host wall microseconds per phase */
+            us_gix, us_seeds, us_extend, us_filter,      /* host wall microseconds per phase */
+            nkmers1_fwd;                                 /* forward-strand entries of table 1 (what the merge reads) */
 } fgb_run_stats;
 
 typedef struct
@@ -92,6 +93,9 @@ long long fgb_genome_words(const fgb_genome *g);
  * (strand|contig rank, post).  msd_sort leaves that order to its unstable in-place permutation
  * (MSDsort.c:211-360); no consumer depends on it (seeds are fully re-sorted, FastGA.c:4320). */
 int  fgb_gix_build(const fgb_genome *g, fgb_gix **out, void *stream);
+/* forward-strand entries only: enough for the genome that supplies the adaptamers (its reverse
+   entries never seed, FastGA.c:921-928); fgb_seeds_find compacts a both-strand table itself */
+int  fgb_gix_build_forward(const fgb_genome *g, fgb_gix **out, void *stream);
 /* one rank's share (12-base prefix in [plo,phi)) of a cooperatively built table, and the pieces
    to assemble the shares gathered over NCCL (fastga_b200/shard.py) */
 int  fgb_gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi, fgb_gix **out, void *stream);

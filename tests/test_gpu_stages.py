@@ -136,6 +136,50 @@ def test_merge_against_a_denser_second_table(copies):
     assert np.array_equal(ds.download(), want)
 
 
+def test_forward_only_table_is_the_forward_subset_and_merges_identically(small_pair):
+    """the fused path builds the adaptamer side forward-strand-only (fgb_gix_build_forward): the table
+    must be exactly the forward entries of the both-strand table, in order, and seed identically"""
+    gA, gB = small_pair
+    dA, dB = lib.DeviceGenome(gA), lib.DeviceGenome(gB)
+    xA, xF, xB = lib.DeviceGix.build(dA), lib.DeviceGix.build_forward(dA), lib.DeviceGix.build(dB)
+    tA, pA, _ = xA.download()
+    tF, pF, _ = xF.download()
+    fwd = ((tA[:, 0] >> np.uint64(47)) & np.uint64(1)) == 0
+    assert np.array_equal(tF, tA[fwd])
+    pre = (tF[:, 1] >> np.uint64(40)).astype(np.int64)
+    assert np.array_equal(pF.astype(np.int64), np.searchsorted(pre, np.arange((1 << 24) + 1)))
+    amx, bmx = int(gA.clen.max()), int(gB.clen.max())
+    s1 = lib.DeviceSeeds.find(xA, xB, amx, bmx, 10)
+    s2 = lib.DeviceSeeds.find(xF, xB, amx, bmx, 10)
+    assert s1.n == s2.n and s1.sumlen == s2.sumlen
+    assert np.array_equal(s1.download(), s2.download())
+
+
+def test_merge_with_repeats_takes_the_unstaged_and_the_crowded_paths():
+    """long exact repeats: (1) a T1 tile whose T2 slice exceeds the staging buffer (searched straight
+    from HBM), (2) a tile with more seeds than descriptors at a high -f (entry-wise write-out);
+    both must equal the oracle's state machine"""
+    rng = np.random.default_rng(123)
+    unit = rng.integers(0, 4, 997, dtype=np.uint8)
+    a = np.concatenate([rng.integers(0, 4, 100_000, dtype=np.uint8), np.tile(unit, 100),
+                        np.zeros(60, dtype=np.uint8), rng.integers(0, 4, 50_000, dtype=np.uint8)])
+    b = np.concatenate([rng.integers(0, 4, 50_000, dtype=np.uint8), np.tile(unit, 40),
+                        np.zeros(3000, dtype=np.uint8),
+                        synth.diverged_copy(rng, a[:100_000], 0.04, sv_every=50_000)])
+    gA, gB = formats.genome_from_arrays([a]), formats.genome_from_arrays([b])
+    dA, dB = lib.DeviceGenome(gA), lib.DeviceGenome(gB)
+    xA, xB = lib.DeviceGix.build(dA), lib.DeviceGix.build(dB)
+    amx, bmx = int(gA.clen.max()), int(gB.clen.max())
+    tA, _, _ = xA.download(False)
+    tB, pB, _ = xB.download()
+    for freq in (10, 64, 200):
+        ds = lib.DeviceSeeds.find(xA, xB, amx, bmx, freq)
+        seeds, sumlen = ol.merge(tA, tB, pB, freq)
+        assert ds.n == len(seeds) and ds.sumlen == sumlen, freq
+        want = ol.seed_records(seeds, ds.layout + (amx, bmx), sort=True)
+        assert np.array_equal(ds.download(), want), freq
+
+
 def _canon(recs, pool, aread=None, bread=None, comp=None):
     out = []
     for i, r in enumerate(recs):
