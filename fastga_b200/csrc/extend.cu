@@ -35,7 +35,7 @@ typedef unsigned long long u64;
 #define EX_WARPS     8
 #endif
 #ifndef EX_MINBLK
-#define EX_MINBLK    1
+#define EX_MINBLK    2
 #endif
 #define EX_W         256                 // diagonals of wave state per warp (shared memory)
 #define FULL         0xffffffffu
@@ -85,6 +85,7 @@ struct Ctx
   int tspace, path_ave; const short *score, *table; const short *ttab; int sc15;
   u64 nwaves, ncells, cyc_wave, cyc_extract, pwaves, npairs, fwait, ftot, bwait, btot;
   struct PairBox *box;                   // front/back warp pair mailbox (NULL: this warp runs waves alone)
+  unsigned box_off;                      //   and its offset inside the dynamic shared memory
 };
 
 //  Front/back pairing of a wave pass.  The recurrence that makes a pass serial is only the
@@ -138,6 +139,19 @@ static __device__ __forceinline__ Peb ldpeb(const Peb *p)        // pebbles may 
 }
 
 #define EX_WBIG      8192                // diagonals of wave state per warp in the wide-band retry kernel (HBM)
+
+//  The kernel's dynamic shared memory.  Device functions address the pair mailboxes as offsets from
+//  THIS symbol, so the compiler knows the state space (LDS/STS instead of generic loads).
+extern __shared__ __align__(16) unsigned char ex_smem[];
+
+//  flag hand-off between the two warps of a pair: release store (fence + STS) / acquire load (LDS)
+static __device__ __forceinline__ void st_release_smem(volatile int *p, int v)
+{ asm volatile("st.release.cta.shared.b32 [%0], %1;" :: "r"(smem_u32((const void *) p)), "r"(v) : "memory"); }
+static __device__ __forceinline__ int ld_acquire_smem(const volatile int *p)
+{ int v;
+  asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32((const void *) p)) : "memory");
+  return v;
+}
 #define IX(k) ((k) & (W-1))
 
 static __device__ __forceinline__ u64 get_bits(const rec128 &r, int pos, int n)
@@ -154,25 +168,25 @@ static __device__ __forceinline__ u64 get_bits(const rec128 &r, int pos, int n)
 
 static __device__ __forceinline__ u64 win(const unsigned *__restrict__ w, int boff)
 { int q = boff >> 4, s = (boff & 15) << 1;
-  unsigned w0 = w[q], w1 = w[q+1], w2 = w[q+2];
+  unsigned w0 = __ldg(w+q), w1 = __ldg(w+q+1), w2 = __ldg(w+q+2);      // staged contigs are read-only: LDG through L1
   return (u64) __funnelshift_r(w0,w1,s) | ((u64) __funnelshift_r(w1,w2,s) << 32);
 }
 
 static __device__ __forceinline__ int base_at(const unsigned *__restrict__ w, int len, int i)
 { if (i < 0 || i >= len) return 4;
-  return (int) (w[i >> 4] >> ((i & 15) << 1)) & 3;
+  return (int) (__ldg(w + (i >> 4)) >> ((i & 15) << 1)) & 3;
 }
 
-template<int S> static __device__ __forceinline__ int a_at(const Ctx &c, int xn)
+template<int S, class CX> static __device__ __forceinline__ int a_at(const CX &c, int xn)
 { return base_at(c.A,c.alen,(S > 0) ? xn : -xn-1); }
-template<int S> static __device__ __forceinline__ int b_at(const Ctx &c, int yn)
+template<int S, class CX> static __device__ __forceinline__ int b_at(const CX &c, int yn)
 { return base_at(c.B,c.blen,(S > 0) ? yn : -yn-1); }
 
 //  slide along diagonal kk from normalised xn; returns #matches, flag 0 mismatch / 1 B end / 2 A end
 //    (B is tested first, align.c:683-697)
 
-template<int S>
-static __device__ __forceinline__ int snake(const Ctx &c, int xn, int kk, int &flag)
+template<int S, class CX>
+static __device__ __forceinline__ int snake(const CX &c, int xn, int kk, int &flag)
 { int yn = xn - kk, t = 0, tmax;
   if (S > 0)
     { const int x = xn, y = yn;
@@ -204,11 +218,17 @@ static __device__ __forceinline__ int snake(const Ctx &c, int xn, int kk, int &f
 }
 
 //  TABLE[x] / SCORE[x] of align.c:207-220 for a 15-bit column pattern x.  TABLE (64 KB of int16)
-//  is staged in shared memory once per block; SCORE[x] = popc(x)*1000 - 15*dscore needs no table.
+//  stays in HBM and is read through L1 (the patterns met in practice are almost all ones: a few
+//  hundred hot rows), which leaves the shared memory for a second CTA per SM;
+//  SCORE[x] = popc(x)*1000 - 15*dscore needs no table.
 
-static __device__ __forceinline__ bool trim_ok(const Ctx &c, u64 b)
+struct SeqV { const unsigned *A, *B; int alen, blen; };       // the two contigs of a pass, by value (registers)
+struct TrimV { const short *ttab; int sc15; };
+
+template<class CX>
+static __device__ __forceinline__ bool trim_ok(const CX &c, u64 b)
 { int lo15 = (int) (b & TRIM_MASK), hi15 = (int) ((b >> TRIM_LEN) & TRIM_MASK);
-  int tl = c.ttab[lo15], th = c.ttab[hi15];
+  int tl = __ldg(c.ttab + lo15), th = __ldg(c.ttab + hi15);       // 64 KB table in HBM, its hot rows live in L1
   int sl = __popc(lo15)*1000 - c.sc15;
   return tl >= 0 && th + sl >= 0;                        // TABLE[lo] >= 0 && TABLE[hi] + SCORE[lo] >= 0
 }
@@ -253,8 +273,10 @@ static __device__ __forceinline__ void back_results(PairBox *bx, int status, int
 }
 
 template<int s>
-static __device__ void wave_back(const Ctx &c, PairBox *bx)
-{ const int lane = threadIdx.x & 31;
+static __device__ __noinline__ void wave_back(const unsigned box_off, const short *__restrict__ ttab, const int sc15)
+{ PairBox *const bx = reinterpret_cast<PairBox *>(ex_smem + box_off);
+  const TrimV c = { ttab, sc15 };
+  const int lane = threadIdx.x & 31;
   const unsigned lt = lanemask_lt();
   const int FRESH = (s > 0) ? -1 : -INT_MAX;
   const int lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;
@@ -277,11 +299,10 @@ static __device__ void wave_back(const Ctx &c, PairBox *bx)
         { int spin = 0;
           long long w0 = DIAG_CLOCK();
           if (EX_DIAG && lane == 0) { bx->r_bwait = bwait; bx->r_btot = w0 - bt0; }
-          while ((head_seen = bx->head) < d)
+          while ((head_seen = ld_acquire_smem(&bx->head)) < d)
             if (++spin > SPIN_LIMIT)
               { back_results(bx,ST_STAGE,lasta,trima,trimx,trimd,trimha,avail,dif0+d-1,ncell,1); return; }
           bwait += DIAG_CLOCK() - w0;
-          __threadfence_block();
         }
       const RingEnt *e = &bx->ring[d & (EX_RING-1)];
       const int4 hd = *(const int4 *) e;                       // cmd, top, lowk, mx
@@ -376,7 +397,7 @@ static __device__ void wave_back(const Ctx &c, PairBox *bx)
 }
 
 template<int s, int W>
-static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, int maxp,
+static __device__ __noinline__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, int maxp,
                            const int aoff, int &endx, int &endy, int &diffs, int &trimha_out)
 { const int lane = threadIdx.x & 31;
   const unsigned lt = lanemask_lt();
@@ -468,7 +489,8 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
     {
       //  ---- front/back pairing (see PairBox): this warp keeps only V and the band ----
       if (EX_PAIR && pair_ok && hghk >= lowk && hghk - lowk <= 24)
-        { PairBox *bx = c.box;
+        { PairBox *const bx = reinterpret_cast<PairBox *>(ex_smem + c.box_off);
+          const SeqV q = { c.A, c.B, c.alen, c.blen };
           if (inreg)                                   // the band of the last wave goes to the arrays
             { const int kk = hghk - ((lane - ((-hghk) & 31)) & 31);
               if (kk >= lowk)
@@ -483,8 +505,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
               bx->cells = c.cells; bx->V = c.V; bx->HA = c.HA; bx->HM = c.HM; bx->NA = c.NA; bx->T = c.T;
               bx->head = 0; bx->tail = 0; bx->stop = 0;
               bx->cmd = (s > 0) ? 1 : 2;
-              __threadfence_block();
-              bx->seq = bx->seq + 1;
+              st_release_smem(&bx->seq,bx->seq + 1);
             }
           __syncwarp();
           { const int kk = hghk - ((lane - ((-hghk) & 31)) & 31);
@@ -507,7 +528,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
                 { int vp = __shfl_sync(FULL,rV,lane_up), vm = __shfl_sync(FULL,rV,lane_dn);
                   cc = max(max(vp,vm)+1,rV+2);
                   xn = (cc + kk) >> 1;
-                  if (act) xn += snake<s>(c,xn,kk,flag);
+                  if (act) xn += snake<s>(q,xn,kk,flag);
                   cc = 2*xn - kk;
                   mx = __reduce_max_sync(FULL,act ? cc : INT_MIN);
                   if (mx <= besta) bail = true;
@@ -521,7 +542,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
                       int acl = INT_MAX, bcl = -INT_MAX;
                       if (hb) bcl = top - (__ffs(hb)-1);
                       if (hq) acl = top - (31 - __clz(hq));
-                      nmore = (b_at<s>(c,mx-bx_) != 4 && a_at<s>(c,bx_) != 4);
+                      nmore = (b_at<s>(q,mx-bx_) != 4 && a_at<s>(q,bx_) != 4);
                       if (nhgh >= acl) nhgh = acl-1;
                       if (nlow <= bcl) nlow = bcl+1;
                     }
@@ -537,8 +558,7 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
                   __syncwarp();
                   if (lane == 0)
                     { bx->ring[(d+1) & (EX_RING-1)].cmd = 3;
-                      __threadfence_block();
-                      bx->head = d+1;
+                      st_release_smem(&bx->head,d+1);
                     }
                   break;
                 }
@@ -559,16 +579,15 @@ static __device__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, i
                 }
               if (!nmore || (d & 1) == 0)                        // publish every other wave
                 { __syncwarp();
-                  if (lane == 0) { __threadfence_block(); bx->head = d; }
+                  if (lane == 0) st_release_smem(&bx->head,d);
                 }
               if (!nmore || ((d & 7) == 0 && bx->stop != 0)) break;
             }
           { int spin = 0; long long w0 = DIAG_CLOCK();
-            while ((stp = bx->stop) == 0) if (++spin > SPIN_LIMIT) { stp = 1; break; }
+            while ((stp = ld_acquire_smem(&bx->stop)) == 0) if (++spin > SPIN_LIMIT) { stp = 1; break; }
             fwait += DIAG_CLOCK() - w0;
             c.fwait += (u64) fwait; c.ftot += (u64) (DIAG_CLOCK() - ft0);
           }
-          __threadfence_block();
           const int bst = bx->status;
           lasta = bx->r_lasta; trima = bx->r_trima; trimx = bx->r_trimx; trimd = bx->r_trimd; trimha = bx->r_trimha;
           if (EX_DIAG) { c.bwait += (u64) bx->r_bwait; c.btot += (u64) bx->r_btot; }
@@ -1557,7 +1576,7 @@ __global__ void prefilter_kernel(ext_params P, unsigned *__restrict__ work_long,
 template<int W>
 __global__ void __launch_bounds__(EX_WARPS*32,EX_MINBLK)
 extend_kernel(ext_params P)
-{ extern __shared__ __align__(16) unsigned char smem[];
+{ unsigned char *const smem = ex_smem;
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const long long gw = (long long) blockIdx.x * EX_WARPS + wp;
   const size_t per_warp = (W == EX_W) ? STATE_BYTES : BIG_SMEM_PER_WARP;
@@ -1570,29 +1589,25 @@ extend_kernel(ext_params P)
   c.carry = c.NA + W;
   rec128 *stagebuf = (W == EX_W) ? (rec128 *) (sb + WSTATE_BYTES(EX_W))
                                  : (rec128 *) (smem + (size_t) wp * BIG_SMEM_PER_WARP);
-  { short *tt = (short *) (smem + (size_t) EX_WARPS * per_warp);
-    const int4 *src = (const int4 *) P.table;               // 64 KB, 16-byte aligned (fgb_dmalloc)
-    for (int u = threadIdx.x; u < TT_BYTES/16; u += blockDim.x) ((int4 *) tt)[u] = src[u];
-    c.ttab = tt; c.sc15 = TRIM_LEN * P.dscore;
-    c.box = NULL;
-    if (EX_PAIR)
-      { c.box = (PairBox *) (smem + (size_t) EX_WARPS * per_warp + TT_BYTES) + (wp >> 1);
-        if ((wp & 1) == 0 && lane == 0) { c.box->seq = 0; c.box->cmd = 0; c.box->stop = 0; }
-      }
-    __syncthreads();
-  }
+  c.ttab = P.table; c.sc15 = TRIM_LEN * P.dscore;
+  c.box = NULL; c.box_off = 0;
+  if (EX_PAIR)
+    { c.box_off = (unsigned) ((size_t) EX_WARPS * per_warp + (size_t) (wp >> 1) * sizeof(PairBox));
+      c.box = (PairBox *) (smem + c.box_off);
+      if ((wp & 1) == 0 && lane == 0) { c.box->seq = 0; c.box->cmd = 0; c.box->stop = 0; }
+    }
+  __syncthreads();
   if (EX_PAIR && (wp & 1))
     { //  back warp of pair wp/2: serves the passes its front warp (wp-1) starts
       PairBox *bx = c.box;
       int myseq = 0;
       while (true)
         { int sq;
-          while ((sq = bx->seq) == myseq) __nanosleep(200);
+          while ((sq = ld_acquire_smem(&bx->seq)) == myseq) __nanosleep(100);
           myseq = sq;
-          __threadfence_block();
           int cm = bx->cmd;
           if (cm == 9) break;
-          if (cm == 1) wave_back<1>(c,bx); else wave_back<-1>(c,bx);
+          if (cm == 1) wave_back<1>(c.box_off,c.ttab,c.sc15); else wave_back<-1>(c.box_off,c.ttab,c.sc15);
           __syncwarp();
         }
       return;
@@ -1627,8 +1642,7 @@ extend_kernel(ext_params P)
     }
   if (EX_PAIR && lane == 0)
     { c.box->cmd = 9;                              // release the back warp
-      __threadfence_block();
-      c.box->seq = c.box->seq + 1;
+      st_release_smem(&c.box->seq,c.box->seq + 1);
     }
   if (lane == 0)
     { atomicAdd(&P.counters[0],nhits);
@@ -1805,8 +1819,8 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
     { int dev = 0, nsm = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&nsm,cudaDevAttrMultiProcessorCount,dev);
-      size_t smem = (size_t) EX_WARPS * STATE_BYTES + TT_BYTES + BOX_BYTES;
-      size_t smem_big = (size_t) EX_WARPS * BIG_SMEM_PER_WARP + TT_BYTES + BOX_BYTES;
+      size_t smem = (size_t) EX_WARPS * STATE_BYTES + BOX_BYTES;
+      size_t smem_big = (size_t) EX_WARPS * BIG_SMEM_PER_WARP + BOX_BYTES;
       CUDA_TRY(cudaFuncSetAttribute(extend_kernel<EX_W>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem));
       CUDA_TRY(cudaFuncSetAttribute(extend_kernel<EX_WBIG>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem_big));
       int bps = 0;

@@ -1,7 +1,8 @@
 // Host side of the path after the kernels: the redundancy filter of align_contigs and the final
 // (aread, abpos, bread, comp) ordering.  Stays host C++ on purpose ("stays host C; must
 // be bit-compatible"): it is <1 % of the work, is driven by libc qsort's tie order, and works on
-// the few hundred thousand records the device returns.
+// the few hundred thousand records the device returns.  A host that prefers the reference's own
+// filter takes the raw, discovery-ordered records of fgb_extend instead.
 //
 // Replaces (reference file:line):
 //   entwine                         FastGA.c:2818-2941
@@ -22,161 +23,129 @@ struct fgb_overlaps;
 extern "C" long long fgb_overlaps_bytes(const fgb_overlaps *o);
 extern "C" const unsigned char *fgb_overlaps_data(const fgb_overlaps *o);
 
-struct HPath { int abpos, bbpos, aepos, bepos, diffs, tlen; };
+//  The rules below are the reference's (their result is part of the .1aln contract, libc qsort tie
+//  order and the `diffs < aepos` comparison of FastGA.c:3456 included); the implementation is this
+//  repo's own: paths are compared by sampling both on the common trace-point grid and reducing the
+//  separations, the group lives in one array in sweep order, and the two sweeps share one driver.
 
-struct HOvl
-{ HPath p;
-  unsigned flags;                 // ELIMINATED / OWNS_MEMORY
-  const unsigned char *trace;     // into the record buffer, or an owned fused trace
-  unsigned char *owned;
+namespace {
+
+struct Aln                                   // one local alignment of a (A-contig, B-contig, strand) group
+{ int ab, bb, ae, be, diffs, tlen;
+  const unsigned char *trace;                // (diffs, B-advance) byte pairs, one per trace interval
+  std::vector<unsigned char> spliced;        // backing store once two alignments have been fused
+  bool dead;
+  int bstep(int i) const { return trace[2*i+1]; }
 };
 
-#define ELIMINATED  0x4
-#define OWNS_MEMORY 0x8
+int by_abpos(const void *l, const void *r)   // the comparator of FastGA.c:2962 on the same libc qsort
+{ return (*(Aln * const *) l)->ab - (*(Aln * const *) r)->ab; }
 
-static int ALIGN_SORT(const void *l, const void *r)          // FastGA.c:2962-2967
-{ const HOvl *ol = *((HOvl * const *) l), *orr = *((HOvl * const *) r);
-  return (ol->p.abpos - orr->p.abpos);
+struct Braid { bool apart; int meet; };      // apart: the paths never touch; meet: last shared trace point, -1 if none
+
+//  J starts at or before K on A.  Both paths are sampled at K's start, at every trace point they
+//  share, and at the end of the shorter one (linear interpolation inside a trace interval with the
+//  reference's integer arithmetic, FastGA.c:2818-2941); `apart` iff every separation has one sign.
+Braid braid(const Aln &J, const Aln &K)
+{ const int g0 = (K.ab / TSPACE) * TSPACE;                 // trace point at or before K's start
+  const int skip = K.ab / TSPACE - J.ab / TSPACE;          // whole intervals of J before it
+  int yj = J.bb;
+  for (int u = 0; u < skip; u++) yj += J.bstep(u);
+  const int from = skip ? g0 : J.ab, span = skip ? TSPACE : g0 + TSPACE - J.ab;
+  int sep = K.bb - (yj + J.bstep(skip) * (K.ab - from) / span);
+  int lo = sep, hi = sep, meet = -1, yk = K.bb, t = 0;
+  const int end = J.ae < K.ae ? J.ae : K.ae;
+  for (int g = g0 + TSPACE; g < end; g += TSPACE, t++)
+    { yj += J.bstep(skip + t);
+      yk += K.bstep(t);
+      sep = yk - yj;
+      if (sep < lo) lo = sep;
+      if (sep > hi) hi = sep;
+      if (sep == 0) meet = g;
+    }
+  const int rest = end - (g0 + t*TSPACE);                  // into the last, partial interval
+  if (end == J.ae) { yj = J.be; yk += K.bstep(t) * rest / TSPACE; }
+  else             { yk = K.be; yj += J.bstep(skip + t) * rest / TSPACE; }
+  sep = yk - yj;
+  if (sep < lo) lo = sep;
+  if (sep > hi) hi = sep;
+  Braid r; r.apart = (lo > 0 || hi < 0); r.meet = meet;
+  return r;
 }
 
-//  Walks two trace-point paths over their common A-interval; returns the signed minimum
-//  B-separation (0 if they cross) and the last trace point at which they coincide.
+inline int intervals_to(const Aln &p, int apoint)          // trace intervals of p covering [p.ab, apoint]
+{ return (apoint - p.ab + TSPACE - 1) / TSPACE; }
 
-static int entwine(const HPath *jp, const unsigned char *jt, const HPath *kp, const unsigned char *kt,
-                   int *where)
-{ int ac, b2, y2, yp, ae, i, j, k, mn;
-
-  *where = -1;
-  y2 = jp->bbpos;
-  b2 = kp->bbpos;
-  j  = jp->abpos/TSPACE;
-  k  = kp->abpos/TSPACE;
-  ac = k*TSPACE;
-  j = 1 + 2*(k-j);
-  k = 1;
-  for (i = 1; i < j; i += 2)
-    y2 += jt[i];
-  if (j == 1)
-    yp = y2 + (jt[j] * (kp->abpos - jp->abpos)) / (ac+TSPACE - jp->abpos);
-  else
-    yp = y2 + (jt[j] * (kp->abpos - ac)) / TSPACE;
-  mn = b2-yp;
-
-  ae = jp->aepos;
-  if (ae > kp->aepos) ae = kp->aepos;
-
-  for (ac += TSPACE; ac < ae; ac += TSPACE)
-    { y2 += jt[j];
-      b2 += kt[k];
-      j += 2;
-      k += 2;
-      i = b2-y2;
-      if (mn < 0 && mn < i)      mn = (i >= 0) ? 0 : i;
-      else if (mn > 0 && mn > i) mn = (i <= 0) ? 0 : i;
-      if (i == 0) *where = ac;
-    }
-
-  ac -= TSPACE;
-  if (ae == jp->aepos)
-    { y2 = jp->bepos;
-      if (kp->aepos >= ac) b2 += (kt[k] * (ae - ac)) / TSPACE;
-      else                 b2 += (kt[k] * (ae - ac)) / (kp->aepos - ac);
-    }
-  else
-    { b2 = kp->bepos;
-      if (jp->aepos >= ac) y2 += (jt[j] * (ae - ac)) / TSPACE;
-      else                 y2 += (jt[j] * (ae - ac)) / (jp->aepos - ac);
-    }
-  i = b2-y2;
-  if (mn < 0 && mn < i)      mn = (i >= 0) ? 0 : i;
-  else if (mn > 0 && mn > i) mn = (i <= 0) ? 0 : i;
-  return mn;
+//  o keeps its head up to the shared trace point and continues as w (FastGA.c:3524-3569)
+void splice(Aln &o, const Aln &w, int at)
+{ const int ocut = 2*intervals_to(o,at), wcut = 2*intervals_to(w,at);
+  std::vector<unsigned char> t;
+  t.reserve(ocut + (w.tlen > wcut ? w.tlen - wcut : 0));
+  t.insert(t.end(),o.trace,o.trace + ocut);
+  if (w.tlen > wcut) t.insert(t.end(),w.trace + wcut,w.trace + w.tlen);
+  int d = 0;
+  for (size_t q = 0; q < t.size(); q += 2) d += t[q];
+  o.spliced.swap(t);
+  o.trace = o.spliced.data();
+  o.tlen  = (int) o.spliced.size();
+  o.diffs = d;
+  o.ae = w.ae; o.be = w.be;
 }
 
-static void filter_group(std::vector<HOvl> &g)
-{ int nlas = (int) g.size(), j, k, where, dist;
-  std::vector<HOvl *> perm(nlas);
-  for (j = 0; j < nlas; j++) perm[j] = &g[j];
-  qsort(perm.data(),nlas,sizeof(HOvl *),ALIGN_SORT);          // libc, as FastGA.c:3435
+inline bool inside(const Aln &in, const Aln &out, bool also_start)   // box test with BOX_FUZZ slack (:3571-3587)
+{ return in.ae <= out.ae + BOX_FUZZ && in.bb >= out.bb - BOX_FUZZ && in.be <= out.be + BOX_FUZZ &&
+         (!also_start || in.ab >= out.ab - BOX_FUZZ);
+}
 
-  for (j = nlas-1; j >= 0; j--)                               // pass 1 (:3441-3491)
-    { HOvl *o = perm[j]; HPath *op = &o->p;
-      for (k = j+1; k < nlas; k++)
-        { HOvl *w = perm[k]; HPath *wp = &w->p;
-          if (op->aepos <= wp->abpos) break;
-          if (w->flags & ELIMINATED) continue;
-          if (op->abpos == wp->abpos && op->bbpos == wp->bbpos)
-            { if (op->aepos == wp->aepos && op->bepos == wp->bepos)
-                { if (op->diffs < wp->aepos) { w->flags |= ELIMINATED; continue; }   // sic (:3456)
-                  else                       { o->flags |= ELIMINATED; break; }
-                }
-              else
-                { if (op->aepos > wp->aepos) { w->flags |= ELIMINATED; continue; }
-                  else                       { o->flags |= ELIMINATED; break; }
-                }
-            }
-          else if (op->aepos == wp->aepos && op->bepos == wp->bepos)
-            { if (op->abpos < wp->abpos) { w->flags |= ELIMINATED; continue; }
-              else                       { o->flags |= ELIMINATED; break; }
-            }
+//  Visits, for every alignment o from the last to the first of the sweep order, the later
+//  alignments w whose A-interval starts before o (currently) ends.  rule(o,w) returns false to
+//  leave o's row early.
+template<class Rule> void sweep(std::vector<Aln *> &row, bool live_o_only, Rule rule)
+{ const int n = (int) row.size();
+  for (int j = n-1; j >= 0; j--)
+    { Aln &o = *row[j];
+      if (live_o_only && o.dead) continue;
+      for (int k = j+1; k < n && o.ae > row[k]->ab; k++)
+        if (!row[k]->dead && !rule(o,*row[k])) break;
+    }
+}
+
+void filter_group(std::vector<Aln> &g)
+{ std::vector<Aln *> row(g.size());
+  for (size_t i = 0; i < g.size(); i++) row[i] = &g[i];
+  qsort(row.data(),row.size(),sizeof(Aln *),by_abpos);     // libc: its tie order is part of the result (:3435)
+
+  //  sweep 1: two alignments with the same start point, or the same end point, are one finding
+  sweep(row,false,[](Aln &o, Aln &w)
+    { const bool start = (o.ab == w.ab && o.bb == w.bb), stop = (o.ae == w.ae && o.be == w.be);
+      if (!start && !stop) return true;
+      bool keep_o;
+      if (start && stop) keep_o = o.diffs < w.ae;          // sic: diffs against aepos (FastGA.c:3456)
+      else if (start)    keep_o = o.ae > w.ae;             // the longer one survives
+      else               keep_o = o.ab < w.ab;
+      (keep_o ? w : o).dead = true;
+      return keep_o;                                       // a dead o stops looking
+    });
+
+  //  sweep 2: overlapping boxes -- fuse at a shared trace point, else drop a contained box
+  sweep(row,true,[](Aln &o, Aln &w)
+    { if (o.be <= w.bb || o.bb >= w.be) return true;       // B-intervals apart
+      const Braid x = braid(o,w);
+      if (x.meet >= 0) { splice(o,w,x.meet); w.dead = true; }
+      else if (x.apart)
+        { if ((o.ae - o.ab) + BOX_FUZZ >= w.ae - w.ab) { if (inside(w,o,false)) w.dead = true; }
+          else if (inside(o,w,true)) o.dead = true;        // o, though dead, finishes its row (:3583)
         }
-    }
+      return true;
+    });
 
-  for (j = nlas-1; j >= 0; j--)                               // pass 2 (:3493-3592)
-    { HOvl *o = perm[j]; HPath *op = &o->p;
-      if (o->flags & ELIMINATED) continue;
-      for (k = j+1; k < nlas; k++)
-        { HOvl *w = perm[k]; HPath *wp = &w->p;
-          if (op->aepos <= wp->abpos) break;
-          if (w->flags & ELIMINATED) continue;
-          if (op->bepos <= wp->bbpos || op->bbpos >= wp->bepos) continue;
-
-          const unsigned char *otrace = o->trace, *wtrace = w->trace;
-          dist = entwine(op,otrace,wp,wtrace,&where);
-          if (where != -1)                                    // fuse o[..where] + w[where..]
-            { int ocut = 2 * (((where-op->abpos)-1)/TSPACE+1);
-              int wcut = 2 * (((where-wp->abpos)-1)/TSPACE+1);
-              int ntlen = ocut + (wp->tlen-wcut), d = 0, h = 0, q;
-              unsigned char *nt = (unsigned char *) malloc(ntlen > 0 ? ntlen : 1);
-              for (q = 0; q < ocut; q += 2)
-                { d += (nt[h] = otrace[q]); nt[h+1] = otrace[q+1]; h += 2; }
-              for (q = wcut; q < wp->tlen; q += 2)
-                { d += (nt[h] = wtrace[q]); nt[h+1] = wtrace[q+1]; h += 2; }
-              if (o->flags & OWNS_MEMORY) free(o->owned);
-              if (w->flags & OWNS_MEMORY) { free(w->owned); w->owned = NULL; }
-              op->tlen  = ntlen;
-              op->diffs = d;
-              op->aepos = wp->aepos;
-              op->bepos = wp->bepos;
-              w->flags |= ELIMINATED;
-              o->flags |= OWNS_MEMORY;
-              o->owned = nt; o->trace = nt;
-              continue;
-            }
-          if (dist != 0)                                      // BOX_ELIM (:3571-3588)
-            { if ((op->aepos - op->abpos) + BOX_FUZZ >= wp->aepos - wp->abpos)
-                { if (wp->aepos <= op->aepos+BOX_FUZZ && wp->bbpos >= op->bbpos-BOX_FUZZ &&
-                      wp->bepos <= op->bepos+BOX_FUZZ)
-                    { w->flags |= ELIMINATED; continue; }
-                }
-              else
-                { if (op->aepos <= wp->aepos+BOX_FUZZ && op->bbpos >= wp->bbpos-BOX_FUZZ &&
-                      op->bepos <= wp->bepos+BOX_FUZZ && op->abpos >= wp->abpos-BOX_FUZZ)
-                    { o->flags |= ELIMINATED; continue; }
-                }
-            }
-        }
-    }
-
-  //  survivors in perm (abpos) order, as written to the per-thread file (:3649-3680)
-  std::vector<HOvl> out;
-  for (j = 0; j < nlas; j++)
-    if (!(perm[j]->flags & ELIMINATED))
-      out.push_back(*perm[j]);
-    else if (perm[j]->flags & OWNS_MEMORY)
-      { free(perm[j]->owned); perm[j]->owned = NULL; }
-  g.swap(out);
+  std::vector<Aln> kept;                                   // survivors in sweep order (:3649-3680)
+  for (Aln *p : row) if (!p->dead) kept.push_back(std::move(*p));
+  for (Aln &k : kept) if (!k.spliced.empty()) k.trace = k.spliced.data();
+  g.swap(kept);
 }
+
+}  // namespace
 
 struct fgb_alns
 { long long n = 0, nraw = 0;
@@ -206,29 +175,29 @@ extern "C" int fgb_filter(const fgb_overlaps *O, const int *perm1, const int *pe
 
   fgb_alns *R = new fgb_alns();
   R->nraw = (long long) refs.size();
-  struct Fin { int comp, aread, bread; HOvl o; };
+  struct Fin { int comp, aread, bread; Aln o; };
   std::vector<Fin> fin;
   size_t i = 0;
   while (i < refs.size())
     { int pk = ((const int *) (buf + refs[i].off))[2];
-      std::vector<HOvl> g;
+      std::vector<Aln> g;
       size_t e = i;
       while (e < refs.size() && ((const int *) (buf + refs[e].off))[2] == pk)
         { const int *h = (const int *) (buf + refs[e].off);
-          HOvl o;
-          o.p.abpos = h[3]; o.p.bbpos = h[4]; o.p.aepos = h[5]; o.p.bepos = h[6];
-          o.p.diffs = h[7]; o.p.tlen = h[8];
-          o.flags = 0; o.owned = NULL;
+          Aln o;
+          o.ab = h[3]; o.bb = h[4]; o.ae = h[5]; o.be = h[6]; o.diffs = h[7]; o.tlen = h[8];
+          o.dead = false;
           o.trace = buf + refs[e].off + OUT_HDR;
-          g.push_back(o);
+          g.push_back(std::move(o));
           e += 1;
         }
       if (do_filter) filter_group(g);
       int jc = pk & ((1 << jc_bits) - 1), ic = (pk >> jc_bits) & ((1 << ic_bits) - 1);
       int comp = (pk >> (jc_bits + ic_bits)) & 1;
       for (size_t q = 0; q < g.size(); q++)
-        { Fin f; f.comp = comp; f.aread = perm1[ic]; f.bread = perm2[jc]; f.o = g[q];
-          fin.push_back(f);
+        { Fin f; f.comp = comp; f.aread = perm1[ic]; f.bread = perm2[jc]; f.o = std::move(g[q]);
+          fin.push_back(std::move(f));
+          if (!fin.back().o.spliced.empty()) fin.back().o.trace = fin.back().o.spliced.data();
         }
       i = e;
     }
@@ -240,7 +209,7 @@ extern "C" int fgb_filter(const fgb_overlaps *O, const int *perm1, const int *pe
   std::stable_sort(ord.begin(),ord.end(),[&](int a, int b)
     { const Fin &x = fin[a], &y = fin[b];
       if (x.aread != y.aread) return x.aread < y.aread;
-      if (x.o.p.abpos != y.o.p.abpos) return x.o.p.abpos < y.o.p.abpos;
+      if (x.o.ab != y.o.ab) return x.o.ab < y.o.ab;
       if (x.bread != y.bread) return x.bread < y.bread;
       return x.comp < y.comp;
     });
@@ -251,13 +220,11 @@ extern "C" int fgb_filter(const fgb_overlaps *O, const int *perm1, const int *pe
     { const Fin &f = fin[ord[q]];
       int *d = &R->fields[q*9];
       d[0] = f.comp; d[1] = f.aread; d[2] = f.bread;
-      d[3] = f.o.p.abpos; d[4] = f.o.p.bbpos; d[5] = f.o.p.aepos; d[6] = f.o.p.bepos;
-      d[7] = f.o.p.diffs; d[8] = f.o.p.tlen;
+      d[3] = f.o.ab; d[4] = f.o.bb; d[5] = f.o.ae; d[6] = f.o.be;
+      d[7] = f.o.diffs; d[8] = f.o.tlen;
       R->toff[q] = (long long) R->pool.size();
-      R->pool.insert(R->pool.end(),f.o.trace,f.o.trace + f.o.p.tlen);
+      R->pool.insert(R->pool.end(),f.o.trace,f.o.trace + f.o.tlen);
     }
-  for (size_t q = 0; q < fin.size(); q++)
-    if (fin[q].o.flags & OWNS_MEMORY) free(fin[q].o.owned);
   *out = R;
   return FGB_OK;
 }

@@ -88,42 +88,59 @@ template<int TILE> struct mg_stage
   rec128   t1[TILE];                      // the T1 tile (TMA destination)
   unsigned desc[MG_DCAP];                 // per seed: T2 slot (11) | T1 slot (9) << 11 | (plen-12) << 20
   unsigned wtot[2*MG_WARPS], wsum[2*MG_WARPS];
+  unsigned char adj[MG_T2CAP+16];         // adj[i] = LCP in bases of slice entries i-1 and i; 0 at both ends
   unsigned rng[4];
   unsigned long long gbase;
   unsigned long long bar;
 };
 
 //  Adaptamer of one T1 entry against the staged slice: |R| (0 if no seed), first slice slot of R, plen.
-static __device__ __forceinline__ unsigned adaptamer_staged(const rec128 *__restrict__ t2, unsigned nsl,
+//  Written for the WARP, not the lane: the panel search runs a warp-uniform number of predicated
+//  halving steps (no divergent loop), and the extent of R comes from the slice's adjacent-entry LCP
+//  bytes (adj[i] = LCP(t2[i-1],t2[i]); T2 is sorted, so t2[i-1] belongs to R iff t2[i] does and
+//  adj[i] >= plen -- the LCP byte of the reference's .ktab entries, rebuilt per slice): two predicated
+//  steps per side, then a rarely entered warp-uniform loop.  adj[0] = adj[nsl] = 0 end every walk.
+static __device__ __forceinline__ unsigned adaptamer_staged(const rec128 *__restrict__ t2,
+                                                            const unsigned char *__restrict__ adj, unsigned nsl,
                                                             const rec128 &r1, unsigned lo, unsigned hi, int freq,
                                                             unsigned &lowi, int &plen)
 { const u64 k1 = r1.lo >> 48;
   unsigned a = lo, b = hi;                                    // lower bound of r1's k-mer inside its panel [lo,hi)
-  while (a < b)
-    { unsigned m = (a + b) >> 1;
-      rec128 q = ld_rec(t2 + m);
-      if (q.hi < r1.hi || (q.hi == r1.hi && (q.lo >> 48) < k1)) a = m+1; else b = m;
-    }
+  for (unsigned w = __reduce_max_sync(0xffffffffu,hi - lo); w > 0; w >>= 1)
+    if (a < b)
+      { unsigned m = (a + b) >> 1;
+        rec128 q = ld_rec(t2 + m);
+        if (q.hi < r1.hi || (q.hi == r1.hi && (q.lo >> 48) < k1)) a = m+1; else b = m;
+      }
   //  the neighbours of the insertion point decide plen; a neighbour in another panel (the slice only
   //  holds the tile's panels, so this covers the slice ends too) shares fewer than 12 bases
-  int ll = (a > 0)   ? lcp_rec(r1,ld_rec(t2 + a - 1)) : 0;
-  int lr = (a < nsl) ? lcp_rec(r1,ld_rec(t2 + a))     : 0;
-  int m  = ll > lr ? ll : lr;
-  lowi = 0; plen = 0;
-  if (m < 12) return 0;
-  plen = m;
+  int ll = 0, lr = 0;
+  if (lo < hi)
+    { if (a > 0)   ll = lcp_rec(r1,ld_rec(t2 + a - 1));
+      if (a < nsl) lr = lcp_rec(r1,ld_rec(t2 + a));
+    }
+  const int m = ll > lr ? ll : lr;
+  const unsigned fq = (unsigned) freq;
   unsigned lft = a, rgt = a;
-  if (ll == m)
-    { lft = a-1;
-      while (lft > 0 && rgt - lft < (unsigned) freq && lcp_rec(r1,ld_rec(t2 + lft - 1)) >= m) lft -= 1;
+  bool goL = (m >= 12 && ll == m), goR = (m >= 12 && lr == m);
+  if (goL) lft = a-1;
+  if (goR) rgt = a+1;
+  //  each side on its own up to FREQ members: |R| >= FREQ is all that matters beyond that (:799-823)
+#pragma unroll
+  for (int u = 0; u < 2; u++)
+    { goL = goL && a - lft < fq && (int) adj[lft] >= m;
+      if (goL) lft -= 1;
+      goR = goR && rgt - a < fq && (int) adj[rgt] >= m;
+      if (goR) rgt += 1;
     }
-  if (lr == m)
-    { rgt = a+1;
-      while (rgt < nsl && rgt - lft < (unsigned) freq && lcp_rec(r1,ld_rec(t2 + rgt)) >= m) rgt += 1;
+  while (__any_sync(0xffffffffu,goL || goR))
+    { goL = goL && a - lft < fq && (int) adj[lft] >= m;
+      if (goL) lft -= 1;
+      goR = goR && rgt - a < fq && (int) adj[rgt] >= m;
+      if (goR) rgt += 1;
     }
-  if (rgt - lft >= (unsigned) freq) return 0;                 // |R| < FREQ (:799-823)
-  lowi = lft;
-  return rgt - lft;
+  lowi = lft; plen = m;
+  return (m >= 12 && rgt - lft < fq) ? rgt - lft : 0u;
 }
 
 //  Same straight from HBM (a tile whose slice does not fit the staging buffers: long repeats).
@@ -201,6 +218,11 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
   const unsigned lo2 = S->rng[2], nsl = S->rng[3];
   const bool staged = (nsl <= MG_T2CAP);
   mbar_wait(&S->bar,0);
+  if (staged)
+    { for (unsigned j = tid; j <= nsl; j += MG_THREADS)
+        S->adj[j] = (j > 0 && j < nsl) ? (unsigned char) lcp_rec(ld_rec(&S->t2[j-1]),ld_rec(&S->t2[j])) : (unsigned char) 0;
+      __syncthreads();
+    }
 
   //  search: thread tid owns tile entries tid, tid+256, ...
   const u64 *t2k = reinterpret_cast<const u64 *>(S->t2);
@@ -211,16 +233,19 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
   for (int r = 0; r < ROUNDS; r++)
     { const unsigned j = r*MG_THREADS + tid;
       cnt[r] = 0; lowi[r] = 0; plen[r] = 0;
-      if (j < nt1)
-        { const rec128 r1 = ld_rec(&S->t1[j]);
-          if (staged)
-            { const unsigned p = KREC_PREFIX24(r1.hi);
-              const unsigned lo = __ldg(pstart2 + p) - lo2, hi = __ldg(pstart2 + p + 1) - lo2;
-              if (lo < hi) cnt[r] = adaptamer_staged(S->t2,nsl,r1,lo,hi,freq,lowi[r],plen[r]);
+      if (staged)
+        { //  all 32 lanes take part (warp-uniform search steps); lanes past the tile search nothing
+          rec128 r1; r1.lo = r1.hi = 0;
+          unsigned lo = 0, hi = 0;
+          if (j < nt1)
+            { r1 = ld_rec(&S->t1[j]);
+              const unsigned p = KREC_PREFIX24(r1.hi);
+              lo = __ldg(pstart2 + p) - lo2; hi = __ldg(pstart2 + p + 1) - lo2;
             }
-          else
-            cnt[r] = adaptamer_direct(T2,pstart2,r1,freq,lowi[r],plen[r]);
+          cnt[r] = adaptamer_staged(S->t2,S->adj,nsl,r1,lo,hi,freq,lowi[r],plen[r]);
         }
+      else if (j < nt1)
+        cnt[r] = adaptamer_direct(T2,pstart2,ld_rec(&S->t1[j]),freq,lowi[r],plen[r]);
       unsigned inc = cnt[r];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1)
@@ -281,7 +306,7 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
       if (cnt[r] == 0) continue;
       const u64 p1 = t1k[2*j] & PAY;
       for (unsigned k = 0; k < cnt[r]; k++)
-        { const u64 p2 = staged ? t2k[2*(lowi[r]+k)+1] : (T2[lowi[r]+k].lo & 0xffffffffffffull);
+        { const u64 p2 = (staged ? t2k[2*(lowi[r]+k)] : T2[lowi[r]+k].lo) & PAY;
           const unsigned long long o = gbase + excl[r] + k;
           if (o < capacity) st_rec(seeds + o,make_seed((unsigned) plen[r],p1,p2,K));
         }
