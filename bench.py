@@ -300,10 +300,11 @@ def run():
 
     A, B = workload(world, args.per_gpu_bp)
     from fastga_b200 import shard
-    mine = shard.shard_contigs([len(a) for a in A], rank, world)
-    gA = formats.genome_from_arrays([A[i] for i in mine])
+    #  every rank holds both genomes (2 bits per base: 50 MB per 100 Mbp pair member); the WORK is
+    #  sharded -- scanning by contig, index + merge by k-mer prefix range, extension by A-contig
+    gA = formats.genome_from_arrays(A)
     gB = formats.genome_from_arrays(B)
-    freqA = formats.genome_from_arrays(A).freq if world > 1 else gA.freq
+    freqA = gA.freq
     total_gbp = (sum(len(a) for a in A) + sum(len(b) for b in B)) / 1e9
 
     dA = lib.DeviceGenome(gA, want_revcomp=True)
@@ -335,14 +336,7 @@ def run():
 
     if world > 1:
         dev = torch.device("cuda", local_rank)
-
-        def step():
-            xA = lib.DeviceGix.build_forward(dA)
-            xB = shard.build_table_cooperatively(dB, dist, dev)       # NCCL all-gather of sorted shares
-            out = lib.align_tables(dA, dB, xA, xB, freqA)
-            xA.close()
-            xB.close()
-            return out
+        step = lambda: shard.align_sharded(dA, dB, freqA, dist, dev)
     else:
         step = lambda: lib.align_resident(dA, dB, freqA)
     for _ in range(args.warmup):
@@ -368,7 +362,22 @@ def run():
         q._freq = g.freq
         return q
     pA, pB = pinned(gA), pinned(gB)
-    e2e_step = lambda: lib.fastga(pA, pB)
+    if world > 1:
+        def e2e_step():
+            # the sharded call on host buffers: every rank stages both .bps images (H2D), runs its
+            # share, reads its records back; the gather of the records to rank 0 is part of the step
+            eA = lib.DeviceGenome(pA, want_revcomp=True)
+            eB = lib.DeviceGenome(pB)
+            out = shard.align_sharded(eA, eB, freqA, dist, dev)
+            shard.gather_alignments(out[0], None, dist, dev)
+            h2d = pA.bps.size + pB.bps.size
+            out[1]["h2d_bytes"] = int(h2d)
+            out[1]["d2h_bytes"] = int(out[0].pool.size + out[0].fields.nbytes)
+            eA.close()
+            eB.close()
+            return out
+    else:
+        e2e_step = lambda: lib.fastga(pA, pB)
     e2e_step()
     ms_e2e, outs2 = timed(e2e_step, max(1, min(args.steps, 3)))
     st2 = outs2[-1][1]
@@ -377,7 +386,7 @@ def run():
     nrec = len(alns)
     final = alns
     if world > 1:
-        merged = shard.gather_alignments(alns, np.array(mine, dtype=np.int32), dist, torch.device("cuda", local_rank))
+        merged = shard.gather_alignments(alns, None, dist, torch.device("cuda", local_rank))
         if rank == 0:
             nrec = len(merged)
             final = merged
@@ -397,8 +406,10 @@ def run():
     pb = max(1, (int(max(gA.clen.max(), gB.clen.max())).bit_length() + 7) // 8)
     E1 = 9 + pb + 1
     R = 1 + 2 * (pb + 1)
-    algo = (stats["nkmers1_fwd"] + stats["nkmers2"]) * E1 + stats["nseeds"] * R
-    algo_ondisk = (stats["nkmers1"] + stats["nkmers2"]) * E1 + stats["nseeds"] * R
+    #  (N > 1: this rank's slices of the two tables and the seeds ITS merge produced)
+    merged_seeds = stats.get("nseeds_merged", stats["nseeds"])
+    algo = (stats["nkmers1_fwd"] + stats["nkmers2"]) * E1 + merged_seeds * R
+    algo_ondisk = (stats.get("nkmers1", 2 * stats["nkmers1_fwd"]) + stats["nkmers2"]) * E1 + merged_seeds * R
     merge_ms = tm["merge_ms"] / max(1, tm["merge_launches"])
     # byte passes of the seed sort: key = lcp(6) drem(6) anti band jcont icont strand (api.cu:fgb_seeds_find)
     abits = int(gA.clen.max() + gB.clen.max()).bit_length()
@@ -408,7 +419,7 @@ def run():
     ach = algo / (merge_ms * 1e-3) / 1e9 if merge_ms > 0 else 0.0
     dev_ms = {k: v / steps for k, v in tm.items() if k.endswith("_ms")}
     # records this rank's k-mer sorts handled per step: table 1 forward-only + its share of table 2
-    nk_sorted = stats["nkmers1_fwd"] + (stats["nkmers2"] // world if world > 1 else stats["nkmers2"])
+    nk_sorted = stats["nkmers1_fwd"] + stats["nkmers2"]
     step_ms = sorted(per_step_ms)
 
     line = {"metric": "Gbp aligned/sec (genome x genome)", "value": total_gbp / (ms_step / 1000.0),
@@ -417,17 +428,20 @@ def run():
             "data": "synthetic",
             "config": {"workload": workload_text(args.per_gpu_bp, world) +
                                    "; k-mer tables and seed sets are larger than L2 (no flush needed)",
-                       "sharding": "genome-1 contigs by rank; genome-2 table built cooperatively (k-mer prefix "
-                                   "slices sorted per rank, NCCL all-gather)" if world > 1 else "single GPU",
+                       "sharding": ("k-mer space: every rank scans its contigs, k-mer records go to the owner of "
+                                    "their prefix range and seeds to the owner of their A-contig (two NCCL "
+                                    "all-to-alls of 16-byte records), nothing replicated; counts below are rank 0's share")
+                                   if world > 1 else "single GPU",
                        "alignments": nrec, "aln_md5": gpu_md5,
-                       "seeds": stats["nseeds"], "kmers": [stats["nkmers1"], stats["nkmers2"]],
+                       "seeds": stats["nseeds"], "kmers": [stats.get("nkmers1"), stats["nkmers2"]],
                        "kmers1_forward": stats["nkmers1_fwd"],
                        "hits": stats["nhits"], "la_calls": stats["nla"], "waves": stats["nwaves"],
                        "wave_cells": stats["ncells"], "stage_ms": dev_ms,
                        "step_ms_min_med_max": [step_ms[0], step_ms[len(step_ms) // 2], step_ms[-1]],
                        "triples": [stats["nseg"], stats["nwork"]],
-                       "host_wall_us": {k: stats[k] for k in ("us_gix", "us_seeds", "us_extend", "us_filter")},
-                       "extend_cycles": {k: stats[k] for k in ("warp_cycles", "wave_cycles", "extract_cycles")}},
+                       "host_wall_us": {k: stats.get(k) for k in ("us_gix", "us_seeds", "us_extend", "us_filter")},
+                       "extend_cycles": {k: stats[k] for k in ("warp_cycles", "wave_cycles", "extract_cycles", "slow_cycles",
+                                                                "slow_waves", "paired_waves", "pairings")}},
             "roofline": {"bound": "hbm", "kernel": "adaptamer_merge_kernel", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic_bytes() if (world == 1 and args.per_gpu_bp == PER_GPU_BP) else None,

@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfastga_b200.so")
+# FGB_LIB: an alternative build of the SAME library (tuning variants made by profiles/build_variant.sh)
+LIB_PATH = os.environ.get("FGB_LIB") or os.path.join(_HERE, "libfastga_b200.so")
 _lib = None
 
 

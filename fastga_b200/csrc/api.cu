@@ -31,12 +31,17 @@ int fgb_syncmer_emit_device(const void *d_seq, const long long *d_clen, const lo
                             const int *d_crank, const int *d_tile_contig, const int *d_tile_start,
                             int ntiles, unsigned *d_tile_offset, void *d_records, unsigned plo,
                             unsigned phi, void *stream);
-int fgb_kix_index_device(const void *d_tab, long long n, unsigned *d_pstart, void *stream);
+int fgb_kix_index_device(const void *d_tab, long long n, unsigned *d_pstart, unsigned char *d_adj, void *stream);
 int fgb_ktab_export_device(const void *d_tab, long long n, int pbytes, int cbytes,
                            const long long *d_part_first, int nparts, void *d_out, void *stream);
 int fgb_ktab_import_device(const void *d_ent, long long n, int pbytes, int cbytes,
                            const long long *d_index, void *d_tab, void *stream);
 int fgb_sc_tile();
+int fgb_owner_count_device(const void *d_seeds, long long n, int p_ic, int ic_bits, const int *d_owner, int nrc,
+                           int world, unsigned long long *d_cnt, void *stream);
+int fgb_owner_scatter_device(const void *d_seeds, long long n, int p_ic, int ic_bits, const int *d_owner, int nrc,
+                             int world, unsigned long long *d_base, void *d_out, void *stream);
+int fgb_kmer_bins_device(const void *d_tab, long long n, int binshift, unsigned *d_bins, void *stream);
 int fgb_self_merge_device(const void *d_T, long long n, const unsigned *d_pstart, int freq,
                           int anti_bits, int band_bits, int jc_bits, int ic_bits,
                           long long amxpos, void *d_seeds, long long capacity,
@@ -44,7 +49,7 @@ int fgb_self_merge_device(const void *d_T, long long n, const unsigned *d_pstart
                           unsigned long long *h_sumlen, void *stream);
 int fgb_forward_view_device(const void *d_T, long long n, void *d_out, long long *h_nfwd, void *stream);
 int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2, long long n2, const unsigned *d_pstart2,
-                     int freq, int anti_bits, int band_bits, int jc_bits, int ic_bits,
+                     const unsigned char *d_adj2, int freq, int anti_bits, int band_bits, int jc_bits, int ic_bits,
                      long long amxpos, long long bmxpos, void *d_seeds, long long capacity,
                      unsigned long long *d_counters, unsigned long long *h_nseeds,
                      unsigned long long *h_sumlen, void *stream);
@@ -235,7 +240,7 @@ extern "C" long long fgb_genome_words(const fgb_genome *g) { return g->total_wor
 extern "C" void fgb_gix_free(fgb_gix *x)
 { cudaStream_t st = 0;
   if (!x) return;
-  fgb_dfree(x->d_tab,st); fgb_dfree(x->d_pstart,st);
+  fgb_dfree(x->d_tab,st); fgb_dfree(x->d_pstart,st); fgb_dfree(x->d_adj,st);
   delete x;
 }
 
@@ -270,74 +275,159 @@ extern "C" int fgb_gix_build_range(const fgb_genome *g, unsigned plo, unsigned p
   return gix_build_range(g,plo,phi,out,stream);
 }
 
-static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi_flags, fgb_gix **out, void *stream)
-{ cudaStream_t st = (cudaStream_t) stream;
-  const unsigned phi = phi_flags & ~GIX_FWD_ONLY;
-  int T = fgb_sc_tile();
+//  K1/K2: syncmer scan + record build of the contigs selected by `mask` (NULL: all) into a fresh
+//  device buffer of *n unsorted records (room for n+1).  *nrev = reverse entries left out (fwd-only).
+static int gix_scan(const fgb_genome *g, const unsigned char *mask, unsigned plo, unsigned phi_flags,
+                    rec128 **d_recs, long long *n_out, long long *nrev, unsigned long long *buck1024, cudaStream_t st)
+{ int T = fgb_sc_tile();
   std::vector<int> tc, ts;
   for (int c = 0; c < g->ncontig; c++)
-    if (g->clen[c] >= 12 && g->boff[c] >= 0)
+    if (g->clen[c] >= 12 && g->boff[c] >= 0 && (mask == NULL || mask[c]))
       for (long long t0 = 0; t0 + 12 <= g->clen[c]; t0 += T)
         { tc.push_back(c); ts.push_back((int) t0); }
   int ntiles = (int) tc.size();
-
-  fgb_gix *x = new fgb_gix();
-  gix_bytes(g,x);
-  x->ncontig = g->ncontig;
-
   int *d_tc = NULL, *d_ts = NULL; unsigned *d_cnt = NULL;
   u64 *d_buck = NULL, *d_total = NULL; void *d_tmp = NULL;
+  rec128 *d_a = NULL;
   long long tmpb = fgb_dev_scan_tmp_bytes(ntiles);
-  CUDA_TRY(fgb_dmalloc((void **) &d_tc,sizeof(int)*(ntiles+1),st));
-  CUDA_TRY(fgb_dmalloc((void **) &d_ts,sizeof(int)*(ntiles+1),st));
-  CUDA_TRY(fgb_dmalloc((void **) &d_cnt,sizeof(unsigned)*(ntiles+1),st));
-  CUDA_TRY(fgb_dmalloc((void **) &d_buck,8*1025,st));
-  CUDA_TRY(fgb_dmalloc((void **) &d_total,8,st));
-  CUDA_TRY(fgb_dmalloc((void **) &d_tmp,tmpb,st));
-  CUDA_TRY(cudaMemcpyAsync(d_tc,tc.data(),sizeof(int)*ntiles,cudaMemcpyHostToDevice,st));
-  CUDA_TRY(cudaMemcpyAsync(d_ts,ts.data(),sizeof(int)*ntiles,cudaMemcpyHostToDevice,st));
-
-  int rc;
+  int rc = FGB_OK;
   u64 total = 0, rdropped = 0;
+#define GS_TRY(call) do { if ((call) != cudaSuccess) { rc = FGB_ERR_CUDA; goto done; } } while (0)
+  GS_TRY(fgb_dmalloc((void **) &d_tc,sizeof(int)*(ntiles+1),st));
+  GS_TRY(fgb_dmalloc((void **) &d_ts,sizeof(int)*(ntiles+1),st));
+  GS_TRY(fgb_dmalloc((void **) &d_cnt,sizeof(unsigned)*(ntiles+1),st));
+  GS_TRY(fgb_dmalloc((void **) &d_buck,8*1025,st));
+  GS_TRY(fgb_dmalloc((void **) &d_total,8,st));
+  GS_TRY(fgb_dmalloc((void **) &d_tmp,tmpb,st));
+  GS_TRY(cudaMemcpyAsync(d_tc,tc.data(),sizeof(int)*ntiles,cudaMemcpyHostToDevice,st));
+  GS_TRY(cudaMemcpyAsync(d_ts,ts.data(),sizeof(int)*ntiles,cudaMemcpyHostToDevice,st));
   { stage_timer t(&g_timings.scan_ms,st);
     rc = fgb_syncmer_count_device(g->d_seq,g->d_clen,g->d_woff,g->d_crank,d_tc,d_ts,ntiles,d_cnt,
                                   d_buck,d_total,d_tmp,tmpb,plo,phi_flags,st);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(&total,d_total,8,cudaMemcpyDeviceToHost,st));
-    CUDA_TRY(cudaMemcpyAsync(x->buck1024,d_buck,8*1024,cudaMemcpyDeviceToHost,st));
-    CUDA_TRY(cudaMemcpyAsync(&rdropped,d_buck + 1024,8,cudaMemcpyDeviceToHost,st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    if (rc) goto done;
+    GS_TRY(cudaMemcpyAsync(&total,d_total,8,cudaMemcpyDeviceToHost,st));
+    if (buck1024) GS_TRY(cudaMemcpyAsync(buck1024,d_buck,8*1024,cudaMemcpyDeviceToHost,st));
+    GS_TRY(cudaMemcpyAsync(&rdropped,d_buck + 1024,8,cudaMemcpyDeviceToHost,st));
+    GS_TRY(cudaStreamSynchronize(st));
   }
-  if (total >= 0xfffffff0ull) return FGB_ERR_LIMIT;
-  long long n = (long long) total;
-  x->n = n;
-  x->fwd_only = (phi_flags & GIX_FWD_ONLY) ? 1 : 0;
-  x->n_both = n + (long long) rdropped;
-
-  rec128 *d_a = NULL, *d_b = NULL; void *d_stmp = NULL;
-  long long stmpb = fgb_sort128_tmp_bytes(n);
-  CUDA_TRY(fgb_dmalloc((void **) &d_a,sizeof(rec128)*(n+1),st));
-  CUDA_TRY(fgb_dmalloc((void **) &d_b,sizeof(rec128)*(n+1),st));
-  CUDA_TRY(fgb_dmalloc((void **) &d_stmp,stmpb,st));
+  if (total >= 0xfffffff0ull) { rc = FGB_ERR_LIMIT; goto done; }
+  GS_TRY(fgb_dmalloc((void **) &d_a,sizeof(rec128)*(total+1),st));
   { stage_timer t(&g_timings.scan_ms,st);
     rc = fgb_syncmer_emit_device(g->d_seq,g->d_clen,g->d_woff,g->d_crank,d_tc,d_ts,ntiles,d_cnt,d_a,plo,phi_flags,st);
-    if (rc) return rc;
   }
-  int inb = 0;
-  { stage_timer t(&g_timings.ksort_ms,st);
-    rc = fgb_kmer_sort_range_device(d_a,d_b,n,plo,phi,d_stmp,stmpb,&inb,st);
-    if (rc) return rc;
-  }
-  x->d_tab = inb ? d_b : d_a;
-  CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
-  if (plo == 0 && phi == (1u << 24))              // a share is indexed after assembly, not here
-    { stage_timer t(&g_timings.index_ms,st);
-      rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
-      if (rc) return rc;
-    }
-  CUDA_TRY(cudaStreamSynchronize(st));
-  fgb_dfree(inb ? d_a : d_b,st); fgb_dfree(d_stmp,st);
+  if (rc == FGB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = FGB_ERR_CUDA;   // tc/ts must outlive the copies
+done:
+#undef GS_TRY
   fgb_dfree(d_tc,st); fgb_dfree(d_ts,st); fgb_dfree(d_cnt,st); fgb_dfree(d_buck,st); fgb_dfree(d_total,st); fgb_dfree(d_tmp,st);
+  if (rc) { fgb_dfree(d_a,st); return rc; }
+  *d_recs = d_a; *n_out = (long long) total; *nrev = (long long) rdropped;
+  return FGB_OK;
+}
+
+//  K3/K4: sorts the records in d_a (consumed: it ends up inside the handle or is released) whose
+//  12-base prefixes lie in [plo,phi), builds the prefix index and the LCP bytes.
+static int gix_finish(fgb_gix *x, rec128 *d_a, long long n, unsigned plo, unsigned phi, cudaStream_t st)
+{ rec128 *d_b = NULL; void *d_stmp = NULL;
+  long long stmpb = fgb_sort128_tmp_bytes(n);
+  int rc = FGB_OK, inb = 0;
+  x->n = n;
+  if (fgb_dmalloc((void **) &d_b,sizeof(rec128)*(n+1),st) != cudaSuccess ||
+      fgb_dmalloc((void **) &d_stmp,stmpb,st) != cudaSuccess ||
+      fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st) != cudaSuccess ||
+      fgb_dmalloc((void **) &x->d_adj,(size_t) n + 32,st) != cudaSuccess)
+    rc = FGB_ERR_CUDA;
+  if (!rc)
+    { stage_timer t(&g_timings.ksort_ms,st);
+      rc = fgb_kmer_sort_range_device(d_a,d_b,n,plo,phi,d_stmp,stmpb,&inb,st);
+    }
+  if (!rc)
+    { x->d_tab = inb ? d_b : d_a;
+      if (inb) d_b = NULL; else d_a = NULL;
+      stage_timer t(&g_timings.index_ms,st);
+      rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,x->d_adj,st);
+    }
+  if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = FGB_ERR_CUDA;
+  fgb_dfree(d_a,st); fgb_dfree(d_b,st); fgb_dfree(d_stmp,st);
+  return rc;
+}
+
+static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi_flags, fgb_gix **out, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  const unsigned phi = phi_flags & ~GIX_FWD_ONLY;
+  fgb_gix *x = new fgb_gix();
+  gix_bytes(g,x);
+  x->ncontig = g->ncontig;
+  x->fwd_only = (phi_flags & GIX_FWD_ONLY) ? 1 : 0;
+  rec128 *d_a = NULL; long long n = 0, nrev = 0;
+  int rc = gix_scan(g,NULL,plo,phi_flags,&d_a,&n,&nrev,x->buck1024,st);
+  if (!rc) { x->n_both = n + nrev; rc = gix_finish(x,d_a,n,plo,phi,st); }
+  if (rc) { fgb_gix_free(x); return rc; }
+  *out = x;
+  return FGB_OK;
+}
+
+/***********************************************************************************************
+ *  Building blocks of the k-mer-space sharded path (several GPUs, fastga_b200/shard.py): every rank
+ *  scans ITS contigs of both genomes, the k-mer records travel to the rank that owns their prefix
+ *  range, each rank merges its slice of the two tables, and the seeds travel to the rank that owns
+ *  their A-contig.  Nothing is replicated; the two exchanges are all-to-alls of 16-byte records.
+ **********************************************************************************************/
+
+extern "C" int fgb_device_alloc(long long bytes, void **out, void *stream)
+{ CUDA_TRY(fgb_dmalloc(out,(size_t) (bytes > 0 ? bytes : 16),(cudaStream_t) stream)); return FGB_OK; }
+extern "C" void fgb_device_free(void *p) { fgb_dfree(p,0); }
+
+//  unsorted k-mer records of the contigs with mask[c] != 0 (device buffer handed to the caller:
+//  fgb_device_free); fwd_only: forward-strand entries only (the adaptamer side)
+extern "C" int fgb_kmers_scan(const fgb_genome *g, const unsigned char *mask, int fwd_only,
+                              void **d_recs, long long *n, void *stream)
+{ rec128 *d = NULL; long long nrev = 0;
+  int rc = gix_scan(g,mask,0u,(1u << 24) | (fwd_only ? GIX_FWD_ONLY : 0u),&d,n,&nrev,NULL,(cudaStream_t) stream);
+  if (rc) return rc;
+  *d_recs = d;
+  return FGB_OK;
+}
+
+//  records grouped by the top byte of the k-mer (its first four bases): d_out[bounds[b] .. bounds[b+1])
+//  holds those with top byte b, b = 0..255.  One Onesweep pass; the owner of a record is any
+//  monotone function of that byte, so the send blocks of an all-to-all are contiguous.
+extern "C" int fgb_records_group_by_top_byte(void *d_recs, long long n, void *d_out, long long *bounds257,
+                                             void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  for (int b = 0; b <= 256; b++) bounds257[b] = 0;
+  if (n <= 0) return FGB_OK;
+  void *d_tmp = NULL; unsigned *d_bins = NULL;
+  long long tmpb = fgb_sort128_tmp_bytes(n);
+  int rc = FGB_OK, inb = 0;
+  std::vector<unsigned> bins(65537);
+  if (fgb_dmalloc(&d_tmp,tmpb,st) != cudaSuccess || fgb_dmalloc((void **) &d_bins,sizeof(unsigned)*65537,st) != cudaSuccess)
+    rc = FGB_ERR_CUDA;
+  if (!rc) rc = fgb_sort128_device(d_recs,d_out,n,15,16,d_tmp,tmpb,&inb,st);
+  if (!rc && !inb && cudaMemcpyAsync(d_out,d_recs,sizeof(rec128)*n,cudaMemcpyDeviceToDevice,st) != cudaSuccess) rc = FGB_ERR_CUDA;
+  if (!rc) rc = fgb_kmer_bins_device(d_out,n,56,d_bins,st);
+  if (!rc && (cudaMemcpyAsync(bins.data(),d_bins,sizeof(unsigned)*65537,cudaMemcpyDeviceToHost,st) != cudaSuccess ||
+              cudaStreamSynchronize(st) != cudaSuccess)) rc = FGB_ERR_CUDA;
+  fgb_dfree(d_tmp,st); fgb_dfree(d_bins,st);
+  if (rc) return rc;
+  for (int b = 0; b <= 256; b++) bounds257[b] = bins[b];
+  return FGB_OK;
+}
+
+//  a table over n unsorted device records (copied) whose 12-base prefixes lie in [plo,phi): one
+//  rank's slice of a k-mer-space sharded table
+extern "C" int fgb_gix_from_records(const void *d_recs, long long n, unsigned plo, unsigned phi, int fwd_only,
+                                    int post_bytes, int cont_bytes, int ncontig, fgb_gix **out, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  if (n < 0 || n >= 0xfffffff0ll || plo >= phi || phi > (1u << 24)) return FGB_ERR_ARG;
+  fgb_gix *x = new fgb_gix();
+  x->n_both = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
+  x->fwd_only = fwd_only ? 1 : 0;
+  rec128 *d_a = NULL;
+  int rc = FGB_OK;
+  if (fgb_dmalloc((void **) &d_a,sizeof(rec128)*(n+1),st) != cudaSuccess) rc = FGB_ERR_CUDA;
+  if (!rc && n > 0 && cudaMemcpyAsync(d_a,d_recs,sizeof(rec128)*n,cudaMemcpyDeviceToDevice,st) != cudaSuccess) rc = FGB_ERR_CUDA;
+  if (!rc) rc = gix_finish(x,d_a,n,plo,phi,st); else fgb_dfree(d_a,st);
+  if (rc) { fgb_gix_free(x); return rc; }
   *out = x;
   return FGB_OK;
 }
@@ -360,10 +450,11 @@ extern "C" int fgb_gix_from_device(const void *d_tab, long long n, int post_byte
   x->n = n; x->n_both = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
   CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
   CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &x->d_adj,(size_t) x->n + 32,st));
   CUDA_TRY(cudaMemcpyAsync(x->d_tab,d_tab,sizeof(rec128)*n,cudaMemcpyDeviceToDevice,st));
   int rc;
   { stage_timer t(&g_timings.index_ms,st);
-    rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
+    rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,x->d_adj,st);
   }
   CUDA_TRY(cudaStreamSynchronize(st));
   if (rc) return rc;
@@ -390,8 +481,9 @@ extern "C" int fgb_gix_upload(const void *tab, long long n, int post_bytes, int 
   x->n = n; x->n_both = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
   CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
   CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &x->d_adj,(size_t) x->n + 32,st));
   CUDA_TRY(cudaMemcpyAsync(x->d_tab,tab,sizeof(rec128)*n,cudaMemcpyHostToDevice,st));
-  int rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
+  int rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,x->d_adj,st);
   CUDA_TRY(cudaStreamSynchronize(st));
   if (rc) return rc;
   *out = x;
@@ -413,10 +505,11 @@ extern "C" int fgb_gix_import_ktab(const unsigned char *entries, long long n, in
   CUDA_TRY(fgb_dmalloc((void **) &d_index,8ll<<24,st));
   CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
   CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &x->d_adj,(size_t) x->n + 32,st));
   CUDA_TRY(cudaMemcpyAsync(d_ent,entries,E*n,cudaMemcpyHostToDevice,st));
   CUDA_TRY(cudaMemcpyAsync(d_index,index,8ll<<24,cudaMemcpyHostToDevice,st));
   int rc = fgb_ktab_import_device(d_ent,n,post_bytes,cont_bytes,d_index,x->d_tab,st);
-  if (!rc) rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,st);
+  if (!rc) rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,x->d_adj,st);
   CUDA_TRY(cudaStreamSynchronize(st));
   fgb_dfree(d_ent,st); fgb_dfree(d_index,st);
   if (rc) return rc;
@@ -465,74 +558,164 @@ extern "C" int fgb_seeds_find(const fgb_gix *x1, const fgb_gix *x2, long long am
 extern "C" int fgb_seeds_find_self(const fgb_gix *x, long long amxpos, int freq, fgb_seeds **out, void *stream)
 { return seeds_find_impl(x,x,amxpos,amxpos,freq,true,out,stream); }
 
-static int seeds_find_impl(const fgb_gix *x1, const fgb_gix *x2, long long amxpos,
-                           long long bmxpos, int freq, bool self, fgb_seeds **out, void *stream)
-{ cudaStream_t st = (cudaStream_t) stream;
-  const int anti_bits = bitlen(amxpos + bmxpos);
-  const int band_bits = anti_bits > 6 ? anti_bits - 6 : 1;
-  const int jc_bits   = bitlen(x2->ncontig > 1 ? x2->ncontig-1 : 1);
-  const int ic_bits   = bitlen(x1->ncontig > 1 ? x1->ncontig-1 : 1);
-  const int keybits   = 12 + anti_bits + band_bits + jc_bits + ic_bits + 1;
-  if (keybits > 128) return FGB_ERR_LIMIT;
-  if (self && x1->fwd_only) return FGB_ERR_ARG;                // SELF mode needs both strands
+struct seed_bits { int anti, band, jc, ic, key; };
 
+static int seed_layout_of(const fgb_gix *x1, const fgb_gix *x2, long long amxpos, long long bmxpos, seed_bits *L)
+{ L->anti = bitlen(amxpos + bmxpos);
+  L->band = L->anti > 6 ? L->anti - 6 : 1;
+  L->jc   = bitlen(x2->ncontig > 1 ? x2->ncontig-1 : 1);
+  L->ic   = bitlen(x1->ncontig > 1 ? x1->ncontig-1 : 1);
+  L->key  = 12 + L->anti + L->band + L->jc + L->ic + 1;
+  return L->key > 128 ? FGB_ERR_LIMIT : FGB_OK;
+}
+
+//  K5: the unsorted seed records of x1 against x2 in a fresh device buffer (room for n+1)
+static int seeds_merge_impl(const fgb_gix *x1, const fgb_gix *x2, long long amxpos, long long bmxpos, int freq,
+                            bool self, const seed_bits &L, rec128 **d_out, long long *nseeds_out,
+                            long long *sumlen_out, long long *n1m_out, cudaStream_t st)
+{ if (self && x1->fwd_only) return FGB_ERR_ARG;                // SELF mode needs both strands
   //  every device block of this call is released on every exit path
-  u64 *d_counters = NULL; rec128 *d_fwd = NULL, *d_a = NULL, *d_b = NULL; void *d_tmp = NULL;
-  fgb_seeds *s = NULL;
+  u64 *d_counters = NULL; rec128 *d_fwd = NULL, *d_a = NULL;
   int rc = FGB_OK;
   u64 nseeds = 0, sumlen = 0;
+  //  the adaptamer side must be a forward-strand table (reverse entries never seed): a both-strand
+  //  table (imported .ktab, fgb_gix_build) is compacted once; the fused path builds it forward-only
+  const rec128 *t1 = x1->d_tab; long long n1 = x1->n;
 #define SF_TRY(call) do { if ((call) != cudaSuccess) { rc = FGB_ERR_CUDA; goto done; } } while (0)
-
   SF_TRY(fgb_dmalloc((void **) &d_counters,16,st));
-  { //  the adaptamer side must be a forward-strand table (reverse entries never seed): a both-strand
-    //  table (imported .ktab, fgb_gix_build) is compacted once; the fused path builds it forward-only
-    const rec128 *t1 = x1->d_tab; long long n1 = x1->n;
-    if (!self && !x1->fwd_only && n1 > 0)
-      { SF_TRY(fgb_dmalloc((void **) &d_fwd,sizeof(rec128)*(n1+1),st));
-        if ((rc = fgb_forward_view_device(x1->d_tab,n1,d_fwd,&n1,st))) goto done;
-        t1 = d_fwd;
-      }
-    long long cap = (self ? 2*x1->n : 2*n1 + (n1 >> 1)) + 1024;
+  if (!self && !x1->fwd_only && n1 > 0)
+    { SF_TRY(fgb_dmalloc((void **) &d_fwd,sizeof(rec128)*(n1+1),st));
+      if ((rc = fgb_forward_view_device(x1->d_tab,n1,d_fwd,&n1,st))) goto done;
+      t1 = d_fwd;
+    }
+  { long long cap = (self ? 2*x1->n : 2*n1 + (n1 >> 1)) + 1024;
     for (int attempt = 0; ; attempt++)
       { SF_TRY(fgb_dmalloc((void **) &d_a,sizeof(rec128)*(cap+1),st));
         if (self)
-          rc = fgb_self_merge_device(x1->d_tab,x1->n,x1->d_pstart,freq,anti_bits,band_bits,
-                                     jc_bits,ic_bits,amxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
+          rc = fgb_self_merge_device(x1->d_tab,x1->n,x1->d_pstart,freq,L.anti,L.band,L.jc,L.ic,amxpos,
+                                     d_a,cap,d_counters,&nseeds,&sumlen,st);
         else
-          rc = fgb_merge_device(t1,n1,x2->d_tab,x2->n,x2->d_pstart,freq,anti_bits,band_bits,
-                                jc_bits,ic_bits,amxpos,bmxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
+          rc = fgb_merge_device(t1,n1,x2->d_tab,x2->n,x2->d_pstart,x2->d_adj,freq,L.anti,L.band,L.jc,L.ic,
+                                amxpos,bmxpos,d_a,cap,d_counters,&nseeds,&sumlen,st);
         if (rc == FGB_OK) break;
         fgb_dfree(d_a,st); d_a = NULL;
         if (rc != FGB_ERR_OVERFLOW || attempt > 0) goto done;
         cap = (long long) nseeds + 1024;
         g_timings.merge_ms = 0; g_timings.merge_launches = 0;   // only the successful launch is reported
       }
-    fgb_dfree(d_fwd,st); d_fwd = NULL;
-    if (nseeds >= 0xfffffff0ull) { rc = FGB_ERR_LIMIT; goto done; }
-    s = new fgb_seeds();
-    s->self_mode = self ? 1 : 0;
-    s->anti_bits = anti_bits; s->band_bits = band_bits; s->jc_bits = jc_bits; s->ic_bits = ic_bits;
-    s->amxpos = amxpos; s->bmxpos = bmxpos;
-    s->n = (long long) nseeds; s->sumlen = (long long) sumlen; s->n1_merged = n1;
   }
-  { long long tmpb = fgb_sort128_tmp_bytes(s->n);
-    SF_TRY(fgb_dmalloc((void **) &d_b,sizeof(rec128)*(s->n+1),st));
-    SF_TRY(fgb_dmalloc((void **) &d_tmp,tmpb,st));
-    int inb = 0;
-    { stage_timer t(&g_timings.ssort_ms,st);
-      rc = fgb_sort128_device(d_a,d_b,s->n,0,(keybits+7)/8,d_tmp,tmpb,&inb,st);
-    }
-    if (rc == FGB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = FGB_ERR_CUDA;
-    if (rc) goto done;
-    s->d_rec = inb ? d_b : d_a;
-    if (inb) d_b = NULL; else d_a = NULL;                       // ownership moved to the handle
-  }
+  if (nseeds >= 0xfffffff0ull) rc = FGB_ERR_LIMIT;
 done:
 #undef SF_TRY
-  fgb_dfree(d_counters,st); fgb_dfree(d_fwd,st); fgb_dfree(d_a,st); fgb_dfree(d_b,st); fgb_dfree(d_tmp,st);
+  fgb_dfree(d_counters,st); fgb_dfree(d_fwd,st);
+  if (rc) { fgb_dfree(d_a,st); return rc; }
+  *d_out = d_a; *nseeds_out = (long long) nseeds; *sumlen_out = (long long) sumlen; *n1m_out = n1;
+  return FGB_OK;
+}
+
+//  K6: sorts n seed records in d_a (consumed) into a handle
+static int seeds_sort_impl(rec128 *d_a, long long n, const seed_bits &L, long long amxpos, long long bmxpos,
+                           bool self, long long sumlen, long long n1m, fgb_seeds **out, cudaStream_t st)
+{ rec128 *d_b = NULL; void *d_tmp = NULL;
+  fgb_seeds *s = new fgb_seeds();
+  s->self_mode = self ? 1 : 0;
+  s->anti_bits = L.anti; s->band_bits = L.band; s->jc_bits = L.jc; s->ic_bits = L.ic;
+  s->amxpos = amxpos; s->bmxpos = bmxpos;
+  s->n = n; s->sumlen = sumlen; s->n1_merged = n1m;
+  long long tmpb = fgb_sort128_tmp_bytes(n);
+  int rc = FGB_OK, inb = 0;
+  if (fgb_dmalloc((void **) &d_b,sizeof(rec128)*(n+1),st) != cudaSuccess ||
+      fgb_dmalloc((void **) &d_tmp,tmpb,st) != cudaSuccess) rc = FGB_ERR_CUDA;
+  if (!rc)
+    { stage_timer t(&g_timings.ssort_ms,st);
+      rc = fgb_sort128_device(d_a,d_b,n,0,(L.key+7)/8,d_tmp,tmpb,&inb,st);
+    }
+  if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = FGB_ERR_CUDA;
+  if (!rc)
+    { s->d_rec = inb ? d_b : d_a;
+      if (inb) d_b = NULL; else d_a = NULL;                     // ownership moved to the handle
+    }
+  fgb_dfree(d_a,st); fgb_dfree(d_b,st); fgb_dfree(d_tmp,st);
   if (rc) { delete s; return rc; }
   *out = s;
   return FGB_OK;
+}
+
+static int seeds_find_impl(const fgb_gix *x1, const fgb_gix *x2, long long amxpos,
+                           long long bmxpos, int freq, bool self, fgb_seeds **out, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  seed_bits L;
+  int rc = seed_layout_of(x1,x2,amxpos,bmxpos,&L);
+  if (rc) return rc;
+  rec128 *d_a = NULL; long long n = 0, sumlen = 0, n1m = 0;
+  if ((rc = seeds_merge_impl(x1,x2,amxpos,bmxpos,freq,self,L,&d_a,&n,&sumlen,&n1m,st))) return rc;
+  return seeds_sort_impl(d_a,n,L,amxpos,bmxpos,self,sumlen,n1m,out,st);
+}
+
+//  ---- sharded path: seeds leave the merge unsorted, travel to their A-contig's owner, are sorted there ----
+
+//  unsorted seed records of x1 against x2 (device buffer handed to the caller: fgb_device_free);
+//  bits[4] = anti, band, jcont, icont field widths; info[2] = sum of seed lengths, T1 entries merged
+extern "C" int fgb_seeds_merge(const fgb_gix *x1, const fgb_gix *x2, long long amxpos, long long bmxpos, int freq,
+                               void **d_seeds, long long *n, int *bits, long long *info, void *stream)
+{ seed_bits L;
+  int rc = seed_layout_of(x1,x2,amxpos,bmxpos,&L);
+  if (rc) return rc;
+  rec128 *d_a = NULL; long long sumlen = 0, n1m = 0;
+  if ((rc = seeds_merge_impl(x1,x2,amxpos,bmxpos,freq,false,L,&d_a,n,&sumlen,&n1m,(cudaStream_t) stream))) return rc;
+  *d_seeds = d_a;
+  bits[0] = L.anti; bits[1] = L.band; bits[2] = L.jc; bits[3] = L.ic;
+  if (info) { info[0] = sumlen; info[1] = n1m; }
+  return FGB_OK;
+}
+
+//  seeds grouped by the rank that owns their A-contig: owner[r] for contig RANK r (the icont field);
+//  d_out[bounds[w] .. bounds[w+1]) are the seeds of owner w.  Count + scatter, order inside a group free.
+extern "C" int fgb_seeds_group_by_owner(const void *d_seeds, long long n, const int *bits, const int *owner,
+                                        int nrank_contigs, int world, void *d_out, long long *bounds,
+                                        void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  if (world < 1 || world > 64) return FGB_ERR_ARG;
+  for (int w = 0; w <= world; w++) bounds[w] = 0;
+  if (n <= 0) return FGB_OK;
+  int *d_owner = NULL; u64 *d_cnt = NULL;
+  int rc = FGB_OK;
+  u64 cnt[64], base[65];
+  const int p_ic = 12 + bits[0] + bits[1] + bits[2];
+  if (fgb_dmalloc((void **) &d_owner,sizeof(int)*(size_t) nrank_contigs,st) != cudaSuccess ||
+      fgb_dmalloc((void **) &d_cnt,8*64*2,st) != cudaSuccess) rc = FGB_ERR_CUDA;
+  if (!rc && (cudaMemcpyAsync(d_owner,owner,sizeof(int)*(size_t) nrank_contigs,cudaMemcpyHostToDevice,st) != cudaSuccess ||
+              cudaMemsetAsync(d_cnt,0,8*64*2,st) != cudaSuccess)) rc = FGB_ERR_CUDA;
+  if (!rc) rc = fgb_owner_count_device(d_seeds,n,p_ic,bits[3],d_owner,nrank_contigs,world,d_cnt,st);
+  if (!rc && (cudaMemcpyAsync(cnt,d_cnt,8*64,cudaMemcpyDeviceToHost,st) != cudaSuccess ||
+              cudaStreamSynchronize(st) != cudaSuccess)) rc = FGB_ERR_CUDA;
+  if (!rc)
+    { base[0] = 0;
+      for (int w = 0; w < world; w++) base[w+1] = base[w] + cnt[w];
+      if (cudaMemcpyAsync(d_cnt + 64,base,8*64,cudaMemcpyHostToDevice,st) != cudaSuccess) rc = FGB_ERR_CUDA;
+    }
+  if (!rc) rc = fgb_owner_scatter_device(d_seeds,n,p_ic,bits[3],d_owner,nrank_contigs,world,d_cnt + 64,d_out,st);
+  if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = FGB_ERR_CUDA;
+  fgb_dfree(d_owner,st); fgb_dfree(d_cnt,st);
+  if (rc) return rc;
+  for (int w = 0; w <= world; w++) bounds[w] = (long long) base[w];
+  return FGB_OK;
+}
+
+//  sorted seed set over n unsorted device records (copied); bits as fgb_seeds_merge returns them
+extern "C" int fgb_seeds_from_records(const void *d_recs, long long n, const int *bits, long long amxpos,
+                                      long long bmxpos, long long sumlen, fgb_seeds **out, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  if (n < 0 || n >= 0xfffffff0ll) return FGB_ERR_LIMIT;
+  seed_bits L;
+  L.anti = bits[0]; L.band = bits[1]; L.jc = bits[2]; L.ic = bits[3];
+  L.key = 12 + L.anti + L.band + L.jc + L.ic + 1;
+  if (L.key > 128) return FGB_ERR_LIMIT;
+  rec128 *d_a = NULL;
+  CUDA_TRY(fgb_dmalloc((void **) &d_a,sizeof(rec128)*(n+1),st));
+  if (n > 0 && cudaMemcpyAsync(d_a,d_recs,sizeof(rec128)*n,cudaMemcpyDeviceToDevice,st) != cudaSuccess)
+    { fgb_dfree(d_a,st); return FGB_ERR_CUDA; }
+  return seeds_sort_impl(d_a,n,L,amxpos,bmxpos,false,sumlen,0,out,st);
 }
 
 extern "C" long long fgb_seeds_size(const fgb_seeds *s) { return s->n; }
@@ -588,7 +771,8 @@ int fgb_filter(const fgb_overlaps *O, const int *perm1, const int *perm2, int jc
 struct fgb_run_stats
 { long long nkmers1, nkmers2, nseeds, sumlen, nhits, nla, nwaves, ncells, nraw, h2d_bytes, d2h_bytes,
             nseg, nwork, warp_cycles, wave_cycles, extract_cycles,
-            us_gix, us_seeds, us_extend, us_filter, nkmers1_fwd; };
+            us_gix, us_seeds, us_extend, us_filter, nkmers1_fwd,
+            slow_cycles, slow_waves, paired_waves, pairings; };
 
 //  Merge + seed sort + extension + filter from prebuilt tables (x2 may have been assembled from
 //  shares built on several ranks).
@@ -647,6 +831,8 @@ extern "C" int fgb_align_tables(const fgb_genome *A, const fgb_genome *B, const 
       stats->nseg = (long long) c[5]; stats->nwork = (long long) c[6];
       stats->warp_cycles = (long long) c[8]; stats->wave_cycles = (long long) c[9];
       stats->extract_cycles = (long long) c[10];
+      stats->slow_cycles = (long long) ((c[15] >> 40) << 12); stats->slow_waves = (long long) ((c[15] >> 16) & 0xffffff);
+      stats->paired_waves = (long long) c[11]; stats->pairings = (long long) c[12];
       stats->h2d_bytes = A->h2d_bytes + B->h2d_bytes + 65536*2;
       stats->d2h_bytes = fgb_overlaps_bytes(ov) + 16 + 8*1024*2 + 64;
     }

@@ -396,6 +396,135 @@ static __device__ __noinline__ void wave_back(const unsigned box_off, const shor
     }
 }
 
+//  FRONT warp of a pair: the waves of one pass from the band [lowk,hghk] (V of the last wave in rV,
+//  lane (-kk & 31) owning diagonal kk) until the pass ends, the back warp stops it, or a wave is
+//  not a plain one (then it is undone and handed back).  Everything a wave needs lives in
+//  registers; the control flow is warp-uniform by construction (the branches test ballots, redux
+//  results and band scalars only), so there is no divergence bookkeeping on the chain V -> snake
+//  -> maximum -> band trim -> V that bounds how fast one alignment can grow.
+//  Returns (lowk, hghk, besta, 1 if the pass must finish on the single-warp code without pairing).
+
+template<int s>
+static __device__ __forceinline__ int snake_u(const unsigned *__restrict__ A, const unsigned *__restrict__ B,
+                                              const int alen, const int blen, const bool act, const int xn,
+                                              const int kk, bool &ended)
+{ //  direction-normalised coordinates -> contig coordinates; `lim` = bases left on the diagonal
+  const int x = (s > 0) ? xn : -xn, y = (s > 0) ? xn - kk : kk - xn;
+  const int lim = (s > 0) ? min(alen - x,blen - y) : min(x,y);
+  const bool ok = (s > 0) ? (act && (x | y) >= 0 && lim > 0) : (act && lim > 0 && y <= blen && x <= alen);
+  const int xo = ok ? x : ((s > 0) ? 0 : 32), yo = ok ? y : ((s > 0) ? 0 : 32);     // idle lanes read a valid window
+  int t;
+  { const u64 dd = (s > 0) ? (win(A,xo) ^ win(B,yo)) : (win(A,xo-32) ^ win(B,yo-32));
+    t = dd ? ((s > 0) ? ((__ffsll((long long) dd)-1) >> 1) : (__clzll((long long) dd) >> 1)) : 32;
+  }
+  bool cont = ok && t == 32 && 32 < lim;
+  while (__any_sync(FULL,cont))                                   // a run of 32+ matches (one lane in five at 5 %)
+    { const int o = cont ? t : 0;
+      const u64 dd = (s > 0) ? (win(A,xo+o) ^ win(B,yo+o)) : (win(A,xo-o-32) ^ win(B,yo-o-32));
+      const int m = dd ? ((s > 0) ? ((__ffsll((long long) dd)-1) >> 1) : (__clzll((long long) dd) >> 1)) : 32;
+      if (cont) t += m;
+      cont = cont && m == 32 && t < lim;
+    }
+  ended = act && (!ok || t >= lim);
+  return ok ? min(t,lim) : 0;
+}
+
+//  which end stopped the slide: 1 = B's, 2 = A's (B is tested first, align.c:683-697)
+template<int s>
+static __device__ __forceinline__ int end_flag(const int alen, const int blen, const int xn0, const int kk, const int t)
+{ const int x = (s > 0) ? xn0 : -xn0, y = (s > 0) ? xn0 - kk : kk - xn0;
+  const int lim = (s > 0) ? min(alen - x,blen - y) : min(x,y);
+  if (s > 0)
+    { if ((x | y) < 0 || lim <= 0) return (y < 0 || y >= blen) ? 1 : 2;
+      return (y + t == blen) ? 1 : 2;
+    }
+  if (lim <= 0 || y > blen || x > alen) return (y <= 0 || y > blen) ? 1 : 2;
+  return (y - t == 0) ? 1 : 2;
+}
+
+template<int s>
+static __device__ __noinline__ int4 front_run(const unsigned box_off, const unsigned *__restrict__ A,
+                                              const unsigned *__restrict__ B, const int alen, const int blen,
+                                              int lowk, int hghk, int besta, int rV)
+{ PairBox *const bx = reinterpret_cast<PairBox *>(ex_smem + box_off);
+  const SeqV q = { A, B, alen, blen };
+  const int lane = threadIdx.x & 31;
+  const int FRESH = (s > 0) ? -1 : -INT_MAX;
+  const int lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;      // owners of kk+1 / kk-1
+  int d = 0, tail_seen = 0, alone = 0;
+  while (true)
+    { const int lowk0 = lowk, hghk0 = hghk;
+      lowk -= 1; hghk += 1;
+      const int top = hghk, ltop = (-top) & 31;
+      const int kk = top - ((top + lane) & 31);
+      const bool act = kk >= lowk;
+      bool bail = (hghk - lowk > 30);
+      const bool wide = bail;
+      int cc = 0, mx = 0, nmore = 1;
+      unsigned m = 0;
+      if (!bail)
+        { const int vp = __shfl_sync(FULL,rV,lane_up), vm = __shfl_sync(FULL,rV,lane_dn);
+          const int c0 = max(max(vp,vm)+1,rV+2);
+          const int xn0 = (c0 + kk) >> 1;
+          bool ended;
+          const int t = snake_u<s>(A,B,alen,blen,act,xn0,kk,ended);
+          const int xn = xn0 + t;
+          cc = 2*xn - kk;
+          mx = __reduce_max_sync(FULL,act ? cc : INT_MIN);
+          int nlow = lowk, nhgh = hghk;
+          if (mx <= besta) bail = true;
+          else
+            { const unsigned en = __ballot_sync(FULL,ended);
+              if (en)                                              // a slide reached a contig end (rare)
+                { const int flag = ended ? end_flag<s>(alen,blen,xn0,kk,t) : 0;
+                  const unsigned hb = rotr32(__ballot_sync(FULL,flag == 1),ltop);
+                  const unsigned hq = rotr32(__ballot_sync(FULL,flag == 2),ltop);
+                  const unsigned eq = rotr32(__ballot_sync(FULL,act && cc == mx),ltop);
+                  const int bx_ = __shfl_sync(FULL,xn,(ltop + __ffs(eq) - 1) & 31);
+                  if (hb) { const int bcl = top - (__ffs(hb)-1);     if (nlow <= bcl) nlow = bcl+1; }
+                  if (hq) { const int acl = top - (31 - __clz(hq));  if (nhgh >= acl) nhgh = acl-1; }
+                  nmore = (b_at<s>(q,mx-bx_) != 4 && a_at<s>(q,bx_) != 4);
+                }
+              m = rotr32(__ballot_sync(FULL,kk >= nlow && kk <= nhgh && cc >= mx - WAVE_LAG),ltop);
+              if (m == 0) bail = true;
+            }
+        }
+      if (bail)
+        { //  not a plain wave: undo it, let the back warp spill, finish alone
+          lowk = lowk0; hghk = hghk0;
+          if (!wide) alone = 1;                          // pathological wave: stay alone for the rest of the pass
+          int spin = 0;
+          while (d + 1 - bx->tail > EX_RING-1 && bx->stop == 0) if (++spin > SPIN_LIMIT) break;
+          __syncwarp();
+          if (lane == 0)
+            { bx->ring[(d+1) & (EX_RING-1)].cmd = 3;
+              st_release_smem(&bx->head,d+1);
+            }
+          break;
+        }
+      d += 1;
+      besta = mx;
+      hghk = top - (__ffs(m)-1); lowk = top - (31 - __clz(m));
+      rV = (kk >= lowk && kk <= hghk) ? cc : FRESH;
+      if (d - tail_seen > EX_RING-1)
+        { int spin = 0;
+          while (d - (tail_seen = bx->tail) > EX_RING-1 && bx->stop == 0) if (++spin > SPIN_LIMIT) break;
+        }
+      RingEnt *e = &bx->ring[d & (EX_RING-1)];
+      e->cc[lane] = cc;
+      if (lane == 0)
+        { *(int4 *) e = make_int4(nmore ? 1 : 2,top,lowk0-1,mx);
+          *(int2 *) &e->lowk_after = make_int2(lowk,hghk);
+        }
+      if (!nmore || (d & 1) == 0)                        // publish every other wave
+        { __syncwarp();
+          if (lane == 0) st_release_smem(&bx->head,d);
+        }
+      if (!nmore || ((d & 7) == 0 && bx->stop != 0)) break;
+    }
+  return make_int4(lowk,hghk,besta,alone);
+}
+
 template<int s, int W>
 static __device__ __noinline__ int wave(Ctx &c, int low, int hgh, const int mida, int minp, int maxp,
                            const int aoff, int &endx, int &endy, int &diffs, int &trimha_out)
@@ -511,78 +640,12 @@ static __device__ __noinline__ int wave(Ctx &c, int low, int hgh, const int mida
           { const int kk = hghk - ((lane - ((-hghk) & 31)) & 31);
             rV = (kk >= lowk) ? c.V[IX(kk)] : FRESH;
           }
-          int d = 0, stp = 0, tail_seen = 0;
+          int stp = 0;
           long long fwait = 0; const long long ft0 = DIAG_CLOCK();
-          while (true)
-            { const int lowk0 = lowk, hghk0 = hghk;
-              lowk -= 1; hghk += 1;
-              const int top = hghk, ltop = (-top) & 31;
-              const int kk = top - ((lane - ltop) & 31);
-              const bool act = kk >= lowk;
-              bool bail = (hghk - lowk > 30);
-              const bool wide = bail;
-              int cc = 0, xn = 0, flag = 0, mx = 0;
-              unsigned m = 0;
-              int nlow = lowk, nhgh = hghk, nmore = 1;
-              if (!bail)
-                { int vp = __shfl_sync(FULL,rV,lane_up), vm = __shfl_sync(FULL,rV,lane_dn);
-                  cc = max(max(vp,vm)+1,rV+2);
-                  xn = (cc + kk) >> 1;
-                  if (act) xn += snake<s>(q,xn,kk,flag);
-                  cc = 2*xn - kk;
-                  mx = __reduce_max_sync(FULL,act ? cc : INT_MIN);
-                  if (mx <= besta) bail = true;
-                }
-              if (!bail)
-                { if (__any_sync(FULL,act && flag != 0))
-                    { unsigned hb = rotr32(__ballot_sync(FULL,act && flag == 1),ltop);
-                      unsigned hq = rotr32(__ballot_sync(FULL,act && flag == 2),ltop);
-                      unsigned eq = rotr32(__ballot_sync(FULL,act && cc == mx),ltop);
-                      int bx_ = __shfl_sync(FULL,xn,(ltop + __ffs(eq) - 1) & 31);
-                      int acl = INT_MAX, bcl = -INT_MAX;
-                      if (hb) bcl = top - (__ffs(hb)-1);
-                      if (hq) acl = top - (31 - __clz(hq));
-                      nmore = (b_at<s>(q,mx-bx_) != 4 && a_at<s>(q,bx_) != 4);
-                      if (nhgh >= acl) nhgh = acl-1;
-                      if (nlow <= bcl) nlow = bcl+1;
-                    }
-                  m = rotr32(__ballot_sync(FULL,kk >= nlow && kk <= nhgh && cc >= mx - WAVE_LAG),ltop);
-                  if (m == 0) bail = true;
-                }
-              if (bail)
-                { //  not a plain wave: undo it, let the back warp spill, finish alone below
-                  lowk = lowk0; hghk = hghk0;
-                  if (!wide) pair_ok = false;                  // pathological wave: stay alone for the rest of the pass
-                  int spin = 0;
-                  while (d + 1 - bx->tail > EX_RING-1 && bx->stop == 0) if (++spin > SPIN_LIMIT) break;
-                  __syncwarp();
-                  if (lane == 0)
-                    { bx->ring[(d+1) & (EX_RING-1)].cmd = 3;
-                      st_release_smem(&bx->head,d+1);
-                    }
-                  break;
-                }
-              d += 1;
-              besta = mx;
-              hghk = top - (__ffs(m)-1); lowk = top - (31 - __clz(m));
-              rV = (kk >= lowk && kk <= hghk) ? cc : FRESH;
-              if (d - tail_seen > EX_RING-1)
-                { int spin = 0; long long w0 = DIAG_CLOCK();
-                  while (d - (tail_seen = bx->tail) > EX_RING-1 && bx->stop == 0) if (++spin > SPIN_LIMIT) break;
-                  fwait += DIAG_CLOCK() - w0;
-                }
-              RingEnt *e = &bx->ring[d & (EX_RING-1)];
-              e->cc[lane] = cc;
-              if (lane == 0)
-                { *(int4 *) e = make_int4(nmore ? 1 : 2,top,lowk0-1,mx);
-                  e->lowk_after = lowk; e->hghk_after = hghk;
-                }
-              if (!nmore || (d & 1) == 0)                        // publish every other wave
-                { __syncwarp();
-                  if (lane == 0) st_release_smem(&bx->head,d);
-                }
-              if (!nmore || ((d & 7) == 0 && bx->stop != 0)) break;
-            }
+          { const int4 fr = front_run<s>(c.box_off,q.A,q.B,q.alen,q.blen,lowk,hghk,besta,rV);
+            lowk = fr.x; hghk = fr.y; besta = fr.z;
+            if (fr.w) pair_ok = false;
+          }
           { int spin = 0; long long w0 = DIAG_CLOCK();
             while ((stp = ld_acquire_smem(&bx->stop)) == 0) if (++spin > SPIN_LIMIT) { stp = 1; break; }
             fwait += DIAG_CLOCK() - w0;

@@ -324,13 +324,29 @@ syncmer_kernel(const u64 *__restrict__ seq, const long long *__restrict__ clen,
  **********************************************************************************************/
 
 __global__ void kix_index_kernel(const rec128 *__restrict__ tab, long long n,
-                                 unsigned *__restrict__ pstart)
+                                 unsigned *__restrict__ pstart, unsigned char *__restrict__ adj)
 { long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
-  long long plo = (i == 0) ? -1 : (long long) KREC_PREFIX24(tab[i-1].hi);
-  long long phi = (i == n) ? (1ll << 24) : (long long) KREC_PREFIX24(tab[i].hi);
+  rec128 a, b;
+  a.lo = a.hi = b.lo = b.hi = 0;
+  if (i > 0) a = ld_rec(tab + i - 1);
+  if (i < n) b = ld_rec(tab + i);
+  long long plo = (i == 0) ? -1 : (long long) KREC_PREFIX24(a.hi);
+  long long phi = (i == n) ? (1ll << 24) : (long long) KREC_PREFIX24(b.hi);
   for (long long x = plo+1; x <= phi; x++)
     pstart[x] = (unsigned) i;
+  //  adj[i] = LCP in bases of entries i-1 and i (the LCP byte of the reference's .ktab entries,
+  //  GIXmake.c:1249-1254), 0 at both ends of the table: the merge takes block extents from it
+  int l = 0;
+  if (i > 0 && i < n)
+    { unsigned long long x = a.hi ^ b.hi;
+      if (x) l = __clzll(x) >> 1;
+      else
+        { unsigned y = (unsigned) ((a.lo ^ b.lo) >> 48);
+          l = y ? 32 + ((__clz(y) - 16) >> 1) : 40;
+        }
+    }
+  adj[i] = (unsigned char) l;
 }
 
 static __device__ __forceinline__ int krec_lcp(const rec128 &a, const rec128 &b)
@@ -467,10 +483,13 @@ extern "C" int fgb_syncmer_emit_device(const void *d_seq, const long long *d_cle
   return FGB_OK;
 }
 
-extern "C" int fgb_kix_index_device(const void *d_tab, long long n, unsigned *d_pstart, void *stream)
+//  d_adj: n + 32 bytes (entries past n are zeroed: the merge's slice loads run up to 31 bytes over)
+extern "C" int fgb_kix_index_device(const void *d_tab, long long n, unsigned *d_pstart, unsigned char *d_adj,
+                                    void *stream)
 { cudaStream_t st = (cudaStream_t) stream;
   int nb = (int) ((n + 1 + 255) / 256);
-  kix_index_kernel<<<nb,256,0,st>>>((const rec128 *) d_tab,n,d_pstart);
+  CUDA_TRY(cudaMemsetAsync(d_adj + n,0,32,st));
+  kix_index_kernel<<<nb,256,0,st>>>((const rec128 *) d_tab,n,d_pstart,d_adj);
   fgb_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return FGB_OK;

@@ -22,6 +22,7 @@ struct fgb_gix
 { long long n = 0;
   struct rec128 *d_tab = nullptr;
   unsigned *d_pstart = nullptr;            // [2^24+1] lower-bound index by 12-base prefix
+  unsigned char *d_adj = nullptr;          // [n+32] LCP in bases of entries i-1 and i (0 at the table ends)
   unsigned long long buck1024[1024] = {0}; // sampler histogram (decides the .ktab part split)
   int post_bytes = 0, cont_bytes = 0, ncontig = 0;
   int fwd_only = 0;                        // forward-strand entries only (adaptamer side of a merge)

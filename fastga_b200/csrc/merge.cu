@@ -36,8 +36,8 @@ static __host__ __device__ __forceinline__ int seed_key_bits(const seed_layout &
 
 #define MG_THREADS 256
 #define MG_WARPS   (MG_THREADS/32)
-#define MG_T2CAP   1536                   // staged T2 entries per CTA (24 KB)
-#define MG_DCAP    4608                   // seed descriptors per CTA (512 entries x (FREQ-1 = 9))
+#define MG_T2CAP   1280                   // staged T2 entries per CTA (20 KB)
+#define MG_DCAP    2560                   // seed descriptors per CTA (5 per T1 entry; crowded tiles write entry-wise)
 //  lcp (in bases, 0..28) of two 56-bit suffixes
 static __device__ __forceinline__ int lcp56(u64 a, u64 b)
 { u64 x = a ^ b;
@@ -88,7 +88,7 @@ template<int TILE> struct mg_stage
   rec128   t1[TILE];                      // the T1 tile (TMA destination)
   unsigned desc[MG_DCAP];                 // per seed: T2 slot (11) | T1 slot (9) << 11 | (plen-12) << 20
   unsigned wtot[2*MG_WARPS], wsum[2*MG_WARPS];
-  unsigned char adj[MG_T2CAP+16];         // adj[i] = LCP in bases of slice entries i-1 and i; 0 at both ends
+  unsigned char adj[MG_T2CAP+48];         // LCP bytes of the slice (TMA destination; starts at the 16-byte boundary below the slice)
   unsigned rng[4];
   unsigned long long gbase;
   unsigned long long bar;
@@ -96,22 +96,26 @@ template<int TILE> struct mg_stage
 
 //  Adaptamer of one T1 entry against the staged slice: |R| (0 if no seed), first slice slot of R, plen.
 //  Written for the WARP, not the lane: the panel search runs a warp-uniform number of predicated
-//  halving steps (no divergent loop), and the extent of R comes from the slice's adjacent-entry LCP
-//  bytes (adj[i] = LCP(t2[i-1],t2[i]); T2 is sorted, so t2[i-1] belongs to R iff t2[i] does and
-//  adj[i] >= plen -- the LCP byte of the reference's .ktab entries, rebuilt per slice): two predicated
-//  steps per side, then a rarely entered warp-uniform loop.  adj[0] = adj[nsl] = 0 end every walk.
+//  halving steps (no divergent loop), and the extent of R comes from the table's adjacent-entry LCP
+//  bytes (adj[i] = LCP(t2[i-1],t2[i]), the LCP byte of the reference's .ktab entries; T2 is sorted, so
+//  t2[i-1] belongs to R iff t2[i] does and adj[i] >= plen): two predicated steps per side, then a
+//  warp-uniform loop.  The bytes either side of the slice belong to other panels (< 12) and end every walk.
 static __device__ __forceinline__ unsigned adaptamer_staged(const rec128 *__restrict__ t2,
                                                             const unsigned char *__restrict__ adj, unsigned nsl,
                                                             const rec128 &r1, unsigned lo, unsigned hi, int freq,
                                                             unsigned &lowi, int &plen)
-{ const u64 k1 = r1.lo >> 48;
+{ const unsigned k1 = (unsigned) (r1.lo >> 48);
+  const u64 *t2w = reinterpret_cast<const u64 *>(t2);
   unsigned a = lo, b = hi;                                    // lower bound of r1's k-mer inside its panel [lo,hi)
   for (unsigned w = __reduce_max_sync(0xffffffffu,hi - lo); w > 0; w >>= 1)
-    if (a < b)
-      { unsigned m = (a + b) >> 1;
-        rec128 q = ld_rec(t2 + m);
-        if (q.hi < r1.hi || (q.hi == r1.hi && (q.lo >> 48) < k1)) a = m+1; else b = m;
-      }
+    { const unsigned m = (a + b) >> 1;                        // a == b: a probe with no effect
+      const u64 qh = t2w[2*m+1];
+      const unsigned ql = (unsigned) (t2w[2*m] >> 48);
+      const bool less = (qh < r1.hi) || (qh == r1.hi && ql < k1);
+      const bool live = a < b;
+      if (live && less) a = m+1;
+      if (live && !less) b = m;
+    }
   //  the neighbours of the insertion point decide plen; a neighbour in another panel (the slice only
   //  holds the tile's panels, so this covers the slice ends too) shares fewer than 12 bases
   int ll = 0, lr = 0;
@@ -192,10 +196,10 @@ __global__ void merge_ranges_kernel(const rec128 *__restrict__ T1, unsigned n1, 
 }
 
 template<int TILE>
-__global__ void __launch_bounds__(MG_THREADS)
+__global__ void __launch_bounds__(MG_THREADS,5)
 adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
                        const rec128 *__restrict__ T2, const unsigned *__restrict__ pstart2,
-                       const uint4 *__restrict__ rng, int freq, seed_pack K,
+                       const unsigned char *__restrict__ adj2, const uint4 *__restrict__ rng, int freq, seed_pack K,
                        rec128 *__restrict__ seeds, unsigned long long capacity,
                        unsigned long long *__restrict__ counters /* [0]=nseeds [1]=sum plen */)
 { extern __shared__ __align__(16) unsigned char mg_smem[];
@@ -210,19 +214,20 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
       S->rng[0] = r.x; S->rng[1] = r.y; S->rng[2] = r.z; S->rng[3] = r.w;
       mbar_init(&S->bar,1);
       const bool st = (r.w <= MG_T2CAP);
-      mbar_expect_tx(&S->bar,nt1*16u + ((st && r.w) ? r.w*16u : 0u));
+      //  LCP bytes of the slice and one beyond, from the 16-byte boundary at or below the slice start
+      const unsigned ab = ((r.z & 15u) + r.w + 1u + 15u) & ~15u;
+      mbar_expect_tx(&S->bar,nt1*16u + ((st && r.w) ? r.w*16u + ab : 0u));
       tma_copy_1d(S->t1,T1 + b0,nt1*16u,&S->bar);
-      if (st && r.w) tma_copy_1d(S->t2,T2 + r.z,r.w*16u,&S->bar);
+      if (st && r.w)
+        { tma_copy_1d(S->t2,T2 + r.z,r.w*16u,&S->bar);
+          tma_copy_1d(S->adj,adj2 + (r.z & ~15u),ab,&S->bar);
+        }
     }
   __syncthreads();
   const unsigned lo2 = S->rng[2], nsl = S->rng[3];
   const bool staged = (nsl <= MG_T2CAP);
   mbar_wait(&S->bar,0);
-  if (staged)
-    { for (unsigned j = tid; j <= nsl; j += MG_THREADS)
-        S->adj[j] = (j > 0 && j < nsl) ? (unsigned char) lcp_rec(ld_rec(&S->t2[j-1]),ld_rec(&S->t2[j])) : (unsigned char) 0;
-      __syncthreads();
-    }
+  const unsigned char *const adj = S->adj + (lo2 & 15u);       // adj[i]: slice entries i-1 and i
 
   //  search: thread tid owns tile entries tid, tid+256, ...
   const u64 *t2k = reinterpret_cast<const u64 *>(S->t2);
@@ -242,7 +247,7 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
               const unsigned p = KREC_PREFIX24(r1.hi);
               lo = __ldg(pstart2 + p) - lo2; hi = __ldg(pstart2 + p + 1) - lo2;
             }
-          cnt[r] = adaptamer_staged(S->t2,S->adj,nsl,r1,lo,hi,freq,lowi[r],plen[r]);
+          cnt[r] = adaptamer_staged(S->t2,adj,nsl,r1,lo,hi,freq,lowi[r],plen[r]);
         }
       else if (j < nt1)
         cnt[r] = adaptamer_direct(T2,pstart2,ld_rec(&S->t1[j]),freq,lowi[r],plen[r]);
@@ -474,7 +479,8 @@ extern "C" int fgb_self_merge_device(const void *d_T, long long n, const unsigne
 //  (FGB_ERR_OVERFLOW).
 
 template<int TILE>
-static int merge_launch(const rec128 *T1, unsigned n1, const rec128 *T2, const unsigned *pstart2, int freq,
+static int merge_launch(const rec128 *T1, unsigned n1, const rec128 *T2, const unsigned *pstart2,
+                        const unsigned char *adj2, int freq,
                         const seed_pack &K, rec128 *seeds, unsigned long long capacity,
                         unsigned long long *counters, cudaStream_t st)
 { const int smem = (int) sizeof(mg_stage<TILE>);
@@ -486,7 +492,7 @@ static int merge_launch(const rec128 *T1, unsigned n1, const rec128 *T2, const u
   cudaEventCreate(&ea); cudaEventCreate(&eb);
   cudaEventRecord(ea,st);
   merge_ranges_kernel<<<(nb + 255)/256,256,0,st>>>(T1,n1,pstart2,(unsigned) TILE,nb,d_rng);
-  adaptamer_merge_kernel<TILE><<<nb,MG_THREADS,smem,st>>>(T1,n1,T2,pstart2,d_rng,freq,K,seeds,capacity,counters);
+  adaptamer_merge_kernel<TILE><<<nb,MG_THREADS,smem,st>>>(T1,n1,T2,pstart2,adj2,d_rng,freq,K,seeds,capacity,counters);
   cudaEventRecord(eb,st);
   cudaEventSynchronize(eb);
   float ms = 0; cudaEventElapsedTime(&ms,ea,eb);
@@ -498,7 +504,7 @@ static int merge_launch(const rec128 *T1, unsigned n1, const rec128 *T2, const u
 }
 
 extern "C" int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2, long long n2,
-                                const unsigned *d_pstart2, int freq,
+                                const unsigned *d_pstart2, const unsigned char *d_adj2, int freq,
                                 int anti_bits, int band_bits, int jc_bits, int ic_bits,
                                 long long amxpos, long long bmxpos,
                                 void *d_seeds, long long capacity, unsigned long long *d_counters,
@@ -521,11 +527,11 @@ extern "C" int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2
       //  all of genome 2), the smaller the tile, so that the CTA's T2 slice fits the staging buffer
       double ratio = (double) (n2 > 0 ? n2 : 1) / (double) n1;
       int rc;
-#define MG_ARGS (const rec128 *) d_T1,(unsigned) n1,(const rec128 *) d_T2,d_pstart2,freq,K,(rec128 *) d_seeds, \
+#define MG_ARGS (const rec128 *) d_T1,(unsigned) n1,(const rec128 *) d_T2,d_pstart2,d_adj2,freq,K,(rec128 *) d_seeds, \
                 (unsigned long long) capacity,d_counters,st
-      if (ratio <= 2.5)       rc = merge_launch<512>(MG_ARGS);
-      else if (ratio <= 5.0)  rc = merge_launch<256>(MG_ARGS);
-      else if (ratio <= 10.0) rc = merge_launch<128>(MG_ARGS);
+      if (ratio <= 2.2)       rc = merge_launch<512>(MG_ARGS);
+      else if (ratio <= 4.4)  rc = merge_launch<256>(MG_ARGS);
+      else if (ratio <= 8.8)  rc = merge_launch<128>(MG_ARGS);
       else                    rc = merge_launch<64>(MG_ARGS);
 #undef MG_ARGS
       if (rc) return rc;
@@ -537,4 +543,67 @@ extern "C" int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2
   *h_nseeds = h[0];
   if (h_sumlen) *h_sumlen = h[1];
   return (h[0] > (unsigned long long) capacity) ? FGB_ERR_OVERFLOW : FGB_OK;
+}
+
+/***********************************************************************************************
+ *  Seeds to their A-contig's owner (k-mer-space sharded path): count per owner, then scatter.
+ *  A CTA counts / places its 2048 seeds in shared memory first, so the global counters see one
+ *  atomic per owner and CTA.
+ **********************************************************************************************/
+
+static __device__ __forceinline__ unsigned seed_icont(const rec128 &r, int p_ic, int ic_bits)
+{ u64 v = (p_ic >= 64) ? (r.hi >> (p_ic - 64)) : ((r.lo >> p_ic) | (p_ic ? (r.hi << (64 - p_ic)) : 0ull));
+  return (unsigned) (v & ((1ull << ic_bits) - 1));
+}
+
+#define OW_ITEMS 8
+template<bool SCATTER>
+__global__ void __launch_bounds__(256)
+seed_owner_kernel(const rec128 *__restrict__ seeds, long long n, int p_ic, int ic_bits,
+                  const int *__restrict__ owner, int nrc, int world, unsigned long long *__restrict__ cnt_or_base,
+                  rec128 *__restrict__ out)
+{ __shared__ unsigned s_cnt[64];
+  __shared__ unsigned long long s_base[64];
+  if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const long long t0 = (long long) blockIdx.x * (256*OW_ITEMS);
+  rec128 r[OW_ITEMS]; int w[OW_ITEMS]; unsigned slot[OW_ITEMS];
+#pragma unroll
+  for (int it = 0; it < OW_ITEMS; it++)
+    { const long long i = t0 + it*256 + threadIdx.x;
+      w[it] = -1;
+      if (i < n)
+        { r[it] = ld_rec(seeds + i);
+          const unsigned ic = seed_icont(r[it],p_ic,ic_bits);
+          w[it] = (ic < (unsigned) nrc) ? owner[ic] : 0;
+          slot[it] = atomicAdd(&s_cnt[w[it]],1u);
+        }
+    }
+  __syncthreads();
+  if (threadIdx.x < world && s_cnt[threadIdx.x])
+    s_base[threadIdx.x] = atomicAdd(&cnt_or_base[threadIdx.x],(unsigned long long) s_cnt[threadIdx.x]);
+  if (!SCATTER) return;
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < OW_ITEMS; it++)
+    if (w[it] >= 0) st_rec(out + s_base[w[it]] + slot[it],r[it]);
+}
+
+extern "C" int fgb_owner_count_device(const void *d_seeds, long long n, int p_ic, int ic_bits, const int *d_owner,
+                                      int nrc, int world, unsigned long long *d_cnt, void *stream)
+{ unsigned nb = (unsigned) ((n + 256*OW_ITEMS - 1) / (256*OW_ITEMS));
+  seed_owner_kernel<false><<<nb,256,0,(cudaStream_t) stream>>>((const rec128 *) d_seeds,n,p_ic,ic_bits,d_owner,nrc,
+                                                              world,d_cnt,NULL);
+  fgb_count_launch(1);
+  CUDA_TRY(cudaGetLastError());
+  return FGB_OK;
+}
+extern "C" int fgb_owner_scatter_device(const void *d_seeds, long long n, int p_ic, int ic_bits, const int *d_owner,
+                                        int nrc, int world, unsigned long long *d_base, void *d_out, void *stream)
+{ unsigned nb = (unsigned) ((n + 256*OW_ITEMS - 1) / (256*OW_ITEMS));
+  seed_owner_kernel<true><<<nb,256,0,(cudaStream_t) stream>>>((const rec128 *) d_seeds,n,p_ic,ic_bits,d_owner,nrc,
+                                                             world,d_base,(rec128 *) d_out);
+  fgb_count_launch(1);
+  CUDA_TRY(cudaGetLastError());
+  return FGB_OK;
 }

@@ -311,6 +311,15 @@ __global__ void kmer_bins_kernel(const rec128 *__restrict__ tab, long long n, in
   for (long long p = lo+1; p <= hi; p++) bin_start[p] = (unsigned) i;
 }
 
+//  bin_start[p], p = 0..65536, for bins = hi >> binshift (host-callable)
+extern "C" int fgb_kmer_bins_device(const void *d_tab, long long n, int binshift, unsigned *d_bins, void *stream)
+{ int nb = (int) ((n + 1 + 255) / 256);
+  kmer_bins_kernel<<<nb,256,0,(cudaStream_t) stream>>>((const rec128 *) d_tab,n,binshift,0ull,d_bins);
+  fgb_count_launch(1);
+  CUDA_TRY(cudaGetLastError());
+  return FGB_OK;
+}
+
 //  One CTA sorts one group (<= BK_CAP records of <= BK_SPAN consecutive bins) by the full 128-bit
 //  value.  Fast path: a counting split on the next 10 key bits (shared-memory atomics) leaves
 //  sub-bins of one or two records, and every record finds its place by comparing itself with its

@@ -419,7 +419,7 @@ class RunStats(C.Structure):
     _fields_ = [(n, c_ll) for n in ("nkmers1", "nkmers2", "nseeds", "sumlen", "nhits", "nla", "nwaves",
                                     "ncells", "nraw", "h2d_bytes", "d2h_bytes", "nseg", "nwork", "warp_cycles",
                                     "wave_cycles", "extract_cycles", "us_gix", "us_seeds", "us_extend", "us_filter",
-                                    "nkmers1_fwd")]
+                                    "nkmers1_fwd", "slow_cycles", "slow_waves", "paired_waves", "pairings")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -510,3 +510,102 @@ def fastga(gA, gB, stream=None, **kw):
                         p["freq"], p["chain_break"], p["chain_min"], p["align_min"], float(p["align_rate"]),
                         C.byref(h), C.byref(st), stream), "fgb_fastga")
     return _alns_out(h), st.asdict()
+
+
+def compute_trace_pts(dA, dB, alns, tspace=100, stream=None):
+    """Compute_Trace_PTS for every alignment of `alns` (an Alignments): returns (soff, script, diffs) --
+    script[soff[i]:soff[i+1]] is the edit script the reference leaves in path->trace, diffs[i] its
+    path->diffs (-1: trace points inconsistent with the sequences).  dB needs want_revcomp=True when
+    strand-C records are present."""
+    L = load_library()
+    h = c_void_p()
+    fields = np.ascontiguousarray(alns.fields, dtype=np.int32)
+    toff = np.ascontiguousarray(alns.toff, dtype=np.int64)
+    pool = np.ascontiguousarray(alns.pool, dtype=np.uint8)
+    L.fgb_compute_trace_pts.argtypes = [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_int,
+                                        C.POINTER(c_void_p), c_void_p]
+    _check(L.fgb_compute_trace_pts(dA.h, dB.h, len(alns), _ptr(fields), _ptr(toff), _ptr(pool), tspace,
+                                   C.byref(h), stream), "fgb_compute_trace_pts")
+    L.fgb_scripts_total.restype = c_ll
+    L.fgb_scripts_total.argtypes = [c_void_p]
+    n, tot = len(alns), L.fgb_scripts_total(h)
+    soff = np.zeros(n + 1, dtype=np.int64)
+    script = np.zeros(max(tot, 1), dtype=np.int32)
+    diffs = np.zeros(max(n, 1), dtype=np.int32)
+    L.fgb_scripts_get.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    _check(L.fgb_scripts_get(h, _ptr(soff), _ptr(script), _ptr(diffs)), "fgb_scripts_get")
+    L.fgb_scripts_free.argtypes = [c_void_p]
+    L.fgb_scripts_free(h)
+    return soff, script[:tot], diffs[:n]
+
+
+# ---- building blocks of the k-mer-space sharded path (several GPUs; orchestrated by shard.py) ----
+
+def device_free(ptr):
+    L = load_library()
+    L.fgb_device_free.argtypes = [c_void_p]
+    L.fgb_device_free(c_void_p(ptr))
+
+
+def kmers_scan(dgenome, mask, fwd_only, stream=None):
+    """unsorted k-mer records of the contigs with mask[c] != 0 -> (device pointer, n); free with device_free"""
+    L = load_library()
+    ptr, n = c_void_p(), c_ll()
+    m = np.ascontiguousarray(mask, dtype=np.uint8)
+    L.fgb_kmers_scan.argtypes = [c_void_p, c_void_p, c_int, C.POINTER(c_void_p), C.POINTER(c_ll), c_void_p]
+    _check(L.fgb_kmers_scan(dgenome.h, _ptr(m), int(fwd_only), C.byref(ptr), C.byref(n), stream), "fgb_kmers_scan")
+    return ptr.value, n.value
+
+
+def records_group_by_top_byte(src_ptr, n, dst_ptr, stream=None):
+    """groups n records by the first four bases of the k-mer into dst; returns bounds[257]"""
+    L = load_library()
+    bounds = np.zeros(257, dtype=np.int64)
+    L.fgb_records_group_by_top_byte.argtypes = [c_void_p, c_ll, c_void_p, c_void_p, c_void_p]
+    _check(L.fgb_records_group_by_top_byte(c_void_p(src_ptr), n, c_void_p(dst_ptr), _ptr(bounds), stream),
+           "fgb_records_group_by_top_byte")
+    return bounds
+
+
+def gix_from_records(ptr, n, plo, phi, fwd_only, post_bytes, cont_bytes, ncontig, stream=None):
+    L = load_library()
+    h = c_void_p()
+    L.fgb_gix_from_records.argtypes = [c_void_p, c_ll, C.c_uint, C.c_uint, c_int, c_int, c_int, c_int,
+                                       C.POINTER(c_void_p), c_void_p]
+    _check(L.fgb_gix_from_records(c_void_p(ptr), n, plo, phi, int(fwd_only), post_bytes, cont_bytes, ncontig,
+                                  C.byref(h), stream), "fgb_gix_from_records")
+    return DeviceGix(h)
+
+
+def seeds_merge(gix1, gix2, amxpos, bmxpos, freq=10, stream=None):
+    """unsorted seeds of gix1 x gix2 -> (device pointer, n, bits[4], sumlen, n1_merged); free with device_free"""
+    L = load_library()
+    ptr, n = c_void_p(), c_ll()
+    bits = (c_int * 4)()
+    info = (c_ll * 2)()
+    L.fgb_seeds_merge.argtypes = [c_void_p, c_void_p, c_ll, c_ll, c_int, C.POINTER(c_void_p), C.POINTER(c_ll),
+                                  c_void_p, c_void_p, c_void_p]
+    _check(L.fgb_seeds_merge(gix1.h, gix2.h, amxpos, bmxpos, freq, C.byref(ptr), C.byref(n), bits, info, stream),
+           "fgb_seeds_merge")
+    return ptr.value, n.value, tuple(bits), info[0], info[1]
+
+
+def seeds_group_by_owner(src_ptr, n, bits, owner_by_rank, world, dst_ptr, stream=None):
+    L = load_library()
+    bounds = np.zeros(world + 1, dtype=np.int64)
+    b = (c_int * 4)(*bits)
+    ow = np.ascontiguousarray(owner_by_rank, dtype=np.int32)
+    L.fgb_seeds_group_by_owner.argtypes = [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    _check(L.fgb_seeds_group_by_owner(c_void_p(src_ptr), n, b, _ptr(ow), len(ow), world, c_void_p(dst_ptr),
+                                      _ptr(bounds), stream), "fgb_seeds_group_by_owner")
+    return bounds
+
+
+def seeds_from_records(ptr, n, bits, amxpos, bmxpos, sumlen=0, stream=None):
+    L = load_library()
+    h = c_void_p()
+    b = (c_int * 4)(*bits)
+    L.fgb_seeds_from_records.argtypes = [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_ll, C.POINTER(c_void_p), c_void_p]
+    _check(L.fgb_seeds_from_records(c_void_p(ptr), n, b, amxpos, bmxpos, sumlen, C.byref(h), stream),
+           "fgb_seeds_from_records")
+    return DeviceSeeds(h)

@@ -114,3 +114,115 @@ def build_table_cooperatively(dgenome, dist, device):
     gx = DeviceGix.from_device(full.data_ptr(), total, pb, cb, dgenome.genome.ncontig)
     del gathered, full, local
     return gx
+
+
+# ---------------------------------------------------------------------------------------------
+#  k-mer-space sharding (the N > 1 path of bench.py): nothing is replicated.
+#    1. every rank scans ITS contigs of both genomes (syncmer scan + record build);
+#    2. the k-mer records travel to the rank that owns their prefix range (all-to-all #1);
+#    3. every rank sorts + indexes its slice of both tables and merges them -> seeds;
+#    4. the seeds travel to the rank that owns their A-contig (all-to-all #2);
+#    5. every rank sorts its seeds and extends them; rank 0 gathers the records.
+#  Both exchanges move 16-byte records between device buffers with NCCL (all_to_all_single).
+# ---------------------------------------------------------------------------------------------
+
+def owner_of_contigs(lengths, world):
+    """greedy length balance, longest first: owner[c] for every contig (deterministic on every rank)"""
+    order = np.argsort(-np.asarray(lengths, dtype=np.int64), kind="stable")
+    load = [0] * world
+    owner = np.zeros(len(lengths), dtype=np.int32)
+    for i in order:
+        r = int(np.argmin(load))
+        owner[int(i)] = r
+        load[r] += int(lengths[int(i)])
+    return owner
+
+
+def top_byte_cuts(world):
+    """rank r owns the k-mers whose first four bases (top byte) lie in [cuts[r], cuts[r+1])"""
+    return [(256 * r + world - 1) // world for r in range(world + 1)]
+
+
+def exchange_rows(dist, rows, send_rows):
+    """all-to-all of 16-byte records: `rows` is an (n,2) int64 tensor whose rows
+    [sum(send_rows[:r]), +send_rows[r]) go to rank r.  Returns the (m,2) tensor of received rows, in
+    source-rank order (NCCL on GPUs, gloo in the CPU tests)."""
+    import torch
+    world = dist.get_world_size()
+    device = rows.device
+    sr = torch.tensor([int(v) for v in send_rows], dtype=torch.int64, device=device)
+    rr = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_to_all_single(rr, sr)
+    recv_rows = [int(v) for v in rr.tolist()]
+    n_send, n_recv = int(sum(send_rows)), int(sum(recv_rows))
+    dst = torch.empty((max(n_recv, 1), 2), dtype=torch.int64, device=device)[:n_recv]
+    dist.all_to_all_single(dst, rows[:n_send].contiguous(), output_split_sizes=recv_rows,
+                           input_split_sizes=[int(v) for v in send_rows])
+    return dst
+
+
+def align_sharded(dA, dB, freqA, dist, device, **kw):
+    """The whole path on world GPUs from device-resident genomes (every rank holds both genomes:
+    2 bits per base).  Returns (Alignments of this rank's A-contigs with GLOBAL contig numbers, stats)."""
+    import torch
+    from . import lib
+    rank, world = dist.get_rank(), dist.get_world_size()
+    gA, gB = dA.genome, dB.genome
+    p = dict(lib.DEFAULTS)
+    p.update(kw)
+    ownA = owner_of_contigs(gA.clen, world)
+    ownB = owner_of_contigs(gB.clen, world)
+    cuts = top_byte_cuts(world)
+    plo, phi = cuts[rank] << 16, cuts[rank + 1] << 16
+    from .formats import gix_bytes
+    tables, nk = [], []
+    for dg, own, fwd in ((dA, ownA, True), (dB, ownB, False)):
+        ptr, n = lib.kmers_scan(dg, own == rank, fwd)
+        grouped = torch.empty((max(n, 1), 2), dtype=torch.int64, device=device)
+        bounds = lib.records_group_by_top_byte(ptr, n, grouped.data_ptr())
+        lib.device_free(ptr)
+        send = [int(bounds[cuts[r + 1]] - bounds[cuts[r]]) for r in range(world)]
+        recv = exchange_rows(dist, grouped, send)
+        pb, cb = gix_bytes(dg.genome)
+        if phi > plo:
+            x = lib.gix_from_records(recv.data_ptr() if recv.shape[0] else 0, int(recv.shape[0]), plo, phi, fwd,
+                                     pb, cb, dg.genome.ncontig)
+        else:
+            x = None
+        tables.append(x)
+        nk.append(int(recv.shape[0]))
+        del grouped, recv
+    xA, xB = tables
+    amx, bmx = int(gA.clen.max()), int(gB.clen.max())
+    if xA is not None:
+        sptr, ns, bits, sumlen, n1m = lib.seeds_merge(xA, xB, amx, bmx, p["freq"])
+        xA.close()
+        xB.close()
+    else:
+        sptr, ns, sumlen, n1m = 0, 0, 0, 0
+        ab = int(amx + bmx).bit_length()
+        bits = (ab, max(ab - 6, 1), max(1, (gB.ncontig - 1).bit_length()), max(1, (gA.ncontig - 1).bit_length()))
+    # owner of every A-contig RANK (the icont field of a seed)
+    own_by_rank = ownA[dA.perm]
+    grouped = torch.empty((max(ns, 1), 2), dtype=torch.int64, device=device)
+    bounds = lib.seeds_group_by_owner(sptr, ns, bits, own_by_rank, world, grouped.data_ptr())
+    if sptr:
+        lib.device_free(sptr)
+    send = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
+    recv = exchange_rows(dist, grouped, send)
+    del grouped
+    S = lib.seeds_from_records(recv.data_ptr() if recv.shape[0] else 0, int(recv.shape[0]), bits, amx, bmx)
+    nseeds_mine = int(recv.shape[0])
+    del recv
+    ov = lib.DeviceOverlaps.extend(S, dA, dB, freqA, p["chain_break"], p["chain_min"], p["align_min"], p["align_rate"])
+    cnt = ov.counters()
+    alns = lib.filter_overlaps(ov.h, dA.perm, dB.perm, bits[2], bits[3])
+    ov.close()
+    S.close()
+    stats = {"nkmers1_fwd": nk[0], "nkmers2": nk[1], "nseeds_merged": ns, "nseeds": nseeds_mine, "sumlen": sumlen,
+             "nhits": cnt["hits"], "nla": cnt["la_calls"], "nwaves": cnt["waves"], "ncells": cnt["cells"],
+             "nseg": cnt["nseg"], "nwork": cnt["nwork"], "warp_cycles": cnt["warp_cycles"],
+             "wave_cycles": cnt["wave_cycles"], "extract_cycles": cnt["extract_cycles"],
+             "slow_cycles": cnt["slowest_warp"]["cycles"], "slow_waves": cnt["slowest_warp"]["waves"],
+             "paired_waves": cnt["paired_waves"], "pairings": cnt["pairings"]}
+    return alns, stats

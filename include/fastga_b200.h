@@ -31,12 +31,15 @@ typedef struct fgb_gix      fgb_gix;       /* sorted k-mer table + 2^24 prefix i
 typedef struct fgb_seeds    fgb_seeds;     /* sorted adaptive-seed records in HBM              */
 typedef struct fgb_overlaps fgb_overlaps;  /* raw local alignments, host resident              */
 typedef struct fgb_alns     fgb_alns;      /* final alignments in .1aln order, host resident   */
+typedef struct fgb_scripts  fgb_scripts;   /* explicit edit scripts of alignments, host resident */
 
 typedef struct
 { long long nkmers1, nkmers2, nseeds, sumlen, nhits, nla, nwaves, ncells, nraw, h2d_bytes, d2h_bytes,
             nseg, nwork, warp_cycles, wave_cycles, extract_cycles,
             us_gix, us_seeds, us_extend, us_filter,      /* host wall microseconds per phase */
-            nkmers1_fwd;                                 /* forward-strand entries of table 1 (what the merge reads) */
+            nkmers1_fwd,                                 /* forward-strand entries of table 1 (what the merge reads) */
+            slow_cycles, slow_waves,                     /* the extension warp that finished last: its cycles and waves */
+            paired_waves, pairings;                      /* waves run by front/back warp pairs, passes handed to a pair */
 } fgb_run_stats;
 
 typedef struct
@@ -151,6 +154,23 @@ long long fgb_alns_pool_bytes(const fgb_alns *a);
 /* fields: n x 9 ints (comp aread bread abpos bbpos aepos bepos diffs tlen); toff: n; pool: traces */
 int  fgb_alns_get(const fgb_alns *a, int *fields, long long *toff, unsigned char *pool);
 void fgb_alns_free(fgb_alns *a);
+
+/* ---- trace points -> edit scripts (Compute_Trace_PTS align.c:6171 with iter_np :5584, mode
+ *      GREEDIEST, band unbounded: the call of ALNtoPAF.c:272 / ALNtoPSL.c:193 / ALNshow) ----
+ * fields/toff/pool as fgb_alns_get returns them (B coordinates of strand-C records in complemented
+ * B, as in the .1aln).  B needs its reverse complement (fgb_genome_create want_revcomp) when any
+ * record is strand C.  Script of alignment i = script[soff[i]..soff[i+1]): the int list
+ * Compute_Trace_PTS leaves in path->trace (align.h:330-349: -(A position+1) = a dash goes into A
+ * before that base, +(B position+1) likewise for B); diffs[i] = path->diffs, -1 when the trace
+ * points contradict the sequences (the reference exits there, align.c:5655). */
+int  fgb_compute_trace_pts(const fgb_genome *A, const fgb_genome *B, long long n, const int *fields,
+                           const long long *toff, const unsigned char *pool, int tspace,
+                           fgb_scripts **out, void *stream);
+long long fgb_scripts_count(const fgb_scripts *s);
+long long fgb_scripts_total(const fgb_scripts *s);
+long long fgb_scripts_bad(const fgb_scripts *s);
+int  fgb_scripts_get(const fgb_scripts *s, long long *soff /* n+1 */, int *script, int *diffs /* n */);
+void fgb_scripts_free(fgb_scripts *s);
 
 /* ---- sort seam (building block of msd_sort / rmsd_sort, MSDsort.c:404 / RSDsort.c:292) ---- */
 int  fgb_sort128_host(void *recs, long long n, int byte_lo, int byte_hi, void *stream);

@@ -1,6 +1,7 @@
-"""torchrun worker for tests/test_gpu_multi.py: every rank aligns its shard of genome-1 contigs
-against all of genome 2 on its own GPU; rank 0 gathers the record streams over NCCL and checks the
-union against a single-GPU run of the whole pair."""
+"""torchrun worker for tests/test_gpu_multi.py: the k-mer-space sharded path (shard.align_sharded:
+every rank scans its contigs, k-mer records and seeds are exchanged with NCCL all-to-alls, every rank
+extends the seeds of its A-contigs); rank 0 gathers the record streams over NCCL and checks the union
+against a single-GPU run of the whole pair."""
 import os
 import sys
 
@@ -17,26 +18,25 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    A, B = synth.make_pair(77, 6_000_000, 6, 0.05, sv_every=80_000)
-    gA_full, gB = formats.genome_from_arrays(A), formats.genome_from_arrays(B)
-    mine = shard.shard_contigs([len(a) for a in A], rank, world)
-    gA = formats.genome_from_arrays([A[i] for i in mine])
-    dA, dB = lib.DeviceGenome(gA, want_revcomp=True), lib.DeviceGenome(gB)
     dev = torch.device("cuda", local)
-    xA = lib.DeviceGix.build(dA)
-    xB = shard.build_table_cooperatively(dB, dist, dev)          # shares all-gathered over NCCL
-    alns, _ = lib.align_tables(dA, dB, xA, xB, gA_full.freq)
-    if rank == 0:                                                # the assembled table == a local build
-        want, wps, _ = lib.DeviceGix.build(dB).download()
-        got, gps, _ = xB.download()
-        assert np.array_equal(got, want) and np.array_equal(gps, wps)
-    merged = shard.gather_alignments(alns, np.array(mine, dtype=np.int32), dist, torch.device("cuda", local))
+    dist.init_process_group("nccl", device_id=dev)
+    A, B = synth.make_pair(77, 6_000_000, 6, 0.05, sv_every=80_000)
+    gA, gB = formats.genome_from_arrays(A), formats.genome_from_arrays(B)
+    dA, dB = lib.DeviceGenome(gA, want_revcomp=True), lib.DeviceGenome(gB)
+    alns, st = shard.align_sharded(dA, dB, gA.freq, dist, dev)
+    tot = torch.tensor([st["nkmers1_fwd"], st["nkmers2"], st["nseeds_merged"], st["nseeds"], st["nhits"]],
+                       dtype=torch.int64, device=dev)
+    dist.all_reduce(tot)
+    merged = shard.gather_alignments(alns, None, dist, dev)
     if rank == 0:
-        dF = lib.DeviceGenome(gA_full, want_revcomp=True)
-        whole, _ = lib.align_resident(dF, dB, gA_full.freq)
+        whole, ws = lib.align_resident(dA, dB, gA.freq)
+        t = [int(v) for v in tot.tolist()]
+        assert t[0] == ws["nkmers1_fwd"] and t[1] == ws["nkmers2"], (t, ws["nkmers1_fwd"], ws["nkmers2"])
+        assert t[2] == t[3] == ws["nseeds"], (t, ws["nseeds"])
+        assert t[4] == ws["nhits"], (t, ws["nhits"])
         a, b = merged.canonical_lines(), whole.canonical_lines()
         assert len(a) == len(b) and a == b, (len(a), len(b))
+        assert merged.nraw == whole.nraw
         print("MULTI_OK world=%d records=%d" % (world, len(a)))
     dist.destroy_process_group()
 

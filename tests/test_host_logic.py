@@ -86,6 +86,50 @@ def test_shard_contigs_partition():
         assert max(loads) - min(loads) <= max(lens)
 
 
+def test_kmer_space_ownership_covers_everything_once():
+    """the sharded path's two ownership maps: k-mer prefix ranges (by the first four bases) tile the
+    prefix space, contigs are spread by length"""
+    for world in (1, 2, 3, 4, 8):
+        cuts = shard.top_byte_cuts(world)
+        assert cuts[0] == 0 and cuts[-1] == 256 and all(a <= b for a, b in zip(cuts, cuts[1:]))
+        assert max(b - a for a, b in zip(cuts, cuts[1:])) - min(b - a for a, b in zip(cuts, cuts[1:])) <= 1
+        lens = [50, 10, 40, 30, 20, 60, 5, 33]
+        own = shard.owner_of_contigs(lens, world)
+        assert set(own.tolist()) <= set(range(world))
+        loads = [sum(l for l, o in zip(lens, own) if o == r) for r in range(world)]
+        assert max(loads) - min(loads) <= max(lens)
+
+
+_XWORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from fastga_b200 import shard
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(7)                       # same stream on every rank: everybody knows every block
+send = rng.integers(0, 50, (world, world))           # send[src][dst] rows
+send[0, 1] = 0                                       # an empty block
+blocks = [[rng.integers(-2**62, 2**62, (int(send[s, d]), 2)) for d in range(world)] for s in range(world)]
+mine = np.concatenate(blocks[rank]) if send[rank].sum() else np.zeros((0, 2), np.int64)
+got = shard.exchange_rows(dist, torch.from_numpy(mine.astype(np.int64)), [int(v) for v in send[rank]])
+want = np.concatenate([blocks[s][rank] for s in range(world)])
+assert got.shape == want.shape and np.array_equal(got.numpy(), want), (rank, got.shape, want.shape)
+print("XCHG_OK", rank)
+dist.destroy_process_group()
+'''
+
+
+def test_record_exchange_gloo_world2(tmp_path):
+    """the all-to-all of 16-byte records that moves k-mer records and seeds between ranks (N > 1 path)"""
+    script = tmp_path / "xworker.py"
+    script.write_text(_XWORKER % {"root": ROOT})
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29583", str(script)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.count("XCHG_OK") == 2, r.stdout[-3000:]
+
+
 _WORKER = r'''
 import os, sys
 sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
