@@ -272,6 +272,41 @@ static __device__ __forceinline__ void back_results(PairBox *bx, int status, int
   __syncwarp();
 }
 
+//  What the back warp derives from ONE ring entry and the band-filtered V of the wave before it --
+//  nothing here depends on the back warp's own state (bit-vectors, pebbles), so the entry of wave
+//  d+1 is decoded while wave d is still being finished (software pipeline of the loop below).
+struct BackIn
+{ int cmd, top, lowb, mx, la, ha;         // ring header
+  int cc, kk, ltop, src, xn, t;           // this lane: furthest point, diagonal, predecessor lane, slide length
+  bool act, fresh;
+  int rv;                                 // V of this wave after the band trim (input of the next decode)
+};
+
+template<int s>
+static __device__ __forceinline__ void back_decode(const PairBox *bx, const int d, const int rVprev, const int lane,
+                                                   BackIn &I)
+{ const int FRESH = (s > 0) ? -1 : -INT_MAX;
+  const RingEnt *e = &bx->ring[d & (EX_RING-1)];
+  const int4 hd = *(const int4 *) e;                         // cmd, top, lowk, mx
+  const int2 af = *(const int2 *) &e->lowk_after;
+  I.cmd = hd.x; I.top = hd.y; I.lowb = hd.z; I.mx = hd.w; I.la = af.x; I.ha = af.y;
+  I.cc = e->cc[lane];
+  I.ltop = (-I.top) & 31;
+  I.kk = I.top - ((I.top + lane) & 31);
+  I.act = I.kk >= I.lowb;
+  I.fresh = (I.kk == I.top || I.kk == I.lowb);
+  //  replay the predecessor choice (align.c:625-660): out-of-band lanes hold FRESH
+  const int ap = __shfl_sync(FULL,rVprev,(lane + 31) & 31), am = __shfl_sync(FULL,rVprev,(lane + 1) & 31), ac = rVprev;
+  int pred, cp;
+  if (ap > max(ac,am)) { pred = 1;  cp = ap+1; }
+  else if (am > ac)    { pred = -1; cp = am+1; }
+  else                 { pred = 0;  cp = ac+2; }
+  I.src = (lane - pred) & 31;
+  I.xn = (I.cc + I.kk) >> 1;
+  I.t = I.xn - ((cp + I.kk) >> 1);                           // matches the snake slid over
+  I.rv = (I.kk >= I.la && I.kk <= I.ha && I.act) ? I.cc : FRESH;
+}
+
 template<int s>
 static __device__ __noinline__ void wave_back(const unsigned box_off, const short *__restrict__ ttab, const int sc15)
 { PairBox *const bx = reinterpret_cast<PairBox *>(ex_smem + box_off);
@@ -279,7 +314,6 @@ static __device__ __noinline__ void wave_back(const unsigned box_off, const shor
   const int lane = threadIdx.x & 31;
   const unsigned lt = lanemask_lt();
   const int FRESH = (s > 0) ? -1 : -INT_MAX;
-  const int lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;
   int lowk = bx->lowk, hghk = bx->hghk, besta = bx->besta, lasta = bx->lasta, trima = bx->trima;
   int trimx = bx->trimx, trimd = bx->trimd, trimha = bx->trimha, avail = bx->avail;
   const int tspace = bx->tspace, path_ave = bx->path_ave, cmax = bx->cmax, wmask = bx->wmask, dif0 = bx->dif0;
@@ -291,22 +325,24 @@ static __device__ __noinline__ void wave_back(const unsigned box_off, const shor
     rV = (kk >= lowk) ? bx->V[ix] : FRESH;
     rT = bx->T[ix]; rHA = bx->HA[ix]; rHM = bx->HM[ix]; rNA = bx->NA[ix];
   }
-  int d = 0, head_seen = 0;
+  int d = 1, head_seen = 0;
   long long bwait = 0; const long long bt0 = DIAG_CLOCK();
+  BackIn I, Inx;
+  bool have = false;                                         // I holds the decoded entry of wave d
   while (true)
-    { d += 1;
-      if (d > head_seen)
-        { int spin = 0;
-          long long w0 = DIAG_CLOCK();
-          if (EX_DIAG && lane == 0) { bx->r_bwait = bwait; bx->r_btot = w0 - bt0; }
-          while ((head_seen = ld_acquire_smem(&bx->head)) < d)
-            if (++spin > SPIN_LIMIT)
-              { back_results(bx,ST_STAGE,lasta,trima,trimx,trimd,trimha,avail,dif0+d-1,ncell,1); return; }
-          bwait += DIAG_CLOCK() - w0;
+    { if (!have)
+        { if (d > head_seen)
+            { int spin = 0;
+              long long w0 = DIAG_CLOCK();
+              if (EX_DIAG && lane == 0) { bx->r_bwait = bwait; bx->r_btot = w0 - bt0; }
+              while ((head_seen = ld_acquire_smem(&bx->head)) < d)
+                if (++spin > SPIN_LIMIT)
+                  { back_results(bx,ST_STAGE,lasta,trima,trimx,trimd,trimha,avail,dif0+d-1,ncell,1); return; }
+              bwait += DIAG_CLOCK() - w0;
+            }
+          back_decode<s>(bx,d,rV,lane,I);
         }
-      const RingEnt *e = &bx->ring[d & (EX_RING-1)];
-      const int4 hd = *(const int4 *) e;                       // cmd, top, lowk, mx
-      if (hd.x == 3)
+      if (I.cmd == 3)
         { //  hand back: the band of the last wave goes to the front warp's arrays
           const int kk = hghk - ((lane - ((-hghk) & 31)) & 31);
           if (kk >= lowk)
@@ -316,26 +352,20 @@ static __device__ __noinline__ void wave_back(const unsigned box_off, const shor
           back_results(bx,ST_OK,lasta,trima,trimx,trimd,trimha,avail,dif0+d-1,ncell,2);
           return;
         }
-      const int top = hd.y, lowb = hd.z, mx = hd.w;
-      const int la = e->lowk_after, ha_ = e->hghk_after;
-      int cc = e->cc[lane];
-      const int ltop = (-top) & 31;
-      const int kk = top - ((lane - ltop) & 31);
-      const bool act = kk >= lowb;
-      const bool fresh = (kk == top || kk == lowb);
-      //  replay the predecessor choice (align.c:625-660): out-of-band lanes hold FRESH
-      const int ap = __shfl_sync(FULL,rV,lane_up), am = __shfl_sync(FULL,rV,lane_dn), ac = rV;
-      int pred, cp;
-      if (ap > max(ac,am)) { pred = 1;  cp = ap+1; }
-      else if (am > ac)    { pred = -1; cp = am+1; }
-      else                 { pred = 0;  cp = ac+2; }
-      const int src = (lane - pred) & 31;
-      u64 b  = __shfl_sync(FULL,rT,src);
-      int ha = __shfl_sync(FULL,rHA,src), hm = __shfl_sync(FULL,rHM,src);
-      int nn = __shfl_sync(FULL,rNA,src);
-      int nan = fresh ? nn : rNA;
-      const int xn = (cc + kk) >> 1, k = s*kk;
-      { int t = xn - ((cp + kk) >> 1);                        // matches the snake slid over
+      //  stage 1 of the NEXT wave, if the front has published it already: its chain (ring loads, two
+      //  shuffles, predecessor choice) overlaps the chain of this wave below
+      if (d + 1 > head_seen) head_seen = ld_acquire_smem(&bx->head);
+      have = (d + 1 <= head_seen);
+      if (have) back_decode<s>(bx,d+1,I.rv,lane,Inx);
+
+      //  stage 2 of wave d: path state of the predecessor, slide, pebbles, trim tests
+      const int top = I.top, ltop = I.ltop, kk = I.kk, mx = I.mx, cc = I.cc, xn = I.xn, k = s*kk;
+      const bool act = I.act;
+      u64 b  = __shfl_sync(FULL,rT,I.src);
+      int ha = __shfl_sync(FULL,rHA,I.src), hm = __shfl_sync(FULL,rHM,I.src);
+      int nn = __shfl_sync(FULL,rNA,I.src);
+      int nan = I.fresh ? nn : rNA;
+      { const int t = I.t;
         b <<= 1;
         b = (t >= 64) ? ~0ull : ((b << t) | ((1ull << t) - 1));
       }
@@ -386,13 +416,15 @@ static __device__ __noinline__ void wave_back(const unsigned box_off, const shor
         besta = mx;
       }
       if (act) { rT = b; rHA = ha; rHM = hm; rNA = nan; }
-      rV = (kk >= la && kk <= ha_ && act) ? cc : FRESH;
-      lowk = la; hghk = ha_;
-      ncell += (u64) (top - lowb + 1);
+      rV = I.rv;
+      lowk = I.la; hghk = I.ha;
+      ncell += (u64) (top - I.lowb + 1);
       __syncwarp();
       if (lane == 0) bx->tail = d;
-      if (hd.x == 2 || lasta < besta - TRIM_MLAG)
+      if (I.cmd == 2 || lasta < besta - TRIM_MLAG)
         { back_results(bx,ST_OK,lasta,trima,trimx,trimd,trimha,avail,dif0+d,ncell,1); return; }
+      d += 1;
+      if (have) I = Inx;
     }
 }
 
@@ -1728,6 +1760,53 @@ extend_kernel(ext_params P)
 }
 
 /***********************************************************************************************
+ *  The align.h seam: Local_Alignment (align.c:1423, align.h:262-298) as a batched export.  One
+ *  warp per call tuple (contig pair, strand, low, hgh, anti, lbord, hbord) on the single-warp wave
+ *  code; the Path comes back as Local_Alignment leaves it (ACOMP flip applied), the trace as bytes.
+ **********************************************************************************************/
+
+struct la_job { int actg, bctg, comp, low, hgh, anti, lbord, hbord; };
+
+__global__ void __launch_bounds__(EX_WARPS*32,EX_MINBLK)
+la_batch_kernel(ext_params P, const la_job *__restrict__ jobs, int njobs, int *__restrict__ status)
+{ unsigned char *const smem = ex_smem;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const long long gw = (long long) blockIdx.x * EX_WARPS + wp;
+  unsigned char *sb = smem + (size_t) wp * STATE_BYTES;
+  Ctx c;
+  c.T  = (u64 *) sb;
+  c.V  = (int *) (sb + EX_W*8);
+  c.HA = c.V + EX_W; c.HM = c.HA + EX_W; c.NA = c.HM + EX_W;
+  c.carry = c.NA + EX_W;
+  c.ttab = P.table; c.sc15 = TRIM_LEN * P.dscore;
+  c.box = NULL; c.box_off = 0;
+  c.cells = P.cells + gw * P.cells_per_warp;
+  c.cmax  = (int) P.cells_per_warp;
+  c.avail = 0;
+  c.fstage = P.stage + gw * 2ll * P.stage_bytes;
+  c.rstage = c.fstage + P.stage_bytes;
+  c.smax = P.stage_bytes;
+  c.tspace = P.tspace; c.path_ave = P.path_ave; c.score = P.score; c.table = P.table;
+  c.nwaves = 0; c.ncells = 0; c.cyc_wave = 0; c.cyc_extract = 0; c.pwaves = 0; c.npairs = 0; c.fwait = 0; c.ftot = 0; c.bwait = 0; c.btot = 0;
+  while (true)
+    { unsigned w = 0;
+      if (lane == 0) w = atomicAdd(P.queue,1u);
+      w = __shfl_sync(FULL,w,0);
+      if (w >= (unsigned) njobs) break;
+      const la_job J = jobs[w];
+      c.A = (const unsigned *) ((J.comp ? P.arseq : P.aseq) + P.awoff[J.actg]);
+      c.B = (const unsigned *) (P.bseq + P.bwoff[J.bctg]);
+      c.alen = (int) P.aclen[J.actg]; c.blen = (int) P.bclen[J.bctg];
+      c.anw = (c.alen + 31) >> 5; c.bnw = (c.blen + 31) >> 5;
+      LAres R;
+      int st = local_alignment<EX_W>(c,J.comp,J.low,J.hgh,J.anti,R,J.lbord,J.hbord);
+      if (st == ST_OK) emit_record(P,c,R,J.comp,w,0,0u);
+      if (lane == 0) status[w] = st;
+      __syncwarp();
+    }
+}
+
+/***********************************************************************************************
  *  Host side of the stage
  **********************************************************************************************/
 
@@ -2038,6 +2117,98 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
   tr_mark("extend: leave");
   *out = O;
   return FGB_OK;
+}
+
+//  jobs: n x 8 ints (A contig, B contig, comp, low, hgh, anti, lbord, hbord) -- the arguments of
+//  Local_Alignment with aseq/bseq = those contigs (A reverse-complemented and ACOMP_FLAG set when comp,
+//  as align_contigs calls it, FastGA.c:3184-3260).  paths: n x 7 ints (abpos bbpos aepos bepos diffs tlen
+//  status), status 0 or the ST_* code of a call that did not fit the device arenas; toff: n offsets into
+//  `traces` (uint8 pairs, what Compress_TraceTo8 leaves).  traces_cap bytes are available; *traces_used
+//  returns the bytes needed (call again with a larger buffer if it exceeds the capacity).
+extern "C" int fgb_local_alignments(const fgb_genome *A, const fgb_genome *B, long long n, const int *jobs,
+                                    const short *tables, int ave_path, int tspace,
+                                    int *paths, long long *toff, unsigned char *traces, long long traces_cap,
+                                    long long *traces_used, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  if (n < 0 || n > 0x7fffffff) return FGB_ERR_ARG;
+  *traces_used = 0;
+  if (n == 0) return FGB_OK;
+  for (long long i = 0; i < n; i++)
+    { const int *j = jobs + 8*i;
+      if (j[0] < 0 || j[0] >= A->ncontig || j[1] < 0 || j[1] >= B->ncontig) return FGB_ERR_ARG;
+      if (j[2] && A->d_rseq == NULL) return FGB_ERR_ARG;
+    }
+  ext_params P;
+  memset(&P,0,sizeof(P));
+  P.aseq = A->d_seq; P.arseq = A->d_rseq; P.awoff = A->d_woff; P.aclen = A->d_clen; P.aperm = A->d_perm;
+  P.bseq = B->d_seq; P.bwoff = B->d_woff; P.bclen = B->d_clen; P.bperm = B->d_perm;
+  P.tspace = tspace; P.path_ave = ave_path;
+  P.dscore = -tables[0] / TRIM_LEN;
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm,cudaDevAttrMultiProcessorCount,dev);
+  long long nblocks = (n + EX_WARPS - 1) / EX_WARPS;
+  if (nblocks > nsm) nblocks = nsm;
+  const long long nwarps = nblocks * EX_WARPS;
+  const long long cells_per_warp = 1ll << 18;
+  const int stage_bytes = 1 << 16;
+  const size_t smem = (size_t) EX_WARPS * STATE_BYTES;
+  short *d_tables = NULL; la_job *d_jobs = NULL; int *d_status = NULL; unsigned *d_misc = NULL;
+  Peb *d_cells = NULL; unsigned char *d_stage = NULL, *d_out = NULL;
+  std::vector<unsigned char> h;
+  std::vector<int> hs(n);
+  u64 out_cap = (u64) n * 256 + (u64) traces_cap + (1ull << 20), out_used = 0;
+  int rc = FGB_OK;
+#define LA_TRY(call) do { if ((call) != cudaSuccess) { rc = FGB_ERR_CUDA; goto done; } } while (0)
+  LA_TRY(cudaFuncSetAttribute(la_batch_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem));
+  LA_TRY(fgb_dmalloc((void **) &d_tables,65536*sizeof(short),st));
+  LA_TRY(fgb_dmalloc((void **) &d_jobs,sizeof(la_job)*(size_t) n,st));
+  LA_TRY(fgb_dmalloc((void **) &d_status,sizeof(int)*(size_t) n,st));
+  LA_TRY(fgb_dmalloc((void **) &d_misc,64,st));
+  LA_TRY(fgb_dmalloc((void **) &d_cells,sizeof(Peb)*cells_per_warp*nwarps,st));
+  LA_TRY(fgb_dmalloc((void **) &d_stage,2ll*stage_bytes*nwarps,st));
+  LA_TRY(fgb_dmalloc((void **) &d_out,out_cap,st));
+  LA_TRY(cudaMemcpyAsync(d_tables,tables,65536*sizeof(short),cudaMemcpyHostToDevice,st));
+  LA_TRY(cudaMemcpyAsync(d_jobs,jobs,sizeof(la_job)*(size_t) n,cudaMemcpyHostToDevice,st));
+  LA_TRY(cudaMemsetAsync(d_misc,0,64,st));
+  P.score = d_tables; P.table = d_tables + 32768;
+  P.cells = d_cells; P.cells_per_warp = cells_per_warp;
+  P.stage = d_stage; P.stage_bytes = stage_bytes;
+  P.out = d_out; P.out_cap = out_cap; P.out_used = (u64 *) (d_misc + 4);
+  P.queue = d_misc + 1;
+  la_batch_kernel<<<(unsigned) nblocks,EX_WARPS*32,smem,st>>>(P,d_jobs,(int) n,d_status);
+  fgb_count_launch(1);
+  LA_TRY(cudaGetLastError());
+  LA_TRY(cudaMemcpyAsync(&out_used,d_misc + 4,8,cudaMemcpyDeviceToHost,st));
+  LA_TRY(cudaMemcpyAsync(hs.data(),d_status,sizeof(int)*(size_t) n,cudaMemcpyDeviceToHost,st));
+  LA_TRY(cudaStreamSynchronize(st));
+  if (out_used > out_cap) { rc = FGB_ERR_OVERFLOW; goto done; }
+  h.resize((size_t) out_used + 64);
+  LA_TRY(cudaMemcpy(h.data(),d_out,out_used,cudaMemcpyDeviceToHost));
+  { long long used = 0;
+    for (long long i = 0; i < n; i++)
+      { int *p = paths + 7*i;
+        p[0] = p[1] = p[2] = p[3] = p[4] = p[5] = 0; p[6] = hs[i];
+        toff[i] = 0;
+      }
+    for (u64 off = 0; off < out_used; )
+      { const int *r = (const int *) (h.data() + off);
+        const long long i = r[0];
+        int *p = paths + 7*i;
+        p[0] = r[3]; p[1] = r[4]; p[2] = r[5]; p[3] = r[6]; p[4] = r[7]; p[5] = r[8];
+        toff[i] = used;
+        if (used + r[8] <= traces_cap) memcpy(traces + used,h.data() + off + OUT_HDR,(size_t) r[8]);
+        used += r[8];
+        off += OUT_HDR + ((r[8] + 7) & ~7);
+      }
+    *traces_used = used;
+    if (used > traces_cap) rc = FGB_ERR_OVERFLOW;
+  }
+done:
+#undef LA_TRY
+  fgb_dfree(d_tables,st); fgb_dfree(d_jobs,st); fgb_dfree(d_status,st); fgb_dfree(d_misc,st);
+  fgb_dfree(d_cells,st); fgb_dfree(d_stage,st); fgb_dfree(d_out,st);
+  return rc;
 }
 
 extern "C" long long fgb_overlaps_count(const fgb_overlaps *o) { return o->nrec; }

@@ -609,3 +609,27 @@ def seeds_from_records(ptr, n, bits, amxpos, bmxpos, sumlen=0, stream=None):
     _check(L.fgb_seeds_from_records(c_void_p(ptr), n, b, amxpos, bmxpos, sumlen, C.byref(h), stream),
            "fgb_seeds_from_records")
     return DeviceSeeds(h)
+
+
+def local_alignments(dA, dB, jobs, freq, align_rate=0.3, tspace=100, stream=None):
+    """Local_Alignment (align.h) for a batch: jobs (n,8) int32 = (A contig, B contig, comp, low, hgh, anti,
+    lbord, hbord).  Returns (paths (n,7) int32: abpos bbpos aepos bepos diffs tlen status, toff, traces)."""
+    L = load_library()
+    jobs = np.ascontiguousarray(jobs, dtype=np.int32).reshape(-1, 8)
+    n = jobs.shape[0]
+    tables, ave = align_spec(1.0 - align_rate, freq)
+    paths = np.zeros((max(n, 1), 7), dtype=np.int32)
+    toff = np.zeros(max(n, 1), dtype=np.int64)
+    cap = 1 << 20
+    L.fgb_local_alignments.argtypes = [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int,
+                                       c_void_p, c_void_p, c_void_p, c_ll, C.POINTER(c_ll), c_void_p]
+    while True:
+        traces = np.zeros(cap, dtype=np.uint8)
+        used = c_ll()
+        rc = L.fgb_local_alignments(dA.h, dB.h, n, _ptr(jobs), _ptr(tables), ave, tspace, _ptr(paths), _ptr(toff),
+                                    _ptr(traces), cap, C.byref(used), stream)
+        if rc == -4 and used.value > cap:
+            cap = used.value + 1024
+            continue
+        _check(rc, "fgb_local_alignments")
+        return paths[:n], toff[:n], traces[:used.value]
