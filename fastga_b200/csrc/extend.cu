@@ -35,7 +35,7 @@ typedef unsigned long long u64;
 #define EX_WARPS     8
 #endif
 #ifndef EX_MINBLK
-#define EX_MINBLK    2
+#define EX_MINBLK    1
 #endif
 #define EX_W         256                 // diagonals of wave state per warp (shared memory)
 #define FULL         0xffffffffu
@@ -147,6 +147,13 @@ extern __shared__ __align__(16) unsigned char ex_smem[];
 //  flag hand-off between the two warps of a pair: release store (fence + STS) / acquire load (LDS)
 static __device__ __forceinline__ void st_release_smem(volatile int *p, int v)
 { asm volatile("st.release.cta.shared.b32 [%0], %1;" :: "r"(smem_u32((const void *) p)), "r"(v) : "memory"); }
+static __device__ __forceinline__ int ld_acquire_smem_a(unsigned a)          // a = shared-window address
+{ int v;
+  asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+static __device__ __forceinline__ void st_release_smem_a(unsigned a, int v)
+{ asm volatile("st.release.cta.shared.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 static __device__ __forceinline__ int ld_acquire_smem(const volatile int *p)
 { int v;
   asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32((const void *) p)) : "memory");
@@ -272,41 +279,6 @@ static __device__ __forceinline__ void back_results(PairBox *bx, int status, int
   __syncwarp();
 }
 
-//  What the back warp derives from ONE ring entry and the band-filtered V of the wave before it --
-//  nothing here depends on the back warp's own state (bit-vectors, pebbles), so the entry of wave
-//  d+1 is decoded while wave d is still being finished (software pipeline of the loop below).
-struct BackIn
-{ int cmd, top, lowb, mx, la, ha;         // ring header
-  int cc, kk, ltop, src, xn, t;           // this lane: furthest point, diagonal, predecessor lane, slide length
-  bool act, fresh;
-  int rv;                                 // V of this wave after the band trim (input of the next decode)
-};
-
-template<int s>
-static __device__ __forceinline__ void back_decode(const PairBox *bx, const int d, const int rVprev, const int lane,
-                                                   BackIn &I)
-{ const int FRESH = (s > 0) ? -1 : -INT_MAX;
-  const RingEnt *e = &bx->ring[d & (EX_RING-1)];
-  const int4 hd = *(const int4 *) e;                         // cmd, top, lowk, mx
-  const int2 af = *(const int2 *) &e->lowk_after;
-  I.cmd = hd.x; I.top = hd.y; I.lowb = hd.z; I.mx = hd.w; I.la = af.x; I.ha = af.y;
-  I.cc = e->cc[lane];
-  I.ltop = (-I.top) & 31;
-  I.kk = I.top - ((I.top + lane) & 31);
-  I.act = I.kk >= I.lowb;
-  I.fresh = (I.kk == I.top || I.kk == I.lowb);
-  //  replay the predecessor choice (align.c:625-660): out-of-band lanes hold FRESH
-  const int ap = __shfl_sync(FULL,rVprev,(lane + 31) & 31), am = __shfl_sync(FULL,rVprev,(lane + 1) & 31), ac = rVprev;
-  int pred, cp;
-  if (ap > max(ac,am)) { pred = 1;  cp = ap+1; }
-  else if (am > ac)    { pred = -1; cp = am+1; }
-  else                 { pred = 0;  cp = ac+2; }
-  I.src = (lane - pred) & 31;
-  I.xn = (I.cc + I.kk) >> 1;
-  I.t = I.xn - ((cp + I.kk) >> 1);                           // matches the snake slid over
-  I.rv = (I.kk >= I.la && I.kk <= I.ha && I.act) ? I.cc : FRESH;
-}
-
 template<int s>
 static __device__ __noinline__ void wave_back(const unsigned box_off, const short *__restrict__ ttab, const int sc15)
 { PairBox *const bx = reinterpret_cast<PairBox *>(ex_smem + box_off);
@@ -314,6 +286,7 @@ static __device__ __noinline__ void wave_back(const unsigned box_off, const shor
   const int lane = threadIdx.x & 31;
   const unsigned lt = lanemask_lt();
   const int FRESH = (s > 0) ? -1 : -INT_MAX;
+  const int lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;
   int lowk = bx->lowk, hghk = bx->hghk, besta = bx->besta, lasta = bx->lasta, trima = bx->trima;
   int trimx = bx->trimx, trimd = bx->trimd, trimha = bx->trimha, avail = bx->avail;
   const int tspace = bx->tspace, path_ave = bx->path_ave, cmax = bx->cmax, wmask = bx->wmask, dif0 = bx->dif0;
@@ -325,24 +298,23 @@ static __device__ __noinline__ void wave_back(const unsigned box_off, const shor
     rV = (kk >= lowk) ? bx->V[ix] : FRESH;
     rT = bx->T[ix]; rHA = bx->HA[ix]; rHM = bx->HM[ix]; rNA = bx->NA[ix];
   }
-  int d = 1, head_seen = 0;
+  int d = 0, head_seen = 0;
   long long bwait = 0; const long long bt0 = DIAG_CLOCK();
-  BackIn I, Inx;
-  bool have = false;                                         // I holds the decoded entry of wave d
+  const unsigned head_a = smem_u32((const void *) &bx->head);     // hoisted: the acquire load is inline asm
   while (true)
-    { if (!have)
-        { if (d > head_seen)
-            { int spin = 0;
-              long long w0 = DIAG_CLOCK();
-              if (EX_DIAG && lane == 0) { bx->r_bwait = bwait; bx->r_btot = w0 - bt0; }
-              while ((head_seen = ld_acquire_smem(&bx->head)) < d)
-                if (++spin > SPIN_LIMIT)
-                  { back_results(bx,ST_STAGE,lasta,trima,trimx,trimd,trimha,avail,dif0+d-1,ncell,1); return; }
-              bwait += DIAG_CLOCK() - w0;
-            }
-          back_decode<s>(bx,d,rV,lane,I);
+    { d += 1;
+      if (d > head_seen)
+        { int spin = 0;
+          long long w0 = DIAG_CLOCK();
+          if (EX_DIAG && lane == 0) { bx->r_bwait = bwait; bx->r_btot = w0 - bt0; }
+          while ((head_seen = ld_acquire_smem_a(head_a)) < d)
+            if (++spin > SPIN_LIMIT)
+              { back_results(bx,ST_STAGE,lasta,trima,trimx,trimd,trimha,avail,dif0+d-1,ncell,1); return; }
+          bwait += DIAG_CLOCK() - w0;
         }
-      if (I.cmd == 3)
+      const RingEnt *e = &bx->ring[d & (EX_RING-1)];
+      const int4 hd = *(const int4 *) e;                       // cmd, top, lowk, mx
+      if (hd.x == 3)
         { //  hand back: the band of the last wave goes to the front warp's arrays
           const int kk = hghk - ((lane - ((-hghk) & 31)) & 31);
           if (kk >= lowk)
@@ -352,20 +324,26 @@ static __device__ __noinline__ void wave_back(const unsigned box_off, const shor
           back_results(bx,ST_OK,lasta,trima,trimx,trimd,trimha,avail,dif0+d-1,ncell,2);
           return;
         }
-      //  stage 1 of the NEXT wave, if the front has published it already: its chain (ring loads, two
-      //  shuffles, predecessor choice) overlaps the chain of this wave below
-      if (d + 1 > head_seen) head_seen = ld_acquire_smem(&bx->head);
-      have = (d + 1 <= head_seen);
-      if (have) back_decode<s>(bx,d+1,I.rv,lane,Inx);
-
-      //  stage 2 of wave d: path state of the predecessor, slide, pebbles, trim tests
-      const int top = I.top, ltop = I.ltop, kk = I.kk, mx = I.mx, cc = I.cc, xn = I.xn, k = s*kk;
-      const bool act = I.act;
-      u64 b  = __shfl_sync(FULL,rT,I.src);
-      int ha = __shfl_sync(FULL,rHA,I.src), hm = __shfl_sync(FULL,rHM,I.src);
-      int nn = __shfl_sync(FULL,rNA,I.src);
-      int nan = I.fresh ? nn : rNA;
-      { const int t = I.t;
+      const int top = hd.y, lowb = hd.z, mx = hd.w;
+      const int la = e->lowk_after, ha_ = e->hghk_after;
+      int cc = e->cc[lane];
+      const int ltop = (-top) & 31;
+      const int kk = top - ((lane - ltop) & 31);
+      const bool act = kk >= lowb;
+      const bool fresh = (kk == top || kk == lowb);
+      //  replay the predecessor choice (align.c:625-660): out-of-band lanes hold FRESH
+      const int ap = __shfl_sync(FULL,rV,lane_up), am = __shfl_sync(FULL,rV,lane_dn), ac = rV;
+      int pred, cp;
+      if (ap > max(ac,am)) { pred = 1;  cp = ap+1; }
+      else if (am > ac)    { pred = -1; cp = am+1; }
+      else                 { pred = 0;  cp = ac+2; }
+      const int src = (lane - pred) & 31;
+      u64 b  = __shfl_sync(FULL,rT,src);
+      int ha = __shfl_sync(FULL,rHA,src), hm = __shfl_sync(FULL,rHM,src);
+      int nn = __shfl_sync(FULL,rNA,src);
+      int nan = fresh ? nn : rNA;
+      const int xn = (cc + kk) >> 1, k = s*kk;
+      { int t = xn - ((cp + kk) >> 1);                        // matches the snake slid over
         b <<= 1;
         b = (t >= 64) ? ~0ull : ((b << t) | ((1ull << t) - 1));
       }
@@ -416,15 +394,13 @@ static __device__ __noinline__ void wave_back(const unsigned box_off, const shor
         besta = mx;
       }
       if (act) { rT = b; rHA = ha; rHM = hm; rNA = nan; }
-      rV = I.rv;
-      lowk = I.la; hghk = I.ha;
-      ncell += (u64) (top - I.lowb + 1);
+      rV = (kk >= la && kk <= ha_ && act) ? cc : FRESH;
+      lowk = la; hghk = ha_;
+      ncell += (u64) (top - lowb + 1);
       __syncwarp();
       if (lane == 0) bx->tail = d;
-      if (I.cmd == 2 || lasta < besta - TRIM_MLAG)
+      if (hd.x == 2 || lasta < besta - TRIM_MLAG)
         { back_results(bx,ST_OK,lasta,trima,trimx,trimd,trimha,avail,dif0+d,ncell,1); return; }
-      d += 1;
-      if (have) I = Inx;
     }
 }
 
@@ -484,6 +460,7 @@ static __device__ __noinline__ int4 front_run(const unsigned box_off, const unsi
   const int FRESH = (s > 0) ? -1 : -INT_MAX;
   const int lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;      // owners of kk+1 / kk-1
   int d = 0, tail_seen = 0, alone = 0;
+  const unsigned head_a = smem_u32((const void *) &bx->head);
   while (true)
     { const int lowk0 = lowk, hghk0 = hghk;
       lowk -= 1; hghk += 1;
@@ -550,7 +527,7 @@ static __device__ __noinline__ int4 front_run(const unsigned box_off, const unsi
         }
       if (!nmore || (d & 1) == 0)                        // publish every other wave
         { __syncwarp();
-          if (lane == 0) st_release_smem(&bx->head,d);
+          if (lane == 0) st_release_smem_a(head_a,d);
         }
       if (!nmore || ((d & 7) == 0 && bx->stop != 0)) break;
     }

@@ -36,8 +36,15 @@ static __host__ __device__ __forceinline__ int seed_key_bits(const seed_layout &
 
 #define MG_THREADS 256
 #define MG_WARPS   (MG_THREADS/32)
+#ifndef MG_T2CAP
 #define MG_T2CAP   1280                   // staged T2 entries per CTA (20 KB)
+#endif
+#ifndef MG_DCAP
 #define MG_DCAP    2560                   // seed descriptors per CTA (5 per T1 entry; crowded tiles write entry-wise)
+#endif
+#ifndef MG_MINBLK
+#define MG_MINBLK  5
+#endif
 //  lcp (in bases, 0..28) of two 56-bit suffixes
 static __device__ __forceinline__ int lcp56(u64 a, u64 b)
 { u64 x = a ^ b;
@@ -196,7 +203,7 @@ __global__ void merge_ranges_kernel(const rec128 *__restrict__ T1, unsigned n1, 
 }
 
 template<int TILE>
-__global__ void __launch_bounds__(MG_THREADS,5)
+__global__ void __launch_bounds__(MG_THREADS,MG_MINBLK)
 adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
                        const rec128 *__restrict__ T2, const unsigned *__restrict__ pstart2,
                        const unsigned char *__restrict__ adj2, const uint4 *__restrict__ rng, int freq, seed_pack K,
