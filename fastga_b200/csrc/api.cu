@@ -189,8 +189,8 @@ extern "C" int fgb_genome_create(const unsigned char *bps, long long bps_bytes, 
   CUDA_TRY(fgb_dmalloc((void **) &g->d_woff,sizeof(long long)*(ncontig+1),st));
   CUDA_TRY(fgb_dmalloc((void **) &g->d_crank,sizeof(int)*ncontig,st));
   CUDA_TRY(fgb_dmalloc((void **) &g->d_perm,sizeof(int)*ncontig,st));
-  CUDA_TRY(fgb_dmalloc((void **) &g->d_seq,sizeof(u64)*w,st));
-  if (want_revcomp) CUDA_TRY(fgb_dmalloc((void **) &g->d_rseq,sizeof(u64)*w,st));
+  CUDA_TRY(fgb_dmalloc((void **) &g->d_seq,sizeof(u64)*(w + 1024),st));      // slack: the extension stages 1 KB tiles that may start near a contig end
+  if (want_revcomp) CUDA_TRY(fgb_dmalloc((void **) &g->d_rseq,sizeof(u64)*(w + 1024),st));
   { stage_timer t(&g_timings.h2d_ms,st);
     CUDA_TRY(cudaMemcpyAsync(d_bps,bps,bps_bytes,cudaMemcpyHostToDevice,st));
     CUDA_TRY(cudaMemcpyAsync(d_boff,boff,sizeof(long long)*ncontig,cudaMemcpyHostToDevice,st));

@@ -32,8 +32,9 @@
 typedef unsigned long long u64;
 
 #ifndef EX_WARPS
-#define EX_WARPS     8
+#define EX_WARPS     12                  // four triples at a time per CTA, three warps each (front, T, P)
 #endif
+#define EX_TEAM      3
 #ifndef EX_MINBLK
 #define EX_MINBLK    1
 #endif
@@ -107,6 +108,8 @@ struct Ctx
 #define EX_NOREG 0                       // 1 (debug): never use the register path of the single-warp waves
 #endif
 #define EX_RING 32
+#define EX_TILEW 256                     // 32-bit words per staged sequence tile: 4096 bases
+#define EX_TILEB (16*EX_TILEW)
 
 struct __align__(16) RingEnt
 { int cmd, top, lowk, mx;                // cmd 1 wave, 2 last wave (more == 0), 3 hand back; band [lowk,top] of the wave
@@ -116,13 +119,18 @@ struct __align__(16) RingEnt
 
 struct __align__(16) PairBox
 { volatile int seq, cmd;                 // front -> back: seq bumps per request; cmd 1 / 2 = forward / reverse pass, 9 exit
-  volatile int head, tail;               // last wave pushed / consumed
-  volatile int stop;                     // back -> front: 0 running, 1 pass finished, 2 handed back
+  volatile int head, tail;               // last wave pushed / consumed by the pebble warp (ring slots are free up to here)
+  volatile int stop;                     // T warp -> front, P warp: 0 running, 1 pass finished, 2 handed back
+  volatile int tailt, stopp;             // last wave the T warp finished (P may process up to here); P warp done (1 / 2)
+  int pstatus;                           // ST_* of the P warp
   int lowk, hghk, besta, lasta, trima, trimx, trimd, trimha, avail;
   int tspace, path_ave, cmax, wmask, dif0;
   Peb *cells; int *V, *HA, *HM, *NA; u64 *T;
   int status, r_lasta, r_trima, r_trimx, r_trimd, r_trimha, r_avail, r_dif; u64 r_ncell;
-  long long r_bwait, r_btot;             // diagnostics: back warp cycles waiting for the front / in the pass
+  long long r_bwait, r_btot;             // diagnostics: T warp cycles waiting for the front / P warp cycles waiting for T
+  long long r_fwait, r_ffast;            //   front: cycles waiting for ring space, waves on the fast path
+  int tring[EX_RING];                    // T -> P: lane holding the new trim point of a wave, -1 none
+  unsigned tileA[EX_TILEW], tileB[EX_TILEW];   // 2-bit sequence tiles of the two contigs around the band (front warp)
   RingEnt ring[EX_RING];
 };
 
@@ -267,92 +275,181 @@ static __device__ __forceinline__ unsigned rotr32(unsigned x, int r) { return __
 //  BACK warp of a pair: one wave pass (direction s) from the state the front warp left after
 //  wave 0.  Returns when the pass is finished (stop = 1) or handed back (stop = 2).
 
-static __device__ __forceinline__ void back_results(PairBox *bx, int status, int lasta, int trima, int trimx,
-                                                    int trimd, int trimha, int avail, int dif, u64 ncell, int stop)
-{ __syncwarp();
-  if ((threadIdx.x & 31) == 0)
-    { bx->status = status; bx->r_lasta = lasta; bx->r_trima = trima; bx->r_trimx = trimx; bx->r_trimd = trimd;
-      bx->r_trimha = trimha; bx->r_avail = avail; bx->r_dif = dif; bx->r_ncell = ncell;
-      __threadfence();                               // pebbles (HBM) before the flag
-      bx->stop = stop;
-    }
-  __syncwarp();
-}
+//  The BACK of a pass is two warps.  Both replay the predecessor choice from consecutive V's (two
+//  shuffles); the T warp carries the match bit-vectors, tests trim points and decides when the pass
+//  stops; the P warp, one or more waves behind it, carries the pebble lists (HA / HM / NA), drops
+//  pebbles and picks up the pebble head of every trim point the T warp announces (tring).  Per wave
+//  each executes about half of what one back warp did, and the wave rate of a pass is set by the
+//  slowest of the three warps.
 
+//  T warp: one wave pass (direction s) from the state the front warp left after wave 0.
 template<int s>
-static __device__ __noinline__ void wave_back(const unsigned box_off, const short *__restrict__ ttab, const int sc15)
+static __device__ __noinline__ void wave_T(const unsigned box_off, const short *__restrict__ ttab, const int sc15)
 { PairBox *const bx = reinterpret_cast<PairBox *>(ex_smem + box_off);
   const TrimV c = { ttab, sc15 };
   const int lane = threadIdx.x & 31;
-  const unsigned lt = lanemask_lt();
   const int FRESH = (s > 0) ? -1 : -INT_MAX;
   const int lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;
   int lowk = bx->lowk, hghk = bx->hghk, besta = bx->besta, lasta = bx->lasta, trima = bx->trima;
-  int trimx = bx->trimx, trimd = bx->trimd, trimha = bx->trimha, avail = bx->avail;
-  const int tspace = bx->tspace, path_ave = bx->path_ave, cmax = bx->cmax, wmask = bx->wmask, dif0 = bx->dif0;
-  Peb *cells = bx->cells;
-  u64 ncell = 0;
-  int rV, rHA, rHM, rNA; u64 rT;
-  { const int kk = hghk - ((lane - ((-hghk) & 31)) & 31);
+  int trimx = bx->trimx, trimd = bx->trimd;
+  const int path_ave = bx->path_ave, wmask = bx->wmask, dif0 = bx->dif0;
+  int rV; u64 rT;
+  { const int kk = hghk - ((hghk + lane) & 31);
     const int ix = kk & wmask;
     rV = (kk >= lowk) ? bx->V[ix] : FRESH;
-    rT = bx->T[ix]; rHA = bx->HA[ix]; rHM = bx->HM[ix]; rNA = bx->NA[ix];
+    rT = bx->T[ix];
   }
-  int d = 0, head_seen = 0;
-  long long bwait = 0; const long long bt0 = DIAG_CLOCK();
-  const unsigned head_a = smem_u32((const void *) &bx->head);     // hoisted: the acquire load is inline asm
+  int d = 0, head_seen = 0, fin = 0;                         // fin: 1 pass finished, 2 handed back
+  long long dg_wait = 0;
+  const unsigned head_a = smem_u32((const void *) &bx->head), tailt_a = smem_u32((const void *) &bx->tailt);
   while (true)
     { d += 1;
       if (d > head_seen)
-        { int spin = 0;
-          long long w0 = DIAG_CLOCK();
-          if (EX_DIAG && lane == 0) { bx->r_bwait = bwait; bx->r_btot = w0 - bt0; }
+        { int spin = 0; const long long w0 = DIAG_CLOCK();
           while ((head_seen = ld_acquire_smem_a(head_a)) < d)
-            if (++spin > SPIN_LIMIT)
-              { back_results(bx,ST_STAGE,lasta,trima,trimx,trimd,trimha,avail,dif0+d-1,ncell,1); return; }
-          bwait += DIAG_CLOCK() - w0;
+            if (bx->stopp != 0 || ++spin > SPIN_LIMIT) { fin = 1; break; }     // the P warp gave up (arena full)
+          dg_wait += DIAG_CLOCK() - w0;
+          if (fin) { d -= 1; break; }
         }
       const RingEnt *e = &bx->ring[d & (EX_RING-1)];
       const int4 hd = *(const int4 *) e;                       // cmd, top, lowk, mx
       if (hd.x == 3)
         { //  hand back: the band of the last wave goes to the front warp's arrays
-          const int kk = hghk - ((lane - ((-hghk) & 31)) & 31);
-          if (kk >= lowk)
-            { const int ix = kk & wmask;
-              bx->V[ix] = rV; bx->T[ix] = rT; bx->HA[ix] = rHA; bx->HM[ix] = rHM; bx->NA[ix] = rNA;
-            }
-          back_results(bx,ST_OK,lasta,trima,trimx,trimd,trimha,avail,dif0+d-1,ncell,2);
-          return;
+          const int kk = hghk - ((hghk + lane) & 31);
+          if (kk >= lowk) { const int ix = kk & wmask; bx->V[ix] = rV; bx->T[ix] = rT; }
+          d -= 1; fin = 2;
+          break;
         }
-      const int top = hd.y, lowb = hd.z, mx = hd.w;
-      const int la = e->lowk_after, ha_ = e->hghk_after;
-      int cc = e->cc[lane];
+      const int2 af = *(const int2 *) &e->lowk_after;
+      const int top = hd.y, lowb = hd.z, mx = hd.w, la = af.x, ha_ = af.y;
+      const int cc = e->cc[lane];
       const int ltop = (-top) & 31;
-      const int kk = top - ((lane - ltop) & 31);
+      const int kk = top - ((top + lane) & 31);
       const bool act = kk >= lowb;
-      const bool fresh = (kk == top || kk == lowb);
       //  replay the predecessor choice (align.c:625-660): out-of-band lanes hold FRESH
       const int ap = __shfl_sync(FULL,rV,lane_up), am = __shfl_sync(FULL,rV,lane_dn), ac = rV;
       int pred, cp;
       if (ap > max(ac,am)) { pred = 1;  cp = ap+1; }
       else if (am > ac)    { pred = -1; cp = am+1; }
       else                 { pred = 0;  cp = ac+2; }
+      u64 b = __shfl_sync(FULL,rT,(lane - pred) & 31);
+      const int xn = (cc + kk) >> 1;
+      { const int t = xn - ((cp + kk) >> 1);                   // matches the snake slid over
+        b <<= 1;
+        b = (t >= 64) ? ~0ull : ((b << t) | ((1ull << t) - 1));
+      }
+      //  the front warp only pushes waves that advance the best point (mx > besta)
+      int tlane = -1;                                          // lane of this wave's new trim point
+      { const int cm = act ? cc : INT_MIN;
+        unsigned eq = rotr32(__ballot_sync(FULL,cm == mx),ltop);
+        int Lb = (ltop + __ffs(eq) - 1) & 31;
+        bool qual = act && cc > besta && __popcll(b & PATH_WIN) >= path_ave;
+        bool tq = qual && trim_ok(c,b);
+        //  Lb = highest diagonal reaching the wave maximum = the last record setter of the sequential
+        //  scan: if it passes both tests it alone decides (one shuffle); else the full prefix-max
+        const int tqL = __shfl_sync(FULL,(int) tq,Lb), xL = __shfl_sync(FULL,xn,Lb);
+        if (tqL)
+          { lasta = mx; trima = mx; trimd = dif0+d;
+            trimx = xL;
+            tlane = Lb;
+          }
+        else
+          { unsigned ql = __ballot_sync(FULL,qual), tl = __ballot_sync(FULL,tq);
+            int cpos = __shfl_sync(FULL,cm,(ltop + lane) & 31);   // value at position = lane
+            int ex = max(warp_prefix_max_excl(cpos,lane),besta);
+            unsigned rm = __ballot_sync(FULL,cpos > ex);
+            unsigned qm = rm & rotr32(ql,ltop), tm = rm & rotr32(tl,ltop);
+            if (qm) lasta = __shfl_sync(FULL,cc,(ltop + 31 - __clz(qm)) & 31);
+            if (tm)
+              { int L3 = (ltop + 31 - __clz(tm)) & 31;
+                trima = __shfl_sync(FULL,cc,L3);
+                trimx = __shfl_sync(FULL,xn,L3);
+                trimd = dif0+d;
+                tlane = L3;
+              }
+          }
+        besta = mx;
+      }
+      if (act) rT = b;
+      rV = (kk >= la && kk <= ha_ && act) ? cc : FRESH;
+      lowk = la; hghk = ha_;
+      __syncwarp();
+      if (lane == 0)
+        { bx->tring[d & (EX_RING-1)] = tlane;
+          st_release_smem_a(tailt_a,d);
+        }
+      if (hd.x == 2 || lasta < besta - TRIM_MLAG) { fin = 1; break; }
+    }
+  __syncwarp();
+  if (lane == 0)
+    { bx->status = ST_OK; bx->r_lasta = lasta; bx->r_trima = trima; bx->r_trimx = trimx; bx->r_trimd = trimd;
+      bx->r_dif = dif0 + d;
+      if (EX_DIAG) bx->r_bwait = dg_wait;
+      st_release_smem(&bx->stop,fin);
+    }
+  __syncwarp();
+}
+
+//  P warp: the pebble side of the same pass, following the T warp.
+template<int s>
+static __device__ __noinline__ void wave_P(const unsigned box_off)
+{ PairBox *const bx = reinterpret_cast<PairBox *>(ex_smem + box_off);
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = lanemask_lt();
+  const int FRESH = (s > 0) ? -1 : -INT_MAX;
+  const int lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;
+  int lowk = bx->lowk, hghk = bx->hghk, trimha = bx->trimha, avail = bx->avail;
+  const int tspace = bx->tspace, cmax = bx->cmax, wmask = bx->wmask, dif0 = bx->dif0;
+  Peb *cells = bx->cells;
+  u64 ncell = 0;
+  int rV, rHA, rHM, rNA;
+  { const int kk = hghk - ((hghk + lane) & 31);
+    const int ix = kk & wmask;
+    rV = (kk >= lowk) ? bx->V[ix] : FRESH;
+    rHA = bx->HA[ix]; rHM = bx->HM[ix]; rNA = bx->NA[ix];
+  }
+  int d = 0, seen = 0, fin = 0, status = ST_OK;
+  long long dg_wait = 0;
+  const unsigned tailt_a = smem_u32((const void *) &bx->tailt), stop_a = smem_u32((const void *) &bx->stop);
+  const unsigned tail_a = smem_u32((const void *) &bx->tail);
+  while (true)
+    { d += 1;
+      if (d > seen)
+        { int spin = 0; const long long w0 = DIAG_CLOCK();
+          while ((seen = ld_acquire_smem_a(tailt_a)) < d)
+            { const int st = ld_acquire_smem_a(stop_a);
+              if (st != 0)
+                { seen = ld_acquire_smem_a(tailt_a);             // T published its last wave before it stopped
+                  if (seen < d) { fin = st; break; }
+                }
+              if (++spin > SPIN_LIMIT) { fin = 1; status = ST_STAGE; break; }
+            }
+          dg_wait += DIAG_CLOCK() - w0;
+          if (fin) { d -= 1; break; }
+        }
+      const RingEnt *e = &bx->ring[d & (EX_RING-1)];
+      const int4 hd = *(const int4 *) e;                       // cmd, top, lowk, mx
+      const int2 af = *(const int2 *) &e->lowk_after;
+      const int top = hd.y, lowb = hd.z, la = af.x, ha_ = af.y;
+      const int cc = e->cc[lane];
+      const int tln = bx->tring[d & (EX_RING-1)];
+      const int kk = top - ((top + lane) & 31);
+      const bool act = kk >= lowb;
+      const bool fresh = (kk == top || kk == lowb);
+      const int ap = __shfl_sync(FULL,rV,lane_up), am = __shfl_sync(FULL,rV,lane_dn), ac = rV;
+      int pred;
+      if (ap > max(ac,am)) pred = 1;
+      else if (am > ac)    pred = -1;
+      else                 pred = 0;
       const int src = (lane - pred) & 31;
-      u64 b  = __shfl_sync(FULL,rT,src);
       int ha = __shfl_sync(FULL,rHA,src), hm = __shfl_sync(FULL,rHM,src);
       int nn = __shfl_sync(FULL,rNA,src);
       int nan = fresh ? nn : rNA;
       const int xn = (cc + kk) >> 1, k = s*kk;
-      { int t = xn - ((cp + kk) >> 1);                        // matches the snake slid over
-        b <<= 1;
-        b = (t >= 64) ? ~0ull : ((b << t) | ((1ull << t) - 1));
-      }
-
       bool need = act && xn >= nan;
       while (__any_sync(FULL,need))
         { bool create = need && (s*hm < nan);
-          if (avail + 32 > cmax)
-            { back_results(bx,ST_CELLS,lasta,trima,trimx,trimd,trimha,avail,dif0+d-1,ncell,1); return; }
+          if (avail + 32 > cmax) { fin = 1; status = ST_CELLS; break; }
           unsigned m = __ballot_sync(FULL,create);
           int idx = avail + __popc(m & lt);
           avail += __popc(m);
@@ -364,44 +461,28 @@ static __device__ __noinline__ void wave_back(const unsigned box_off, const shor
           if (need) nan += tspace;
           need = act && xn >= nan;
         }
-
-      //  the front warp only pushes waves that advance the best point (mx > besta)
-      { const int cm = act ? cc : INT_MIN;
-        unsigned eq = rotr32(__ballot_sync(FULL,cm == mx),ltop);
-        int Lb = (ltop + __ffs(eq) - 1) & 31;
-        bool qual = act && cc > besta && __popcll(b & PATH_WIN) >= path_ave;
-        bool tq = qual && trim_ok(c,b);
-        unsigned ql = __ballot_sync(FULL,qual), tl = __ballot_sync(FULL,tq);
-        if ((tl >> Lb) & 1)
-          { lasta = mx; trima = mx; trimd = dif0+d;
-            trimx  = __shfl_sync(FULL,xn,Lb);
-            trimha = __shfl_sync(FULL,ha,Lb);
-          }
-        else
-          { int cpos = __shfl_sync(FULL,cm,(ltop + lane) & 31);   // value at position = lane
-            int ex = max(warp_prefix_max_excl(cpos,lane),besta);
-            unsigned rm = __ballot_sync(FULL,cpos > ex);
-            unsigned qm = rm & rotr32(ql,ltop), tm = rm & rotr32(tl,ltop);
-            if (qm) lasta = __shfl_sync(FULL,cc,(ltop + 31 - __clz(qm)) & 31);
-            if (tm)
-              { int L3 = (ltop + 31 - __clz(tm)) & 31;
-                trima  = __shfl_sync(FULL,cc,L3);
-                trimx  = __shfl_sync(FULL,xn,L3);
-                trimha = __shfl_sync(FULL,ha,L3);
-                trimd  = dif0+d;
-              }
-          }
-        besta = mx;
-      }
-      if (act) { rT = b; rHA = ha; rHM = hm; rNA = nan; }
+      if (fin) { d -= 1; break; }
+      if (tln >= 0) trimha = __shfl_sync(FULL,ha,tln);         // pebble head of the new trim point
+      if (act) { rHA = ha; rHM = hm; rNA = nan; }
       rV = (kk >= la && kk <= ha_ && act) ? cc : FRESH;
       lowk = la; hghk = ha_;
       ncell += (u64) (top - lowb + 1);
       __syncwarp();
-      if (lane == 0) bx->tail = d;
-      if (hd.x == 2 || lasta < besta - TRIM_MLAG)
-        { back_results(bx,ST_OK,lasta,trima,trimx,trimd,trimha,avail,dif0+d,ncell,1); return; }
+      if (lane == 0) st_release_smem_a(tail_a,d);
     }
+  if (fin == 2)
+    { //  handed back after wave d: the pebble state of the band goes to the front warp's arrays
+      const int kk = hghk - ((hghk + lane) & 31);
+      if (kk >= lowk) { const int ix = kk & wmask; bx->HA[ix] = rHA; bx->HM[ix] = rHM; bx->NA[ix] = rNA; }
+    }
+  __syncwarp();
+  if (lane == 0)
+    { bx->pstatus = status; bx->r_trimha = trimha; bx->r_avail = avail; bx->r_ncell = ncell;
+      if (EX_DIAG) bx->r_btot = dg_wait;
+      __threadfence();                                         // pebbles (HBM) before the flag
+      st_release_smem(&bx->stopp,fin);
+    }
+  __syncwarp();
 }
 
 //  FRONT warp of a pair: the waves of one pass from the band [lowk,hghk] (V of the last wave in rV,
@@ -450,6 +531,56 @@ static __device__ __forceinline__ int end_flag(const int alen, const int blen, c
   return (y - t == 0) ? 1 : 2;
 }
 
+//  32 bases at base offset off (>= 0) of a staged sequence tile (shared memory)
+static __device__ __forceinline__ u64 win_t(const unsigned *tile, int off)
+{ const int q = off >> 4, sh = (off & 15) << 1;
+  const unsigned w0 = tile[q], w1 = tile[q+1], w2 = tile[q+2];
+  return (u64) __funnelshift_r(w0,w1,sh) | ((u64) __funnelshift_r(w1,w2,sh) << 32);
+}
+
+//  stages 4096 bases of a contig from base t0 (a multiple of 64: 16-byte aligned; >= -64: the zero
+//  pad ahead of every contig) into a tile: two 128-bit read-only loads and stores per lane
+static __device__ __forceinline__ void tile_fill(unsigned *tile, const unsigned *__restrict__ G, int t0, int lane)
+{ const uint4 *src = reinterpret_cast<const uint4 *>(G + (t0 >> 4));
+  uint4 *dst = reinterpret_cast<uint4 *>(tile);
+  dst[lane] = __ldg(src + lane);
+  dst[lane + 32] = __ldg(src + lane + 32);
+  __syncwarp();
+}
+
+//  Can the next EX_FASTN waves run on the interior fast path?  Every lane of those waves slides from
+//  x in [xlo,xhi] / y in [ylo,yhi] (direction-normalised; from the band scalars: a live diagonal has
+//  V >= besta - WAVE_LAG, besta grows by at most 2*65 a wave, the band by one diagonal each side);
+//  the fast path needs both 32-base windows of every slide inside the staged tiles and inside the
+//  contigs.  Re-stages a tile when the band has moved out of it.  Warp-uniform.
+#define EX_FASTN 8
+template<int s>
+static __device__ __forceinline__ bool fast_window(unsigned *tA, unsigned *tB, const unsigned *__restrict__ A,
+                                                   const unsigned *__restrict__ B, int alen, int blen,
+                                                   int besta, int lowk, int hghk, int &a0, int &b0, int lane)
+{ const int clo = besta - WAVE_LAG, chi = besta + 2 + EX_FASTN*130;
+  const int xlo = (clo + lowk - EX_FASTN) >> 1, xhi = ((chi + hghk + EX_FASTN) >> 1) + 1;
+  const int ylo = (clo - hghk - EX_FASTN) >> 1, yhi = ((chi - lowk + EX_FASTN) >> 1) + 1;
+  //  real coordinates touched: s > 0 [lo, hi+64+48);  s < 0: positions -hi-64-16 .. -lo+48
+  const int ra0 = (s > 0) ? xlo : -xhi - 80, ra1 = (s > 0) ? xhi + 112 : -xlo + 48;
+  const int rb0 = (s > 0) ? ylo : -yhi - 80, rb1 = (s > 0) ? yhi + 112 : -ylo + 48;
+  if (s > 0) { if (xlo < 0 || ylo < 0 || xhi + 64 > alen || yhi + 64 > blen) return false; }
+  else       { if (-xhi - 64 < 0 || -yhi - 64 < 0 || -xlo > alen || -ylo > blen) return false; }
+  if (ra0 < a0 || ra1 > a0 + EX_TILEB)
+    { a0 = (s > 0) ? ((ra0 - 64) & ~63) : (((ra1 + 64 + 63) & ~63) - EX_TILEB);
+      if (a0 < -64) a0 = -64;
+      if (ra0 < a0 || ra1 > a0 + EX_TILEB) return false;
+      tile_fill(tA,A,a0,lane);
+    }
+  if (rb0 < b0 || rb1 > b0 + EX_TILEB)
+    { b0 = (s > 0) ? ((rb0 - 64) & ~63) : (((rb1 + 64 + 63) & ~63) - EX_TILEB);
+      if (b0 < -64) b0 = -64;
+      if (rb0 < b0 || rb1 > b0 + EX_TILEB) return false;
+      tile_fill(tB,B,b0,lane);
+    }
+  return true;
+}
+
 template<int s>
 static __device__ __noinline__ int4 front_run(const unsigned box_off, const unsigned *__restrict__ A,
                                               const unsigned *__restrict__ B, const int alen, const int blen,
@@ -460,6 +591,9 @@ static __device__ __noinline__ int4 front_run(const unsigned box_off, const unsi
   const int FRESH = (s > 0) ? -1 : -INT_MAX;
   const int lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;      // owners of kk+1 / kk-1
   int d = 0, tail_seen = 0, alone = 0;
+  long long dg_wait = 0, dg_fast = 0;                        // EX_DIAG: cycles waiting for ring space, fast-path waves
+  int a0 = INT_MAX/2, b0 = INT_MAX/2, fleft = 0;             // staged tiles (none yet); waves until the next fast-path check
+  bool fok = false;
   const unsigned head_a = smem_u32((const void *) &bx->head);
   while (true)
     { const int lowk0 = lowk, hghk0 = hghk;
@@ -471,8 +605,38 @@ static __device__ __noinline__ int4 front_run(const unsigned box_off, const unsi
       const bool wide = bail;
       int cc = 0, mx = 0, nmore = 1;
       unsigned m = 0;
-      if (!bail)
+      //  ---- interior fast path: both contigs' 2-bit windows come from tiles staged in shared memory,
+      //  no contig end within reach, at most two 32-base windows per slide.  Anything else (a longer
+      //  run, a wave that does not advance the best point) is recomputed by the general code below.
+      if (fleft == 0)
+        { fok = (hghk - lowk <= 24 - EX_FASTN) && fast_window<s>(bx->tileA,bx->tileB,A,B,alen,blen,besta,lowk,hghk,a0,b0,lane);
+          fleft = EX_FASTN;
+        }
+      fleft -= 1;
+      bool fast = false;
+      if (fok)
         { const int vp = __shfl_sync(FULL,rV,lane_up), vm = __shfl_sync(FULL,rV,lane_dn);
+          const int c0 = max(max(vp,vm)+1,rV+2);
+          const int xn0 = (c0 + kk) >> 1, yn0 = xn0 - kk;
+          const int oa = act ? ((s > 0) ? xn0 - a0 : -xn0 - 32 - a0) : 64;    // idle lanes read a valid spot
+          const int ob = act ? ((s > 0) ? yn0 - b0 : -yn0 - 32 - b0) : 64;
+          u64 dd = win_t(bx->tileA,oa) ^ win_t(bx->tileB,ob);
+          int t = dd ? ((s > 0) ? ((__ffsll((long long) dd)-1) >> 1) : (__clzll((long long) dd) >> 1)) : 32;
+          bool lng = act && t == 32;
+          if (__any_sync(FULL,lng))                                  // one more window for the 32-base runs
+            { dd = win_t(bx->tileA,(s > 0) ? oa+32 : oa-32) ^ win_t(bx->tileB,(s > 0) ? ob+32 : ob-32);
+              const int t2 = dd ? ((s > 0) ? ((__ffsll((long long) dd)-1) >> 1) : (__clzll((long long) dd) >> 1)) : 32;
+              if (lng) t += t2;
+              lng = lng && t2 == 32;
+            }
+          cc = c0 + 2*t;                                             // c0 + kk is even on every live diagonal
+          mx = __reduce_max_sync(FULL,act ? cc : INT_MIN);
+          m = rotr32(__ballot_sync(FULL,act && cc >= mx - WAVE_LAG),ltop);
+          fast = !__any_sync(FULL,lng) && mx > besta;                // else: this wave over again, the general way
+        }
+      if (!fast && !bail)
+        { fleft = 0;                                                 // a general wave may slide any distance: re-check
+          const int vp = __shfl_sync(FULL,rV,lane_up), vm = __shfl_sync(FULL,rV,lane_dn);
           const int c0 = max(max(vp,vm)+1,rV+2);
           const int xn0 = (c0 + kk) >> 1;
           bool ended;
@@ -503,7 +667,7 @@ static __device__ __noinline__ int4 front_run(const unsigned box_off, const unsi
           lowk = lowk0; hghk = hghk0;
           if (!wide) alone = 1;                          // pathological wave: stay alone for the rest of the pass
           int spin = 0;
-          while (d + 1 - bx->tail > EX_RING-1 && bx->stop == 0) if (++spin > SPIN_LIMIT) break;
+          while (d + 1 - bx->tail > EX_RING-1 && (bx->stop | bx->stopp) == 0) if (++spin > SPIN_LIMIT) break;
           __syncwarp();
           if (lane == 0)
             { bx->ring[(d+1) & (EX_RING-1)].cmd = 3;
@@ -515,9 +679,11 @@ static __device__ __noinline__ int4 front_run(const unsigned box_off, const unsi
       besta = mx;
       hghk = top - (__ffs(m)-1); lowk = top - (31 - __clz(m));
       rV = (kk >= lowk && kk <= hghk) ? cc : FRESH;
+      if (EX_DIAG && fast) dg_fast += 1;
       if (d - tail_seen > EX_RING-1)
-        { int spin = 0;
-          while (d - (tail_seen = bx->tail) > EX_RING-1 && bx->stop == 0) if (++spin > SPIN_LIMIT) break;
+        { int spin = 0; const long long w0 = DIAG_CLOCK();
+          while (d - (tail_seen = bx->tail) > EX_RING-1 && (bx->stop | bx->stopp) == 0) if (++spin > SPIN_LIMIT) break;
+          dg_wait += DIAG_CLOCK() - w0;
         }
       RingEnt *e = &bx->ring[d & (EX_RING-1)];
       e->cc[lane] = cc;
@@ -529,8 +695,9 @@ static __device__ __noinline__ int4 front_run(const unsigned box_off, const unsi
         { __syncwarp();
           if (lane == 0) st_release_smem_a(head_a,d);
         }
-      if (!nmore || ((d & 7) == 0 && bx->stop != 0)) break;
+      if (!nmore || ((d & 7) == 0 && (bx->stop | bx->stopp) != 0)) break;
     }
+  if (EX_DIAG && lane == 0) { bx->r_fwait = dg_wait; bx->r_ffast = dg_fast; }
   return make_int4(lowk,hghk,besta,alone);
 }
 
@@ -641,7 +808,7 @@ static __device__ __noinline__ int wave(Ctx &c, int low, int hgh, const int mida
               bx->trimx = trimx; bx->trimd = trimd; bx->trimha = trimha; bx->avail = c.avail;
               bx->tspace = tspace; bx->path_ave = c.path_ave; bx->cmax = c.cmax; bx->wmask = W-1; bx->dif0 = dif;
               bx->cells = c.cells; bx->V = c.V; bx->HA = c.HA; bx->HM = c.HM; bx->NA = c.NA; bx->T = c.T;
-              bx->head = 0; bx->tail = 0; bx->stop = 0;
+              bx->head = 0; bx->tail = 0; bx->stop = 0; bx->tailt = 0; bx->stopp = 0;
               bx->cmd = (s > 0) ? 1 : 2;
               st_release_smem(&bx->seq,bx->seq + 1);
             }
@@ -657,12 +824,14 @@ static __device__ __noinline__ int wave(Ctx &c, int low, int hgh, const int mida
           }
           { int spin = 0; long long w0 = DIAG_CLOCK();
             while ((stp = ld_acquire_smem(&bx->stop)) == 0) if (++spin > SPIN_LIMIT) { stp = 1; break; }
+            spin = 0;
+            while (ld_acquire_smem(&bx->stopp) == 0) if (++spin > SPIN_LIMIT) break;      // the pebble warp too
             fwait += DIAG_CLOCK() - w0;
-            c.fwait += (u64) fwait; c.ftot += (u64) (DIAG_CLOCK() - ft0);
+            (void) fwait; (void) ft0;
           }
-          const int bst = bx->status;
+          const int bst = bx->pstatus != ST_OK ? bx->pstatus : bx->status;
           lasta = bx->r_lasta; trima = bx->r_trima; trimx = bx->r_trimx; trimd = bx->r_trimd; trimha = bx->r_trimha;
-          if (EX_DIAG) { c.bwait += (u64) bx->r_bwait; c.btot += (u64) bx->r_btot; }
+          if (EX_DIAG) { c.bwait += (u64) bx->r_bwait; c.btot += (u64) bx->r_btot; c.fwait += (u64) bx->r_fwait; c.ftot += (u64) bx->r_ffast; }
           c.avail = bx->r_avail; c.pwaves += (u64) (bx->r_dif - dif); c.npairs += 1; dif = bx->r_dif; ncell += bx->r_ncell;
           __syncwarp();
           if (bst != ST_OK) return bst;
@@ -1642,8 +1811,8 @@ __global__ void prefilter_kernel(ext_params P, unsigned *__restrict__ work_long,
 #define STATE_BYTES (WSTATE_BYTES(EX_W) + SCAN_SMEM)
 #define BIG_SMEM_PER_WARP (SCAN_SMEM)
 #define TT_BYTES    (32768*2)
-#define EX_NFRONT   (EX_PAIR ? EX_WARPS/2 : EX_WARPS)       // warps of a block that take triples
-#define BOX_BYTES   (EX_PAIR ? (EX_WARPS/2)*((int) sizeof(PairBox)) : 0)
+#define EX_NFRONT   (EX_PAIR ? EX_WARPS/EX_TEAM : EX_WARPS)  // warps of a block that take triples
+#define BOX_BYTES   (EX_PAIR ? (EX_WARPS/EX_TEAM)*((int) sizeof(PairBox)) : 0)
 
 template<int W>
 __global__ void __launch_bounds__(EX_WARPS*32,EX_MINBLK)
@@ -1664,14 +1833,15 @@ extend_kernel(ext_params P)
   c.ttab = P.table; c.sc15 = TRIM_LEN * P.dscore;
   c.box = NULL; c.box_off = 0;
   if (EX_PAIR)
-    { c.box_off = (unsigned) ((size_t) EX_WARPS * per_warp + (size_t) (wp >> 1) * sizeof(PairBox));
+    { c.box_off = (unsigned) ((size_t) EX_WARPS * per_warp + (size_t) (wp / EX_TEAM) * sizeof(PairBox));
       c.box = (PairBox *) (smem + c.box_off);
-      if ((wp & 1) == 0 && lane == 0) { c.box->seq = 0; c.box->cmd = 0; c.box->stop = 0; }
+      if ((wp % EX_TEAM) == 0 && lane == 0) { c.box->seq = 0; c.box->cmd = 0; c.box->stop = 0; c.box->stopp = 0; }
     }
   __syncthreads();
-  if (EX_PAIR && (wp & 1))
-    { //  back warp of pair wp/2: serves the passes its front warp (wp-1) starts
+  if (EX_PAIR && (wp % EX_TEAM))
+    { //  T warp (1) / P warp (2) of team wp/3: serve the passes their front warp starts
       PairBox *bx = c.box;
+      const int role = wp % EX_TEAM;
       int myseq = 0;
       while (true)
         { int sq;
@@ -1679,7 +1849,8 @@ extend_kernel(ext_params P)
           myseq = sq;
           int cm = bx->cmd;
           if (cm == 9) break;
-          if (cm == 1) wave_back<1>(c.box_off,c.ttab,c.sc15); else wave_back<-1>(c.box_off,c.ttab,c.sc15);
+          if (role == 1) { if (cm == 1) wave_T<1>(c.box_off,c.ttab,c.sc15); else wave_T<-1>(c.box_off,c.ttab,c.sc15); }
+          else           { if (cm == 1) wave_P<1>(c.box_off); else wave_P<-1>(c.box_off); }
           __syncwarp();
         }
       return;
@@ -1725,10 +1896,13 @@ extend_kernel(ext_params P)
       atomicAdd(&P.counters[9],c.cyc_wave);
       atomicAdd(&P.counters[10],c.cyc_extract);
       atomicAdd(&P.counters[11],c.pwaves);
-      atomicAdd(&P.counters[12],c.npairs);
+      if (EX_DIAG)                                                    // slowest warp: cycles, of which in waves / read-outs (all >> 12)
+        atomicMax(&P.counters[12],(((u64) (clock64() - t_start) >> 12) << 40) | ((c.cyc_wave >> 12) << 20) | (c.cyc_extract >> 12));
+      else atomicAdd(&P.counters[12],c.npairs);
       atomicAdd(&P.counters[4],c.fwait); atomicAdd(&P.counters[7],c.ftot);
       atomicAdd(&P.counters[13],c.bwait);
-      atomicMax(&P.counters[14],(u64) (clock64() - t_start));
+      if (EX_DIAG) atomicAdd(&P.counters[14],c.btot);                 // P warp wait cycles (diagnostic builds)
+      else atomicMax(&P.counters[14],(u64) (clock64() - t_start));
       { u64 cy = (u64) (clock64() - t_start) >> 12, wv = c.nwaves > 0xffffff ? 0xffffff : c.nwaves;
         u64 la = nla > 0xffff ? 0xffff : nla;
         atomicMax(&P.counters[15],(cy << 40) | (wv << 16) | la);      // the slowest warp: cycles/4096, waves, LA calls

@@ -331,10 +331,14 @@ __global__ void kix_index_kernel(const rec128 *__restrict__ tab, long long n,
   a.lo = a.hi = b.lo = b.hi = 0;
   if (i > 0) a = ld_rec(tab + i - 1);
   if (i < n) b = ld_rec(tab + i);
-  long long plo = (i == 0) ? -1 : (long long) KREC_PREFIX24(a.hi);
-  long long phi = (i == n) ? (1ll << 24) : (long long) KREC_PREFIX24(b.hi);
-  for (long long x = plo+1; x <= phi; x++)
-    pstart[x] = (unsigned) i;
+  //  the two open ends (everything up to the first prefix, everything above the last one) are
+  //  filled by kix_ends_kernel with full parallelism: a slice of a sharded table covers only part
+  //  of the prefix space, and one thread writing millions of index entries would take 60 ms
+  if (i > 0 && i < n)
+    { long long plo = (long long) KREC_PREFIX24(a.hi), phi = (long long) KREC_PREFIX24(b.hi);
+      for (long long x = plo+1; x <= phi; x++)
+        pstart[x] = (unsigned) i;
+    }
   //  adj[i] = LCP in bases of entries i-1 and i (the LCP byte of the reference's .ktab entries,
   //  GIXmake.c:1249-1254), 0 at both ends of the table: the merge takes block extents from it
   int l = 0;
@@ -484,12 +488,22 @@ extern "C" int fgb_syncmer_emit_device(const void *d_seq, const long long *d_cle
 }
 
 //  d_adj: n + 32 bytes (entries past n are zeroed: the merge's slice loads run up to 31 bytes over)
+__global__ void kix_ends_kernel(const rec128 *__restrict__ tab, long long n, unsigned *__restrict__ pstart)
+{ long long x = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (x > (1ll << 24)) return;
+  if (n == 0) { pstart[x] = 0; return; }
+  long long p0 = (long long) KREC_PREFIX24(tab[0].hi), pl = (long long) KREC_PREFIX24(tab[n-1].hi);
+  if (x <= p0) pstart[x] = 0;
+  else if (x > pl) pstart[x] = (unsigned) n;
+}
+
 extern "C" int fgb_kix_index_device(const void *d_tab, long long n, unsigned *d_pstart, unsigned char *d_adj,
                                     void *stream)
 { cudaStream_t st = (cudaStream_t) stream;
   int nb = (int) ((n + 1 + 255) / 256);
   CUDA_TRY(cudaMemsetAsync(d_adj + n,0,32,st));
   kix_index_kernel<<<nb,256,0,st>>>((const rec128 *) d_tab,n,d_pstart,d_adj);
+  kix_ends_kernel<<<((1 << 24) + 256)/256,256,0,st>>>((const rec128 *) d_tab,n,d_pstart);
   fgb_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return FGB_OK;

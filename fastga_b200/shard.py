@@ -22,7 +22,7 @@ def pack_alignments(alns, contig_map=None):
     fields = alns.fields.copy()
     if contig_map is not None and len(fields):
         fields[:, 1] = np.asarray(contig_map, dtype=np.int32)[fields[:, 1]]
-    n = np.array([len(alns), alns.pool.size if len(alns) else 0], dtype=np.int64)
+    n = np.array([len(alns), alns.pool.size if len(alns) else 0, alns.nraw], dtype=np.int64)
     pool = alns.pool if len(alns) else np.zeros(0, np.uint8)
     return np.concatenate([n.view(np.uint8), fields.reshape(-1).view(np.uint8),
                            alns.toff.view(np.uint8), pool.view(np.uint8)])
@@ -31,14 +31,14 @@ def pack_alignments(alns, contig_map=None):
 def unpack_alignments(buf):
     from .lib import Alignments
     buf = np.ascontiguousarray(buf, dtype=np.uint8)
-    n, pb = (int(x) for x in buf[:16].view(np.int64))
-    o = 16
+    n, pb, nraw = (int(x) for x in buf[:24].view(np.int64))
+    o = 24
     fields = buf[o:o + n * 36].view(np.int32).reshape(n, 9).copy()
     o += n * 36
     toff = buf[o:o + n * 8].view(np.int64).copy()
     o += n * 8
     pool = buf[o:o + pb].copy()
-    return Alignments(fields, toff, pool if pb else np.zeros(1, np.uint8), n)
+    return Alignments(fields, toff, pool if pb else np.zeros(1, np.uint8), nraw)
 
 
 def gather_alignments(alns, contig_map, dist, device):

@@ -17,5 +17,7 @@ for it in range(3):
     c = ov.counters()
     ov.close()
 c["extend_ms"] = tm["extend_ms"]; c["triples_ms"] = tm["triples_ms"]
+v = c["pairings"]
+c["diag_slowest"] = {"cycles": (v >> 40) << 12, "wave_cycles": ((v >> 20) & 0xfffff) << 12, "extract_cycles": (v & 0xfffff) << 12}
 c["cycles_per_wave_slowest"] = c["slowest_warp"]["cycles"] / max(1, c["slowest_warp"]["waves"])
 print(json.dumps(c))
