@@ -59,12 +59,17 @@ typedef unsigned long long u64;
 
 struct __align__(16) Peb { int ptr, diag, diff, mark; };
 
+struct ChainHit;
 struct ext_params
 { const rec128 *seeds; long long nseeds;
   int p_anti, anti_bits, p_band, band_bits, p_jc, jc_bits, p_ic, ic_bits, p_cp;
   long long amxpos, bmxpos;
   const unsigned *seg_start; int nseg;
   const unsigned *work; int nwork; unsigned *queue;
+  const unsigned *widx;                                // retry launches: position of work[w] in the first launch's list
+  const ChainHit *hits; const uint2 *hit_range;        // pre-scanned chains of every triple of the first list (NULL: scan here)
+  unsigned *failed_w;                                  // positions (first list) of the triples in failed[]
+  unsigned *need;                                      // bit ST_* set when a triple failed for that reason
   const u64 *aseq, *arseq; const long long *awoff, *aclen; const int *aperm;
   const u64 *bseq;         const long long *bwoff, *bclen; const int *bperm;
   int chain_break, chain_min, aln_min; double aln_rate;
@@ -1567,18 +1572,12 @@ static __device__ int handle_hit(const ext_params &P, Ctx &c, TripleCtx &T, long
 
 #define SCAN_SMEM 1536          // per warp: La Ua (32 x i64) Lm Um (32 x int) Ma (64 x i64) Mm (64 x int)
 
-template<int W>
-static __device__ int scan_triple_warp(const ext_params &P, Ctx &c, unsigned j, unsigned &nhit_out,
-                                       u64 &nla, unsigned char *wsm)
-{ const int lane = threadIdx.x & 31;
-  const rec128 *S = P.seeds;
-  long long *La = (long long *) wsm, *Ua = La + 32, *Ma = Ua + 32;
-  int *Lm = (int *) (Ma + 64), *Um = Lm + 32, *Mm = Um + 32;
-
-  unsigned b = P.seg_start[j], m = P.seg_start[j+1], e = m;
+//  Bands of a triple: L = [b,m) (band c), U = [m,e) (band c+1, if present).  False: nothing to scan.
+static __device__ bool triple_setup(const ext_params &P, unsigned j, TripleCtx &T, unsigned &b, unsigned &m, unsigned &e)
+{ const rec128 *S = P.seeds;
+  b = P.seg_start[j]; m = P.seg_start[j+1]; e = m;
   rec128 r0 = S[b];
   u64 grp = get_bits(r0,P.p_jc,P.jc_bits + P.ic_bits + 1);
-  TripleCtx T;
   T.cdiag = (long long) get_bits(r0,P.p_band,P.band_bits);
   T.isnew = true;
   bool aux = false;
@@ -1594,28 +1593,45 @@ static __device__ int scan_triple_warp(const ext_params &P, Ctx &c, unsigned j, 
           (long long) get_bits(rn,P.p_band,P.band_bits) == T.cdiag+1)
         { aux = true; e = P.seg_start[j+2]; }
     }
-  nhit_out = 0;
-  if (!T.isnew && !aux) return ST_OK;
-
+  if (!T.isnew && !aux) return false;
   T.j = j; T.seq = 0; T.alast = -1;
   T.comp = (int) get_bits(r0,P.p_cp,1);
   T.pairkey = (unsigned) grp;
-  { int ctg1 = P.aperm[get_bits(r0,P.p_ic,P.ic_bits)];
-    int ctg2 = P.bperm[get_bits(r0,P.p_jc,P.jc_bits)];
-    T.selfpair = (P.self_mode != 0 && ctg1 == ctg2 && T.comp == 0);
-    T.alen = P.aclen[ctg1]; T.blen = P.bclen[ctg2]; T.mlen = T.alen + T.blen;
-    T.doffset = T.alen - (P.amxpos + P.bmxpos); T.aoffset = T.alen - P.amxpos;
-    c.A = (const unsigned *) ((T.comp ? P.arseq : P.aseq) + P.awoff[ctg1]);
-    c.B = (const unsigned *) (P.bseq + P.bwoff[ctg2]);
-    c.alen = (int) T.alen; c.blen = (int) T.blen;
-    c.anw = (T.alen + 31) >> 5; c.bnw = (T.blen + 31) >> 5;
-  }
+  return true;
+}
 
+static __device__ void triple_contigs(const ext_params &P, Ctx &c, TripleCtx &T)
+{ rec128 r0 = P.seeds[P.seg_start[T.j]];
+  int ctg1 = P.aperm[get_bits(r0,P.p_ic,P.ic_bits)];
+  int ctg2 = P.bperm[get_bits(r0,P.p_jc,P.jc_bits)];
+  T.selfpair = (P.self_mode != 0 && ctg1 == ctg2 && T.comp == 0);
+  T.alen = P.aclen[ctg1]; T.blen = P.bclen[ctg2]; T.mlen = T.alen + T.blen;
+  T.doffset = T.alen - (P.amxpos + P.bmxpos); T.aoffset = T.alen - P.amxpos;
+  c.A = (const unsigned *) ((T.comp ? P.arseq : P.aseq) + P.awoff[ctg1]);
+  c.B = (const unsigned *) (P.bseq + P.bwoff[ctg2]);
+  c.alen = (int) T.alen; c.blen = (int) T.blen;
+  c.anw = (T.alen + 31) >> 5; c.bnw = (T.blen + 31) >> 5;
+}
+
+//  The open chain at the end of a scanned range, and the running maximum of anti + 2*lcp
+struct ChainOpen { long long alow, carryP; int cov, mix, dgmin, dgmax, cnt; bool head; };
+
+//  Chain detection over the merged seeds of L[s,m) and U[t,e), 32 at a time, starting from the
+//  running maximum carryP of everything before the range.  sink.closed(alow,ahgh,cov,mix,dmin,dmax,
+//  cnt,head) is called for every chain a break closes (head: the chain contains the range's start;
+//  cnt: its seeds inside the range); O returns the chain left open.
+template<class Sink>
+static __device__ int scan_core(const ext_params &P, unsigned s, unsigned m, unsigned t, unsigned e,
+                                long long carryP, unsigned char *wsm, Sink &sink, ChainOpen &O)
+{ const int lane = threadIdx.x & 31;
+  const rec128 *S = P.seeds;
+  long long *La = (long long *) wsm, *Ua = La + 32, *Ma = Ua + 32;
+  int *Lm = (int *) (Ma + 64), *Um = Lm + 32, *Mm = Um + 32;
   const long long NEG = -0x7fffffffffffffffll;
   const long long CB = P.chain_break;
-  long long carryP = -CB, c_alow = 0;
-  int c_cov = 0, c_mix = 0, c_dgmin = 2*BUCK_WIDTH, c_dgmax = 0;
-  unsigned s = b, t = m;
+  long long c_alow = 0;
+  int c_cov = 0, c_mix = 0, c_dgmin = 2*BUCK_WIDTH, c_dgmax = 0, c_cnt = 0;
+  bool head = true;
 
   while (s < m || t < e)
     { int nl = (int) min(32u,m - s), nu = (int) min(32u,e - t);
@@ -1693,36 +1709,256 @@ static __device__ int scan_triple_warp(const ext_params &P, Ctx &c, unsigned j, 
               unsigned R = ((q >= 32) ? 0xffffffffu : ((1u << q) - 1)) & ~((1u << seglo) - 1);
               int cov = (q > 0 ? __shfl_sync(FULL,Ssum,q-1) : 0) - (seglo > 0 ? __shfl_sync(FULL,Ssum,seglo-1) : 0);
               int mix = ((w1 & R) ? 1 : 0) | ((w2 & R) ? 2 : 0);
+              int cnt = __popc(R);
               bool inR = (R >> lane) & 1;
               int dmin = __reduce_min_sync(FULL,inR ? dg : 255);
               int dmax = __reduce_max_sync(FULL,inR ? dg : -1);
               long long alow = c_alow;
               if (cont)
-                { cov += c_cov; mix |= c_mix;
+                { cov += c_cov; mix |= c_mix; cnt += c_cnt;
                   dmin = min(dmin,c_dgmin); dmax = max(dmax,c_dgmax);
                 }
               else
                 alow = __shfl_sync(FULL,anti,seglo);
               if (last)                                           // open chain -> carry
-                { c_cov = cov; c_mix = mix; c_dgmin = dmin; c_dgmax = dmax; c_alow = alow;
+                { c_cov = cov; c_mix = mix; c_dgmin = dmin; c_dgmax = dmax; c_alow = alow; c_cnt = cnt;
                   break;
                 }
               long long ahgh = __shfl_sync(FULL,Pl,q);
-              if (cov >= P.chain_min && (mix != 1 || T.isnew))
-                { nhit_out += 1;
-                  int st = handle_hit<W>(P,c,T,alow,ahgh,dmin,dmax,nla);
-                  if (st) return st;
-                }
+              int st = sink.closed(alow,ahgh,cov,mix,dmin,dmax,cnt,head);
+              if (st) return st;
+              head = false;
               seglo = q; cont = false;
             }
           long long pmx = __shfl_sync(FULL,pm,n-1);
           if (pmx > carryP) carryP = pmx;
         }
     }
+  O.alow = c_alow; O.carryP = carryP; O.cov = c_cov; O.mix = c_mix; O.dgmin = c_dgmin; O.dgmax = c_dgmax;
+  O.cnt = c_cnt; O.head = head;
+  return ST_OK;
+}
+
+//  in-kernel scan of a whole triple (triples whose pre-scanned chunks overflowed): chains go straight
+//  to the tube stepping
+template<int W> struct HitNow
+{ const ext_params &P; Ctx &c; TripleCtx &T; u64 &nla; unsigned &nhit;
+  __device__ int closed(long long alow, long long ahgh, int cov, int mix, int dmin, int dmax, int, bool)
+  { if (cov >= P.chain_min && (mix != 1 || T.isnew))
+      { nhit += 1;
+        return handle_hit<W>(P,c,T,alow,ahgh,dmin,dmax,nla);
+      }
+    return ST_OK;
+  }
+};
+
+template<int W>
+static __device__ int scan_triple_warp(const ext_params &P, Ctx &c, unsigned j, unsigned &nhit_out,
+                                       u64 &nla, unsigned char *wsm)
+{ TripleCtx T;
+  unsigned b, m, e;
+  nhit_out = 0;
+  if (!triple_setup(P,j,T,b,m,e)) return ST_OK;
+  triple_contigs(P,c,T);
+  HitNow<W> sink = { P, c, T, nla, nhit_out };
+  ChainOpen O;
+  int st = scan_core(P,b,m,m,e,-(long long) P.chain_break,wsm,sink,O);
+  if (st) return st;
   //  the scan's final iteration (anti = MAX) closes the last chain
-  if (c_cov >= P.chain_min && (c_mix != 1 || T.isnew))
-    { nhit_out += 1;
-      int st = handle_hit<W>(P,c,T,c_alow,carryP,c_dgmin,c_dgmax,nla);
+  return sink.closed(O.alow,O.carryP,O.cov,O.mix,O.dgmin,O.dgmax,O.cnt,false);
+}
+
+/***********************************************************************************************
+ *  Chain detection ahead of the extension, in parallel over CHUNKS of a triple.  A long triple's
+ *  chain scan is a serial walk over up to millions of seeds; inside extend_kernel it sat on the
+ *  critical path of the kernel's longest triple.  Chain breaks only depend on the running maximum
+ *  of anti + 2*lcp, and a seed spans at most 80 anti-diagonals, so that maximum at any cut point is
+ *  found by looking back a few dozen seeds: the merged seed sequence is cut at anti values
+ *  (chain_plan_kernel), every chunk is scanned by its own warp (chain_chunk_kernel: chains inside
+ *  the chunk become hits, the pieces touching its two ends are returned as partial sums), and one
+ *  thread per triple stitches the partial chains of consecutive chunks (chain_stitch_kernel).
+ *  extend_kernel then only walks the hit list of its triple (run_hits).
+ **********************************************************************************************/
+
+#define CH_SEEDS 4096            // seeds of the longer band per chunk
+#define CH_HCAP  48              // hits recorded per chunk (more: the triple is scanned in extend_kernel)
+
+struct ChainHit { long long alow, ahgh; int dgmin, dgmax; };
+
+struct ChunkPlan { unsigned w, j, k, nch, sL, sU; };            // work-list position, triple, chunk number, chunks of the triple, band starts
+
+struct ChunkOut
+{ int nhit, over, first_break, head_closed, tail_valid, empty;
+  int h_cov, h_mix, h_dgmin, h_dgmax;
+  int t_cov, t_mix, t_dgmin, t_dgmax;
+  long long h_ahgh, t_alow, carry_start, carry_end;
+  ChainHit hits[CH_HCAP];
+};
+
+__global__ void chain_plan_kernel(ext_params P, ChunkPlan *__restrict__ plan, int nplan)
+{ int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nplan) return;
+  ChunkPlan c = plan[i];
+  c.j = P.work[c.w];
+  TripleCtx T; unsigned b, m, e;
+  if (!triple_setup(P,c.j,T,b,m,e)) { c.sL = P.seg_start[c.j+1]; c.sU = c.sL; plan[i] = c; return; }
+  if (c.k == 0) { c.sL = b; c.sU = m; plan[i] = c; return; }
+  const rec128 *S = P.seeds;
+  const unsigned nL = m - b, nU = e - m;
+  const bool useL = nL >= nU;
+  const unsigned nX = useL ? nL : nU, x0 = useL ? b : m;
+  const unsigned long long idx = (unsigned long long) c.k * ((nX + c.nch - 1) / c.nch);
+  if (idx >= nX) { c.sL = m; c.sU = e; plan[i] = c; return; }   // an empty chunk at the end
+  const long long a = (long long) get_bits(S[x0 + idx],P.p_anti,P.anti_bits);
+  unsigned lo = b, hi = m;                                       // first L seed with anti >= a
+  while (lo < hi) { unsigned md = (lo + hi) >> 1; if ((long long) get_bits(S[md],P.p_anti,P.anti_bits) < a) lo = md+1; else hi = md; }
+  c.sL = lo;
+  lo = m; hi = e;
+  while (lo < hi) { unsigned md = (lo + hi) >> 1; if ((long long) get_bits(S[md],P.p_anti,P.anti_bits) < a) lo = md+1; else hi = md; }
+  c.sU = lo;
+  plan[i] = c;
+}
+
+struct ChunkSink
+{ const ext_params &P; ChunkOut *out; bool isnew; int lane;
+  __device__ int closed(long long alow, long long ahgh, int cov, int mix, int dmin, int dmax, int cnt, bool head)
+  { if (head)
+      { if (lane == 0)
+          { out->first_break = (cnt == 0); out->head_closed = 1;
+            out->h_cov = cov; out->h_mix = mix; out->h_dgmin = dmin; out->h_dgmax = dmax; out->h_ahgh = ahgh;
+          }
+        return ST_OK;
+      }
+    if (cov >= P.chain_min && (mix != 1 || isnew))
+      { if (lane == 0)
+          { int k = out->nhit;
+            if (k < CH_HCAP) { ChainHit h; h.alow = alow; h.ahgh = ahgh; h.dgmin = dmin; h.dgmax = dmax; out->hits[k] = h; }
+            else out->over = 1;
+            out->nhit = k + 1;
+          }
+      }
+    return ST_OK;
+  }
+};
+
+__global__ void __launch_bounds__(128)
+chain_chunk_kernel(ext_params P, const ChunkPlan *__restrict__ plan, int nplan, ChunkOut *__restrict__ outs)
+{ __shared__ __align__(16) unsigned char sm[4*SCAN_SMEM];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 4 + wp;
+  if (i >= nplan) return;
+  const ChunkPlan c = plan[i];
+  ChunkOut *out = outs + i;
+  TripleCtx T; unsigned b, m, e;
+  const bool ok = triple_setup(P,c.j,T,b,m,e);
+  unsigned sL = c.sL, sU = c.sU, eL = m, eU = e;
+  if (ok && c.k + 1 < c.nch) { eL = plan[i+1].sL; eU = plan[i+1].sU; }
+  if (lane == 0)
+    { out->nhit = 0; out->over = 0; out->first_break = 0; out->head_closed = 0; out->tail_valid = 0;
+      out->empty = (!ok || (sL >= eL && sU >= eU));
+    }
+  __syncwarp();
+  if (!ok || (sL >= eL && sU >= eU)) return;
+  const rec128 *S = P.seeds;
+  //  running maximum of anti + 2*lcp over everything before the chunk: only seeds within 80
+  //  anti-diagonals of the last one can hold it
+  long long carry = -(long long) P.chain_break;
+  if (c.k > 0)
+    { long long best = -0x7fffffffffffffffll, top = -0x7fffffffffffffffll;
+      for (int band = 0; band < 2; band++)
+        { const unsigned lo = band ? m : b, hi = band ? sU : sL;
+          if (hi > lo) { long long a = (long long) get_bits(S[hi-1],P.p_anti,P.anti_bits); if (a > top) top = a; }
+        }
+      for (int band = 0; band < 2; band++)
+        { const unsigned lo = band ? m : b; unsigned hi = band ? sU : sL;
+          while (hi > lo)
+            { long long a = -0x7fffffffffffffffll, v = -0x7fffffffffffffffll;
+              if (hi >= lo + 1 + (unsigned) lane)
+                { rec128 r = ld_rec(S + hi - 1 - lane);
+                  a = (long long) get_bits(r,P.p_anti,P.anti_bits);
+                  v = a + (long long) ((r.lo & 63) << 1);
+                }
+              for (int o = 16; o > 0; o >>= 1)
+                { long long w = __shfl_xor_sync(FULL,v,o); if (w > v) v = w; }
+              if (v > best) best = v;
+              const long long amin = __shfl_sync(FULL,a,31);       // the farthest seed looked at (NEG if fewer than 32)
+              if (hi < lo + 32 || amin < top - 80) break;
+              hi -= 32;
+            }
+        }
+      if (best > carry) carry = best;
+    }
+  if (lane == 0) out->carry_start = carry;
+  ChunkSink sink = { P, out, T.isnew, lane };
+  ChainOpen O;
+  scan_core(P,sL,eL,sU,eU,carry,sm + wp*SCAN_SMEM,sink,O);
+  if (lane == 0)
+    { out->carry_end = O.carryP;
+      if (O.head)                                                 // no break inside: the whole chunk continues the open chain
+        { out->h_cov = O.cov; out->h_mix = O.mix; out->h_dgmin = O.dgmin; out->h_dgmax = O.dgmax; }
+      else
+        { out->tail_valid = 1; out->t_alow = O.alow;
+          out->t_cov = O.cov; out->t_mix = O.mix; out->t_dgmin = O.dgmin; out->t_dgmax = O.dgmax;
+        }
+    }
+}
+
+//  one thread per work triple: its chunks in order -> the ordered hit list of the triple
+__global__ void chain_stitch_kernel(ext_params P, const ChunkPlan *__restrict__ plan, const ChunkOut *__restrict__ outs,
+                                    const unsigned *__restrict__ first_chunk, int ntrip, ChainHit *__restrict__ hits,
+                                    unsigned long long *__restrict__ hit_used, unsigned long long hit_cap,
+                                    uint2 *__restrict__ hit_range /* start, count | 0x80000000: scan in extend_kernel */)
+{ int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= ntrip) return;
+  const unsigned c0 = first_chunk[w], c1 = first_chunk[w+1];
+  TripleCtx T; unsigned b, m, e;
+  if (c1 == c0 || !triple_setup(P,plan[c0].j,T,b,m,e)) { hit_range[w] = make_uint2(0u,0u); return; }
+  unsigned long long total = 0; bool over = false;
+  for (unsigned k = c0; k < c1; k++) { total += (unsigned long long) outs[k].nhit + 1; over |= (outs[k].over != 0); }
+  total += 1;
+  unsigned long long base = atomicAdd(hit_used,total);
+  if (over || base + total > hit_cap) { hit_range[w] = make_uint2(0u,0x80000000u); return; }
+  ChainHit *H = hits + base;
+  unsigned n = 0;
+  bool open = false; long long o_alow = 0; int o_cov = 0, o_mix = 0, o_dmin = 2*BUCK_WIDTH, o_dmax = 0;
+  long long last_carry = -(long long) P.chain_break;
+#define CH_EMIT(AHGH) do { if (open && o_cov >= P.chain_min && (o_mix != 1 || T.isnew)) \
+                             { ChainHit h; h.alow = o_alow; h.ahgh = (AHGH); h.dgmin = o_dmin; h.dgmax = o_dmax; H[n++] = h; } \
+                           open = false; } while (0)
+  for (unsigned k = c0; k < c1; k++)
+    { const ChunkOut &C = outs[k];
+      if (C.empty) continue;
+      if (C.first_break) CH_EMIT(C.carry_start);
+      else
+        { //  the chunk's head continues the open chain (an open chain always exists: chunk 0 starts with a break)
+          o_cov += C.h_cov; o_mix |= C.h_mix;
+          if (C.h_dgmin < o_dmin) o_dmin = C.h_dgmin;
+          if (C.h_dgmax > o_dmax) o_dmax = C.h_dgmax;
+          if (C.head_closed) CH_EMIT(C.h_ahgh);
+        }
+      for (int q = 0; q < C.nhit; q++) H[n++] = C.hits[q];
+      if (C.tail_valid)
+        { open = true; o_alow = C.t_alow; o_cov = C.t_cov; o_mix = C.t_mix; o_dmin = C.t_dgmin; o_dmax = C.t_dgmax; }
+      last_carry = C.carry_end;
+    }
+  CH_EMIT(last_carry);                                             // the scan's final iteration closes the last chain
+#undef CH_EMIT
+  hit_range[w] = make_uint2((unsigned) base,n);
+}
+
+//  extend_kernel's side: the tube stepping of every pre-scanned chain of a triple, in order
+template<int W>
+static __device__ int run_hits(const ext_params &P, Ctx &c, unsigned j, const ChainHit *__restrict__ H, unsigned n,
+                               unsigned &nhit_out, u64 &nla)
+{ TripleCtx T;
+  unsigned b, m, e;
+  nhit_out = 0;
+  if (n == 0 || !triple_setup(P,j,T,b,m,e)) return ST_OK;
+  triple_contigs(P,c,T);
+  for (unsigned q = 0; q < n; q++)
+    { const ChainHit h = H[q];
+      nhit_out += 1;
+      int st = handle_hit<W>(P,c,T,h.alow,h.ahgh,h.dgmin,h.dgmax,nla);
       if (st) return st;
     }
   return ST_OK;
@@ -1872,11 +2108,17 @@ extend_kernel(ext_params P)
       w = __shfl_sync(FULL,w,0);
       if (w >= (unsigned) P.nwork) break;
       unsigned j = P.work[w], nh = 0;
-      int st = scan_triple_warp<W>(P,c,j,nh,nla,(unsigned char *) stagebuf);
+      const unsigned w0 = P.widx ? P.widx[w] : w;
+      uint2 hr = make_uint2(0u,0x80000000u);
+      if (P.hit_range != NULL) hr = P.hit_range[w0];
+      int st;
+      if (hr.y & 0x80000000u) st = scan_triple_warp<W>(P,c,j,nh,nla,(unsigned char *) stagebuf);
+      else                    st = run_hits<W>(P,c,j,P.hits + hr.x,hr.y,nh,nla);
       if (st != ST_OK)
         { if (lane == 0)
             { unsigned o = atomicAdd(P.nfailed,1u);
-              P.failed[o] = j;
+              P.failed[o] = j; P.failed_w[o] = w0;
+              atomicOr(P.need,1u << st);
             }
         }
       else
@@ -2060,6 +2302,9 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
   P.counters = d_counters;
 
   unsigned nseg = 0, nwork = 0;
+  std::vector<unsigned> wsize; bool sizes_known = false;
+  ChunkPlan *d_plan = NULL; ChunkOut *d_couts = NULL; unsigned *d_first = NULL, *d_failed_w = NULL;
+  ChainHit *d_hits = NULL; uint2 *d_hrange = NULL; unsigned long long hit_cap = 0;
   if (n > 0)
     { ev_timer t(0,st);
       long long tmpb = fgb_dev_scan_tmp_bytes(n);
@@ -2086,7 +2331,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       CUDA_TRY(cudaStreamSynchronize(st));
       //  long triples first, largest first (the kernel's makespan is its longest triple, so it
       //  must not start late), then the exact short hits
-      if (nw2[0] > 1 && nw2[0] <= (1u << 20))
+      if (nw2[0] >= 1 && nw2[0] <= (1u << 20))
         { std::vector<unsigned> lj(nw2[0]), ls(nw2[0]), ord(nw2[0]);
           CUDA_TRY(cudaMemcpyAsync(lj.data(),d_work,4ull*nw2[0],cudaMemcpyDeviceToHost,st));
           CUDA_TRY(cudaMemcpyAsync(ls.data(),d_work + 2ll*nseg + 2,4ull*nw2[0],cudaMemcpyDeviceToHost,st));
@@ -2095,13 +2340,50 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           std::sort(ord.begin(),ord.end(),[&](unsigned a, unsigned b)
                     { return ls[a] != ls[b] ? ls[a] > ls[b] : lj[a] < lj[b]; });
           std::vector<unsigned> sj(nw2[0]);
-          for (unsigned q = 0; q < nw2[0]; q++) sj[q] = lj[ord[q]];
+          wsize.resize(nw2[0]);
+          for (unsigned q = 0; q < nw2[0]; q++) { sj[q] = lj[ord[q]]; wsize[q] = ls[ord[q]]; }
           CUDA_TRY(cudaMemcpyAsync(d_work,sj.data(),4ull*nw2[0],cudaMemcpyHostToDevice,st));
           CUDA_TRY(cudaStreamSynchronize(st));
+          sizes_known = true;
         }
+      else if (nw2[0] == 0) sizes_known = true;
       CUDA_TRY(cudaMemcpyAsync(d_work + nw2[0],d_work + nseg + 1,sizeof(unsigned)*nw2[1],
                                cudaMemcpyDeviceToDevice,st));
       nwork = nw2[0] + nw2[1];
+
+      //  chain detection of every work triple, chunk-parallel (chain_plan / chain_chunk / chain_stitch)
+      if (sizes_known && nwork > 0)
+        { std::vector<ChunkPlan> plan;
+          std::vector<unsigned> first(nwork + 1);
+          for (unsigned w = 0; w < nwork; w++)
+            { unsigned size = w < wsize.size() ? wsize[w] : 0;
+              unsigned nch = (unsigned) (((unsigned long long) size + CH_SEEDS + CH_SEEDS/2 - 1) / (CH_SEEDS + CH_SEEDS/2));
+              if (nch < 1) nch = 1;
+              first[w] = (unsigned) plan.size();
+              for (unsigned k = 0; k < nch; k++)
+                { ChunkPlan c; c.w = w; c.j = 0; c.k = k; c.nch = nch; c.sL = c.sU = 0; plan.push_back(c); }
+            }
+          first[nwork] = (unsigned) plan.size();
+          const int nplan = (int) plan.size();
+          hit_cap = (unsigned long long) nplan * (CH_HCAP + 1) + nwork + 16;
+          CUDA_TRY(fgb_dmalloc((void **) &d_plan,sizeof(ChunkPlan)*(size_t) nplan,st));
+          CUDA_TRY(fgb_dmalloc((void **) &d_couts,sizeof(ChunkOut)*(size_t) nplan,st));
+          CUDA_TRY(fgb_dmalloc((void **) &d_first,sizeof(unsigned)*(size_t) (nwork + 1),st));
+          CUDA_TRY(fgb_dmalloc((void **) &d_hits,sizeof(ChainHit)*(size_t) hit_cap,st));
+          CUDA_TRY(fgb_dmalloc((void **) &d_hrange,sizeof(uint2)*(size_t) nwork,st));
+          CUDA_TRY(cudaMemcpyAsync(d_plan,plan.data(),sizeof(ChunkPlan)*(size_t) nplan,cudaMemcpyHostToDevice,st));
+          CUDA_TRY(cudaMemcpyAsync(d_first,first.data(),sizeof(unsigned)*(size_t) (nwork + 1),cudaMemcpyHostToDevice,st));
+          CUDA_TRY(cudaMemsetAsync(d_misc + 8,0,8,st));
+          P.work = d_work; P.nwork = (int) nwork;
+          chain_plan_kernel<<<(nplan + 127)/128,128,0,st>>>(P,d_plan,nplan);
+          chain_chunk_kernel<<<(nplan + 3)/4,128,0,st>>>(P,d_plan,nplan,d_couts);
+          chain_stitch_kernel<<<(nwork + 127)/128,128,0,st>>>(P,d_plan,d_couts,d_first,(int) nwork,d_hits,
+                                                             (unsigned long long *) (d_misc + 8),hit_cap,d_hrange);
+          fgb_count_launch(3);
+          CUDA_TRY(cudaGetLastError());
+          CUDA_TRY(cudaStreamSynchronize(st));                 // plan / first are host vectors
+          P.hits = d_hits; P.hit_range = d_hrange;
+        }
     }
   O->nseg = nseg; O->nwork = nwork;
   tr_mark("extend: triples+prefilter");
@@ -2125,8 +2407,9 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       long long nwarps = nblocks * EX_WARPS;
 
       CUDA_TRY(fgb_dmalloc((void **) &d_failed,sizeof(unsigned)*(nwork+1),st));
+      CUDA_TRY(fgb_dmalloc((void **) &d_failed_w,sizeof(unsigned)*(nwork+1),st));
       P.work = d_work; P.nwork = (int) nwork;
-      P.queue = d_misc + 1; P.nfailed = d_misc + 2; P.failed = d_failed;
+      P.queue = d_misc + 1; P.nfailed = d_misc + 2; P.failed = d_failed; P.failed_w = d_failed_w; P.widx = NULL; P.need = d_misc + 10;
       P.out_used = (u64 *) (d_misc + 4);
 
       long long cells_per_warp = 1ll << 17;          // 128 K pebbles = 2 MB per warp
@@ -2152,6 +2435,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
             }
           tr_mark("extend: arenas allocated");
           CUDA_TRY(cudaMemsetAsync(d_misc+1,0,8,st));          // queue, nfailed
+          CUDA_TRY(cudaMemsetAsync(d_misc+10,0,4,st));         // reasons of this attempt's failures
           { ev_timer t(1,st);
             if (attempt == 0)
               extend_kernel<EX_W><<<(unsigned) nblocks,EX_WARPS*32,smem,st>>>(P);
@@ -2160,8 +2444,8 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           }
           fgb_count_launch(1);
           CUDA_TRY(cudaGetLastError());
-          unsigned misc[8];
-          CUDA_TRY(cudaMemcpyAsync(misc,d_misc,32,cudaMemcpyDeviceToHost,st));
+          unsigned misc[12];
+          CUDA_TRY(cudaMemcpyAsync(misc,d_misc,48,cudaMemcpyDeviceToHost,st));
           CUDA_TRY(cudaStreamSynchronize(st));
           tr_mark("extend: kernel done");
           fgb_dfree(d_cells,st); fgb_dfree(d_stage,st); fgb_dfree(d_big,st);
@@ -2188,10 +2472,16 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           std::vector<unsigned> f(nfailed);
           CUDA_TRY(cudaMemcpy(f.data(),d_failed,sizeof(unsigned)*nfailed,cudaMemcpyDeviceToHost));
           todo.insert(todo.end(),f.begin(),f.end());
-          if (d_work2 == NULL) CUDA_TRY(cudaMalloc(&d_work2,sizeof(unsigned)*(nwork+1)));
+          if (d_work2 == NULL) CUDA_TRY(cudaMalloc(&d_work2,sizeof(unsigned)*2*(nwork+1)));
           CUDA_TRY(cudaMemcpy(d_work2,f.data(),sizeof(unsigned)*nfailed,cudaMemcpyHostToDevice));
+          //  their positions in the first launch's list (the pre-scanned hit lists are indexed by it)
+          CUDA_TRY(cudaMemcpy(d_work2 + nwork + 1,d_failed_w,sizeof(unsigned)*nfailed,cudaMemcpyDeviceToDevice));
+          P.widx = d_work2 + nwork + 1;
           d_list = d_work2; nlist = nfailed;
-          cells_per_warp *= 8; stage_bytes *= 4;
+          //  grow only what overflowed: a band too wide for the register / shared-memory state (ST_BAND)
+          //  just moves to the wide-band kernel below with the same arenas
+          if (attempt > 0 || (misc[10] & (1u << ST_CELLS))) cells_per_warp *= 8;
+          if (attempt > 0 || (misc[10] & (1u << ST_STAGE))) stage_bytes *= 4;
           long long nb2 = ((long long) nfailed + EX_NFRONT - 1) / EX_NFRONT;
           long long maxb = (24ll << 30) / ((long long) sizeof(Peb) * cells_per_warp * EX_WARPS);
           if (maxb < 1) maxb = 1;
@@ -2265,6 +2555,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
   }
   fgb_dfree(d_tables,st); fgb_dfree(d_counters,st); fgb_dfree(d_total,st); fgb_dfree(d_misc,st); fgb_dfree(d_flag,st);
   fgb_dfree(d_seg,st); fgb_dfree(d_work,st); fgb_dfree(d_failed,st); fgb_dfree(d_tmp,st); fgb_dfree(d_out,st);
+  fgb_dfree(d_plan,st); fgb_dfree(d_couts,st); fgb_dfree(d_first,st); fgb_dfree(d_failed_w,st); fgb_dfree(d_hits,st); fgb_dfree(d_hrange,st);
   tr_mark("extend: leave");
   *out = O;
   return FGB_OK;
