@@ -399,10 +399,10 @@ def run():
     gpu_md5 = canonical_md5(final.canonical_lines_unsorted())
     steps = args.steps
     # roofline of the seed-merge kernel (the kernel north_star grades): algorithmic bytes on the
-    # on-disk widths, B = (N1 + N2)*E + H*R with N1 = the entries of table 1 the merge
-    # has to see: its forward-strand entries (reverse entries never seed, FastGA.c:921-928, and the
-    # fused path does not build them).  `frac_ondisk_n1` is the same time against the both-strand
-    # table the reference keeps on disk.
+    # on-disk widths, B = (N1 + N2)*E + H*R, N1 / N2 = the entries of the two tables the
+    # reference's merge walks (both strands of table 1, as in round 1).  This implementation reads only
+    # the forward-strand entries of table 1 (reverse entries never seed, FastGA.c:921-928, and the fused
+    # path does not build them): `frac_forward_n1` is the same time against that smaller B.
     pb = max(1, (int(max(gA.clen.max(), gB.clen.max())).bit_length() + 7) // 8)
     E1 = 9 + pb + 1
     R = 1 + 2 * (pb + 1)
@@ -416,7 +416,7 @@ def run():
     kb = 12 + abits + max(1, abits - 6) + max(1, (gB.ncontig - 1).bit_length()) + max(1, (gA.ncontig - 1).bit_length()) + 1
     seed_passes = (kb + 7) // 8
     peak, peak_src = measured_peak_hbm()
-    ach = algo / (merge_ms * 1e-3) / 1e9 if merge_ms > 0 else 0.0
+    ach = algo_ondisk / (merge_ms * 1e-3) / 1e9 if merge_ms > 0 else 0.0
     dev_ms = {k: v / steps for k, v in tm.items() if k.endswith("_ms")}
     # records this rank's k-mer sorts handled per step: table 1 forward-only + its share of table 2
     nk_sorted = stats["nkmers1_fwd"] + stats["nkmers2"]
@@ -446,8 +446,9 @@ def run():
                          "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic_bytes() if (world == 1 and args.per_gpu_bp == PER_GPU_BP) else None,
                          "peak_source": peak_src,
-                         "algorithmic_bytes": algo, "kernel_ms": merge_ms,
-                         "frac_ondisk_n1": (algo_ondisk / (merge_ms * 1e-3) / 1e9 / peak) if merge_ms > 0 else 0.0},
+                         "algorithmic_bytes": algo_ondisk, "kernel_ms": merge_ms,
+                         "algorithmic_bytes_forward_n1": algo,
+                         "frac_forward_n1": (algo / (merge_ms * 1e-3) / 1e9 / peak) if merge_ms > 0 else 0.0},
             # the other HBM-side stages against the same measured peak (16-byte device records;
             # k-mer sort = 2 Onesweep passes + 1 shared-memory bucket pass, seed sort = ceil(keybits/8) passes)
             "other_kernels": other_kernels(stats, dev_ms, peak, seed_passes, nk_sorted),

@@ -1697,20 +1697,33 @@ static __device__ int scan_core(const ext_params &P, unsigned s, unsigned m, uns
             { int v = __shfl_up_sync(FULL,Ssum,o);
               if (lane >= o) Ssum += v;
             }
-          unsigned bm = __ballot_sync(FULL,brk);
-          unsigned w1 = __ballot_sync(FULL,act && wch == 1), w2 = __ballot_sync(FULL,act && wch == 2);
-          int seglo = 0;
-          bool cont = true;
-          unsigned rem = bm;
+          const unsigned bm = __ballot_sync(FULL,brk);
+          const unsigned w1 = __ballot_sync(FULL,act && wch == 1), w2 = __ballot_sync(FULL,act && wch == 2);
+          //  Segments between breaks: the first continues the carried chain, the last stays open, the
+          //  ones in between are whole chains.  Nearly all of those are stray seeds below chain_min:
+          //  every break lane sizes its own segment, only the ones that reach chain_min are visited.
+          const unsigned above = bm & ~((2u << lane) - 1u);
+          const int qn = above ? (__ffs(above) - 1) : n;              // end of the segment this lane starts (if brk)
+          const int segcov = __shfl_sync(FULL,Ssum,qn > 0 ? qn-1 : 0) - (Ssum - inc);
+          unsigned todo = __ballot_sync(FULL,brk && above != 0 && segcov >= P.chain_min);
+          const int nbrk = __popc(bm);
+          //  visit order: [0,first break) | qualifying middle segments | [last break,n)
+          int stage = 0;
           while (true)
-            { int q = rem ? (__ffs(rem) - 1) : n;                 // segment [seglo,q)
-              bool last = (rem == 0);
-              rem &= rem - 1;
-              unsigned R = ((q >= 32) ? 0xffffffffu : ((1u << q) - 1)) & ~((1u << seglo) - 1);
+            { int seglo, q; bool cont, last;
+              if (stage == 0)
+                { seglo = 0; q = bm ? (__ffs(bm) - 1) : n; cont = true; last = (bm == 0); stage = 1; }
+              else if (todo)
+                { seglo = __ffs(todo) - 1; todo &= todo - 1;
+                  q = __shfl_sync(FULL,qn,seglo); cont = false; last = false;
+                }
+              else
+                { seglo = 31 - __clz(bm); q = n; cont = false; last = true; }
+              const unsigned R = ((q >= 32) ? 0xffffffffu : ((1u << q) - 1)) & ~((1u << seglo) - 1);
               int cov = (q > 0 ? __shfl_sync(FULL,Ssum,q-1) : 0) - (seglo > 0 ? __shfl_sync(FULL,Ssum,seglo-1) : 0);
               int mix = ((w1 & R) ? 1 : 0) | ((w2 & R) ? 2 : 0);
               int cnt = __popc(R);
-              bool inR = (R >> lane) & 1;
+              const bool inR = (R >> lane) & 1;
               int dmin = __reduce_min_sync(FULL,inR ? dg : 255);
               int dmax = __reduce_max_sync(FULL,inR ? dg : -1);
               long long alow = c_alow;
@@ -1724,12 +1737,12 @@ static __device__ int scan_core(const ext_params &P, unsigned s, unsigned m, uns
                 { c_cov = cov; c_mix = mix; c_dgmin = dmin; c_dgmax = dmax; c_alow = alow; c_cnt = cnt;
                   break;
                 }
-              long long ahgh = __shfl_sync(FULL,Pl,q);
+              const long long ahgh = __shfl_sync(FULL,Pl,q);
               int st = sink.closed(alow,ahgh,cov,mix,dmin,dmax,cnt,head);
               if (st) return st;
               head = false;
-              seglo = q; cont = false;
             }
+          if (nbrk > 1) head = false;                             // skipped chains closed too
           long long pmx = __shfl_sync(FULL,pm,n-1);
           if (pmx > carryP) carryP = pmx;
         }
@@ -1780,8 +1793,11 @@ static __device__ int scan_triple_warp(const ext_params &P, Ctx &c, unsigned j, 
  *  extend_kernel then only walks the hit list of its triple (run_hits).
  **********************************************************************************************/
 
-#define CH_SEEDS 4096            // seeds of the longer band per chunk
+#define CH_SEEDS 1024            // seeds per chunk (both bands), x1.5
 #define CH_HCAP  48              // hits recorded per chunk (more: the triple is scanned in extend_kernel)
+#ifndef CH_TOPK
+#define CH_TOPK  (1 << 30)             // only the largest triples are pre-scanned: theirs is the scan that sits on the kernel's
+#endif                           //   critical path; the others are scanned inside extend_kernel, which has idle warps to spare
 
 struct ChainHit { long long alow, ahgh; int dgmin, dgmax; };
 
@@ -1803,24 +1819,27 @@ __global__ void chain_plan_kernel(ext_params P, ChunkPlan *__restrict__ plan, in
   TripleCtx T; unsigned b, m, e;
   if (!triple_setup(P,c.j,T,b,m,e)) { c.sL = P.seg_start[c.j+1]; c.sU = c.sL; plan[i] = c; return; }
   if (c.k == 0) { c.sL = b; c.sU = m; plan[i] = c; return; }
+  //  cut k sits after the first k/nch of the MERGED sequence (lower band first on equal anti, the
+  //  order scan_core merges in): a merge-path search over the two bands, so a chunk holds the same
+  //  number of seeds whichever band they crowd in
   const rec128 *S = P.seeds;
   const unsigned nL = m - b, nU = e - m;
-  const bool useL = nL >= nU;
-  const unsigned nX = useL ? nL : nU, x0 = useL ? b : m;
-  const unsigned long long idx = (unsigned long long) c.k * ((nX + c.nch - 1) / c.nch);
-  if (idx >= nX) { c.sL = m; c.sU = e; plan[i] = c; return; }   // an empty chunk at the end
-  const long long a = (long long) get_bits(S[x0 + idx],P.p_anti,P.anti_bits);
-  unsigned lo = b, hi = m;                                       // first L seed with anti >= a
-  while (lo < hi) { unsigned md = (lo + hi) >> 1; if ((long long) get_bits(S[md],P.p_anti,P.anti_bits) < a) lo = md+1; else hi = md; }
-  c.sL = lo;
-  lo = m; hi = e;
-  while (lo < hi) { unsigned md = (lo + hi) >> 1; if ((long long) get_bits(S[md],P.p_anti,P.anti_bits) < a) lo = md+1; else hi = md; }
-  c.sU = lo;
+  const unsigned long long tgt = (unsigned long long) c.k * ((nL + nU + c.nch - 1) / c.nch);
+  if (tgt >= (unsigned long long) nL + nU) { c.sL = m; c.sU = e; plan[i] = c; return; }   // an empty chunk at the end
+  const unsigned t = (unsigned) tgt;
+  unsigned lo = t > nU ? t - nU : 0u, hi = t < nL ? t : nL;        // L seeds among the first t
+  while (lo < hi)
+    { const unsigned md = (lo + hi) >> 1;
+      const long long al = (long long) get_bits(S[b + md],P.p_anti,P.anti_bits);
+      const long long au = (long long) get_bits(S[m + (t - 1 - md)],P.p_anti,P.anti_bits);
+      if (al <= au) lo = md + 1; else hi = md;
+    }
+  c.sL = b + lo; c.sU = m + (t - lo);
   plan[i] = c;
 }
 
 struct ChunkSink
-{ const ext_params &P; ChunkOut *out; bool isnew; int lane;
+{ const ext_params &P; ChunkOut *out; bool isnew; int lane; int nhit;
   __device__ int closed(long long alow, long long ahgh, int cov, int mix, int dmin, int dmax, int cnt, bool head)
   { if (head)
       { if (lane == 0)
@@ -1830,12 +1849,9 @@ struct ChunkSink
         return ST_OK;
       }
     if (cov >= P.chain_min && (mix != 1 || isnew))
-      { if (lane == 0)
-          { int k = out->nhit;
-            if (k < CH_HCAP) { ChainHit h; h.alow = alow; h.ahgh = ahgh; h.dgmin = dmin; h.dgmax = dmax; out->hits[k] = h; }
-            else out->over = 1;
-            out->nhit = k + 1;
-          }
+      { if (lane == 0 && nhit < CH_HCAP)
+          { ChainHit h; h.alow = alow; h.ahgh = ahgh; h.dgmin = dmin; h.dgmax = dmax; out->hits[nhit] = h; }
+        nhit += 1;
       }
     return ST_OK;
   }
@@ -1889,11 +1905,12 @@ chain_chunk_kernel(ext_params P, const ChunkPlan *__restrict__ plan, int nplan, 
       if (best > carry) carry = best;
     }
   if (lane == 0) out->carry_start = carry;
-  ChunkSink sink = { P, out, T.isnew, lane };
+  ChunkSink sink = { P, out, T.isnew, lane, 0 };
   ChainOpen O;
   scan_core(P,sL,eL,sU,eU,carry,sm + wp*SCAN_SMEM,sink,O);
   if (lane == 0)
     { out->carry_end = O.carryP;
+      out->nhit = sink.nhit; out->over = (sink.nhit > CH_HCAP);
       if (O.head)                                                 // no break inside: the whole chunk continues the open chain
         { out->h_cov = O.cov; out->h_mix = O.mix; out->h_dgmin = O.dgmin; out->h_dgmax = O.dgmax; }
       else
@@ -1912,7 +1929,8 @@ __global__ void chain_stitch_kernel(ext_params P, const ChunkPlan *__restrict__ 
   if (w >= ntrip) return;
   const unsigned c0 = first_chunk[w], c1 = first_chunk[w+1];
   TripleCtx T; unsigned b, m, e;
-  if (c1 == c0 || !triple_setup(P,plan[c0].j,T,b,m,e)) { hit_range[w] = make_uint2(0u,0u); return; }
+  if (c1 == c0) { hit_range[w] = make_uint2(0u,0x80000000u); return; }          // not pre-scanned
+  if (!triple_setup(P,plan[c0].j,T,b,m,e)) { hit_range[w] = make_uint2(0u,0u); return; }
   unsigned long long total = 0; bool over = false;
   for (unsigned k = c0; k < c1; k++) { total += (unsigned long long) outs[k].nhit + 1; over |= (outs[k].over != 0); }
   total += 1;
@@ -2245,6 +2263,9 @@ static void tr_mark(const char *what)
   tr_t0 = t;
 }
 
+static bool tr_on() { static int on = -1; if (on < 0) on = (getenv("FGB_TRACE") != NULL); return on != 0; }
+#define TR_SYNC(what) do { if (tr_on()) { cudaStreamSynchronize(st); tr_mark(what); } } while (0)
+
 struct ev_timer
 { cudaEvent_t a, b; cudaStream_t st; int which;
   ev_timer(int w, cudaStream_t s) : st(s), which(w)
@@ -2318,6 +2339,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       CUDA_TRY(cudaMemcpyAsync(&tot,d_total,8,cudaMemcpyDeviceToHost,st));
       CUDA_TRY(cudaStreamSynchronize(st));
       nseg = (unsigned) tot;
+      TR_SYNC("  seg flags + scan");
       CUDA_TRY(fgb_dmalloc((void **) &d_seg,sizeof(unsigned)*(nseg+2),st));
       CUDA_TRY(fgb_dmalloc((void **) &d_work,sizeof(unsigned)*(3ll*nseg+3),st));
       nb = (int) ((n + 1 + 255) / 256);
@@ -2329,6 +2351,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       unsigned nw2[2];
       CUDA_TRY(cudaMemcpyAsync(nw2,d_misc + 6,8,cudaMemcpyDeviceToHost,st));
       CUDA_TRY(cudaStreamSynchronize(st));
+      TR_SYNC("  seg fill + prefilter");
       //  long triples first, largest first (the kernel's makespan is its longest triple, so it
       //  must not start late), then the exact short hits
       if (nw2[0] >= 1 && nw2[0] <= (1u << 20))
@@ -2350,6 +2373,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       CUDA_TRY(cudaMemcpyAsync(d_work + nw2[0],d_work + nseg + 1,sizeof(unsigned)*nw2[1],
                                cudaMemcpyDeviceToDevice,st));
       nwork = nw2[0] + nw2[1];
+      TR_SYNC("  work list ordered");
 
       //  chain detection of every work triple, chunk-parallel (chain_plan / chain_chunk / chain_stitch)
       if (sizes_known && nwork > 0)
@@ -2359,12 +2383,14 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
             { unsigned size = w < wsize.size() ? wsize[w] : 0;
               unsigned nch = (unsigned) (((unsigned long long) size + CH_SEEDS + CH_SEEDS/2 - 1) / (CH_SEEDS + CH_SEEDS/2));
               if (nch < 1) nch = 1;
+              if (w >= CH_TOPK || w >= wsize.size()) nch = 0;          // scanned inside extend_kernel
               first[w] = (unsigned) plan.size();
               for (unsigned k = 0; k < nch; k++)
                 { ChunkPlan c; c.w = w; c.j = 0; c.k = k; c.nch = nch; c.sL = c.sU = 0; plan.push_back(c); }
             }
           first[nwork] = (unsigned) plan.size();
           const int nplan = (int) plan.size();
+          if (nplan > 0) {
           hit_cap = (unsigned long long) nplan * (CH_HCAP + 1) + nwork + 16;
           CUDA_TRY(fgb_dmalloc((void **) &d_plan,sizeof(ChunkPlan)*(size_t) nplan,st));
           CUDA_TRY(fgb_dmalloc((void **) &d_couts,sizeof(ChunkOut)*(size_t) nplan,st));
@@ -2375,14 +2401,19 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           CUDA_TRY(cudaMemcpyAsync(d_first,first.data(),sizeof(unsigned)*(size_t) (nwork + 1),cudaMemcpyHostToDevice,st));
           CUDA_TRY(cudaMemsetAsync(d_misc + 8,0,8,st));
           P.work = d_work; P.nwork = (int) nwork;
+          TR_SYNC("  chain: plan uploaded");
           chain_plan_kernel<<<(nplan + 127)/128,128,0,st>>>(P,d_plan,nplan);
+          TR_SYNC("  chain: plan kernel");
           chain_chunk_kernel<<<(nplan + 3)/4,128,0,st>>>(P,d_plan,nplan,d_couts);
+          if (tr_on()) { cudaStreamSynchronize(st); fprintf(stderr,"[fgb_trace]   nwork %u nplan %d\n",nwork,nplan); tr_mark("  chain: chunk kernel"); }
           chain_stitch_kernel<<<(nwork + 127)/128,128,0,st>>>(P,d_plan,d_couts,d_first,(int) nwork,d_hits,
                                                              (unsigned long long *) (d_misc + 8),hit_cap,d_hrange);
           fgb_count_launch(3);
           CUDA_TRY(cudaGetLastError());
           CUDA_TRY(cudaStreamSynchronize(st));                 // plan / first are host vectors
+          TR_SYNC("  chain: stitch kernel");
           P.hits = d_hits; P.hit_range = d_hrange;
+          }
         }
     }
   O->nseg = nseg; O->nwork = nwork;

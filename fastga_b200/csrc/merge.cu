@@ -37,13 +37,13 @@ static __host__ __device__ __forceinline__ int seed_key_bits(const seed_layout &
 #define MG_THREADS 256
 #define MG_WARPS   (MG_THREADS/32)
 #ifndef MG_T2CAP
-#define MG_T2CAP   1280                   // staged T2 entries per CTA (20 KB)
+#define MG_T2CAP   1152                   // staged T2 entries per CTA (18 KB)
 #endif
 #ifndef MG_DCAP
-#define MG_DCAP    2560                   // seed descriptors per CTA (5 per T1 entry; crowded tiles write entry-wise)
+#define MG_DCAP    2048                   // seed descriptors per CTA (4 per T1 entry; crowded tiles write entry-wise)
 #endif
 #ifndef MG_MINBLK
-#define MG_MINBLK  5
+#define MG_MINBLK  6
 #endif
 //  lcp (in bases, 0..28) of two 56-bit suffixes
 static __device__ __forceinline__ int lcp56(u64 a, u64 b)
@@ -154,6 +154,77 @@ static __device__ __forceinline__ unsigned adaptamer_staged(const rec128 *__rest
   return (m >= 12 && rgt - lft < fq) ? rgt - lft : 0u;
 }
 
+//  The same for N entries per lane at once (the CTA's rounds): the N searches advance in lock step, so
+//  every dependent shared-memory probe of one has the probes of the others to overlap with.
+template<int N>
+static __device__ __forceinline__ void adaptamer_staged_n(const rec128 *__restrict__ t2,
+                                                          const unsigned char *__restrict__ adj, unsigned nsl,
+                                                          const rec128 (&r1)[N], const unsigned (&lo)[N],
+                                                          const unsigned (&hi)[N], int freq,
+                                                          unsigned (&cnt)[N], unsigned (&lowi)[N], int (&plen)[N])
+{ const u64 *t2w = reinterpret_cast<const u64 *>(t2);
+  const unsigned fq = (unsigned) freq;
+  unsigned a[N], b[N], wmax = 0;
+#pragma unroll
+  for (int r = 0; r < N; r++) { a[r] = lo[r]; b[r] = hi[r]; wmax = max(wmax,hi[r] - lo[r]); }
+  for (unsigned w = __reduce_max_sync(0xffffffffu,wmax); w > 0; w >>= 1)
+    {
+#pragma unroll
+      for (int r = 0; r < N; r++)
+        { const unsigned m = (a[r] + b[r]) >> 1;                // a == b: a probe with no effect
+          const u64 qh = t2w[2*m+1];
+          const unsigned ql = (unsigned) (t2w[2*m] >> 48);
+          const bool less = (qh < r1[r].hi) || (qh == r1[r].hi && ql < (unsigned) (r1[r].lo >> 48));
+          const bool live = a[r] < b[r];
+          if (live && less) a[r] = m+1;
+          if (live && !less) b[r] = m;
+        }
+    }
+  int m[N]; unsigned lft[N], rgt[N]; bool goL[N], goR[N], any = false;
+#pragma unroll
+  for (int r = 0; r < N; r++)
+    { int ll = 0, lr = 0;
+      if (lo[r] < hi[r])
+        { if (a[r] > 0)   ll = lcp_rec(r1[r],ld_rec(t2 + a[r] - 1));
+          if (a[r] < nsl) lr = lcp_rec(r1[r],ld_rec(t2 + a[r]));
+        }
+      m[r] = ll > lr ? ll : lr;
+      lft[r] = rgt[r] = a[r];
+      goL[r] = (m[r] >= 12 && ll == m[r]); goR[r] = (m[r] >= 12 && lr == m[r]);
+      if (goL[r]) lft[r] = a[r]-1;
+      if (goR[r]) rgt[r] = a[r]+1;
+    }
+#pragma unroll
+  for (int u = 0; u < 2; u++)
+    {
+#pragma unroll
+      for (int r = 0; r < N; r++)
+        { goL[r] = goL[r] && a[r] - lft[r] < fq && (int) adj[lft[r]] >= m[r];
+          if (goL[r]) lft[r] -= 1;
+          goR[r] = goR[r] && rgt[r] - a[r] < fq && (int) adj[rgt[r]] >= m[r];
+          if (goR[r]) rgt[r] += 1;
+        }
+    }
+#pragma unroll
+  for (int r = 0; r < N; r++) any = any || goL[r] || goR[r];
+  while (__any_sync(0xffffffffu,any))
+    { any = false;
+#pragma unroll
+      for (int r = 0; r < N; r++)
+        { goL[r] = goL[r] && a[r] - lft[r] < fq && (int) adj[lft[r]] >= m[r];
+          if (goL[r]) lft[r] -= 1;
+          goR[r] = goR[r] && rgt[r] - a[r] < fq && (int) adj[rgt[r]] >= m[r];
+          if (goR[r]) rgt[r] += 1;
+          any = any || goL[r] || goR[r];
+        }
+    }
+#pragma unroll
+  for (int r = 0; r < N; r++)
+    { lowi[r] = lft[r]; plen[r] = m[r];
+      cnt[r] = (m[r] >= 12 && rgt[r] - lft[r] < fq) ? rgt[r] - lft[r] : 0u;
+    }
+}
+
 //  Same straight from HBM (a tile whose slice does not fit the staging buffers: long repeats).
 static __device__ __forceinline__ unsigned adaptamer_direct(const rec128 *__restrict__ T2,
                                                             const unsigned *__restrict__ pstart, const rec128 &r1,
@@ -241,24 +312,33 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
   const u64 *t1k = reinterpret_cast<const u64 *>(S->t1);
   const u64 PAY = 0xffffffffffffull;
   unsigned cnt[ROUNDS], lowi[ROUNDS], excl[ROUNDS]; int plen[ROUNDS];
+  if (staged)
+    { //  all 32 lanes take part (warp-uniform search steps); lanes past the tile search nothing
+      rec128 r1[ROUNDS]; unsigned lo[ROUNDS], hi[ROUNDS];
+#pragma unroll
+      for (int r = 0; r < ROUNDS; r++)
+        { const unsigned j = r*MG_THREADS + tid;
+          r1[r].lo = r1[r].hi = 0; lo[r] = hi[r] = 0;
+          if (j < nt1)
+            { r1[r] = ld_rec(&S->t1[j]);
+              const unsigned p = KREC_PREFIX24(r1[r].hi);
+              lo[r] = __ldg(pstart2 + p) - lo2; hi[r] = __ldg(pstart2 + p + 1) - lo2;
+            }
+        }
+      adaptamer_staged_n<ROUNDS>(S->t2,adj,nsl,r1,lo,hi,freq,cnt,lowi,plen);
+    }
+  else
+    {
+#pragma unroll
+      for (int r = 0; r < ROUNDS; r++)
+        { const unsigned j = r*MG_THREADS + tid;
+          cnt[r] = 0; lowi[r] = 0; plen[r] = 0;
+          if (j < nt1) cnt[r] = adaptamer_direct(T2,pstart2,ld_rec(&S->t1[j]),freq,lowi[r],plen[r]);
+        }
+    }
 #pragma unroll
   for (int r = 0; r < ROUNDS; r++)
-    { const unsigned j = r*MG_THREADS + tid;
-      cnt[r] = 0; lowi[r] = 0; plen[r] = 0;
-      if (staged)
-        { //  all 32 lanes take part (warp-uniform search steps); lanes past the tile search nothing
-          rec128 r1; r1.lo = r1.hi = 0;
-          unsigned lo = 0, hi = 0;
-          if (j < nt1)
-            { r1 = ld_rec(&S->t1[j]);
-              const unsigned p = KREC_PREFIX24(r1.hi);
-              lo = __ldg(pstart2 + p) - lo2; hi = __ldg(pstart2 + p + 1) - lo2;
-            }
-          cnt[r] = adaptamer_staged(S->t2,adj,nsl,r1,lo,hi,freq,lowi[r],plen[r]);
-        }
-      else if (j < nt1)
-        cnt[r] = adaptamer_direct(T2,pstart2,ld_rec(&S->t1[j]),freq,lowi[r],plen[r]);
-      unsigned inc = cnt[r];
+    { unsigned inc = cnt[r];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1)
         { unsigned t = __shfl_up_sync(0xffffffffu,inc,o);
@@ -536,9 +616,9 @@ extern "C" int fgb_merge_device(const void *d_T1, long long n1, const void *d_T2
       int rc;
 #define MG_ARGS (const rec128 *) d_T1,(unsigned) n1,(const rec128 *) d_T2,d_pstart2,d_adj2,freq,K,(rec128 *) d_seeds, \
                 (unsigned long long) capacity,d_counters,st
-      if (ratio <= 2.2)       rc = merge_launch<512>(MG_ARGS);
-      else if (ratio <= 4.4)  rc = merge_launch<256>(MG_ARGS);
-      else if (ratio <= 8.8)  rc = merge_launch<128>(MG_ARGS);
+      if (ratio <= 2.1)       rc = merge_launch<512>(MG_ARGS);
+      else if (ratio <= 4.2)  rc = merge_launch<256>(MG_ARGS);
+      else if (ratio <= 8.4)  rc = merge_launch<128>(MG_ARGS);
       else                    rc = merge_launch<64>(MG_ARGS);
 #undef MG_ARGS
       if (rc) return rc;

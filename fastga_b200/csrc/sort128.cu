@@ -14,7 +14,12 @@
 #include <vector>
 
 #define SORT_THREADS 512
+#ifndef SORT_ITEMS
 #define SORT_ITEMS   8
+#endif
+#ifndef SORT_MINBLK
+#define SORT_MINBLK  2
+#endif
 #define SORT_TILE    (SORT_THREADS*SORT_ITEMS)
 #define SORT_WARPS   (SORT_THREADS/32)
 
@@ -100,7 +105,7 @@ __global__ void sort_bins_kernel(const unsigned long long *__restrict__ ghist, u
   if (tid == 0) *ticket = 0;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS,SORT_MINBLK)
 sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, long long n, int byte,
                      int next_byte /* -1: none */, const unsigned long long *__restrict__ binbase,
                      unsigned long long *__restrict__ nexthist, unsigned long long *status /* [ntiles][256] */,
@@ -292,8 +297,8 @@ extern "C" int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo
  **********************************************************************************************/
 
 #define BK_THREADS SORT_THREADS
-#define BK_ITEMS   SORT_ITEMS
-#define BK_CAP     SORT_TILE
+#define BK_ITEMS   8
+#define BK_CAP     (BK_THREADS*BK_ITEMS)
 #define BK_WARPS   SORT_WARPS
 #define BK_SPAN    4                     // a group covers at most this many consecutive 16-bit bins
 #define BK_SUBBITS 10

@@ -196,6 +196,34 @@ void fgb_msd_sort(unsigned char *array, long long nelem, int rsize, int ksize,
 int  fgb_rmsd_sort(unsigned char *array, long long nelem, int rsize, int ksize, int nparts,
                    long long *part, int nthreads, fgb_range *range);
 
+/* ---- building blocks of the several-GPU path (one process per GPU; fastga_b200/shard.py issues
+ *      them with two all-to-alls of 16-byte device records in between).  The k-mer space is cut by
+ *      the top byte of the k-mer (first four bases), the seed space by the A contig: the same cuts
+ *      the reference makes across threads (GIXmake.c:1426 panels by first byte; FastGA.c:4144, :4320
+ *      Range[] of contigs per thread).  Device pointers are plain CUDA pointers on the calling process's
+ *      current device; buffers handed out are released with fgb_device_free. ---- */
+int  fgb_device_alloc(long long bytes, void **out, void *stream);
+void fgb_device_free(void *p);
+/* unsorted k-mer records of the contigs with mask[c] != 0; fwd_only drops reverse-strand entries */
+int  fgb_kmers_scan(const fgb_genome *g, const unsigned char *mask, int fwd_only,
+                    void **d_recs, long long *n, void *stream);
+/* d_out[bounds257[b] .. bounds257[b+1]) = the records whose top k-mer byte is b (d_recs is scratch) */
+int  fgb_records_group_by_top_byte(void *d_recs, long long n, void *d_out, long long *bounds257,
+                                   void *stream);
+/* sorted + indexed table over records whose 12-base prefix lies in [plo,phi) (one rank's slice) */
+int  fgb_gix_from_records(const void *d_recs, long long n, unsigned plo, unsigned phi, int fwd_only,
+                          int post_bytes, int cont_bytes, int ncontig, fgb_gix **out, void *stream);
+/* adaptamer merge without the seed sort: unsorted seed records, bits[4] = anti/band/jcont/icont
+ * widths, info[2] = sum of seed lengths, T1 entries merged */
+int  fgb_seeds_merge(const fgb_gix *x1, const fgb_gix *x2, long long amxpos, long long bmxpos, int freq,
+                     void **d_seeds, long long *n, int *bits, long long *info, void *stream);
+/* d_out[bounds[w] .. bounds[w+1]) = the seeds whose A contig (rank order) belongs to owner[.] == w */
+int  fgb_seeds_group_by_owner(const void *d_seeds, long long n, const int *bits, const int *owner,
+                              int nrank_contigs, int world, void *d_out, long long *bounds, void *stream);
+/* sorted seed set over received records: input of fgb_extend on the owning rank */
+int  fgb_seeds_from_records(const void *d_recs, long long n, const int *bits, long long amxpos,
+                            long long bmxpos, long long sumlen, fgb_seeds **out, void *stream);
+
 /* ---- housekeeping ---- */
 int  fgb_device_ready(void);
 void fgb_release_cache(void);      /* return cached device blocks to the driver */
