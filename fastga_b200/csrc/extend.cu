@@ -56,10 +56,15 @@ typedef unsigned long long u64;
 #define ST_BAND      1                   // band wider than the state capacity
 #define ST_CELLS     2                   // pebble arena full
 #define ST_STAGE     3                   // trace staging full
+#define ST_SPEC      4                   // a hit group could not run on its own: the triple is re-run in one piece
 
 struct __align__(16) Peb { int ptr, diag, diff, mark; };
 
 struct ChainHit;
+//  Work item of the first launch: hits [h0,h0+hn) of work triple w, whose first hit is number g of
+//  its triple (hn bit 31: no hit list, the triple is scanned in the kernel).
+struct ExItem { unsigned w, h0, hn, g; };
+#define SPEC_SEQ_BITS 14                 // records of a hit group are numbered (g << 14) + 0, 1, ...
 struct ext_params
 { const rec128 *seeds; long long nseeds;
   int p_anti, anti_bits, p_band, band_bits, p_jc, jc_bits, p_ic, ic_bits, p_cp;
@@ -70,6 +75,10 @@ struct ext_params
   const ChainHit *hits; const uint2 *hit_range;        // pre-scanned chains of every triple of the first list (NULL: scan here)
   unsigned *failed_w;                                  // positions (first list) of the triples in failed[]
   unsigned *need;                                      // bit ST_* set when a triple failed for that reason
+  unsigned long long *wlog;                            // diagnostics (FGB_WLOG): 4 words per work item, or NULL
+  const ExItem *items;                                 // first launch: hit groups (NULL: work[] holds whole triples)
+  long long *galast;                                   //   per item: where the tube stood after its last hit
+  int attempt;                                         // launch number, stamped on every record
   const u64 *aseq, *arseq; const long long *awoff, *aclen; const int *aperm;
   const u64 *bseq;         const long long *bwoff, *bclen; const int *bperm;
   int chain_break, chain_min, aln_min; double aln_rate;
@@ -1337,7 +1346,7 @@ static __device__ void emit_record(const ext_params &P, Ctx &c, const LAres &R, 
           bb = c.blen - R.bepos; be = c.blen - R.bbpos;
         }
       h[0] = (int) triple; h[1] = seq; h[2] = (int) pairkey;
-      h[3] = ab; h[4] = bb; h[5] = ae; h[6] = be; h[7] = R.diffs; h[8] = tlen; h[9] = 0;
+      h[3] = ab; h[4] = bb; h[5] = ae; h[6] = be; h[7] = R.diffs; h[8] = tlen; h[9] = P.attempt;
     }
   unsigned char *t = o + OUT_HDR;
   for (int i = lane*2; i < tlen; i += 64)             // pair i/2 of the un-flipped trace
@@ -1516,7 +1525,7 @@ static __device__ int scan_triple(const ext_params &P, Ctx &c, unsigned j, unsig
  **********************************************************************************************/
 
 struct TripleCtx
-{ unsigned j, pairkey; int comp, seq; bool isnew, selfpair;
+{ unsigned j, pairkey; int comp, seq; bool isnew, selfpair, spec;
   long long cdiag, alen, blen, mlen, doffset, aoffset, alast;
 };
 
@@ -1560,6 +1569,7 @@ static __device__ int handle_hit(const ext_params &P, Ctx &c, TripleCtx &T, long
           if (rlen >= P.aln_min && P.aln_rate*rlen >= (double) R.diffs)
             { emit_record(P,c,R,T.comp,T.j,T.seq,T.pairkey);
               T.seq += 1;
+              if (T.spec && (T.seq & ((1 << SPEC_SEQ_BITS) - 1)) == 0) return ST_SPEC;   // numbering exhausted
             }
           eant = (long long) R.aepos + R.bepos;            // un-flipped end (FastGA.c:3309-3312)
           if (eant <= alow) alow = amid; else alow = eant;
@@ -1594,7 +1604,7 @@ static __device__ bool triple_setup(const ext_params &P, unsigned j, TripleCtx &
         { aux = true; e = P.seg_start[j+2]; }
     }
   if (!T.isnew && !aux) return false;
-  T.j = j; T.seq = 0; T.alast = -1;
+  T.j = j; T.seq = 0; T.alast = -1; T.spec = false;
   T.comp = (int) get_bits(r0,P.p_cp,1);
   T.pairkey = (unsigned) grp;
   return true;
@@ -1924,13 +1934,16 @@ chain_chunk_kernel(ext_params P, const ChunkPlan *__restrict__ plan, int nplan, 
 __global__ void chain_stitch_kernel(ext_params P, const ChunkPlan *__restrict__ plan, const ChunkOut *__restrict__ outs,
                                     const unsigned *__restrict__ first_chunk, int ntrip, ChainHit *__restrict__ hits,
                                     unsigned long long *__restrict__ hit_used, unsigned long long hit_cap,
-                                    uint2 *__restrict__ hit_range /* start, count | 0x80000000: scan in extend_kernel */)
+                                    uint2 *__restrict__ hit_range /* start, count | 0x80000000: scan in extend_kernel */,
+                                    int2 *__restrict__ tinfo /* (strand, contig pair) key and band of the triple */)
 { int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= ntrip) return;
+  tinfo[w] = make_int2(-1,0);
   const unsigned c0 = first_chunk[w], c1 = first_chunk[w+1];
   TripleCtx T; unsigned b, m, e;
   if (c1 == c0) { hit_range[w] = make_uint2(0u,0x80000000u); return; }          // not pre-scanned
   if (!triple_setup(P,plan[c0].j,T,b,m,e)) { hit_range[w] = make_uint2(0u,0u); return; }
+  tinfo[w] = make_int2((int) T.pairkey,(int) T.cdiag);
   unsigned long long total = 0; bool over = false;
   for (unsigned k = c0; k < c1; k++) { total += (unsigned long long) outs[k].nhit + 1; over |= (outs[k].over != 0); }
   total += 1;
@@ -1967,18 +1980,23 @@ __global__ void chain_stitch_kernel(ext_params P, const ChunkPlan *__restrict__ 
 //  extend_kernel's side: the tube stepping of every pre-scanned chain of a triple, in order
 template<int W>
 static __device__ int run_hits(const ext_params &P, Ctx &c, unsigned j, const ChainHit *__restrict__ H, unsigned n,
-                               unsigned &nhit_out, u64 &nla)
+                               unsigned &nhit_out, u64 &nla, const unsigned g, const bool spec, long long &alast_out)
 { TripleCtx T;
   unsigned b, m, e;
   nhit_out = 0;
+  alast_out = -0x7fffffffffffffffll;
   if (n == 0 || !triple_setup(P,j,T,b,m,e)) return ST_OK;
   triple_contigs(P,c,T);
+  //  a hit group starts as if nothing of its triple had been aligned before it (the host checks that
+  //  afterwards, fgb_extend); its records are numbered from (g << SPEC_SEQ_BITS)
+  T.spec = spec; T.seq = (int) (g << SPEC_SEQ_BITS);
   for (unsigned q = 0; q < n; q++)
     { const ChainHit h = H[q];
       nhit_out += 1;
       int st = handle_hit<W>(P,c,T,h.alow,h.ahgh,h.dgmin,h.dgmax,nla);
       if (st) return st;
     }
+  if (T.alast >= 0) alast_out = T.alast - (T.comp ? T.aoffset : 0);       // in the hits' own coordinates
   return ST_OK;
 }
 
@@ -2125,13 +2143,23 @@ extend_kernel(ext_params P)
       if (lane == 0) w = atomicAdd(P.queue,1u);
       w = __shfl_sync(FULL,w,0);
       if (w >= (unsigned) P.nwork) break;
-      unsigned j = P.work[w], nh = 0;
-      const unsigned w0 = P.widx ? P.widx[w] : w;
+      unsigned j, w0, nh = 0;
       uint2 hr = make_uint2(0u,0x80000000u);
-      if (P.hit_range != NULL) hr = P.hit_range[w0];
-      int st;
+      unsigned grp = 0; bool spec = false;
+      if (P.items != NULL)
+        { const ExItem it = P.items[w];
+          w0 = it.w; j = P.work[w0]; hr = make_uint2(it.h0,it.hn); grp = it.g; spec = true;
+        }
+      else
+        { j = P.work[w];
+          w0 = P.widx ? P.widx[w] : w;
+          if (P.hit_range != NULL) hr = P.hit_range[w0];
+        }
+      const u64 lg_w = c.nwaves, lg_l = nla; const long long lg_t = clock64();
+      int st; long long alast_out = -0x7fffffffffffffffll;
       if (hr.y & 0x80000000u) st = scan_triple_warp<W>(P,c,j,nh,nla,(unsigned char *) stagebuf);
-      else                    st = run_hits<W>(P,c,j,P.hits + hr.x,hr.y,nh,nla);
+      else                    st = run_hits<W>(P,c,j,P.hits + hr.x,hr.y,nh,nla,grp,spec,alast_out);
+      if (P.items != NULL && lane == 0) P.galast[w] = alast_out;
       if (st != ST_OK)
         { if (lane == 0)
             { unsigned o = atomicAdd(P.nfailed,1u);
@@ -2139,8 +2167,13 @@ extend_kernel(ext_params P)
               atomicOr(P.need,1u << st);
             }
         }
-      else
-        nhits += nh;
+      else if (!spec || (hr.y & 0x80000000u))
+        nhits += nh;                                                // (hit groups are counted by the host)
+      if (P.wlog != NULL && lane == 0)
+        { unsigned long long *L = P.wlog + 4ull*w;
+          L[0] = ((u64) gw << 32) | j; L[1] = ((c.nwaves - lg_w) << 24) | ((nla - lg_l) << 8) | (u64) (st & 0xff);
+          L[2] = (u64) (lg_t - t_start); L[3] = (u64) (clock64() - t_start);
+        }
       __syncwarp();
     }
   if (EX_PAIR && lane == 0)
@@ -2326,6 +2359,12 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
   std::vector<unsigned> wsize; bool sizes_known = false;
   ChunkPlan *d_plan = NULL; ChunkOut *d_couts = NULL; unsigned *d_first = NULL, *d_failed_w = NULL;
   ChainHit *d_hits = NULL; uint2 *d_hrange = NULL; unsigned long long hit_cap = 0;
+  //  hit groups (first launch): items in launch order, and for each the first hit of the NEXT group of
+  //  its triple (what its tube must not have reached for the groups to have been independent)
+  ExItem *d_items = NULL; long long *d_galast = NULL; int2 *d_tinfo = NULL;
+  std::vector<ExItem> items; std::vector<long long> nxt_alow, nxt_ahgh;
+  std::vector<unsigned> hwork, hcount;                 // work triples; hits of each pre-scanned one
+  unsigned long long hits_done = 0;                    // hits of the pre-scanned triples the first launch completed
   if (n > 0)
     { ev_timer t(0,st);
       long long tmpb = fgb_dev_scan_tmp_bytes(n);
@@ -2397,6 +2436,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           CUDA_TRY(fgb_dmalloc((void **) &d_first,sizeof(unsigned)*(size_t) (nwork + 1),st));
           CUDA_TRY(fgb_dmalloc((void **) &d_hits,sizeof(ChainHit)*(size_t) hit_cap,st));
           CUDA_TRY(fgb_dmalloc((void **) &d_hrange,sizeof(uint2)*(size_t) nwork,st));
+          CUDA_TRY(fgb_dmalloc((void **) &d_tinfo,sizeof(int2)*(size_t) nwork,st));
           CUDA_TRY(cudaMemcpyAsync(d_plan,plan.data(),sizeof(ChunkPlan)*(size_t) nplan,cudaMemcpyHostToDevice,st));
           CUDA_TRY(cudaMemcpyAsync(d_first,first.data(),sizeof(unsigned)*(size_t) (nwork + 1),cudaMemcpyHostToDevice,st));
           CUDA_TRY(cudaMemsetAsync(d_misc + 8,0,8,st));
@@ -2407,12 +2447,135 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           chain_chunk_kernel<<<(nplan + 3)/4,128,0,st>>>(P,d_plan,nplan,d_couts);
           if (tr_on()) { cudaStreamSynchronize(st); fprintf(stderr,"[fgb_trace]   nwork %u nplan %d\n",nwork,nplan); tr_mark("  chain: chunk kernel"); }
           chain_stitch_kernel<<<(nwork + 127)/128,128,0,st>>>(P,d_plan,d_couts,d_first,(int) nwork,d_hits,
-                                                             (unsigned long long *) (d_misc + 8),hit_cap,d_hrange);
+                                                             (unsigned long long *) (d_misc + 8),hit_cap,d_hrange,d_tinfo);
           fgb_count_launch(3);
           CUDA_TRY(cudaGetLastError());
           CUDA_TRY(cudaStreamSynchronize(st));                 // plan / first are host vectors
           TR_SYNC("  chain: stitch kernel");
           P.hits = d_hits; P.hit_range = d_hrange;
+
+          //  Hit groups.  Inside a triple a hit is clipped or skipped by the end of the alignments
+          //  before it (alast, FastGA.c:3262-3318), which chains its hits serially.  In practice a hit is
+          //  only ever touched by an alignment of ITS aligned block: the block's seed chains in this band
+          //  pair and in the neighbouring ones, overlapping end to end while the path drifts across
+          //  bands.  Chains of one (strand, contig pair) within SPEC_BANDS bands whose anti-diagonal
+          //  intervals (+- SPEC_SLACK) overlap are joined into components (union-find); a triple's hit list is cut
+          //  wherever the components before and after the cut are disjoint.  Every group is a work
+          //  item of its own that starts with a clear tube; after the launch the host checks that no
+          //  group's tube reached the next group's first hit -- else the triple is re-run in one piece
+          //  (retry ladder below), so a wrong guess costs time, never the result.
+          { int SPEC_BANDS = 1; long long SPEC_SLACK = 1000;
+            if (getenv("FGB_SPEC_BANDS") != NULL) SPEC_BANDS = atoi(getenv("FGB_SPEC_BANDS"));
+            if (getenv("FGB_SPEC_SLACK") != NULL) SPEC_SLACK = atoll(getenv("FGB_SPEC_SLACK"));
+            long long SPEC_GAP = -1;                                   // tests: cut at every gap >= this instead
+            if (getenv("FGB_SPEC_GAP") != NULL) SPEC_GAP = atoll(getenv("FGB_SPEC_GAP"));
+            unsigned long long hused = 0;
+            std::vector<uint2> hrange(nwork);
+            std::vector<int2> tinfo(nwork);
+            hwork.resize(nwork); hcount.assign(nwork,0u);
+            CUDA_TRY(cudaMemcpyAsync(&hused,d_misc + 8,8,cudaMemcpyDeviceToHost,st));
+            CUDA_TRY(cudaMemcpyAsync(hrange.data(),d_hrange,sizeof(uint2)*(size_t) nwork,cudaMemcpyDeviceToHost,st));
+            CUDA_TRY(cudaMemcpyAsync(tinfo.data(),d_tinfo,sizeof(int2)*(size_t) nwork,cudaMemcpyDeviceToHost,st));
+            CUDA_TRY(cudaMemcpyAsync(hwork.data(),d_work,sizeof(unsigned)*(size_t) nwork,cudaMemcpyDeviceToHost,st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (hused > hit_cap) hused = hit_cap;
+            std::vector<ChainHit> hh((size_t) hused + 1);
+            if (hused > 0) CUDA_TRY(cudaMemcpyAsync(hh.data(),d_hits,sizeof(ChainHit)*(size_t) hused,cudaMemcpyDeviceToHost,st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            for (unsigned w = 0; w < nwork; w++)
+              if (!(hrange[w].y & 0x80000000u)) hcount[w] = hrange[w].y;
+
+            //  components of chains (index = position in hh; only listed triples' ranges are used)
+            std::vector<unsigned> comp((size_t) hused + 1);
+            for (size_t q = 0; q <= hused; q++) comp[q] = (unsigned) q;
+            auto find = [&](unsigned x) { while (comp[x] != x) { comp[x] = comp[comp[x]]; x = comp[x]; } return x; };
+            auto unite = [&](unsigned x, unsigned y) { x = find(x); y = find(y); if (x != y) comp[x < y ? y : x] = (x < y ? x : y); };
+            if (SPEC_GAP < 0)
+              { std::vector<std::pair<std::pair<int,int>,unsigned> > byband;       // ((key, band), w)
+                for (unsigned w = 0; w < nwork; w++)
+                  if (hcount[w] > 0) byband.push_back(std::make_pair(std::make_pair(tinfo[w].x,tinfo[w].y),w));
+                std::sort(byband.begin(),byband.end());
+                for (size_t i = 0; i < byband.size(); i++)
+                  { const unsigned w1 = byband[i].second;
+                    const ChainHit *H1 = hh.data() + hrange[w1].x; const unsigned n1 = hcount[w1];
+                    for (unsigned q = 1; q < n1; q++)                                   // neighbours in its own list
+                      if (H1[q].alow - H1[q-1].ahgh < SPEC_SLACK) unite(hrange[w1].x + q - 1,hrange[w1].x + q);
+                    for (size_t k = i + 1; k < byband.size(); k++)
+                      { if (byband[k].first.first != byband[i].first.first ||
+                            byband[k].first.second - byband[i].first.second > SPEC_BANDS) break;
+                        const unsigned w2 = byband[k].second;
+                        const ChainHit *H2 = hh.data() + hrange[w2].x; const unsigned n2 = hcount[w2];
+                        unsigned a = 0, b = 0;                                          // interval join of two sorted lists
+                        while (a < n1 && b < n2)
+                          { if (H1[a].ahgh + SPEC_SLACK < H2[b].alow) a += 1;
+                            else if (H2[b].ahgh + SPEC_SLACK < H1[a].alow) b += 1;
+                            else
+                              { unite(hrange[w1].x + a,hrange[w2].x + b);
+                                if (H1[a].ahgh < H2[b].ahgh) a += 1; else b += 1;
+                              }
+                          }
+                      }
+                  }
+              }
+            //  extent of every component: how long the alignment of its block will be (launch order)
+            std::vector<long long> clo((size_t) hused + 1,0x7fffffffffffffffll), chi((size_t) hused + 1,-0x7fffffffffffffffll);
+            for (unsigned w = 0; w < nwork; w++)
+              for (unsigned q = 0; q < hcount[w]; q++)
+                { const unsigned x = hrange[w].x + q, r = find(x);
+                  if (hh[x].alow < clo[r]) clo[r] = hh[x].alow;
+                  if (hh[x].ahgh > chi[r]) chi[r] = hh[x].ahgh;
+                }
+
+            struct Grp { ExItem it; long long span, na, nh; };
+            std::vector<Grp> G;
+            const long long INF = 0x7fffffffffffffffll;
+            std::vector<unsigned> lastof;                                    // scratch: last list position of a component
+            for (unsigned w = 0; w < nwork; w++)
+              { const uint2 hr = hrange[w];
+                if (hr.y & 0x80000000u)
+                  { Grp g; g.it.w = w; g.it.h0 = 0; g.it.hn = 0x80000000u; g.it.g = 0; g.span = INF; g.na = g.nh = INF;
+                    G.push_back(g); continue;
+                  }
+                if (hr.y == 0) continue;
+                const ChainHit *H = hh.data() + hr.x;
+                const bool one = (hr.y >= (1u << (31 - SPEC_SEQ_BITS)));        // too many hits to number by group
+                //  reach[q] = last position holding a hit of the component of hit q
+                lastof.assign(hr.y,0u);
+                { std::vector<std::pair<unsigned,unsigned> > cq(hr.y);
+                  for (unsigned q = 0; q < hr.y; q++) cq[q] = std::make_pair(find(hr.x + q),q);
+                  std::sort(cq.begin(),cq.end());
+                  for (unsigned q = hr.y; q-- > 0; )
+                    lastof[cq[q].second] = (q + 1 < hr.y && cq[q+1].first == cq[q].first) ? lastof[cq[q+1].second] : cq[q].second;
+                }
+                unsigned a = 0;
+                while (a < hr.y)
+                  { unsigned b = a + 1, reach = lastof[a];
+                    long long span = 0; unsigned lastc = 0xffffffffu;
+                    while (b < hr.y && (one || b <= reach || (SPEC_GAP >= 0 && H[b].alow - H[b-1].ahgh < SPEC_GAP)))
+                      { if (lastof[b] > reach) reach = lastof[b];
+                        b += 1;
+                      }
+                    for (unsigned q = a; q < b; q++)
+                      { const unsigned r = find(hr.x + q);
+                        if (r != lastc) { span += chi[r] - clo[r]; lastc = r; }
+                      }
+                    Grp g; g.it.w = w; g.it.h0 = hr.x + a; g.it.hn = b - a; g.it.g = a; g.span = span;
+                    g.na = (b < hr.y) ? H[b].alow : INF; g.nh = (b < hr.y) ? H[b].ahgh : INF;
+                    G.push_back(g);
+                    a = b;
+                  }
+              }
+            std::stable_sort(G.begin(),G.end(),[](const Grp &x, const Grp &y) { return x.span > y.span; });
+            items.resize(G.size()); nxt_alow.resize(G.size()); nxt_ahgh.resize(G.size());
+            for (size_t q = 0; q < G.size(); q++) { items[q] = G[q].it; nxt_alow[q] = G[q].na; nxt_ahgh[q] = G[q].nh; }
+            if (!items.empty())
+              { CUDA_TRY(fgb_dmalloc((void **) &d_items,sizeof(ExItem)*items.size(),st));
+                CUDA_TRY(fgb_dmalloc((void **) &d_galast,sizeof(long long)*items.size(),st));
+                CUDA_TRY(cudaMemcpyAsync(d_items,items.data(),sizeof(ExItem)*items.size(),cudaMemcpyHostToDevice,st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+              }
+            TR_SYNC("  chain: hit groups");
+          }
           }
         }
     }
@@ -2433,7 +2596,9 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps,extend_kernel<EX_W>,EX_WARPS*32,smem));
       if (bps < 1) bps = 1;
       long long nblocks = (long long) nsm * bps;
-      long long want = ((long long) nwork + EX_NFRONT - 1) / EX_NFRONT;
+      bool use_items = (P.hit_range != NULL);              // first launch over hit groups
+      long long want = ((long long) (use_items ? items.size() : nwork) + EX_NFRONT - 1) / EX_NFRONT;
+      if (want < 1) want = 1;
       if (nblocks > want) nblocks = want;
       long long nwarps = nblocks * EX_WARPS;
 
@@ -2446,11 +2611,11 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       long long cells_per_warp = 1ll << 17;          // 128 K pebbles = 2 MB per warp
       int stage_bytes = 1 << 15;
       out_cap = (u64) nwork * 512 + (64ull << 20);
-      std::vector<unsigned> todo;                    // triples that were re-run at least once
-      unsigned *d_list = d_work; unsigned nlist = nwork;
+      std::vector<std::pair<unsigned,int> > todo;    // (triple, launch number) of every re-run
+      unsigned *d_list = d_work; unsigned nlist = use_items ? (unsigned) items.size() : nwork;
       unsigned *d_work2 = NULL;
       u64 used_before = 0;
-      for (int attempt = 0; ; attempt++)
+      for (int attempt = 0; nlist > 0; attempt++)
         { Peb *d_cells = NULL; unsigned char *d_stage = NULL;
           CUDA_TRY(fgb_dmalloc((void **) &d_cells,sizeof(Peb)*cells_per_warp*nwarps,st));
           CUDA_TRY(fgb_dmalloc((void **) &d_stage,2ll*stage_bytes*nwarps,st));
@@ -2459,12 +2624,19 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           P.stage = d_stage; P.stage_bytes = stage_bytes;
           P.out = d_out; P.out_cap = out_cap;
           P.work = d_list; P.nwork = (int) nlist;
+          P.items = use_items ? d_items : NULL; P.galast = d_galast; P.attempt = attempt;
           unsigned char *d_big = NULL;
           if (attempt > 0)                                     // retries: wide-band kernel, state in HBM
             { CUDA_TRY(fgb_dmalloc((void **) &d_big,(size_t) nwarps * WSTATE_BYTES(EX_WBIG),st));
               P.bigstate = d_big;
             }
           tr_mark("extend: arenas allocated");
+          unsigned long long *d_wlog = NULL;
+          if (attempt == 0 && getenv("FGB_WLOG") != NULL)
+            { CUDA_TRY(fgb_dmalloc((void **) &d_wlog,32ull*(nlist+1),st));
+              CUDA_TRY(cudaMemsetAsync(d_wlog,0,32ull*(nlist+1),st));
+            }
+          P.wlog = d_wlog;
           CUDA_TRY(cudaMemsetAsync(d_misc+1,0,8,st));          // queue, nfailed
           CUDA_TRY(cudaMemsetAsync(d_misc+10,0,4,st));         // reasons of this attempt's failures
           { ev_timer t(1,st);
@@ -2479,6 +2651,21 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           CUDA_TRY(cudaMemcpyAsync(misc,d_misc,48,cudaMemcpyDeviceToHost,st));
           CUDA_TRY(cudaStreamSynchronize(st));
           tr_mark("extend: kernel done");
+          if (d_wlog != NULL)
+            { std::vector<unsigned long long> lg(4ull*nlist);
+              CUDA_TRY(cudaMemcpy(lg.data(),d_wlog,32ull*nlist,cudaMemcpyDeviceToHost));
+              FILE *f = fopen(getenv("FGB_WLOG"),"w");
+              if (f != NULL)
+                { for (unsigned q = 0; q < nlist; q++)
+                    fprintf(f,"%u %llu %llu %llu %llu %llu %llu %llu %u %u %u\n",q,lg[4*q] >> 32,lg[4*q] & 0xffffffffull,
+                            lg[4*q+1] >> 24,(lg[4*q+1] >> 8) & 0xffff,lg[4*q+1] & 0xff,lg[4*q+2],lg[4*q+3],
+                            (P.items != NULL ? (items[q].w < wsize.size() ? wsize[items[q].w] : 0u)
+                                             : (q < wsize.size() ? wsize[q] : 0u)),
+                            P.items != NULL ? (items[q].hn & 0x7fffffffu) : 0u,P.items != NULL ? items[q].g : 0u);
+                  fclose(f);
+                }
+              fgb_dfree(d_wlog,st);
+            }
           fgb_dfree(d_cells,st); fgb_dfree(d_stage,st); fgb_dfree(d_big,st);
           out_used = ((u64) misc[5] << 32) | misc[4];
           unsigned nfailed = misc[2];
@@ -2493,20 +2680,47 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
               fgb_dfree(d_out,st); d_out = d_new; out_cap = ncap;
               CUDA_TRY(cudaMemcpy(d_misc+4,&used_before,8,cudaMemcpyHostToDevice));
               out_used = used_before;
+              for (size_t q = 0; q < todo.size(); q++)            // the repeat runs under the next launch number
+                if (todo[q].second == attempt) todo[q].second = attempt + 1;
               continue;
             }
           used_before = out_used;
+          //  failed triples (and their positions in the first list, which index the hit lists)
+          std::vector<unsigned> f(nfailed), fw(nfailed);
+          if (nfailed > 0)
+            { CUDA_TRY(cudaMemcpy(f.data(),d_failed,sizeof(unsigned)*nfailed,cudaMemcpyDeviceToHost));
+              CUDA_TRY(cudaMemcpy(fw.data(),d_failed_w,sizeof(unsigned)*nfailed,cudaMemcpyDeviceToHost));
+            }
+          if (use_items)
+            { //  were the hit groups independent?  a group's tube must have stopped short of the next group's first hit
+              std::vector<long long> ga(items.size());
+              CUDA_TRY(cudaMemcpy(ga.data(),d_galast,sizeof(long long)*items.size(),cudaMemcpyDeviceToHost));
+              for (size_t q = 0; q < items.size(); q++)
+                if (ga[q] > nxt_alow[q] || ga[q] >= nxt_ahgh[q])
+                  { f.push_back(hwork[items[q].w]); fw.push_back(items[q].w); }
+              //  several groups of a triple may have failed: one re-run each
+              std::vector<std::pair<unsigned,unsigned> > u(f.size());
+              for (size_t q = 0; q < f.size(); q++) u[q] = std::make_pair(fw[q],f[q]);
+              std::sort(u.begin(),u.end());
+              u.erase(std::unique(u.begin(),u.end()),u.end());
+              f.resize(u.size()); fw.resize(u.size());
+              for (size_t q = 0; q < u.size(); q++) { fw[q] = u[q].first; f[q] = u[q].second; }
+              if (tr_on()) fprintf(stderr,"[fgb_trace]   hit groups %zu, triples to re-run %zu (%u arena overflows)\n",items.size(),u.size(),nfailed);
+              nfailed = (unsigned) f.size();
+              use_items = false;
+              //  hit count (the -v line, FastGA.c:4371): the groups do not count their hits, a triple
+              //  that completed in this launch contributes its whole list, a re-run counts for itself
+              for (size_t q = 0; q < hcount.size(); q++) hits_done += hcount[q];
+              for (size_t q = 0; q < fw.size(); q++) hits_done -= hcount[fw[q]];
+            }
           if (nfailed == 0) break;
           if (attempt > 12 || cells_per_warp > (1ll << 27)) return FGB_ERR_OVERFLOW;
-          //  rerun only the failed triples with larger arenas on fewer warps; the records they
-          //  emitted before failing are dropped by the host below.
-          std::vector<unsigned> f(nfailed);
-          CUDA_TRY(cudaMemcpy(f.data(),d_failed,sizeof(unsigned)*nfailed,cudaMemcpyDeviceToHost));
-          todo.insert(todo.end(),f.begin(),f.end());
+          //  rerun only the failed triples (whole, hit after hit) with larger arenas on fewer warps; the
+          //  records of their earlier launches are dropped by the host below.
+          for (size_t q = 0; q < f.size(); q++) todo.push_back(std::make_pair(f[q],attempt + 1));
           if (d_work2 == NULL) CUDA_TRY(cudaMalloc(&d_work2,sizeof(unsigned)*2*(nwork+1)));
           CUDA_TRY(cudaMemcpy(d_work2,f.data(),sizeof(unsigned)*nfailed,cudaMemcpyHostToDevice));
-          //  their positions in the first launch's list (the pre-scanned hit lists are indexed by it)
-          CUDA_TRY(cudaMemcpy(d_work2 + nwork + 1,d_failed_w,sizeof(unsigned)*nfailed,cudaMemcpyDeviceToDevice));
+          CUDA_TRY(cudaMemcpy(d_work2 + nwork + 1,fw.data(),sizeof(unsigned)*nfailed,cudaMemcpyHostToDevice));
           P.widx = d_work2 + nwork + 1;
           d_list = d_work2; nlist = nfailed;
           //  grow only what overflowed: a band too wide for the register / shared-memory state (ST_BAND)
@@ -2540,28 +2754,23 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       memcpy(O->h_buf,pin,out_used);
       tr_mark("extend: d2h");
       if (!todo.empty())
-        { //  a re-run triple may have emitted records before it failed: keep only the LAST
-          //  complete run = records after its final failure.  Runs are appended in time order,
-          //  so scan backwards keeping records until an earlier run of the same triple is met.
+        { //  a re-run triple may have emitted records in earlier launches: keep only those of its
+          //  LAST launch (every record carries its launch number)
           std::sort(todo.begin(),todo.end());
-          todo.erase(std::unique(todo.begin(),todo.end()),todo.end());
+          std::vector<std::pair<unsigned,int> > last;
+          for (size_t q = 0; q < todo.size(); q++)
+            if (q + 1 == todo.size() || todo[q+1].first != todo[q].first) last.push_back(todo[q]);
           std::vector<long long> offs;
           for (long long off = 0; off < O->nbytes; )
             { int *h = (int *) (O->h_buf + off);
               offs.push_back(off);
               off += OUT_HDR + ((h[8] + 7) & ~7);
             }
-          //  a record of triple t with seq s is stale if a later record of t has seq <= s
           std::vector<char> keep(offs.size(),1);
-          std::vector<int> minseq(todo.size(),INT_MAX);
-          for (long long i = (long long) offs.size()-1; i >= 0; i--)
+          for (size_t i = 0; i < offs.size(); i++)
             { int *h = (int *) (O->h_buf + offs[i]);
-              unsigned t = (unsigned) h[0];
-              auto it = std::lower_bound(todo.begin(),todo.end(),t);
-              if (it == todo.end() || *it != t) continue;
-              size_t k = it - todo.begin();
-              if (h[1] >= minseq[k]) keep[i] = 0;
-              else minseq[k] = h[1];
+              auto it = std::lower_bound(last.begin(),last.end(),std::make_pair((unsigned) h[0],INT_MIN));
+              if (it != last.end() && it->first == (unsigned) h[0] && it->second != h[9]) keep[i] = 0;
             }
           long long w = 0;
           for (size_t i = 0; i < offs.size(); i++)
@@ -2576,6 +2785,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
         }
     }
   CUDA_TRY(cudaMemcpy(O->counters,d_counters,16*8,cudaMemcpyDeviceToHost));
+  O->counters[0] += hits_done;
   { long long cnt = 0;
     for (long long off = 0; off < O->nbytes; )
       { int *h = (int *) (O->h_buf + off);
@@ -2587,6 +2797,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
   fgb_dfree(d_tables,st); fgb_dfree(d_counters,st); fgb_dfree(d_total,st); fgb_dfree(d_misc,st); fgb_dfree(d_flag,st);
   fgb_dfree(d_seg,st); fgb_dfree(d_work,st); fgb_dfree(d_failed,st); fgb_dfree(d_tmp,st); fgb_dfree(d_out,st);
   fgb_dfree(d_plan,st); fgb_dfree(d_couts,st); fgb_dfree(d_first,st); fgb_dfree(d_failed_w,st); fgb_dfree(d_hits,st); fgb_dfree(d_hrange,st);
+  fgb_dfree(d_items,st); fgb_dfree(d_galast,st); fgb_dfree(d_tinfo,st);
   tr_mark("extend: leave");
   *out = O;
   return FGB_OK;

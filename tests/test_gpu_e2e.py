@@ -54,6 +54,24 @@ def test_10mbp_bit_exact_vs_reference():
     _vs_reference(14, 10_000_000, 5, 0.05, 200_000)
 
 
+@pytest.mark.parametrize("gap", ["0", "3000", "1000000000"])
+def test_hit_groups_any_cut_gives_the_same_records(gap):
+    # The extension runs the hits of a band-pair triple as independent groups and re-runs the triple in
+    # one piece when a group's alignments reached into the next group (fgb_extend).  Cutting at every
+    # hit (0: covered hits are aligned speculatively, found out, re-run), at 3 kbp, or never must all
+    # give the records of the default cut.
+    A, B = synth.make_pair(21, 3_000_000, 4, 0.08, sv_every=50_000)
+    gA, gB = formats.genome_from_arrays(A), formats.genome_from_arrays(B)
+    base, st0 = lib.fastga(gA, gB)
+    os.environ["FGB_SPEC_GAP"] = gap
+    try:
+        alns, st1 = lib.fastga(gA, gB)
+    finally:
+        del os.environ["FGB_SPEC_GAP"]
+    assert st1["nhits"] == st0["nhits"] and alns.nraw == base.nraw
+    assert ol.md5_lines(alns.canonical_lines()) == ol.md5_lines(base.canonical_lines())
+
+
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
