@@ -16,6 +16,8 @@ static inline long long now_us()
 extern "C" {
 int fgb_kmer_sort_range_device(void *d_a, void *d_b, long long n, unsigned plo, unsigned phi,
                                void *d_tmp, long long tmp_bytes, int *result_in_b, void *stream);
+int fgb_sort128_bits_device(void *d_a, void *d_b, long long n, int bit_lo, int bit_hi,
+                            void *d_tmp, long long tmp_bytes, int *result_in_b, void *stream);
 int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo, int byte_hi,
                        void *d_tmp, long long tmp_bytes, int *result_in_b, void *stream);
 long long fgb_sort128_tmp_bytes(long long n);
@@ -333,7 +335,7 @@ static int gix_finish(fgb_gix *x, rec128 *d_a, long long n, unsigned plo, unsign
   x->n = n;
   if (fgb_dmalloc((void **) &d_b,sizeof(rec128)*(n+1),st) != cudaSuccess ||
       fgb_dmalloc((void **) &d_stmp,stmpb,st) != cudaSuccess ||
-      fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st) != cudaSuccess ||
+      fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1+8),st) != cudaSuccess ||
       fgb_dmalloc((void **) &x->d_adj,(size_t) n + 32,st) != cudaSuccess)
     rc = FGB_ERR_CUDA;
   if (!rc)
@@ -449,7 +451,7 @@ extern "C" int fgb_gix_from_device(const void *d_tab, long long n, int post_byte
   fgb_gix *x = new fgb_gix();
   x->n = n; x->n_both = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
   CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
-  CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1+8),st));
   CUDA_TRY(fgb_dmalloc((void **) &x->d_adj,(size_t) x->n + 32,st));
   CUDA_TRY(cudaMemcpyAsync(x->d_tab,d_tab,sizeof(rec128)*n,cudaMemcpyDeviceToDevice,st));
   int rc;
@@ -480,7 +482,7 @@ extern "C" int fgb_gix_upload(const void *tab, long long n, int post_bytes, int 
   fgb_gix *x = new fgb_gix();
   x->n = n; x->n_both = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
   CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
-  CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1+8),st));
   CUDA_TRY(fgb_dmalloc((void **) &x->d_adj,(size_t) x->n + 32,st));
   CUDA_TRY(cudaMemcpyAsync(x->d_tab,tab,sizeof(rec128)*n,cudaMemcpyHostToDevice,st));
   int rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,x->d_adj,st);
@@ -504,7 +506,7 @@ extern "C" int fgb_gix_import_ktab(const unsigned char *entries, long long n, in
   CUDA_TRY(fgb_dmalloc((void **) &d_ent,E*n + 16,st));
   CUDA_TRY(fgb_dmalloc((void **) &d_index,8ll<<24,st));
   CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
-  CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1),st));
+  CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1+8),st));
   CUDA_TRY(fgb_dmalloc((void **) &x->d_adj,(size_t) x->n + 32,st));
   CUDA_TRY(cudaMemcpyAsync(d_ent,entries,E*n,cudaMemcpyHostToDevice,st));
   CUDA_TRY(cudaMemcpyAsync(d_index,index,8ll<<24,cudaMemcpyHostToDevice,st));
@@ -628,7 +630,9 @@ static int seeds_sort_impl(rec128 *d_a, long long n, const seed_bits &L, long lo
       fgb_dmalloc((void **) &d_tmp,tmpb,st) != cudaSuccess) rc = FGB_ERR_CUDA;
   if (!rc)
     { stage_timer t(&g_timings.ssort_ms,st);
-      rc = fgb_sort128_device(d_a,d_b,n,0,(L.key+7)/8,d_tmp,tmpb,&inb,st);
+      //  from bit 6: the lcp field (bits 0..5) cannot break a tie -- two seeds that agree on strand,
+      //  contigs, band, anti-diagonal and diagonal remainder are the same pair of positions
+      rc = fgb_sort128_bits_device(d_a,d_b,n,6,L.key,d_tmp,tmpb,&inb,st);
     }
   if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = FGB_ERR_CUDA;
   if (!rc)

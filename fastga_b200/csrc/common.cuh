@@ -39,6 +39,13 @@ static __device__ __forceinline__ void st_rec(rec128 *p, rec128 r)
 static __device__ __forceinline__ unsigned rec_byte(const rec128 &r, int b)
 { return (b < 8) ? (unsigned) ((r.lo >> (8*b)) & 0xff) : (unsigned) ((r.hi >> (8*(b-8))) & 0xff); }
 
+//  the 8-bit digit at bit offset sh of the 128-bit value (sh is uniform over a kernel: no divergence)
+static __device__ __forceinline__ unsigned rec_dig(const rec128 &r, int sh)
+{ if (sh >= 64) return (unsigned) ((r.hi >> (sh - 64)) & 0xff);
+  if (sh <= 56) return (unsigned) ((r.lo >> sh) & 0xff);
+  return (unsigned) (((r.lo >> sh) | (r.hi << (64 - sh))) & 0xff);
+}
+
 static __device__ __forceinline__ unsigned lanemask_lt()
 { unsigned m; asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 

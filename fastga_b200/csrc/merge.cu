@@ -40,10 +40,11 @@ static __host__ __device__ __forceinline__ int seed_key_bits(const seed_layout &
 #define MG_T2CAP   1152                   // staged T2 entries per CTA (18 KB)
 #endif
 #ifndef MG_DCAP
-#define MG_DCAP    2048                   // seed descriptors per CTA (4 per T1 entry; crowded tiles write entry-wise)
+#define MG_DCAP    1536                   // seed descriptors per CTA (3 per T1 entry; crowded tiles write entry-wise)
 #endif
 #ifndef MG_MINBLK
 #define MG_MINBLK  6
+#define MG_PCAP    512                    // staged words of the prefix index per CTA (the tile's prefix span + 2)
 #endif
 //  lcp (in bases, 0..28) of two 56-bit suffixes
 static __device__ __forceinline__ int lcp56(u64 a, u64 b)
@@ -96,6 +97,7 @@ template<int TILE> struct mg_stage
   unsigned desc[MG_DCAP];                 // per seed: T2 slot (11) | T1 slot (9) << 11 | (plen-12) << 20
   unsigned wtot[2*MG_WARPS], wsum[2*MG_WARPS];
   unsigned char adj[MG_T2CAP+48];         // LCP bytes of the slice (TMA destination; starts at the 16-byte boundary below the slice)
+  unsigned pst[MG_PCAP];                  // prefix index of the tile's prefix span (TMA destination)
   unsigned rng[4];
   unsigned long long gbase;
   unsigned long long bar;
@@ -154,6 +156,15 @@ static __device__ __forceinline__ unsigned adaptamer_staged(const rec128 *__rest
   return (m >= 12 && rgt - lft < fq) ? rgt - lft : 0u;
 }
 
+//  eight bytes from a byte address in shared memory (three aligned words, two funnel shifts)
+static __device__ __forceinline__ u64 adj8(const unsigned char *p)
+{ const unsigned sa = smem_u32((const void *) p);
+  const unsigned *w = reinterpret_cast<const unsigned *>(p - (sa & 3u));
+  const unsigned sh = (sa & 3u) << 3;
+  const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
+  return (u64) __funnelshift_r(w0,w1,sh) | ((u64) __funnelshift_r(w1,w2,sh) << 32);
+}
+
 //  The same for N entries per lane at once (the CTA's rounds): the N searches advance in lock step, so
 //  every dependent shared-memory probe of one has the probes of the others to overlap with.
 template<int N>
@@ -165,16 +176,20 @@ static __device__ __forceinline__ void adaptamer_staged_n(const rec128 *__restri
 { const u64 *t2w = reinterpret_cast<const u64 *>(t2);
   const unsigned fq = (unsigned) freq;
   unsigned a[N], b[N], wmax = 0;
+  u64 k1[N];
 #pragma unroll
-  for (int r = 0; r < N; r++) { a[r] = lo[r]; b[r] = hi[r]; wmax = max(wmax,hi[r] - lo[r]); }
+  for (int r = 0; r < N; r++)
+    { a[r] = lo[r]; b[r] = hi[r]; wmax = max(wmax,hi[r] - lo[r]);
+      k1[r] = (r1[r].hi << 24) | ((r1[r].lo >> 48) << 8);
+    }
   for (unsigned w = __reduce_max_sync(0xffffffffu,wmax); w > 0; w >>= 1)
     {
 #pragma unroll
       for (int r = 0; r < N; r++)
         { const unsigned m = (a[r] + b[r]) >> 1;                // a == b: a probe with no effect
-          const u64 qh = t2w[2*m+1];
-          const unsigned ql = (unsigned) (t2w[2*m] >> 48);
-          const bool less = (qh < r1[r].hi) || (qh == r1[r].hi && ql < (unsigned) (r1[r].lo >> 48));
+          //  inside a panel the first 12 bases agree: the other 28 (56 bits) order the entries
+          const u64 qk = (t2w[2*m+1] << 24) | ((t2w[2*m] >> 48) << 8);
+          const bool less = qk < k1[r];
           const bool live = a[r] < b[r];
           if (live && less) a[r] = m+1;
           if (live && !less) b[r] = m;
@@ -194,16 +209,26 @@ static __device__ __forceinline__ void adaptamer_staged_n(const rec128 *__restri
       if (goL[r]) lft[r] = a[r]-1;
       if (goR[r]) rgt[r] = a[r]+1;
     }
+  //  Extent of the block either side of the insertion point, EIGHT LCP bytes at a time: t2[i-1] is in R
+  //  iff t2[i] is and adj[i] >= m, so a side extends by the run of bytes >= m next to it (one SIMD byte
+  //  compare + a bit scan; the bytes beyond a panel end are < 12 and stop every run, whatever lies
+  //  past them), capped at FREQ members a side (|R| >= FREQ is all that matters beyond, :799-823).
 #pragma unroll
-  for (int u = 0; u < 2; u++)
-    {
-#pragma unroll
-      for (int r = 0; r < N; r++)
-        { goL[r] = goL[r] && a[r] - lft[r] < fq && (int) adj[lft[r]] >= m[r];
-          if (goL[r]) lft[r] -= 1;
-          goR[r] = goR[r] && rgt[r] - a[r] < fq && (int) adj[rgt[r]] >= m[r];
-          if (goR[r]) rgt[r] += 1;
-        }
+  for (int r = 0; r < N; r++)
+    { const unsigned mm = (unsigned) m[r] * 0x01010101u;
+      unsigned L = 0, R = 0;
+      { const u64 v = adj8(adj + (int) a[r] - 8);                      // bytes a-8 .. a-1, the nearest on top
+        const u64 ge = (u64) __vcmpgeu4((unsigned) v,mm) | ((u64) __vcmpgeu4((unsigned) (v >> 32),mm) << 32);
+        L = (~ge) ? (unsigned) (__clzll((long long) ~ge) >> 3) : 8u;
+      }
+      { const u64 v = adj8(adj + a[r] + 1);                            // bytes a+1 .. a+8, the nearest at the bottom
+        const u64 ge = (u64) __vcmpgeu4((unsigned) v,mm) | ((u64) __vcmpgeu4((unsigned) (v >> 32),mm) << 32);
+        R = (~ge) ? (unsigned) ((__ffsll((long long) ~ge) - 1) >> 3) : 8u;
+      }
+      if (goL[r]) lft[r] -= min(L,fq - 1);
+      if (goR[r]) rgt[r] += min(R,fq - 1);
+      goL[r] = goL[r] && L == 8 && fq > 9;                              // a longer run: the loop below (rare)
+      goR[r] = goR[r] && R == 8 && fq > 9;
     }
 #pragma unroll
   for (int r = 0; r < N; r++) any = any || goL[r] || goR[r];
@@ -294,11 +319,15 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
       const bool st = (r.w <= MG_T2CAP);
       //  LCP bytes of the slice and one beyond, from the 16-byte boundary at or below the slice start
       const unsigned ab = ((r.z & 15u) + r.w + 1u + 15u) & ~15u;
-      mbar_expect_tx(&S->bar,nt1*16u + ((st && r.w) ? r.w*16u + ab : 0u));
+      //  prefix index words pA .. pB+1 (panel bounds of every tile entry), from the 16-byte boundary below pA
+      const unsigned pw = ((r.x & 3u) + r.y + 2u + 3u) & ~3u;
+      const bool sp = (pw <= MG_PCAP);
+      mbar_expect_tx(&S->bar,nt1*16u + ((st && r.w) ? r.w*16u + ab + (sp ? pw*4u : 0u) : 0u));
       tma_copy_1d(S->t1,T1 + b0,nt1*16u,&S->bar);
       if (st && r.w)
         { tma_copy_1d(S->t2,T2 + r.z,r.w*16u,&S->bar);
           tma_copy_1d(S->adj,adj2 + (r.z & ~15u),ab,&S->bar);
+          if (sp) tma_copy_1d(S->pst,pstart2 + (r.x & ~3u),pw*4u,&S->bar);
         }
     }
   __syncthreads();
@@ -315,6 +344,8 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
   if (staged)
     { //  all 32 lanes take part (warp-uniform search steps); lanes past the tile search nothing
       rec128 r1[ROUNDS]; unsigned lo[ROUNDS], hi[ROUNDS];
+      const unsigned pbase = S->rng[0] & ~3u;
+      const bool sp = nsl > 0 && (((S->rng[0] & 3u) + S->rng[1] + 2u + 3u) & ~3u) <= MG_PCAP;   // prefix span staged (else: HBM)
 #pragma unroll
       for (int r = 0; r < ROUNDS; r++)
         { const unsigned j = r*MG_THREADS + tid;
@@ -322,7 +353,8 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
           if (j < nt1)
             { r1[r] = ld_rec(&S->t1[j]);
               const unsigned p = KREC_PREFIX24(r1[r].hi);
-              lo[r] = __ldg(pstart2 + p) - lo2; hi[r] = __ldg(pstart2 + p + 1) - lo2;
+              if (sp) { lo[r] = S->pst[p - pbase] - lo2; hi[r] = S->pst[p - pbase + 1] - lo2; }
+              else    { lo[r] = __ldg(pstart2 + p) - lo2; hi[r] = __ldg(pstart2 + p + 1) - lo2; }
             }
         }
       adaptamer_staged_n<ROUNDS>(S->t2,adj,nsl,r1,lo,hi,freq,cnt,lowi,plen);
@@ -336,33 +368,37 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
           if (j < nt1) cnt[r] = adaptamer_direct(T2,pstart2,ld_rec(&S->t1[j]),freq,lowi[r],plen[r]);
         }
     }
-#pragma unroll
-  for (int r = 0; r < ROUNDS; r++)
-    { unsigned inc = cnt[r];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1)
-        { unsigned t = __shfl_up_sync(0xffffffffu,inc,o);
-          if (lane >= o) inc += t;
-        }
-      excl[r] = inc - cnt[r];
-      const unsigned sl = __reduce_add_sync(0xffffffffu,cnt[r] * (unsigned) plen[r]);
-      if (lane == 31) S->wtot[r*MG_WARPS + wp] = inc;
-      if (lane == 0)  S->wsum[r*MG_WARPS + wp] = sl;
-    }
-  __syncthreads();
+  //  Offsets of every entry's seeds inside the CTA's run (round 0 of all warps, then round 1).  The counts
+  //  of the two rounds ride one register through the scans, 16 bits each: an entry yields < FREQ <= 255
+  //  seeds (FastGA.c:4960), a round of the CTA < 256 * 255.
+  static_assert(ROUNDS <= 2,"two packed rounds at most");
   unsigned total = 0;
-  { unsigned pre[ROUNDS];
+  { unsigned pk = cnt[0], sl = cnt[0] * (unsigned) plen[0];
+    if (ROUNDS == 2) { pk |= cnt[ROUNDS-1] << 16; sl += cnt[ROUNDS-1] * (unsigned) plen[ROUNDS-1]; }
+    unsigned inc = pk;
 #pragma unroll
-    for (int r = 0; r < ROUNDS; r++) pre[r] = 0;
-#pragma unroll
-    for (int q = 0; q < ROUNDS*MG_WARPS; q++)
-      { const unsigned v = S->wtot[q];
-#pragma unroll
-        for (int r = 0; r < ROUNDS; r++) if (q < r*MG_WARPS + wp) pre[r] += v;
-        total += v;
+    for (int o = 1; o < 32; o <<= 1)
+      { const unsigned t = __shfl_up_sync(0xffffffffu,inc,o);
+        if (lane >= o) inc += t;
       }
+    sl = __reduce_add_sync(0xffffffffu,sl);
+    if (lane == 31) S->wtot[wp] = inc;
+    if (lane == 0)  S->wsum[wp] = sl;
+    __syncthreads();
+    //  across the warps: eight packed totals scanned by the first eight lanes of every warp
+    const unsigned v = (lane < MG_WARPS) ? S->wtot[lane] : 0u;
+    unsigned winc = v;
 #pragma unroll
-    for (int r = 0; r < ROUNDS; r++) excl[r] += pre[r];
+    for (int o = 1; o < MG_WARPS; o <<= 1)
+      { const unsigned t = __shfl_up_sync(0xffffffffu,winc,o);
+        if (lane >= o) winc += t;
+      }
+    const unsigned all = __shfl_sync(0xffffffffu,winc,MG_WARPS-1);     // CTA totals of the two rounds
+    const unsigned mine = __shfl_sync(0xffffffffu,winc - v,wp);        // ... of the warps before this one
+    const unsigned t0 = all & 0xffffu;
+    total = t0 + (all >> 16);
+    excl[0] = (inc & 0xffffu) - cnt[0] + (mine & 0xffffu);
+    if (ROUNDS == 2) excl[ROUNDS-1] = (inc >> 16) - cnt[ROUNDS-1] + t0 + (mine >> 16);
   }
   const bool fast = staged && total <= MG_DCAP;
   if (fast)
@@ -376,7 +412,7 @@ adaptamer_merge_kernel(const rec128 *__restrict__ T1, unsigned n1,
   //  ONE atomic per CTA reserves its output run (per-warp atomics on the single counter serialise in L2)
   if (tid == 0)
     { unsigned long long q = 0, g = 0;
-      for (int k = 0; k < ROUNDS*MG_WARPS; k++) q += S->wsum[k];
+      for (int k = 0; k < MG_WARPS; k++) q += S->wsum[k];
       if (total) { g = atomicAdd(&counters[0],(unsigned long long) total); atomicAdd(&counters[1],q); }
       S->gbase = g;
     }

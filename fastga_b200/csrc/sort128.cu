@@ -63,20 +63,23 @@ static __device__ __forceinline__ unsigned match_digit(unsigned d, bool valid)
 #define ST_MASK ((1ull << 62) - 1)
 
 __global__ void __launch_bounds__(SORT_THREADS)
-sort_ghist_kernel(const rec128 *__restrict__ in, long long n, int byte, unsigned long long *__restrict__ ghist)
+sort_ghist_kernel(const rec128 *__restrict__ in, long long n, int dsh /* digit = bits [dsh,dsh+8) */, unsigned long long *__restrict__ ghist)
 { __shared__ unsigned h[256];
   int tid = threadIdx.x;
   if (tid < 256) h[tid] = 0;
   __syncthreads();
-  const unsigned long long *half = reinterpret_cast<const unsigned long long *>(in) + (byte >= 8);
-  int sh = 8*(byte & 7);
+  //  a digit inside one 64-bit half is counted from that half alone (half the traffic)
+  const bool one = (dsh >= 64 || dsh <= 56);
+  const unsigned long long *half = reinterpret_cast<const unsigned long long *>(in) + (dsh >= 64);
+  const int sh = dsh & 63;
   for (long long tile0 = (long long) blockIdx.x * SORT_TILE; tile0 < n; tile0 += (long long) gridDim.x * SORT_TILE)
     {
 #pragma unroll
       for (int it = 0; it < SORT_ITEMS; it++)
         { long long idx = tile0 + it*SORT_THREADS + tid;
           bool valid = idx < n;
-          unsigned d = valid ? (unsigned) ((half[2*idx] >> sh) & 0xff) : 0;
+          unsigned d = 0;
+          if (valid) d = one ? (unsigned) ((half[2*idx] >> sh) & 0xff) : rec_dig(ld_rec(in + idx),dsh);
           unsigned peers = match_digit(d,valid);             // one atomic per distinct digit of the warp
           if (valid && (tid & 31) == __ffs(peers)-1) atomicAdd(&h[d],__popc(peers));
         }
@@ -106,8 +109,8 @@ __global__ void sort_bins_kernel(const unsigned long long *__restrict__ ghist, u
 }
 
 __global__ void __launch_bounds__(SORT_THREADS,SORT_MINBLK)
-sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, long long n, int byte,
-                     int next_byte /* -1: none */, const unsigned long long *__restrict__ binbase,
+sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, long long n, int byte /* bit offset of the digit */,
+                     int next_byte /* bit offset of the next pass's digit, -1: none */, const unsigned long long *__restrict__ binbase,
                      unsigned long long *__restrict__ nexthist, unsigned long long *status /* [ntiles][256] */,
                      unsigned *__restrict__ ticket)
 { extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -151,7 +154,7 @@ sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, lo
       unsigned d = 0;
       if (valid)
         { r[it] = ld_rec(tile + idx);
-          d = rec_byte(r[it],byte);
+          d = rec_dig(r[it],byte);
         }
       unsigned peers = match_digit(d,valid);
       int leader = valid ? __ffs(peers)-1 : lane;
@@ -162,7 +165,7 @@ sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, lo
         }
       b = __shfl_sync(0xffffffffu,b,leader);
       rank[it] = b + __popc(peers & lanemask_lt());
-      if (next_byte >= 0 && valid) atomicAdd(&nhist[rec_byte(r[it],next_byte)],1u);
+      if (next_byte >= 0 && valid) atomicAdd(&nhist[rec_dig(r[it],next_byte)],1u);
       __syncwarp();
     }
   __syncthreads();
@@ -212,7 +215,7 @@ sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, lo
   for (int it = 0; it < SORT_ITEMS; it++)
     { int idx = base + it*32 + lane;
       if (idx < cnt)
-        { unsigned d = rec_byte(r[it],byte);
+        { unsigned d = rec_dig(r[it],byte);
           st_rec(tile + (bexcl[d] + myc[d] + rank[it]),r[it]);
         }
     }
@@ -220,7 +223,7 @@ sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, lo
 
   for (int p = tid; p < cnt; p += SORT_THREADS)
     { rec128 v = ld_rec(tile + p);
-      unsigned d = rec_byte(v,byte);
+      unsigned d = rec_dig(v,byte);
       st_rec(out + (gbase[d] + p),v);
     }
 }
@@ -238,13 +241,15 @@ extern "C" long long fgb_sort128_tmp_bytes(long long n)
 //  d_a holds the input; d_b is a same-size scratch.  Returns via *result_in_b where the sorted
 //  data landed (0 = d_a, 1 = d_b).  All pointers are device pointers.
 
-extern "C" int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo, int byte_hi,
-                                  void *d_tmp, long long tmp_bytes, int *result_in_b, void *stream)
+//  LSD passes on the 8-bit digits at bit offsets bit_lo, bit_lo+8, ... below bit_hi (the last digit may
+//  reach past bit_hi: the bits above a key are part of the order, zero in every record sorted here)
+extern "C" int fgb_sort128_bits_device(void *d_a, void *d_b, long long n, int bit_lo, int bit_hi,
+                                       void *d_tmp, long long tmp_bytes, int *result_in_b, void *stream)
 { cudaStream_t st = (cudaStream_t) stream;
-  if (n < 0 || byte_lo < 0 || byte_hi > 16 || byte_lo > byte_hi) return FGB_ERR_ARG;
+  if (n < 0 || bit_lo < 0 || bit_hi > 128 || bit_lo > bit_hi) return FGB_ERR_ARG;
   if (n >= 0xffffffffll) return FGB_ERR_LIMIT;
   *result_in_b = 0;
-  if (n <= 1 || byte_lo == byte_hi) return FGB_OK;
+  if (n <= 1 || bit_lo == bit_hi) return FGB_OK;
   if (tmp_bytes < fgb_sort128_tmp_bytes(n)) return FGB_ERR_ARG;
 
   int ntiles = (int) ((n + SORT_TILE - 1) / SORT_TILE);
@@ -263,14 +268,14 @@ extern "C" int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo
   rec128 *src = (rec128 *) d_a, *dst = (rec128 *) d_b;
   CUDA_TRY(cudaMemsetAsync(hist[0],0,256*8,st));
   { int nb = ntiles < 1184 ? ntiles : 1184;
-    sort_ghist_kernel<<<nb,SORT_THREADS,0,st>>>(src,n,byte_lo,hist[0]);
+    sort_ghist_kernel<<<nb,SORT_THREADS,0,st>>>(src,n,bit_lo,hist[0]);
     fgb_count_launch(1);
   }
   int cur = 0;
-  for (int b = byte_lo; b < byte_hi; b++)
+  for (int b = bit_lo; b < bit_hi; b += 8)
     { sort_bins_kernel<<<1,256,0,st>>>(hist[cur],binbase,hist[cur^1],ticket);
       CUDA_TRY(cudaMemsetAsync(status,0,256ull*ntiles*8,st));
-      sort_onesweep_kernel<<<ntiles,SORT_THREADS,ONESWEEP_SMEM,st>>>(src,dst,n,b,(b+1 < byte_hi) ? b+1 : -1,
+      sort_onesweep_kernel<<<ntiles,SORT_THREADS,ONESWEEP_SMEM,st>>>(src,dst,n,b,(b+8 < bit_hi) ? b+8 : -1,
                                                                    binbase,hist[cur^1],status,ticket);
       fgb_count_launch(2);
       cur ^= 1;
@@ -279,6 +284,12 @@ extern "C" int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo
     }
   CUDA_TRY(cudaGetLastError());
   return FGB_OK;
+}
+
+extern "C" int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo, int byte_hi,
+                                  void *d_tmp, long long tmp_bytes, int *result_in_b, void *stream)
+{ if (byte_lo < 0 || byte_hi > 16 || byte_lo > byte_hi) return FGB_ERR_ARG;
+  return fgb_sort128_bits_device(d_a,d_b,n,8*byte_lo,8*byte_hi,d_tmp,tmp_bytes,result_in_b,stream);
 }
 
 /***********************************************************************************************

@@ -143,10 +143,11 @@ def top_byte_cuts(world):
     return [(256 * r + world - 1) // world for r in range(world + 1)]
 
 
-def exchange_rows(dist, rows, send_rows):
+def exchange_rows(dist, rows, send_rows, async_op=False):
     """all-to-all of 16-byte records: `rows` is an (n,2) int64 tensor whose rows
     [sum(send_rows[:r]), +send_rows[r]) go to rank r.  Returns the (m,2) tensor of received rows, in
-    source-rank order (NCCL on GPUs, gloo in the CPU tests)."""
+    source-rank order (NCCL on GPUs, gloo in the CPU tests).  async_op: returns (tensor, work) with the
+    transfer still in flight -- work.wait() before the tensor is read (and keep `rows` alive until then)."""
     import torch
     world = dist.get_world_size()
     device = rows.device
@@ -156,9 +157,9 @@ def exchange_rows(dist, rows, send_rows):
     recv_rows = [int(v) for v in rr.tolist()]
     n_send, n_recv = int(sum(send_rows)), int(sum(recv_rows))
     dst = torch.empty((max(n_recv, 1), 2), dtype=torch.int64, device=device)[:n_recv]
-    dist.all_to_all_single(dst, rows[:n_send].contiguous(), output_split_sizes=recv_rows,
-                           input_split_sizes=[int(v) for v in send_rows])
-    return dst
+    work = dist.all_to_all_single(dst, rows[:n_send].contiguous(), output_split_sizes=recv_rows,
+                                  input_split_sizes=[int(v) for v in send_rows], async_op=async_op)
+    return (dst, work) if async_op else dst
 
 
 def align_sharded(dA, dB, freqA, dist, device, **kw):
@@ -170,28 +171,48 @@ def align_sharded(dA, dB, freqA, dist, device, **kw):
     gA, gB = dA.genome, dB.genome
     p = dict(lib.DEFAULTS)
     p.update(kw)
+    import os, sys, time
+    trace = [] if os.environ.get("FGB_SHARD_TRACE") else None
+
+    def mark(what):                      # phase wall clock per rank (diagnostics only: it synchronizes)
+        if trace is not None:
+            torch.cuda.synchronize()
+            trace.append((what, time.perf_counter()))
+    mark("start")
     ownA = owner_of_contigs(gA.clen, world)
     ownB = owner_of_contigs(gB.clen, world)
     cuts = top_byte_cuts(world)
     plo, phi = cuts[rank] << 16, cuts[rank + 1] << 16
     from .formats import gix_bytes
-    tables, nk = [], []
+    #  The two tables are pipelined: while the k-mer records of one travel (NCCL's stream), this rank's
+    #  stream scans / groups the other genome or sorts the slice that already arrived.
+    nk, flight = [], []
     for dg, own, fwd in ((dA, ownA, True), (dB, ownB, False)):
         ptr, n = lib.kmers_scan(dg, own == rank, fwd)
+        mark("scan")
         grouped = torch.empty((max(n, 1), 2), dtype=torch.int64, device=device)
         bounds = lib.records_group_by_top_byte(ptr, n, grouped.data_ptr())
         lib.device_free(ptr)
+        mark("group k-mers")
         send = [int(bounds[cuts[r + 1]] - bounds[cuts[r]]) for r in range(world)]
-        recv = exchange_rows(dist, grouped, send)
+        recv, work = exchange_rows(dist, grouped, send, async_op=True)
+        flight.append((recv, work, grouped))
+        mark("exchange k-mers (issued)")
+    tables = []
+    for (recv, work, grouped), dg, fwd in zip(flight, (dA, dB), (True, False)):
+        work.wait()
+        del grouped
         pb, cb = gix_bytes(dg.genome)
         if phi > plo:
             x = lib.gix_from_records(recv.data_ptr() if recv.shape[0] else 0, int(recv.shape[0]), plo, phi, fwd,
                                      pb, cb, dg.genome.ncontig)
         else:
             x = None
+        mark("sort+index slice")
         tables.append(x)
         nk.append(int(recv.shape[0]))
-        del grouped, recv
+        del recv
+    del flight
     xA, xB = tables
     amx, bmx = int(gA.clen.max()), int(gB.clen.max())
     if xA is not None:
@@ -202,23 +223,32 @@ def align_sharded(dA, dB, freqA, dist, device, **kw):
         sptr, ns, sumlen, n1m = 0, 0, 0, 0
         ab = int(amx + bmx).bit_length()
         bits = (ab, max(ab - 6, 1), max(1, (gB.ncontig - 1).bit_length()), max(1, (gA.ncontig - 1).bit_length()))
+    mark("merge")
     # owner of every A-contig RANK (the icont field of a seed)
     own_by_rank = ownA[dA.perm]
     grouped = torch.empty((max(ns, 1), 2), dtype=torch.int64, device=device)
     bounds = lib.seeds_group_by_owner(sptr, ns, bits, own_by_rank, world, grouped.data_ptr())
     if sptr:
         lib.device_free(sptr)
+    mark("group seeds")
     send = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
     recv = exchange_rows(dist, grouped, send)
+    mark("exchange seeds")
     del grouped
     S = lib.seeds_from_records(recv.data_ptr() if recv.shape[0] else 0, int(recv.shape[0]), bits, amx, bmx)
     nseeds_mine = int(recv.shape[0])
     del recv
+    mark("sort seeds")
     ov = lib.DeviceOverlaps.extend(S, dA, dB, freqA, p["chain_break"], p["chain_min"], p["align_min"], p["align_rate"])
     cnt = ov.counters()
+    mark("extend")
     alns = lib.filter_overlaps(ov.h, dA.perm, dB.perm, bits[2], bits[3])
     ov.close()
     S.close()
+    mark("filter")
+    if trace is not None:
+        sys.stderr.write("[shard %d] " % rank + " | ".join("%s %.2f" % (w, 1e3 * (t - trace[i][1]))
+                                                          for i, (w, t) in enumerate(trace[1:])) + "\n")
     stats = {"nkmers1_fwd": nk[0], "nkmers2": nk[1], "nseeds_merged": ns, "nseeds": nseeds_mine, "sumlen": sumlen,
              "nhits": cnt["hits"], "nla": cnt["la_calls"], "nwaves": cnt["waves"], "ncells": cnt["cells"],
              "nseg": cnt["nseg"], "nwork": cnt["nwork"], "warp_cycles": cnt["warp_cycles"],
