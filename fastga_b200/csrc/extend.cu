@@ -101,6 +101,7 @@ struct Ctx
   u64 nwaves, ncells, cyc_wave, cyc_extract, pwaves, npairs, fwait, ftot, bwait, btot;
   struct PairBox *box;                   // front/back warp pair mailbox (NULL: this warp runs waves alone)
   unsigned box_off;                      //   and its offset inside the dynamic shared memory
+  Peb *pwin; int pwin_n;                 // pwin_n pebbles of shared memory: the window of the trace read-out
 };
 
 //  Front/back pairing of a wave pass.  The recurrence that makes a pass serial is only the
@@ -159,6 +160,31 @@ static __device__ __forceinline__ Peb ldpeb(const Peb *p)        // pebbles may 
   Peb r; r.ptr = v.x; r.diag = v.y; r.diff = v.z; r.mark = v.w;
   return r;
 }
+
+//  The trace read-out walks a pebble chain from the trim point back to the start: every hop used to be
+//  a dependent L2 / HBM round trip (0.5-1 us x thousands of trace points, three walks per alignment:
+//  8 % of the kernel's cycles, all of them on the critical path of an item).  Pebbles are appended in
+//  wave order and a chain only points backwards, a few cells at a time (all diagonals of a band drop
+//  theirs between two of one path's): the walk pulls the c.pwin_n cells ending at the current one into
+//  shared memory with one coalesced load and hops inside that window until the chain leaves it.
+struct PebWalk
+{ const Peb *cells; Peb *win; int lo, hi, n;             // window = cells[lo..hi] (at most n cells), lo > hi: empty
+  __device__ __forceinline__ void init(const Peb *c, Peb *w, int cap) { cells = c; win = w; n = cap; lo = 0; hi = -1; }
+  __device__ __forceinline__ Peb at(int idx)              // idx is warp-uniform
+  { if (idx < lo || idx > hi)
+      { const int lane = threadIdx.x & 31;
+        __syncwarp();
+        hi = idx; lo = idx - (n-1); if (lo < 0) lo = 0;
+#pragma unroll 4
+        for (int q = lane; lo + q <= hi; q += 32)
+          *reinterpret_cast<int4 *>(win + q) = __ldcg(reinterpret_cast<const int4 *>(cells + lo + q));
+        __syncwarp();
+      }
+    const int4 v = *reinterpret_cast<const int4 *>(win + (idx - lo));
+    Peb r; r.ptr = v.x; r.diag = v.y; r.diff = v.z; r.mark = v.w;
+    return r;
+  }
+};
 
 #define EX_WBIG      8192                // diagonals of wave state per warp in the wide-band retry kernel (HBM)
 
@@ -1118,7 +1144,8 @@ static __device__ int fwd_extract(Ctx &c, int trimha, int mida, int trimx, int t
   //  ONE walk of the pebble chain (each hop is a dependent L2 round trip): the pairs come out last
   //  to first, so they are written downwards from the top of the staging buffer and moved to its
   //  start afterwards (warp-parallel) instead of counting the chain first.
-  Peb tip = ldpeb(c.cells+trimha);
+  PebWalk W; W.init(c.cells,c.pwin,c.pwin_n);
+  Peb tip = W.at(trimha);
   int kt = tip.diag, bt, et;
   if (tip.ptr < 0) { bt = (mida - kt) >> 1; et = 0; }
   else             { bt = tip.mark - kt;    et = tip.diff; }
@@ -1139,7 +1166,7 @@ static __device__ int fwd_extract(Ctx &c, int trimha, int mida, int trimx, int t
   Peb cur = tip;
   root_diag = kt;
   while (cur.ptr >= 0)
-    { Peb prv = ldpeb(c.cells+cur.ptr);
+    { Peb prv = W.at(cur.ptr);
       int a = cur.mark - cur.diag, d = cur.diff, bp, ep;
       if (prv.ptr < 0) { bp = (mida - prv.diag) >> 1; ep = 0; }
       else             { bp = prv.mark - prv.diag;    ep = prv.diff; }
@@ -1175,8 +1202,9 @@ static __device__ int rev_extract(Ctx &c, const Peb *cells, int trimha, int aoff
                                   int trimd, int ftlen, int &rtlen)
 { const int lane = threadIdx.x & 31;
   int n = 0, h, root = trimha;
-  for (h = trimha; h >= 0; h = ldpeb(cells+h).ptr) { n += 1; root = h; }
-  Peb r0 = ldpeb(cells+root);
+  PebWalk W; W.init(cells,c.pwin,c.pwin_n);
+  for (h = trimha; h >= 0; h = W.at(h).ptr) { n += 1; root = h; }
+  Peb r0 = W.at(root);
   int b0 = r0.mark - r0.diag;
   bool offpt = ((b0 + r0.diag) % c.tspace != aoff);
   int wr = 0;                                        // bytes written to rstage so far
@@ -1214,7 +1242,7 @@ static __device__ int rev_extract(Ctx &c, const Peb *cells, int trimha, int aoff
 
   //  n >= 2: pairs i = n-1 .. 1 between chain cells c_i and c_(i-1); pair 1 is merged into the
   //  forward trace when the root is off a trace point and a forward trace exists.
-  Peb tip = ldpeb(cells+trimha);
+  Peb tip = W.at(trimha);
   int kt = tip.diag, bt = tip.mark - kt, et = tip.diff;
   bool extra = (bt + kt != trimx);
   int addd = 0, addb = 0;
@@ -1231,7 +1259,7 @@ static __device__ int rev_extract(Ctx &c, const Peb *cells, int trimha, int aoff
   Peb cur = tip;
   int idx = n-1;
   while (cur.ptr >= 0)
-    { Peb prv = ldpeb(cells+cur.ptr);
+    { Peb prv = W.at(cur.ptr);
       int a = cur.mark - cur.diag, d = cur.diff;
       int bp = prv.mark - prv.diag, ep = (prv.ptr < 0) ? 0 : prv.diff;
       int pd = d - ep, pb = bp - a;
@@ -2103,6 +2131,10 @@ extend_kernel(ext_params P)
   rec128 *stagebuf = (W == EX_W) ? (rec128 *) (sb + WSTATE_BYTES(EX_W))
                                  : (rec128 *) (smem + (size_t) wp * BIG_SMEM_PER_WARP);
   c.ttab = P.table; c.sc15 = TRIM_LEN * P.dscore;
+  //  read-out window: the state slot of the team's T warp (T and P keep their state in registers; the
+  //  front warp's own scan buffer is live while a triple scanned here calls into an alignment)
+  c.pwin = EX_PAIR ? (Peb *) (smem + (size_t) (wp + 1) * per_warp) : (Peb *) stagebuf;
+  c.pwin_n = (EX_PAIR && W == EX_W) ? 256 : 64;
   c.box = NULL; c.box_off = 0;
   if (EX_PAIR)
     { c.box_off = (unsigned) ((size_t) EX_WARPS * per_warp + (size_t) (wp / EX_TEAM) * sizeof(PairBox));
@@ -2222,6 +2254,7 @@ la_batch_kernel(ext_params P, const la_job *__restrict__ jobs, int njobs, int *_
   c.V  = (int *) (sb + EX_W*8);
   c.HA = c.V + EX_W; c.HM = c.HA + EX_W; c.NA = c.HM + EX_W;
   c.carry = c.NA + EX_W;
+  c.pwin = (Peb *) (sb + WSTATE_BYTES(EX_W)); c.pwin_n = 64;
   c.ttab = P.table; c.sc15 = TRIM_LEN * P.dscore;
   c.box = NULL; c.box_off = 0;
   c.cells = P.cells + gw * P.cells_per_warp;
