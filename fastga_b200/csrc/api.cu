@@ -258,6 +258,7 @@ static void gix_bytes(const fgb_genome *g, fgb_gix *x)        // GIXmake.c:1888-
 //  2^24 prefix index.
 
 #define GIX_FWD_ONLY 0x80000000u     // flag bit carried in `phi` down to syncmer_kernel
+#define GIX_NO_INDEX 0x40000000u     // table only: no prefix index, no LCP bytes (the T1 side of a merge reads neither)
 
 static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi, fgb_gix **out, void *stream);
 
@@ -328,15 +329,15 @@ done:
 
 //  K3/K4: sorts the records in d_a (consumed: it ends up inside the handle or is released) whose
 //  12-base prefixes lie in [plo,phi), builds the prefix index and the LCP bytes.
-static int gix_finish(fgb_gix *x, rec128 *d_a, long long n, unsigned plo, unsigned phi, cudaStream_t st)
+static int gix_finish(fgb_gix *x, rec128 *d_a, long long n, unsigned plo, unsigned phi, cudaStream_t st, bool index = true)
 { rec128 *d_b = NULL; void *d_stmp = NULL;
   long long stmpb = fgb_sort128_tmp_bytes(n);
   int rc = FGB_OK, inb = 0;
   x->n = n;
   if (fgb_dmalloc((void **) &d_b,sizeof(rec128)*(n+1),st) != cudaSuccess ||
       fgb_dmalloc((void **) &d_stmp,stmpb,st) != cudaSuccess ||
-      fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1+8),st) != cudaSuccess ||
-      fgb_dmalloc((void **) &x->d_adj,(size_t) n + 32,st) != cudaSuccess)
+      (index && fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1+8),st) != cudaSuccess) ||
+      (index && fgb_dmalloc((void **) &x->d_adj,(size_t) n + 32,st) != cudaSuccess))
     rc = FGB_ERR_CUDA;
   if (!rc)
     { stage_timer t(&g_timings.ksort_ms,st);
@@ -345,8 +346,10 @@ static int gix_finish(fgb_gix *x, rec128 *d_a, long long n, unsigned plo, unsign
   if (!rc)
     { x->d_tab = inb ? d_b : d_a;
       if (inb) d_b = NULL; else d_a = NULL;
-      stage_timer t(&g_timings.index_ms,st);
-      rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,x->d_adj,st);
+      if (index)
+        { stage_timer t(&g_timings.index_ms,st);
+          rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,x->d_adj,st);
+        }
     }
   if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = FGB_ERR_CUDA;
   fgb_dfree(d_a,st); fgb_dfree(d_b,st); fgb_dfree(d_stmp,st);
@@ -355,6 +358,8 @@ static int gix_finish(fgb_gix *x, rec128 *d_a, long long n, unsigned plo, unsign
 
 static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi_flags, fgb_gix **out, void *stream)
 { cudaStream_t st = (cudaStream_t) stream;
+  const bool index = !(phi_flags & GIX_NO_INDEX);
+  phi_flags &= ~GIX_NO_INDEX;
   const unsigned phi = phi_flags & ~GIX_FWD_ONLY;
   fgb_gix *x = new fgb_gix();
   gix_bytes(g,x);
@@ -362,7 +367,7 @@ static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi_flags
   x->fwd_only = (phi_flags & GIX_FWD_ONLY) ? 1 : 0;
   rec128 *d_a = NULL; long long n = 0, nrev = 0;
   int rc = gix_scan(g,NULL,plo,phi_flags,&d_a,&n,&nrev,x->buck1024,st);
-  if (!rc) { x->n_both = n + nrev; rc = gix_finish(x,d_a,n,plo,phi,st); }
+  if (!rc) { x->n_both = n + nrev; rc = gix_finish(x,d_a,n,plo,phi,st,index); }
   if (rc) { fgb_gix_free(x); return rc; }
   *out = x;
   return FGB_OK;
@@ -706,6 +711,38 @@ extern "C" int fgb_seeds_group_by_owner(const void *d_seeds, long long n, const 
   return FGB_OK;
 }
 
+//  k-mer records grouped by the rank that owns their first four bases: owner256[b] for top byte b;
+//  d_out[bounds[w] .. bounds[w+1]) are the records of owner w (count + scatter: cheaper than the radix
+//  pass of fgb_records_group_by_top_byte when only the destination matters)
+extern "C" int fgb_records_group_by_owner(const void *d_recs, long long n, const int *owner256, int world,
+                                          void *d_out, long long *bounds, void *stream)
+{ cudaStream_t st = (cudaStream_t) stream;
+  if (world < 1 || world > 64) return FGB_ERR_ARG;
+  for (int w = 0; w <= world; w++) bounds[w] = 0;
+  if (n <= 0) return FGB_OK;
+  int *d_owner = NULL; u64 *d_cnt = NULL;
+  int rc = FGB_OK;
+  u64 cnt[64], base[65];
+  if (fgb_dmalloc((void **) &d_owner,sizeof(int)*256,st) != cudaSuccess ||
+      fgb_dmalloc((void **) &d_cnt,8*64*2,st) != cudaSuccess) rc = FGB_ERR_CUDA;
+  if (!rc && (cudaMemcpyAsync(d_owner,owner256,sizeof(int)*256,cudaMemcpyHostToDevice,st) != cudaSuccess ||
+              cudaMemsetAsync(d_cnt,0,8*64*2,st) != cudaSuccess)) rc = FGB_ERR_CUDA;
+  if (!rc) rc = fgb_owner_count_device(d_recs,n,120,8,d_owner,256,world,d_cnt,st);
+  if (!rc && (cudaMemcpyAsync(cnt,d_cnt,8*64,cudaMemcpyDeviceToHost,st) != cudaSuccess ||
+              cudaStreamSynchronize(st) != cudaSuccess)) rc = FGB_ERR_CUDA;
+  if (!rc)
+    { base[0] = 0;
+      for (int w = 0; w < world; w++) base[w+1] = base[w] + cnt[w];
+      if (cudaMemcpyAsync(d_cnt + 64,base,8*64,cudaMemcpyHostToDevice,st) != cudaSuccess) rc = FGB_ERR_CUDA;
+    }
+  if (!rc) rc = fgb_owner_scatter_device(d_recs,n,120,8,d_owner,256,world,d_cnt + 64,d_out,st);
+  if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = FGB_ERR_CUDA;
+  fgb_dfree(d_owner,st); fgb_dfree(d_cnt,st);
+  if (rc) return rc;
+  for (int w = 0; w <= world; w++) bounds[w] = (long long) base[w];
+  return FGB_OK;
+}
+
 //  sorted seed set over n unsorted device records (copied); bits as fgb_seeds_merge returns them
 extern "C" int fgb_seeds_from_records(const void *d_recs, long long n, const int *bits, long long amxpos,
                                       long long bmxpos, long long sumlen, fgb_seeds **out, void *stream)
@@ -792,7 +829,8 @@ extern "C" int fgb_align_resident(const fgb_genome *A, const fgb_genome *B, cons
 { fgb_gix *x1 = NULL, *x2 = NULL;
   int rc;
   long long t0 = now_us();
-  if ((rc = fgb_gix_build_forward(A,&x1,stream))) return rc;     // adaptamer side: forward strand only
+  //  adaptamer side: forward strand only, and only the table (the merge reads the OTHER table's index)
+  if ((rc = gix_build_range(A,0u,(1u << 24) | GIX_FWD_ONLY | GIX_NO_INDEX,&x1,stream))) return rc;
   if ((rc = fgb_gix_build(B,&x2,stream))) { fgb_gix_free(x1); return rc; }
   long long t1 = now_us();
   rc = fgb_align_tables(A,B,x1,x2,freqA,freq,chain_break,chain_min,align_min,align_rate,out,stats,stream);

@@ -11,6 +11,7 @@
 // runs back coalesced, while counting the next pass's histogram.  HBM-bound integer work: no
 // tensor cores.
 #include "common.cuh"
+#include <stdlib.h>
 #include <vector>
 
 #define SORT_THREADS 512
@@ -316,21 +317,21 @@ extern "C" int fgb_sort128_device(void *d_a, void *d_b, long long n, int byte_lo
 #define BK_NSUB    (BK_SPAN << BK_SUBBITS)
 #define BK_MAXSUB  32                    // a sub-bin longer than this sends the group down the LSD path
 
-//  bin_start[p] = first record whose bin ((hi >> binshift) - base) is >= p, p in [0,65536]
+//  bin_start[p] = first record whose bin ((hi >> binshift) - base) is >= p, p in [0,nbins]
 __global__ void kmer_bins_kernel(const rec128 *__restrict__ tab, long long n, int binshift, unsigned long long base,
-                                 unsigned *__restrict__ bin_start)
+                                 unsigned *__restrict__ bin_start, long long nbins)
 { long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
   long long lo = (i == 0) ? -1 : (long long) ((tab[i-1].hi >> binshift) - base);
-  long long hi = (i == n) ? 65536 : (long long) ((tab[i].hi >> binshift) - base);
-  if (hi > 65536) hi = 65536;
+  long long hi = (i == n) ? nbins : (long long) ((tab[i].hi >> binshift) - base);
+  if (hi > nbins) hi = nbins;
   for (long long p = lo+1; p <= hi; p++) bin_start[p] = (unsigned) i;
 }
 
 //  bin_start[p], p = 0..65536, for bins = hi >> binshift (host-callable)
 extern "C" int fgb_kmer_bins_device(const void *d_tab, long long n, int binshift, unsigned *d_bins, void *stream)
 { int nb = (int) ((n + 1 + 255) / 256);
-  kmer_bins_kernel<<<nb,256,0,(cudaStream_t) stream>>>((const rec128 *) d_tab,n,binshift,0ull,d_bins);
+  kmer_bins_kernel<<<nb,256,0,(cudaStream_t) stream>>>((const rec128 *) d_tab,n,binshift,0ull,d_bins,65536ll);
   fgb_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return FGB_OK;
@@ -518,12 +519,20 @@ extern "C" int fgb_kmer_sort_range_device(void *d_a, void *d_b, long long n, uns
   if (n <= 1) return FGB_OK;
   if (n >= 0xffffffffll) return FGB_ERR_LIMIT;
   if (phi <= plo || phi > (1u << 24)) return FGB_ERR_ARG;
+  //  as many bins as keep the average bin near 1.5 K records (a CTA sorts <= BK_CAP in shared memory):
+  //  65536 up to ~100 M records, one more power of two per doubling beyond (a 1 Gbp genome: 2^19)
+  long long maxbins = 65536, target = 1536;
+  if (getenv("FGB_KSORT_BIN_TARGET") != NULL) target = atoll(getenv("FGB_KSORT_BIN_TARGET"));   // tests: force more bins
+  if (target < 1) target = 1;
+  while (maxbins < (1ll << 24) && n / maxbins > target) maxbins <<= 1;
   int sh = 0;                                            // bins = ((prefix24 - plo') >> sh), plo' = plo rounded down
-  while ((((unsigned long long) (phi - 1) >> sh) - ((unsigned long long) plo >> sh)) >= 65536) sh += 1;
+  while ((long long) ((((unsigned long long) (phi - 1) >> sh) - ((unsigned long long) plo >> sh))) >= maxbins) sh += 1;
   const int binshift = 40 + sh;                          // prefix24 = hi >> 40
   const unsigned long long base = (unsigned long long) plo >> sh;
+  const long long nbins = (long long) (((unsigned long long) (phi - 1) >> sh) - base) + 1;
   int inb = 0;
-  int rc = fgb_sort128_device(d_a,d_b,n,(24 - sh > 16) ? 13 : 14,16,d_tmp,tmp_bytes,&inb,st);
+  //  partition passes: 8-bit digits over the bins' bits (the top 24 - sh bits of the k-mer)
+  int rc = fgb_sort128_bits_device(d_a,d_b,n,64 + binshift,128,d_tmp,tmp_bytes,&inb,st);
   if (rc) return rc;
   rec128 *src = (rec128 *) (inb ? d_b : d_a), *dst = (rec128 *) (inb ? d_a : d_b);
 
@@ -535,20 +544,20 @@ extern "C" int fgb_kmer_sort_range_device(void *d_a, void *d_b, long long n, uns
     }
 
   unsigned *d_bins = NULL;
-  CUDA_TRY(fgb_dmalloc((void **) &d_bins,sizeof(unsigned)*65537,st));
+  CUDA_TRY(fgb_dmalloc((void **) &d_bins,sizeof(unsigned)*(size_t) (nbins+1),st));
   { int nb = (int) ((n + 1 + 255) / 256);
-    kmer_bins_kernel<<<nb,256,0,st>>>(src,n,binshift,base,d_bins);
+    kmer_bins_kernel<<<nb,256,0,st>>>(src,n,binshift,base,d_bins,nbins);
     fgb_count_launch(1);
   }
-  std::vector<unsigned> bins(65537);
-  CUDA_TRY(cudaMemcpyAsync(bins.data(),d_bins,sizeof(unsigned)*65537,cudaMemcpyDeviceToHost,st));
+  std::vector<unsigned> bins((size_t) nbins + 1);
+  CUDA_TRY(cudaMemcpyAsync(bins.data(),d_bins,sizeof(unsigned)*(size_t) (nbins+1),cudaMemcpyDeviceToHost,st));
   CUDA_TRY(cudaStreamSynchronize(st));
 
   std::vector<uint2> groups;
   std::vector<unsigned> ofrom, opre;                    // oversized bins: start, prefix of lengths
   unsigned ototal = 0;
-  { unsigned gs = bins[0], gc = 0; int gp = 0;                 // group start record, size, first bin
-    for (int p = 0; p < 65536; p++)
+  { unsigned gs = bins[0], gc = 0; long long gp = 0;           // group start record, size, first bin
+    for (long long p = 0; p < nbins; p++)
       { unsigned len = bins[p+1] - bins[p];
         if (len == 0) continue;
         if (len > BK_CAP)

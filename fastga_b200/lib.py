@@ -567,6 +567,19 @@ def records_group_by_top_byte(src_ptr, n, dst_ptr, stream=None):
     return bounds
 
 
+def records_group_by_owner(src_ptr, n, owner256, world, dst_ptr, stream=None):
+    """groups n k-mer records by the rank owning their first four bases (owner256[top byte]) into dst;
+    returns bounds[world+1]"""
+    L = load_library()
+    bounds = np.zeros(world + 1, dtype=np.int64)
+    own = np.ascontiguousarray(owner256, dtype=np.int32)
+    assert own.shape == (256,)
+    L.fgb_records_group_by_owner.argtypes = [c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    _check(L.fgb_records_group_by_owner(c_void_p(src_ptr), n, _ptr(own), world, c_void_p(dst_ptr), _ptr(bounds),
+                                        stream), "fgb_records_group_by_owner")
+    return bounds
+
+
 def gix_from_records(ptr, n, plo, phi, fwd_only, post_bytes, cont_bytes, ncontig, stream=None):
     L = load_library()
     h = c_void_p()

@@ -187,14 +187,17 @@ def align_sharded(dA, dB, freqA, dist, device, **kw):
     #  The two tables are pipelined: while the k-mer records of one travel (NCCL's stream), this rank's
     #  stream scans / groups the other genome or sorts the slice that already arrived.
     nk, flight = [], []
+    owner256 = np.zeros(256, dtype=np.int32)
+    for r in range(world):
+        owner256[cuts[r]:cuts[r + 1]] = r
     for dg, own, fwd in ((dA, ownA, True), (dB, ownB, False)):
         ptr, n = lib.kmers_scan(dg, own == rank, fwd)
         mark("scan")
         grouped = torch.empty((max(n, 1), 2), dtype=torch.int64, device=device)
-        bounds = lib.records_group_by_top_byte(ptr, n, grouped.data_ptr())
+        bounds = lib.records_group_by_owner(ptr, n, owner256, world, grouped.data_ptr())
         lib.device_free(ptr)
         mark("group k-mers")
-        send = [int(bounds[cuts[r + 1]] - bounds[cuts[r]]) for r in range(world)]
+        send = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
         recv, work = exchange_rows(dist, grouped, send, async_op=True)
         flight.append((recv, work, grouped))
         mark("exchange k-mers (issued)")

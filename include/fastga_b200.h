@@ -210,6 +210,9 @@ int  fgb_kmers_scan(const fgb_genome *g, const unsigned char *mask, int fwd_only
 /* d_out[bounds257[b] .. bounds257[b+1]) = the records whose top k-mer byte is b (d_recs is scratch) */
 int  fgb_records_group_by_top_byte(void *d_recs, long long n, void *d_out, long long *bounds257,
                                    void *stream);
+/* the same by destination only: owner256[b] = rank owning top byte b; d_out[bounds[w] .. bounds[w+1]) */
+int  fgb_records_group_by_owner(const void *d_recs, long long n, const int *owner256, int world,
+                                void *d_out, long long *bounds, void *stream);
 /* sorted + indexed table over records whose 12-base prefix lies in [plo,phi) (one rank's slice) */
 int  fgb_gix_from_records(const void *d_recs, long long n, unsigned plo, unsigned phi, int fwd_only,
                           int post_bytes, int cont_bytes, int ncontig, fgb_gix **out, void *stream);

@@ -80,6 +80,26 @@ def test_gix_build_with_heavy_repeats_matches_oracle():
     assert np.array_equal(pstart, wstart)
 
 
+@pytest.mark.parametrize("target", ["8", "1"])
+def test_gix_build_with_more_than_65536_bins_is_the_same_table(small_pair, target):
+    """tables beyond ~100 M records are partitioned into more than 2^16 prefix bins (a third, narrower
+    digit pass) so that a bin still fits a CTA's shared memory; FGB_KSORT_BIN_TARGET forces that regime
+    on a small table (2^19 .. 2^22 bins here), whole table and shares alike"""
+    import os
+    g = small_pair[1]
+    dg = lib.DeviceGenome(g)
+    full, pstart, _ = lib.DeviceGix.build(dg).download()
+    os.environ["FGB_KSORT_BIN_TARGET"] = target
+    try:
+        tab2, pstart2, _ = lib.DeviceGix.build(dg).download()
+        parts = [lib.DeviceGix.build_range(dg, lo, hi).download()[0]
+                 for lo, hi in ((0, (1 << 23) + 5), ((1 << 23) + 5, 1 << 24))]
+    finally:
+        del os.environ["FGB_KSORT_BIN_TARGET"]
+    assert np.array_equal(tab2, full) and np.array_equal(pstart2, pstart)
+    assert np.array_equal(np.concatenate(parts), full)
+
+
 def test_gix_shares_of_the_prefix_space_concatenate_to_the_full_table(small_pair):
     """one rank's share of a cooperatively built table (fgb_gix_build_range) is binned relative to
     its own prefix range; uneven shares must concatenate to exactly the single-GPU table"""
