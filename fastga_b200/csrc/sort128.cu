@@ -188,13 +188,23 @@ sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, lo
         atomicExch(mine,ST_INC | c);
       else
         atomicExch(mine,ST_AGG | c);
+      //  four predecessors per round trip (the status words of consecutive tiles are independent loads;
+      //  a serial walk pays one L2 latency per tile, and the walk is as deep as the tiles in flight)
       unsigned long long excl = 0;
       for (long long t = (long long) tileid - 1; t >= 0; )
-        { unsigned long long v = stt[(unsigned long long) t*256 + tid];
-          if ((v >> 62) == 0) continue;                        // predecessor not there yet: spin
-          excl += v & ST_MASK;
-          if (v & ST_INC) break;
-          t -= 1;
+        { unsigned long long v[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            v[q] = (t - q >= 0) ? stt[(unsigned long long) (t - q)*256 + tid] : ST_INC;
+          bool done = false;
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            { if (done || (v[q] >> 62) == 0) break;            // not there yet: spin from this tile on
+              excl += v[q] & ST_MASK;
+              t -= 1;
+              if (v[q] & ST_INC) done = true;
+            }
+          if (done) break;
         }
       if (tileid != 0) atomicExch(mine,ST_INC | (excl + c));
       inc = warp_incl_scan(c,lane);
