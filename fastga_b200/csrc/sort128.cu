@@ -171,7 +171,12 @@ sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, lo
     }
   __syncthreads();
 
+  //  Order of the rest: publish the tile's digit counts at once (the tiles after this one add them up
+  //  while it works on), place the records in digit order inside the tile, and only THEN look back for
+  //  this tile's own bases -- by which time the tiles before it have had the whole placement phase to
+  //  publish theirs, so the walk is short and rarely spins.
   unsigned c = 0, inc = 0;
+  unsigned long long *mine = status + (unsigned long long) tileid*256 + tid;
   if (tid < 256)
     { unsigned sum = 0;
 #pragma unroll
@@ -181,15 +186,33 @@ sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, lo
           sum += t;
         }
       c = sum;
-      //  publish the tile aggregate, then look back for the exclusive prefix of this digit
-      volatile unsigned long long *stt = status;
-      unsigned long long *mine = status + (unsigned long long) tileid*256 + tid;
       if (tileid == 0)
         atomicExch(mine,ST_INC | c);
       else
         atomicExch(mine,ST_AGG | c);
-      //  four predecessors per round trip (the status words of consecutive tiles are independent loads;
+      inc = warp_incl_scan(c,lane);
+      if (lane == 31) wtot[w] = inc;
+    }
+  __syncthreads();
+  if (tid < 256)
+    { unsigned pre = 0;
+      for (int i = 0; i < w; i++) pre += wtot[i];
+      bexcl[tid] = pre + inc - c;
+    }
+  __syncthreads();
+
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; it++)
+    { int idx = base + it*32 + lane;
+      if (idx < cnt)
+        { unsigned d = rec_dig(r[it],byte);
+          st_rec(tile + (bexcl[d] + myc[d] + rank[it]),r[it]);
+        }
+    }
+  if (tid < 256)
+    { //  four predecessors per round trip (the status words of consecutive tiles are independent loads;
       //  a serial walk pays one L2 latency per tile, and the walk is as deep as the tiles in flight)
+      volatile unsigned long long *stt = status;
       unsigned long long excl = 0;
       for (long long t = (long long) tileid - 1; t >= 0; )
         { unsigned long long v[4];
@@ -207,28 +230,8 @@ sort_onesweep_kernel(const rec128 *__restrict__ in, rec128 *__restrict__ out, lo
           if (done) break;
         }
       if (tileid != 0) atomicExch(mine,ST_INC | (excl + c));
-      inc = warp_incl_scan(c,lane);
-      if (lane == 31) wtot[w] = inc;
-      gbase[tid] = binbase[tid] + excl;                        // minus bexcl below
+      gbase[tid] = binbase[tid] + excl - bexcl[tid];
       if (next_byte >= 0 && nhist[tid]) atomicAdd(&nexthist[tid],(unsigned long long) nhist[tid]);
-    }
-  __syncthreads();
-  if (tid < 256)
-    { unsigned pre = 0;
-      for (int i = 0; i < w; i++) pre += wtot[i];
-      unsigned ex = pre + inc - c;
-      bexcl[tid] = ex;
-      gbase[tid] -= ex;
-    }
-  __syncthreads();
-
-#pragma unroll
-  for (int it = 0; it < SORT_ITEMS; it++)
-    { int idx = base + it*32 + lane;
-      if (idx < cnt)
-        { unsigned d = rec_dig(r[it],byte);
-          st_rec(tile + (bexcl[d] + myc[d] + rank[it]),r[it]);
-        }
     }
   __syncthreads();
 
