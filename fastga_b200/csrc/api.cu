@@ -822,6 +822,10 @@ extern "C" int fgb_align_tables(const fgb_genome *A, const fgb_genome *B, const 
                                 int freq, int chain_break, int chain_min, int align_min,
                                 double align_rate, fgb_alns **out, fgb_run_stats *stats, void *stream);
 
+static int align_tables_impl(const fgb_genome *A, const fgb_genome *B, fgb_gix *x1, fgb_gix *x2, bool own,
+                             const float *freqA, int freq, int chain_break, int chain_min, int align_min,
+                             double align_rate, fgb_alns **out, fgb_run_stats *stats, void *stream);
+
 //  Device-resident genomes in, final alignments out (the timed "step" of bench.py).
 extern "C" int fgb_align_resident(const fgb_genome *A, const fgb_genome *B, const float *freqA,
                                   int freq, int chain_break, int chain_min, int align_min,
@@ -833,8 +837,9 @@ extern "C" int fgb_align_resident(const fgb_genome *A, const fgb_genome *B, cons
   if ((rc = gix_build_range(A,0u,(1u << 24) | GIX_FWD_ONLY | GIX_NO_INDEX,&x1,stream))) return rc;
   if ((rc = fgb_gix_build(B,&x2,stream))) { fgb_gix_free(x1); return rc; }
   long long t1 = now_us();
-  rc = fgb_align_tables(A,B,x1,x2,freqA,freq,chain_break,chain_min,align_min,align_rate,out,stats,stream);
-  fgb_gix_free(x1); fgb_gix_free(x2);
+  //  the tables are this call's own: they go back to the allocator as soon as the merge has read them
+  //  (two tables + seeds + sort buffer of a multi-Gbp pair do not fit side by side)
+  rc = align_tables_impl(A,B,x1,x2,true,freqA,freq,chain_break,chain_min,align_min,align_rate,out,stats,stream);
   if (stats) stats->us_gix = t1 - t0;
   return rc;
 }
@@ -843,11 +848,24 @@ extern "C" int fgb_align_tables(const fgb_genome *A, const fgb_genome *B, const 
                                 const fgb_gix *x2, const float *freqA,
                                 int freq, int chain_break, int chain_min, int align_min,
                                 double align_rate, fgb_alns **out, fgb_run_stats *stats, void *stream)
+{ return align_tables_impl(A,B,(fgb_gix *) x1,(fgb_gix *) x2,false,freqA,freq,chain_break,chain_min,align_min,
+                           align_rate,out,stats,stream);
+}
+
+static int align_tables_impl(const fgb_genome *A, const fgb_genome *B, fgb_gix *x1, fgb_gix *x2, bool own,
+                             const float *freqA, int freq, int chain_break, int chain_min, int align_min,
+                             double align_rate, fgb_alns **out, fgb_run_stats *stats, void *stream)
 { fgb_seeds *sd = NULL; fgb_overlaps *ov = NULL;
   int rc;
   long long t0 = now_us(), t1 = t0, t2, t3, t4;
-  rc = fgb_seeds_find(x1,x2,A->maxlen,B->maxlen,freq,&sd,stream);
-  long long n1 = x1->n_both, n2 = x2->n;
+  const long long n1 = x1->n_both, n2 = x2->n;
+  { seed_bits L;
+    rec128 *d_a = NULL; long long n = 0, sumlen = 0, n1m = 0;
+    rc = seed_layout_of(x1,x2,A->maxlen,B->maxlen,&L);
+    if (!rc) rc = seeds_merge_impl(x1,x2,A->maxlen,B->maxlen,freq,false,L,&d_a,&n,&sumlen,&n1m,(cudaStream_t) stream);
+    if (own) { fgb_gix_free(x1); fgb_gix_free(x2); }
+    if (!rc) rc = seeds_sort_impl(d_a,n,L,A->maxlen,B->maxlen,false,sumlen,n1m,&sd,(cudaStream_t) stream);
+  }
   if (rc) return rc;
   const long long n1f = sd->n1_merged;
   t2 = now_us();
