@@ -2502,19 +2502,45 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
             if (getenv("FGB_SPEC_SLACK") != NULL) SPEC_SLACK = atoll(getenv("FGB_SPEC_SLACK"));
             long long SPEC_GAP = -1;                                   // tests: cut at every gap >= this instead
             if (getenv("FGB_SPEC_GAP") != NULL) SPEC_GAP = atoll(getenv("FGB_SPEC_GAP"));
+            //  the small result arrays come back through one pinned scratch buffer (grow-only): four copies in
+            //  flight and one synchronisation instead of a staged, synchronous copy each
+            static unsigned char *hpin = NULL; static size_t hpin_cap = 0;
+            auto pinned = [&](size_t bytes) -> unsigned char *
+              { if (bytes > hpin_cap)
+                  { if (hpin) cudaFreeHost(hpin);
+                    hpin = NULL; hpin_cap = 0;
+                    if (cudaMallocHost(&hpin,bytes*2 + 4096) != cudaSuccess) return NULL;
+                    hpin_cap = bytes*2 + 4096;
+                  }
+                return hpin;
+              };
             unsigned long long hused = 0;
             std::vector<uint2> hrange(nwork);
             std::vector<int2> tinfo(nwork);
             hwork.resize(nwork); hcount.assign(nwork,0u);
-            CUDA_TRY(cudaMemcpyAsync(&hused,d_misc + 8,8,cudaMemcpyDeviceToHost,st));
-            CUDA_TRY(cudaMemcpyAsync(hrange.data(),d_hrange,sizeof(uint2)*(size_t) nwork,cudaMemcpyDeviceToHost,st));
-            CUDA_TRY(cudaMemcpyAsync(tinfo.data(),d_tinfo,sizeof(int2)*(size_t) nwork,cudaMemcpyDeviceToHost,st));
-            CUDA_TRY(cudaMemcpyAsync(hwork.data(),d_work,sizeof(unsigned)*(size_t) nwork,cudaMemcpyDeviceToHost,st));
-            CUDA_TRY(cudaStreamSynchronize(st));
+            { const size_t o1 = 16, o2 = o1 + sizeof(uint2)*(size_t) nwork, o3 = o2 + sizeof(int2)*(size_t) nwork,
+                           o4 = o3 + sizeof(unsigned)*(size_t) nwork;
+              unsigned char *hp = pinned(o4);
+              if (hp == NULL) return FGB_ERR_CUDA;
+              CUDA_TRY(cudaMemcpyAsync(hp,d_misc + 8,8,cudaMemcpyDeviceToHost,st));
+              CUDA_TRY(cudaMemcpyAsync(hp + o1,d_hrange,sizeof(uint2)*(size_t) nwork,cudaMemcpyDeviceToHost,st));
+              CUDA_TRY(cudaMemcpyAsync(hp + o2,d_tinfo,sizeof(int2)*(size_t) nwork,cudaMemcpyDeviceToHost,st));
+              CUDA_TRY(cudaMemcpyAsync(hp + o3,d_work,sizeof(unsigned)*(size_t) nwork,cudaMemcpyDeviceToHost,st));
+              CUDA_TRY(cudaStreamSynchronize(st));
+              memcpy(&hused,hp,8);
+              memcpy(hrange.data(),hp + o1,sizeof(uint2)*(size_t) nwork);
+              memcpy(tinfo.data(),hp + o2,sizeof(int2)*(size_t) nwork);
+              memcpy(hwork.data(),hp + o3,sizeof(unsigned)*(size_t) nwork);
+            }
             if (hused > hit_cap) hused = hit_cap;
             std::vector<ChainHit> hh((size_t) hused + 1);
-            if (hused > 0) CUDA_TRY(cudaMemcpyAsync(hh.data(),d_hits,sizeof(ChainHit)*(size_t) hused,cudaMemcpyDeviceToHost,st));
-            CUDA_TRY(cudaStreamSynchronize(st));
+            if (hused > 0)
+              { unsigned char *hp = pinned(sizeof(ChainHit)*(size_t) hused);
+                if (hp == NULL) return FGB_ERR_CUDA;
+                CUDA_TRY(cudaMemcpyAsync(hp,d_hits,sizeof(ChainHit)*(size_t) hused,cudaMemcpyDeviceToHost,st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                memcpy(hh.data(),hp,sizeof(ChainHit)*(size_t) hused);
+              }
             for (unsigned w = 0; w < nwork; w++)
               if (!(hrange[w].y & 0x80000000u)) hcount[w] = hrange[w].y;
 
@@ -2605,8 +2631,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
               { CUDA_TRY(fgb_dmalloc((void **) &d_items,sizeof(ExItem)*items.size(),st));
                 CUDA_TRY(fgb_dmalloc((void **) &d_galast,sizeof(long long)*items.size(),st));
                 CUDA_TRY(cudaMemcpyAsync(d_items,items.data(),sizeof(ExItem)*items.size(),cudaMemcpyHostToDevice,st));
-                CUDA_TRY(cudaStreamSynchronize(st));
-              }
+              }                                                      // (`items` lives until the launches are over)
             TR_SYNC("  chain: hit groups");
           }
           }
