@@ -262,6 +262,20 @@ static void gix_bytes(const fgb_genome *g, fgb_gix *x)        // GIXmake.c:1888-
 
 static int gix_build_range(const fgb_genome *g, unsigned plo, unsigned phi, fgb_gix **out, void *stream);
 
+//  a table handle (and, with it, its device blocks) is released on every way out of the call that
+//  builds it unless it was handed to the caller; likewise loose device blocks
+struct gix_scope
+{ fgb_gix *x;
+  explicit gix_scope(fgb_gix *p) : x(p) {}
+  fgb_gix *release() { fgb_gix *p = x; x = NULL; return p; }
+  ~gix_scope() { if (x != NULL) fgb_gix_free(x); }
+};
+struct blk_scope
+{ std::vector<void **> slots;
+  template<class T> void own(T *&p) { slots.push_back((void **) &p); }
+  ~blk_scope() { for (void **s : slots) if (*s != NULL) { fgb_dfree(*s,0); *s = NULL; } }
+};
+
 extern "C" int fgb_gix_build(const fgb_genome *g, fgb_gix **out, void *stream)
 { return gix_build_range(g,0u,1u << 24,out,stream); }
 
@@ -454,6 +468,7 @@ extern "C" int fgb_gix_from_device(const void *d_tab, long long n, int post_byte
 { cudaStream_t st = (cudaStream_t) stream;
   if (n >= 0xfffffff0ll) return FGB_ERR_LIMIT;
   fgb_gix *x = new fgb_gix();
+  gix_scope own(x);
   x->n = n; x->n_both = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
   CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
   CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1+8),st));
@@ -465,7 +480,7 @@ extern "C" int fgb_gix_from_device(const void *d_tab, long long n, int post_byte
   }
   CUDA_TRY(cudaStreamSynchronize(st));
   if (rc) return rc;
-  *out = x;
+  *out = own.release();
   return FGB_OK;
 }
 extern "C" int fgb_gix_post_bytes(const fgb_gix *x) { return x->post_bytes; }
@@ -485,6 +500,7 @@ extern "C" int fgb_gix_upload(const void *tab, long long n, int post_bytes, int 
 { cudaStream_t st = (cudaStream_t) stream;
   if (n >= 0xfffffff0ll) return FGB_ERR_LIMIT;
   fgb_gix *x = new fgb_gix();
+  gix_scope own(x);
   x->n = n; x->n_both = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
   CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
   CUDA_TRY(fgb_dmalloc((void **) &x->d_pstart,sizeof(unsigned)*((1<<24)+1+8),st));
@@ -493,7 +509,7 @@ extern "C" int fgb_gix_upload(const void *tab, long long n, int post_bytes, int 
   int rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,x->d_adj,st);
   CUDA_TRY(cudaStreamSynchronize(st));
   if (rc) return rc;
-  *out = x;
+  *out = own.release();
   return FGB_OK;
 }
 
@@ -505,9 +521,11 @@ extern "C" int fgb_gix_import_ktab(const unsigned char *entries, long long n, in
 { cudaStream_t st = (cudaStream_t) stream;
   if (n >= 0xfffffff0ll || post_bytes > 4 || cont_bytes > 2) return FGB_ERR_LIMIT;
   fgb_gix *x = new fgb_gix();
+  gix_scope own(x);
   x->n = n; x->n_both = n; x->post_bytes = post_bytes; x->cont_bytes = cont_bytes; x->ncontig = ncontig;
   long long E = 9 + post_bytes + cont_bytes;
   unsigned char *d_ent = NULL; long long *d_index = NULL;
+  blk_scope B; B.own(d_ent); B.own(d_index);
   CUDA_TRY(fgb_dmalloc((void **) &d_ent,E*n + 16,st));
   CUDA_TRY(fgb_dmalloc((void **) &d_index,8ll<<24,st));
   CUDA_TRY(fgb_dmalloc((void **) &x->d_tab,sizeof(rec128)*(n+1),st));
@@ -518,9 +536,8 @@ extern "C" int fgb_gix_import_ktab(const unsigned char *entries, long long n, in
   int rc = fgb_ktab_import_device(d_ent,n,post_bytes,cont_bytes,d_index,x->d_tab,st);
   if (!rc) rc = fgb_kix_index_device(x->d_tab,n,x->d_pstart,x->d_adj,st);
   CUDA_TRY(cudaStreamSynchronize(st));
-  fgb_dfree(d_ent,st); fgb_dfree(d_index,st);
   if (rc) return rc;
-  *out = x;
+  *out = own.release();
   return FGB_OK;
 }
 
@@ -531,13 +548,13 @@ extern "C" int fgb_gix_export_ktab(const fgb_gix *x, const long long *part_first
 { cudaStream_t st = (cudaStream_t) stream;
   long long E = 9 + x->post_bytes + x->cont_bytes;
   unsigned char *d_out = NULL; long long *d_pf = NULL;
+  blk_scope B; B.own(d_out); B.own(d_pf);
   CUDA_TRY(fgb_dmalloc((void **) &d_out,E*x->n + 16,st));
   CUDA_TRY(fgb_dmalloc((void **) &d_pf,8*(nparts+1),st));
   CUDA_TRY(cudaMemcpyAsync(d_pf,part_first,8*nparts,cudaMemcpyHostToDevice,st));
   int rc = fgb_ktab_export_device(x->d_tab,x->n,x->post_bytes,x->cont_bytes,d_pf,nparts,d_out,st);
   if (!rc) CUDA_TRY(cudaMemcpyAsync(out,d_out,E*x->n,cudaMemcpyDeviceToHost,st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  fgb_dfree(d_out,st); fgb_dfree(d_pf,st);
   return rc;
 }
 

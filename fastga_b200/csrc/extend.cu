@@ -2346,6 +2346,21 @@ struct ev_timer
 //  tables: 2 x 32768 int16 (score, then table) and ave_path from New_Align_Spec's arithmetic,
 //  computed by the host caller (align.c:222-268 is float/double set-up, kept on the host).
 
+//  Device blocks (and the result handle) of a call go back on EVERY way out of it, error returns included:
+//  the pointer variables are registered once, whatever they hold when the scope ends is released.
+struct dev_scope
+{ cudaStream_t st; std::vector<void **> slots;
+  explicit dev_scope(cudaStream_t s) : st(s) {}
+  template<class T> void own(T *&p) { slots.push_back((void **) &p); }
+  ~dev_scope() { for (void **s : slots) if (*s != NULL) { fgb_dfree(*s,st); *s = NULL; } }
+};
+struct ovl_scope
+{ fgb_overlaps *o;
+  explicit ovl_scope(fgb_overlaps *p) : o(p) {}
+  fgb_overlaps *release() { fgb_overlaps *p = o; o = NULL; return p; }
+  ~ovl_scope() { if (o != NULL) fgb_overlaps_free(o); }
+};
+
 extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_genome *B,
                           int chain_break, int chain_min, int align_min, double align_rate,
                           const short *tables, int ave_path, int tspace,
@@ -2354,6 +2369,8 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
   if (A->d_rseq == NULL) return FGB_ERR_ARG;
   if (S->n >= 0xfffffff0ll) return FGB_ERR_LIMIT;
   fgb_overlaps *O = new fgb_overlaps();
+  ovl_scope Oown(O);
+  dev_scope G(st);
   long long n = S->n;
   tr_mark("extend: enter");
 
@@ -2378,6 +2395,8 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
   u64 *d_counters = NULL, *d_total = NULL;
   unsigned *d_flag = NULL, *d_seg = NULL, *d_work = NULL, *d_misc = NULL, *d_failed = NULL;
   void *d_tmp = NULL;
+  G.own(d_tables); G.own(d_counters); G.own(d_total); G.own(d_flag); G.own(d_seg); G.own(d_work);
+  G.own(d_misc); G.own(d_failed); G.own(d_tmp);
   CUDA_TRY(fgb_dmalloc((void **) &d_tables,65536*sizeof(short),st));
   CUDA_TRY(cudaMemcpyAsync(d_tables,tables,65536*sizeof(short),cudaMemcpyHostToDevice,st));
   P.score = d_tables; P.table = d_tables + 32768;
@@ -2395,6 +2414,8 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
   //  hit groups (first launch): items in launch order, and for each the first hit of the NEXT group of
   //  its triple (what its tube must not have reached for the groups to have been independent)
   ExItem *d_items = NULL; long long *d_galast = NULL; int2 *d_tinfo = NULL;
+  G.own(d_plan); G.own(d_couts); G.own(d_first); G.own(d_failed_w); G.own(d_hits); G.own(d_hrange);
+  G.own(d_items); G.own(d_galast); G.own(d_tinfo);
   std::vector<ExItem> items; std::vector<long long> nxt_alow, nxt_ahgh;
   std::vector<unsigned> hwork, hcount;                 // work triples; hits of each pre-scanned one
   unsigned long long hits_done = 0;                    // hits of the pre-scanned triples the first launch completed
@@ -2641,6 +2662,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
   tr_mark("extend: triples+prefilter");
 
   unsigned char *d_out = NULL;
+  G.own(d_out);
   u64 out_cap = 0, out_used = 0;
   if (nwork > 0)
     { int dev = 0, nsm = 148;
@@ -2672,9 +2694,12 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       std::vector<std::pair<unsigned,int> > todo;    // (triple, launch number) of every re-run
       unsigned *d_list = d_work; unsigned nlist = use_items ? (unsigned) items.size() : nwork;
       unsigned *d_work2 = NULL;
+      dev_scope G2(st); G2.own(d_work2);
       u64 used_before = 0;
       for (int attempt = 0; nlist > 0; attempt++)
-        { Peb *d_cells = NULL; unsigned char *d_stage = NULL;
+        { Peb *d_cells = NULL; unsigned char *d_stage = NULL; unsigned char *d_big = NULL;
+          unsigned long long *d_wlog = NULL;
+          dev_scope L(st); L.own(d_cells); L.own(d_stage); L.own(d_big); L.own(d_wlog);
           CUDA_TRY(fgb_dmalloc((void **) &d_cells,sizeof(Peb)*cells_per_warp*nwarps,st));
           CUDA_TRY(fgb_dmalloc((void **) &d_stage,2ll*stage_bytes*nwarps,st));
           if (d_out == NULL) CUDA_TRY(fgb_dmalloc((void **) &d_out,out_cap,st));
@@ -2683,13 +2708,11 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           P.out = d_out; P.out_cap = out_cap;
           P.work = d_list; P.nwork = (int) nlist;
           P.items = use_items ? d_items : NULL; P.galast = d_galast; P.attempt = attempt;
-          unsigned char *d_big = NULL;
           if (attempt > 0)                                     // retries: wide-band kernel, state in HBM
             { CUDA_TRY(fgb_dmalloc((void **) &d_big,(size_t) nwarps * WSTATE_BYTES(EX_WBIG),st));
               P.bigstate = d_big;
             }
           tr_mark("extend: arenas allocated");
-          unsigned long long *d_wlog = NULL;
           if (attempt == 0 && getenv("FGB_WLOG") != NULL)
             { CUDA_TRY(fgb_dmalloc((void **) &d_wlog,32ull*(nlist+1),st));
               CUDA_TRY(cudaMemsetAsync(d_wlog,0,32ull*(nlist+1),st));
@@ -2722,9 +2745,10 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
                             P.items != NULL ? (items[q].hn & 0x7fffffffu) : 0u,P.items != NULL ? items[q].g : 0u);
                   fclose(f);
                 }
-              fgb_dfree(d_wlog,st);
+              fgb_dfree(d_wlog,st); d_wlog = NULL;
             }
           fgb_dfree(d_cells,st); fgb_dfree(d_stage,st); fgb_dfree(d_big,st);
+          d_cells = NULL; d_stage = NULL; d_big = NULL;
           out_used = ((u64) misc[5] << 32) | misc[4];
           unsigned nfailed = misc[2];
           if (out_used > out_cap)
@@ -2791,7 +2815,7 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
           nblocks = nb2 < maxb ? nb2 : maxb;
           nwarps = nblocks * EX_WARPS;
         }
-      fgb_dfree(d_work2,st);
+      fgb_dfree(d_work2,st); d_work2 = NULL;
 
       //  bring the records back and drop partial output of triples that were re-run
       O->nbytes = (long long) out_used;
@@ -2852,12 +2876,8 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
       }
     O->nrec = cnt;
   }
-  fgb_dfree(d_tables,st); fgb_dfree(d_counters,st); fgb_dfree(d_total,st); fgb_dfree(d_misc,st); fgb_dfree(d_flag,st);
-  fgb_dfree(d_seg,st); fgb_dfree(d_work,st); fgb_dfree(d_failed,st); fgb_dfree(d_tmp,st); fgb_dfree(d_out,st);
-  fgb_dfree(d_plan,st); fgb_dfree(d_couts,st); fgb_dfree(d_first,st); fgb_dfree(d_failed_w,st); fgb_dfree(d_hits,st); fgb_dfree(d_hrange,st);
-  fgb_dfree(d_items,st); fgb_dfree(d_galast,st); fgb_dfree(d_tinfo,st);
   tr_mark("extend: leave");
-  *out = O;
+  *out = Oown.release();                                     // (the device blocks go back as G leaves scope)
   return FGB_OK;
 }
 

@@ -10,6 +10,11 @@
  *
  * `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); all work of a
  * call is issued on it and the call returns after the stream has drained.
+ *
+ * Threading contract: ONE calling thread and ONE device per process at a time (what `FastGA`, one
+ * process, and `torchrun`, one process per GPU, do).  The library keeps process-wide state -- a cache
+ * of device blocks without a device id, per-stage timers, a pinned staging buffer, kernel attributes
+ * set on first use -- and does not lock around it.
  */
 #ifndef FASTGA_B200_H
 #define FASTGA_B200_H
