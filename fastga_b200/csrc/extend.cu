@@ -155,12 +155,6 @@ struct __align__(16) PairBox
 #endif
 #define DIAG_CLOCK() (EX_DIAG ? clock64() : 0ll)
 
-static __device__ __forceinline__ Peb ldpeb(const Peb *p)        // pebbles may have been written by the partner warp
-{ int4 v = __ldcg((const int4 *) p);
-  Peb r; r.ptr = v.x; r.diag = v.y; r.diff = v.z; r.mark = v.w;
-  return r;
-}
-
 //  The trace read-out walks a pebble chain from the trim point back to the start: every hop used to be
 //  a dependent L2 / HBM round trip (0.5-1 us x thousands of trace points, three walks per alignment:
 //  8 % of the kernel's cycles, all of them on the critical path of an item).  Pebbles are appended in
@@ -2346,6 +2340,122 @@ struct ev_timer
 //  tables: 2 x 32768 int16 (score, then table) and ave_path from New_Align_Spec's arithmetic,
 //  computed by the host caller (align.c:222-268 is float/double set-up, kept on the host).
 
+//  Hit groups of the work triples (host): see the comment in fgb_extend.  hrange[w] = (first hit, count |
+//  bit 31: no list) into hh[0..hused); tinfo[w] = ((strand, contig pair) key, band); items come out in launch
+//  order (largest estimated cost first) with, for each, the first hit of the next group of its triple.
+static void build_hit_groups(unsigned nwork, const uint2 *hrange, const int2 *tinfo, const ChainHit *hh,
+                             unsigned long long hused, int SPEC_BANDS, long long SPEC_SLACK, long long SPEC_GAP,
+                             std::vector<ExItem> &items, std::vector<long long> &nxt_alow,
+                             std::vector<long long> &nxt_ahgh, std::vector<unsigned> &hcount)
+{ hcount.assign(nwork,0u);
+  for (unsigned w = 0; w < nwork; w++)
+    if (!(hrange[w].y & 0x80000000u)) hcount[w] = hrange[w].y;
+
+  //  components of chains (index = position in hh; only listed triples' ranges are used)
+  std::vector<unsigned> comp((size_t) hused + 1);
+  for (size_t q = 0; q <= hused; q++) comp[q] = (unsigned) q;
+  auto find = [&](unsigned x) { while (comp[x] != x) { comp[x] = comp[comp[x]]; x = comp[x]; } return x; };
+  auto unite = [&](unsigned x, unsigned y) { x = find(x); y = find(y); if (x != y) comp[x < y ? y : x] = (x < y ? x : y); };
+  if (SPEC_GAP < 0)
+    { std::vector<std::pair<std::pair<int,int>,unsigned> > byband;       // ((key, band), w)
+      for (unsigned w = 0; w < nwork; w++)
+        if (hcount[w] > 0) byband.push_back(std::make_pair(std::make_pair(tinfo[w].x,tinfo[w].y),w));
+      std::sort(byband.begin(),byband.end());
+      for (size_t i = 0; i < byband.size(); i++)
+        { const unsigned w1 = byband[i].second;
+          const ChainHit *H1 = hh + hrange[w1].x; const unsigned n1 = hcount[w1];
+          for (unsigned q = 1; q < n1; q++)                                   // neighbours in its own list
+            if (H1[q].alow - H1[q-1].ahgh < SPEC_SLACK) unite(hrange[w1].x + q - 1,hrange[w1].x + q);
+          for (size_t k = i + 1; k < byband.size(); k++)
+            { if (byband[k].first.first != byband[i].first.first ||
+                  byband[k].first.second - byband[i].first.second > SPEC_BANDS) break;
+              const unsigned w2 = byband[k].second;
+              const ChainHit *H2 = hh + hrange[w2].x; const unsigned n2 = hcount[w2];
+              unsigned a = 0, b = 0;                                          // interval join of two sorted lists
+              while (a < n1 && b < n2)
+                { if (H1[a].ahgh + SPEC_SLACK < H2[b].alow) a += 1;
+                  else if (H2[b].ahgh + SPEC_SLACK < H1[a].alow) b += 1;
+                  else
+                    { unite(hrange[w1].x + a,hrange[w2].x + b);
+                      if (H1[a].ahgh < H2[b].ahgh) a += 1; else b += 1;
+                    }
+                }
+            }
+        }
+    }
+  //  extent of every component: how long the alignment of its block will be (launch order)
+  std::vector<long long> clo((size_t) hused + 1,0x7fffffffffffffffll), chi((size_t) hused + 1,-0x7fffffffffffffffll);
+  for (unsigned w = 0; w < nwork; w++)
+    for (unsigned q = 0; q < hcount[w]; q++)
+      { const unsigned x = hrange[w].x + q, r = find(x);
+        if (hh[x].alow < clo[r]) clo[r] = hh[x].alow;
+        if (hh[x].ahgh > chi[r]) chi[r] = hh[x].ahgh;
+      }
+
+  struct Grp { ExItem it; long long span, na, nh; };
+  std::vector<Grp> G;
+  const long long INF = 0x7fffffffffffffffll;
+  std::vector<unsigned> lastof;                                    // scratch: last list position of a component
+  for (unsigned w = 0; w < nwork; w++)
+    { const uint2 hr = hrange[w];
+      if (hr.y & 0x80000000u)
+        { Grp g; g.it.w = w; g.it.h0 = 0; g.it.hn = 0x80000000u; g.it.g = 0; g.span = INF; g.na = g.nh = INF;
+          G.push_back(g); continue;
+        }
+      if (hr.y == 0) continue;
+      const ChainHit *H = hh + hr.x;
+      const bool one = (hr.y >= (1u << (31 - SPEC_SEQ_BITS)));        // too many hits to number by group
+      //  reach[q] = last position holding a hit of the component of hit q
+      lastof.assign(hr.y,0u);
+      { std::vector<std::pair<unsigned,unsigned> > cq(hr.y);
+        for (unsigned q = 0; q < hr.y; q++) cq[q] = std::make_pair(find(hr.x + q),q);
+        std::sort(cq.begin(),cq.end());
+        for (unsigned q = hr.y; q-- > 0; )
+          lastof[cq[q].second] = (q + 1 < hr.y && cq[q+1].first == cq[q].first) ? lastof[cq[q+1].second] : cq[q].second;
+      }
+      unsigned a = 0;
+      while (a < hr.y)
+        { unsigned b = a + 1, reach = lastof[a];
+          long long span = 0; unsigned lastc = 0xffffffffu;
+          while (b < hr.y && (one || b <= reach || (SPEC_GAP >= 0 && H[b].alow - H[b-1].ahgh < SPEC_GAP)))
+            { if (lastof[b] > reach) reach = lastof[b];
+              b += 1;
+            }
+          for (unsigned q = a; q < b; q++)
+            { const unsigned r = find(hr.x + q);
+              if (r != lastc) { span += chi[r] - clo[r]; lastc = r; }
+            }
+          Grp g; g.it.w = w; g.it.h0 = hr.x + a; g.it.hn = b - a; g.it.g = a; g.span = span;
+          g.na = (b < hr.y) ? H[b].alow : INF; g.nh = (b < hr.y) ? H[b].ahgh : INF;
+          G.push_back(g);
+          a = b;
+        }
+    }
+  std::stable_sort(G.begin(),G.end(),[](const Grp &x, const Grp &y) { return x.span > y.span; });
+  items.resize(G.size()); nxt_alow.resize(G.size()); nxt_ahgh.resize(G.size());
+  for (size_t q = 0; q < G.size(); q++) { items[q] = G[q].it; nxt_alow[q] = G[q].na; nxt_ahgh[q] = G[q].nh; }
+}
+
+//  The grouping rule on its own (no device needed): hrange / tinfo as 2 x nwork ints, hits as (alow, ahgh) pairs;
+//  items_out: 4 words per item (work triple, first hit, hits | bit 31, number of the first hit in its triple),
+//  next_out: (alow, ahgh) of the next group's first hit or INT64_MAX.  Returns the number of items
+//  (at most one per hit plus one per triple without a list).
+extern "C" long long fgb_hit_groups_host(int nwork, const unsigned *hrange, const int *tinfo, const long long *hits,
+                                         long long nhits, int bands, long long slack, long long gap,
+                                         unsigned *items_out, long long *next_out)
+{ std::vector<uint2> hr((size_t) nwork); std::vector<int2> ti((size_t) nwork);
+  for (int w = 0; w < nwork; w++) { hr[w] = make_uint2(hrange[2*w],hrange[2*w+1]); ti[w] = make_int2(tinfo[2*w],tinfo[2*w+1]); }
+  std::vector<ChainHit> hh((size_t) nhits + 1);
+  for (long long q = 0; q < nhits; q++) { hh[q].alow = hits[2*q]; hh[q].ahgh = hits[2*q+1]; hh[q].dgmin = hh[q].dgmax = 0; }
+  std::vector<ExItem> items; std::vector<long long> na, nh; std::vector<unsigned> hc;
+  build_hit_groups((unsigned) nwork,hr.data(),ti.data(),hh.data(),(unsigned long long) nhits,bands,slack,gap,items,na,nh,hc);
+  for (size_t q = 0; q < items.size(); q++)
+    { items_out[4*q] = items[q].w; items_out[4*q+1] = items[q].h0; items_out[4*q+2] = items[q].hn; items_out[4*q+3] = items[q].g;
+      next_out[2*q] = na[q]; next_out[2*q+1] = nh[q];
+    }
+  return (long long) items.size();
+}
+
 //  Device blocks (and the result handle) of a call go back on EVERY way out of it, error returns included:
 //  the pointer variables are registered once, whatever they hold when the scope ends is released.
 struct dev_scope
@@ -2562,92 +2672,8 @@ extern "C" int fgb_extend(const fgb_seeds *S, const fgb_genome *A, const fgb_gen
                 CUDA_TRY(cudaStreamSynchronize(st));
                 memcpy(hh.data(),hp,sizeof(ChainHit)*(size_t) hused);
               }
-            for (unsigned w = 0; w < nwork; w++)
-              if (!(hrange[w].y & 0x80000000u)) hcount[w] = hrange[w].y;
-
-            //  components of chains (index = position in hh; only listed triples' ranges are used)
-            std::vector<unsigned> comp((size_t) hused + 1);
-            for (size_t q = 0; q <= hused; q++) comp[q] = (unsigned) q;
-            auto find = [&](unsigned x) { while (comp[x] != x) { comp[x] = comp[comp[x]]; x = comp[x]; } return x; };
-            auto unite = [&](unsigned x, unsigned y) { x = find(x); y = find(y); if (x != y) comp[x < y ? y : x] = (x < y ? x : y); };
-            if (SPEC_GAP < 0)
-              { std::vector<std::pair<std::pair<int,int>,unsigned> > byband;       // ((key, band), w)
-                for (unsigned w = 0; w < nwork; w++)
-                  if (hcount[w] > 0) byband.push_back(std::make_pair(std::make_pair(tinfo[w].x,tinfo[w].y),w));
-                std::sort(byband.begin(),byband.end());
-                for (size_t i = 0; i < byband.size(); i++)
-                  { const unsigned w1 = byband[i].second;
-                    const ChainHit *H1 = hh.data() + hrange[w1].x; const unsigned n1 = hcount[w1];
-                    for (unsigned q = 1; q < n1; q++)                                   // neighbours in its own list
-                      if (H1[q].alow - H1[q-1].ahgh < SPEC_SLACK) unite(hrange[w1].x + q - 1,hrange[w1].x + q);
-                    for (size_t k = i + 1; k < byband.size(); k++)
-                      { if (byband[k].first.first != byband[i].first.first ||
-                            byband[k].first.second - byband[i].first.second > SPEC_BANDS) break;
-                        const unsigned w2 = byband[k].second;
-                        const ChainHit *H2 = hh.data() + hrange[w2].x; const unsigned n2 = hcount[w2];
-                        unsigned a = 0, b = 0;                                          // interval join of two sorted lists
-                        while (a < n1 && b < n2)
-                          { if (H1[a].ahgh + SPEC_SLACK < H2[b].alow) a += 1;
-                            else if (H2[b].ahgh + SPEC_SLACK < H1[a].alow) b += 1;
-                            else
-                              { unite(hrange[w1].x + a,hrange[w2].x + b);
-                                if (H1[a].ahgh < H2[b].ahgh) a += 1; else b += 1;
-                              }
-                          }
-                      }
-                  }
-              }
-            //  extent of every component: how long the alignment of its block will be (launch order)
-            std::vector<long long> clo((size_t) hused + 1,0x7fffffffffffffffll), chi((size_t) hused + 1,-0x7fffffffffffffffll);
-            for (unsigned w = 0; w < nwork; w++)
-              for (unsigned q = 0; q < hcount[w]; q++)
-                { const unsigned x = hrange[w].x + q, r = find(x);
-                  if (hh[x].alow < clo[r]) clo[r] = hh[x].alow;
-                  if (hh[x].ahgh > chi[r]) chi[r] = hh[x].ahgh;
-                }
-
-            struct Grp { ExItem it; long long span, na, nh; };
-            std::vector<Grp> G;
-            const long long INF = 0x7fffffffffffffffll;
-            std::vector<unsigned> lastof;                                    // scratch: last list position of a component
-            for (unsigned w = 0; w < nwork; w++)
-              { const uint2 hr = hrange[w];
-                if (hr.y & 0x80000000u)
-                  { Grp g; g.it.w = w; g.it.h0 = 0; g.it.hn = 0x80000000u; g.it.g = 0; g.span = INF; g.na = g.nh = INF;
-                    G.push_back(g); continue;
-                  }
-                if (hr.y == 0) continue;
-                const ChainHit *H = hh.data() + hr.x;
-                const bool one = (hr.y >= (1u << (31 - SPEC_SEQ_BITS)));        // too many hits to number by group
-                //  reach[q] = last position holding a hit of the component of hit q
-                lastof.assign(hr.y,0u);
-                { std::vector<std::pair<unsigned,unsigned> > cq(hr.y);
-                  for (unsigned q = 0; q < hr.y; q++) cq[q] = std::make_pair(find(hr.x + q),q);
-                  std::sort(cq.begin(),cq.end());
-                  for (unsigned q = hr.y; q-- > 0; )
-                    lastof[cq[q].second] = (q + 1 < hr.y && cq[q+1].first == cq[q].first) ? lastof[cq[q+1].second] : cq[q].second;
-                }
-                unsigned a = 0;
-                while (a < hr.y)
-                  { unsigned b = a + 1, reach = lastof[a];
-                    long long span = 0; unsigned lastc = 0xffffffffu;
-                    while (b < hr.y && (one || b <= reach || (SPEC_GAP >= 0 && H[b].alow - H[b-1].ahgh < SPEC_GAP)))
-                      { if (lastof[b] > reach) reach = lastof[b];
-                        b += 1;
-                      }
-                    for (unsigned q = a; q < b; q++)
-                      { const unsigned r = find(hr.x + q);
-                        if (r != lastc) { span += chi[r] - clo[r]; lastc = r; }
-                      }
-                    Grp g; g.it.w = w; g.it.h0 = hr.x + a; g.it.hn = b - a; g.it.g = a; g.span = span;
-                    g.na = (b < hr.y) ? H[b].alow : INF; g.nh = (b < hr.y) ? H[b].ahgh : INF;
-                    G.push_back(g);
-                    a = b;
-                  }
-              }
-            std::stable_sort(G.begin(),G.end(),[](const Grp &x, const Grp &y) { return x.span > y.span; });
-            items.resize(G.size()); nxt_alow.resize(G.size()); nxt_ahgh.resize(G.size());
-            for (size_t q = 0; q < G.size(); q++) { items[q] = G[q].it; nxt_alow[q] = G[q].na; nxt_ahgh[q] = G[q].nh; }
+            build_hit_groups(nwork,hrange.data(),tinfo.data(),hh.data(),hused,SPEC_BANDS,SPEC_SLACK,SPEC_GAP,
+                             items,nxt_alow,nxt_ahgh,hcount);
             if (!items.empty())
               { CUDA_TRY(fgb_dmalloc((void **) &d_items,sizeof(ExItem)*items.size(),st));
                 CUDA_TRY(fgb_dmalloc((void **) &d_galast,sizeof(long long)*items.size(),st));

@@ -541,6 +541,24 @@ def compute_trace_pts(dA, dB, alns, tspace=100, stream=None):
 
 # ---- building blocks of the k-mer-space sharded path (several GPUs; orchestrated by shard.py) ----
 
+def hit_groups_host(hrange, tinfo, hits, bands=1, slack=1000, gap=-1):
+    """The host rule of fgb_extend that cuts every work triple's chain list into independently extended
+    groups (no device needed).  hrange: (nwork,2) (first hit, count | bit 31); tinfo: (nwork,2) (key,
+    band); hits: (nhits,2) (alow, ahgh).  Returns (items (n,4): triple, first hit, hits, number of the
+    first hit in its triple -- in launch order; next (n,2): first hit of the next group or INT64_MAX)."""
+    L = load_library()
+    hr = np.ascontiguousarray(hrange, dtype=np.uint32).reshape(-1, 2)
+    ti = np.ascontiguousarray(tinfo, dtype=np.int32).reshape(-1, 2)
+    hh = np.ascontiguousarray(hits, dtype=np.int64).reshape(-1, 2)
+    cap = len(hh) + len(hr) + 1
+    items = np.zeros((cap, 4), dtype=np.uint32)
+    nxt = np.zeros((cap, 2), dtype=np.int64)
+    L.fgb_hit_groups_host.restype = c_ll
+    L.fgb_hit_groups_host.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_ll, c_ll, c_void_p, c_void_p]
+    n = L.fgb_hit_groups_host(len(hr), _ptr(hr), _ptr(ti), _ptr(hh), len(hh), bands, slack, gap, _ptr(items), _ptr(nxt))
+    return items[:n].copy(), nxt[:n].copy()
+
+
 def device_free(ptr):
     L = load_library()
     L.fgb_device_free.argtypes = [c_void_p]

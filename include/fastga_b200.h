@@ -232,6 +232,16 @@ int  fgb_seeds_group_by_owner(const void *d_seeds, long long n, const int *bits,
 int  fgb_seeds_from_records(const void *d_recs, long long n, const int *bits, long long amxpos,
                             long long bmxpos, long long sumlen, fgb_seeds **out, void *stream);
 
+/* ---- diagnostics: the host rule that cuts a band-pair triple's chain list into independently
+ *      extended groups (fgb_extend), callable without a device.  hrange / tinfo: 2 ints per
+ *      work triple ((first hit, count | bit 31 = no list), ((strand, contig pair) key, band)); hits:
+ *      (alow, ahgh) per chain; gap < 0: the component rule with `bands` / `slack`, else cut at gaps >= gap.
+ *      items_out: 4 words per item (triple, first hit, hits, number of the first hit in its triple) in
+ *      launch order; next_out: (alow, ahgh) of the next group's first hit (INT64_MAX: none). ---- */
+long long fgb_hit_groups_host(int nwork, const unsigned *hrange, const int *tinfo, const long long *hits,
+                              long long nhits, int bands, long long slack, long long gap,
+                              unsigned *items_out, long long *next_out);
+
 /* ---- housekeeping ---- */
 int  fgb_device_ready(void);
 void fgb_release_cache(void);      /* return cached device blocks to the driver */

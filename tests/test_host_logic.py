@@ -171,3 +171,76 @@ def test_gather_alignments_gloo_world2(tmp_path):
     want = sorted(list(np.load(tmp_path / "lines_0.npy", allow_pickle=True)) +
                   list(np.load(tmp_path / "lines_1.npy", allow_pickle=True)))
     assert merged == want
+
+
+# ---- the hit-group rule of fgb_extend (host code of the library, no device) ----
+
+from fastga_b200 import lib  # noqa: E402  (ctypes mirror; this rule needs no device)
+
+INF = np.iinfo(np.int64).max
+
+
+def _groups(hrange, tinfo, hits, **kw):
+    items, nxt = lib.hit_groups_host(hrange, tinfo, hits, **kw)
+    # per triple: list of (first hit number in the triple, hits) in chain order
+    out = {}
+    for (w, h0, hn, g), (na, nh) in zip(items.tolist(), nxt.tolist()):
+        out.setdefault(w, []).append((g, hn, na, nh))
+    return {w: sorted(v) for w, v in out.items()}, items
+
+
+def test_hit_groups_far_apart_chains_of_one_triple_are_independent():
+    hits = [(0, 5000), (200_000, 260_000), (900_000, 910_000)]
+    g, items = _groups([(0, 3)], [(7, 100)], hits)
+    assert g == {0: [(0, 1, 200_000, 260_000), (1, 1, 900_000, 910_000), (2, 1, INF, INF)]}
+    # launch order: longest component first
+    assert items[:, 3].tolist() == [1, 2, 0]
+
+
+def test_hit_groups_chains_bridged_by_the_neighbouring_band_pair_stay_together():
+    # triple 0 (band 100): two chains 40 kbp apart; triple 1 (band 101, same contig pair) holds one
+    # chain that overlaps both (the block's path drifted into the next band and back)
+    hits = [(0, 50_000), (90_000, 150_000),          # triple 0
+            (45_000, 95_000)]                          # triple 1
+    g, _ = _groups([(0, 2), (2, 1)], [(7, 100), (7, 101)], hits)
+    assert g[0] == [(0, 2, INF, INF)] and g[1] == [(0, 1, INF, INF)]
+    # another contig pair (key) or a band pair further away does not bridge
+    g, _ = _groups([(0, 2), (2, 1)], [(7, 100), (8, 101)], hits)
+    assert [x[:2] for x in g[0]] == [(0, 1), (1, 1)]
+    g, _ = _groups([(0, 2), (2, 1)], [(7, 100), (7, 103)], hits)
+    assert [x[:2] for x in g[0]] == [(0, 1), (1, 1)]
+    g, _ = _groups([(0, 2), (2, 1)], [(7, 100), (7, 103)], hits, bands=3)
+    assert [x[:2] for x in g[0]] == [(0, 2)]
+
+
+def test_hit_groups_a_foreign_chain_between_two_of_one_block_is_not_cut_out():
+    # triple 0: X1, Y, X2 in chain order; X1 and X2 are joined through triple 1's long chain, Y is on
+    # its own: a group must be a contiguous run, so all three stay in one group (cutting Y out would
+    # leave X2 to run as if X1's alignment had not covered it)
+    hits = [(0, 30_000), (40_000, 45_000), (60_000, 90_000),     # triple 0: X1 Y X2
+            (25_000, 65_000)]                                      # triple 1 bridges X1 and X2 ... and Y
+    g, _ = _groups([(0, 3), (3, 1)], [(1, 10), (1, 11)], hits)
+    assert g[0] == [(0, 3, INF, INF)]
+    # a Y that really is foreign: X1 and X2 are joined through band 11 (B1, B2) and band 12 (C, which
+    # overlaps B1 and B2 but is two bands from triple 0, so it does not reach Y): components
+    # {X1, B1, C, B2, X2} and {Y}, chain order X Y X in triple 0 -> still one contiguous group
+    hits = [(0, 30_000), (40_000, 45_000), (60_000, 90_000),     # triple 0, band 10: X1 Y X2
+            (25_000, 32_000), (58_000, 65_000),                  # triple 1, band 11: B1 B2
+            (30_000, 60_000)]                                    # triple 2, band 12: C
+    g, _ = _groups([(0, 3), (3, 2), (5, 1)], [(1, 10), (1, 11), (1, 12)], hits)
+    assert g[0] == [(0, 3, INF, INF)]
+    assert g[1] == [(0, 2, INF, INF)] and g[2] == [(0, 1, INF, INF)]
+    # without the bridge Y and the X's are three components and three groups
+    g, _ = _groups([(0, 3)], [(1, 10)], hits[:3])
+    assert [x[:2] for x in g[0]] == [(0, 1), (1, 1), (2, 1)]
+
+
+def test_hit_groups_gap_rule_and_triples_without_a_list():
+    hits = [(0, 10), (5_000, 5_010), (100_000, 100_010)]
+    g, _ = _groups([(0, 3), (0, 0x80000000), (0, 0)], [(1, 1), (1, 50), (1, 90)], hits, gap=0)
+    assert [x[:2] for x in g[0]] == [(0, 1), (1, 1), (2, 1)]
+    assert g[1] == [(0, 0x80000000, INF, INF)] and 2 not in g
+    g, _ = _groups([(0, 3)], [(1, 1)], hits, gap=50_000)
+    assert [x[:2] for x in g[0]] == [(0, 2), (2, 1)]
+    g, _ = _groups([(0, 3)], [(1, 1)], hits, gap=10**9)
+    assert [x[:2] for x in g[0]] == [(0, 3)]
