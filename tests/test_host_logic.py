@@ -115,6 +115,12 @@ mine = np.concatenate(blocks[rank]) if send[rank].sum() else np.zeros((0, 2), np
 got = shard.exchange_rows(dist, torch.from_numpy(mine.astype(np.int64)), [int(v) for v in send[rank]])
 want = np.concatenate([blocks[s][rank] for s in range(world)])
 assert got.shape == want.shape and np.array_equal(got.numpy(), want), (rank, got.shape, want.shape)
+# the pipelined form the sharded path uses: two exchanges in flight, waited for in issue order
+src = torch.from_numpy(mine.astype(np.int64))
+g1, w1 = shard.exchange_rows(dist, src, [int(v) for v in send[rank]], async_op=True)
+g2, w2 = shard.exchange_rows(dist, src * 3, [int(v) for v in send[rank]], async_op=True)
+w1.wait(); w2.wait()
+assert np.array_equal(g1.numpy(), want) and np.array_equal(g2.numpy(), want * 3)
 print("XCHG_OK", rank)
 dist.destroy_process_group()
 '''
