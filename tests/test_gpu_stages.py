@@ -192,7 +192,7 @@ def test_merge_with_repeats_takes_the_unstaged_and_the_crowded_paths():
     amx, bmx = int(gA.clen.max()), int(gB.clen.max())
     tA, _, _ = xA.download(False)
     tB, pB, _ = xB.download()
-    for freq in (10, 64, 200):
+    for freq in (3, 10, 64, 200, 255):
         ds = lib.DeviceSeeds.find(xA, xB, amx, bmx, freq)
         seeds, sumlen = ol.merge(tA, tB, pB, freq)
         assert ds.n == len(seeds) and ds.sumlen == sumlen, freq
